@@ -1,0 +1,145 @@
+/*
+ * hgk.h -- C-ABI of libhgk.so: the B200 (sm_100a) kernels behind the stacked-hourglass
+ * (+ASN agent) training path of zhiqiangdon/pose-adv-aug.
+ *
+ * The reference has no FFI/plugin layer of its own (it is pure Python on torch 0.3); the
+ * drop-in boundary is the Python module API of models/asn_stacked_hg.py and
+ * pylib/Criterion.py.  Below that API every torch-0.3 op the
+ * reference executes on the hot path is replaced by one entry point of this header; each
+ * entry cites the reference op it replaces (paths relative to the reference repo).
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + sizes, no torch types; all activations are fp32 **NHWC**
+ *     unless the name says nchw; the caller (torch) owns, allocates and frees every buffer;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*), no internal syncs, no
+ *     allocation, no hidden global state; thread-safe for distinct streams;
+ *   - returns 0 on success, <0 on error (HGK_EINVAL bad argument, HGK_ECUDA launch error);
+ *     hgk_last_error() gives the message of the calling thread's last error;
+ *   - a "virtual activation" (z, scale, shift, relu) denotes the tensor
+ *         relu ? max(0, z*scale[c]+shift[c]) : z*scale[c]+shift[c]        (scale==NULL: z)
+ *     i.e. BatchNorm(+ReLU) of the stored pre-BN tensor z applied on load, never materialised.
+ */
+#ifndef HGK_H_
+#define HGK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGK_OK 0
+#define HGK_EINVAL (-1)
+#define HGK_ECUDA (-2)
+
+const char* hgk_last_error(void);
+int hgk_version(void);
+/* 1 if the library was compiled for sm_100a and the current device is compute capability 10.x */
+int hgk_device_ok(void);
+
+/* ---- convolution (nn.Conv2d 1x1 / 3x3 p1, models/asn_stacked_hg.py:17,20,23,242-248,279) ----
+ * y = [accumulate ? y : 0] + conv(T(x), w) + bias + T_res(res)
+ * x: [N,H,W,Cin] virtual activation;  w: [ksize*ksize][Cin][Cout] ("[tap][K][N]", tap = kh*3+kw);
+ * flip!=0 uses w[taps-1-tap] (the data-gradient of a 3x3 conv is the same kernel on dz with
+ * flipped taps and the [tap][Cout_fwd][Cin_fwd] weight array);  bias/res optional (NULL);
+ * stat_sum/stat_sq optional fp64 [Cout] accumulators (+=) of y and y^2 over all pixels: the
+ * batch statistics of the following nn.BatchNorm2d (:19,22,25,243), fused into the epilogue.
+ * path: 0 = auto, 1 = force fp32 SIMT kernel, 2 = force tcgen05 tensor-core kernel.          */
+int hgk_conv_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                  int N, int H, int W, int Cin,
+                  const float* w, int ksize, int flip, const float* bias, int Cout,
+                  const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                  float* y, int accumulate, double* stat_sum, double* stat_sq,
+                  int path, void* stream);
+
+/* weight / bias gradient of the same convolutions (autograd of nn.Conv2d):
+ * dw[co*s_co + ci*s_ci + tap*s_tap] += sum_p dz[p,co] * T(x)[p+off(tap),ci];  dbias[co] += sum_p dz[p,co]
+ * (strides in elements, so gradients land directly in the OIHW-shaped .grad of the parameter). */
+int hgk_conv_wgrad_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                        int N, int H, int W, int Cin, const float* dz, int Cout, int ksize,
+                        float* dw, long long s_co, long long s_ci, long long s_tap,
+                        float* dbias, void* stream);
+
+/* repack many OIHW conv weights in one launch.  table: n_entries x 6 int64 on the device:
+ * {src_offset, dst_offset, O, I, taps, mode}; mode 0: dst[tap][i][o] = src[o][i][tap],
+ * mode 1: dst[tap][o][i] = src[o][i][tap].  Offsets in elements from src_base / dst_base.    */
+int hgk_pack_weights(const float* src_base, float* dst_base, const long long* table, int n_entries,
+                     void* stream);
+
+/* ---- stem: nn.Conv2d(3,64,7,stride=2,padding=3), models/asn_stacked_hg.py:223,283 ----
+ * img: NCHW [N,3,H,W] (the reference's input layout); w: OIHW [Cout,3,7,7]; y: NHWC [N,H/2,W/2,Cout] */
+int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const float* w, const float* bias, int Cout,
+                       float* y, double* stat_sum, double* stat_sq, void* stream);
+int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const float* dz, int Cout,
+                         float* dw, float* dbias, void* stream);
+
+/* ---- nn.BatchNorm2d (eps 1e-5, momentum 0.1), models/asn_stacked_hg.py:19,22,25,224,243 ----
+ * train: (sum, sumsq, count) -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd,
+ * running stats update (unbiased variance).  eval: scale/shift from the running statistics.       */
+int hgk_bn_finalize(const double* sum, const double* sq, long long count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, int C, void* stream);
+int hgk_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, float* scale, float* shift, float* save_mean, float* save_invstd, int C,
+                        void* stream);
+/* backward of y = relu?(bn(z)): g = dy * [z*scale+shift > 0];  sum_g += sum g;  sum_gx += sum g*xhat */
+int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                      const float* mean, const float* invstd, long long P, int C,
+                      double* sum_g, double* sum_gx, void* stream);
+/* dgamma += sum_gx, dbeta += sum_g; coefficients of dz = cA*g + cB*z + cC  (training: full BN backward;
+ * eval: cA = gamma*invstd, cB = cC = 0) */
+int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long count, const float* gamma,
+                        const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
+                        float* cA, float* cB, float* cC, int C, void* stream);
+/* in place: dy <- dz = cA*(dy*mask) + cB*z + cC */
+int hgk_bn_bwd_apply(float* dy, const float* z, const float* scale, const float* shift, int relu,
+                     const float* cA, const float* cB, const float* cC, long long P, int C, void* stream);
+
+/* ---- nn.MaxPool2d(2,2) (:69,227,371) on a virtual activation; backward recomputes the argmax ---- */
+int hgk_maxpool2_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                     int N, int H, int W, int C, float* y, void* stream);
+int hgk_maxpool2_bwd(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                     int N, int H, int W, int C, const float* dy, float* dx, int accumulate, void* stream);
+/* ---- nn.Upsample(scale_factor=2) nearest + skip add (:70,193-203); a_up=0: plain add (:408-417) ----
+ * y[N,H,W,C] = Ta(a[up ? (h/2,w/2) : (h,w)]) + Tb(b)                                                   */
+int hgk_add_fwd(const float* a, const float* a_scale, const float* a_shift, int a_relu, int a_up,
+                const float* b, const float* b_scale, const float* b_shift, int b_relu,
+                int N, int H, int W, int C, float* y, void* stream);
+/* da[N,H/2,W/2,C] = [accumulate ? da : 0] + 2x2 window sums of dy[N,H,W,C] */
+int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, int accumulate, void* stream);
+/* dst = [accumulate ? dst : 0] + src  (gradient fan-in of `x + y + tmp_in`, :334) */
+int hgk_add_into(const float* src, float* dst, long long n, int accumulate, void* stream);
+
+/* ---- layout at the module boundary (the reference API is NCHW) ---- */
+int hgk_nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, void* stream);
+int hgk_nhwc_to_nchw(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                     int N, int H, int W, int C, float* y, void* stream);
+
+/* ---- ASN head: nn.AvgPool2d(k) + nn.Linear (:375-377,431-435) ---- */
+int hgk_avgpool_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                    int N, int H, int W, int C, int k, float* y, void* stream);
+int hgk_avgpool_bwd(const float* dy, int N, int H, int W, int C, int k, float* dx, int accumulate, void* stream);
+int hgk_linear_fwd(const float* x, const float* w, const float* b, int M, int K, int Nout, float* y, void* stream);
+int hgk_linear_bwd(const float* x, const float* w, const float* dy, int M, int K, int Nout,
+                   float* dx, float* dw, float* db, void* stream);
+
+/* ---- losses ----
+ * inline MSE of stack-hg.py:156-159: loss += sum((o-t)^2)*inv_numel; dout = [acc? dout:0] + gscale*2*(o-t)*inv_numel */
+int hgk_mse_fwd_bwd(const float* out, const float* target, long long n, float inv_numel, float gscale,
+                    float* dout, int accumulate, double* loss, void* stream);
+/* pylib/Criterion.py:12-18 and :4-10; kind 0 = weighted_L2, 1 = weighted_sigmoid_crossentropy.
+ * fwd: loss(double, +=);  bwd: dpred = gout[0] * dloss/dpred (gout: device scalar)             */
+int hgk_criterion_fwd(int kind, const float* pred, const float* gt, const float* weight, long long n,
+                      double* loss, void* stream);
+int hgk_criterion_bwd(int kind, const float* pred, const float* gt, const float* weight, long long n,
+                      const float* gout, float* dpred, void* stream);
+
+/* ---- torch.optim.RMSprop(alpha,eps,momentum=0,weight_decay=0), stack-hg.py:51-52,165 ----
+ * one launch over the flat buffers: g' = g*grad_scale; v = alpha v + (1-alpha) g'^2; p -= lr g'/(sqrt(v)+eps) */
+int hgk_rmsprop_flat(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
+                     float grad_scale, void* stream);
+/* y[i] = (float)x[i]  (double loss accumulators -> fp32 scalars) */
+int hgk_f64_to_f32(const double* x, float* y, int n, float mul, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGK_H_ */

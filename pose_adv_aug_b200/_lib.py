@@ -1,0 +1,82 @@
+"""ctypes binding of libhgk.so (the C-ABI declared in include/hgk.h).
+
+There is no CPU / PyTorch fallback: if the shared library is missing or a kernel call
+fails, the product path raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhgk.so")
+
+P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+# name -> argument types (the trailing `void* stream` included).  Mirrors include/hgk.h.
+SIGNATURES = {
+    "hgk_conv_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, I, P, P, P, I, P, I, P, P, I, P],
+    "hgk_conv_wgrad_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, L, L, L, P, P],
+    "hgk_pack_weights": [P, P, P, I, P],
+    "hgk_stem_conv7_fwd": [P, I, I, I, P, P, I, P, P, P, P],
+    "hgk_stem_conv7_wgrad": [P, I, I, I, P, I, P, P, P],
+    "hgk_bn_finalize": [P, P, L, P, P, F, F, P, P, P, P, P, P, I, P],
+    "hgk_bn_eval_prepare": [P, P, P, P, F, P, P, P, P, I, P],
+    "hgk_bn_bwd_reduce": [P, P, P, P, I, P, P, L, I, P, P, P],
+    "hgk_bn_bwd_finalize": [P, P, L, P, P, P, I, P, P, P, P, P, I, P],
+    "hgk_bn_bwd_apply": [P, P, P, P, I, P, P, P, L, I, P],
+    "hgk_maxpool2_fwd": [P, P, P, I, I, I, I, I, P, P],
+    "hgk_maxpool2_bwd": [P, P, P, I, I, I, I, I, P, P, I, P],
+    "hgk_add_fwd": [P, P, P, I, I, P, P, P, I, I, I, I, I, P, P],
+    "hgk_upsample2_bwd": [P, I, I, I, I, P, I, P],
+    "hgk_add_into": [P, P, L, I, P],
+    "hgk_nchw_to_nhwc": [P, I, I, I, I, P, P],
+    "hgk_nhwc_to_nchw": [P, P, P, I, I, I, I, I, P, P],
+    "hgk_avgpool_fwd": [P, P, P, I, I, I, I, I, I, P, P],
+    "hgk_avgpool_bwd": [P, I, I, I, I, I, P, I, P],
+    "hgk_linear_fwd": [P, P, P, I, I, I, P, P],
+    "hgk_linear_bwd": [P, P, P, I, I, I, P, P, P, P],
+    "hgk_mse_fwd_bwd": [P, P, L, F, F, P, I, P, P],
+    "hgk_criterion_fwd": [I, P, P, P, L, P, P],
+    "hgk_criterion_bwd": [I, P, P, P, L, P, P, P],
+    "hgk_rmsprop_flat": [P, P, P, L, F, F, F, F, P],
+    "hgk_f64_to_f32": [P, P, I, F, P],
+}
+
+
+class HGKError(RuntimeError):
+    pass
+
+
+class _Lib(object):
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise HGKError(
+                "libhgk.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the CUDA path)" % path)
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        self.cdll.hgk_last_error.restype = ctypes.c_char_p
+        self.cdll.hgk_last_error.argtypes = []
+        self.cdll.hgk_version.restype = I
+        self.cdll.hgk_device_ok.restype = I
+        for name, args in SIGNATURES.items():
+            fn = getattr(self.cdll, name)      # AttributeError if the symbol is not exported
+            fn.argtypes = args
+            fn.restype = I
+            setattr(self, name[4:], fn)
+
+    def last_error(self):
+        return self.cdll.hgk_last_error().decode()
+
+    def check(self, rc, name="hgk"):
+        if rc != 0:
+            raise HGKError("%s failed (%d): %s" % (name, rc, self.last_error()))
+
+
+_lib = None
+
+
+def get_lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib(LIB_PATH)
+    return _lib

@@ -1,0 +1,224 @@
+// nn.BatchNorm2d (eps 1e-5, momentum 0.1) of the reference (models/asn_stacked_hg.py:19,22,25,
+// 224,243) split the B200 way: the per-channel sums are produced by the convolution epilogues
+// (fp64 accumulators), `bn_finalize` turns them into (scale, shift) that the *consumers* apply on
+// load, and the backward is reduce -> finalize -> apply over the stored pre-BN tensor.
+#include "common.cuh"
+
+namespace hgk {
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* scale,
+                                   float* shift, float* save_mean, float* save_invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean = sum[c] / count;
+    double var = sq[c] / count - mean * mean;      // fp64: no cancellation issue at these magnitudes
+    if (var < 0.0) var = 0.0;
+    double invstd = 1.0 / sqrt(var + (double)eps);
+    float sc = (float)((double)gamma[c] * invstd);
+    scale[c] = sc;
+    shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)invstd;
+    if (running_mean != nullptr) {
+        double unb = count > 1.0 ? var * (count / (count - 1.0)) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+    }
+}
+
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                       float* scale, float* shift, float* save_mean, float* save_invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double invstd = 1.0 / sqrt((double)rv[c] + (double)eps);
+    scale[c] = (float)((double)gamma[c] * invstd);
+    shift[c] = (float)((double)beta[c] - (double)rm[c] * (double)gamma[c] * invstd);
+    save_mean[c] = rm[c];
+    save_invstd[c] = (float)invstd;
+}
+
+// One block = 256 threads = rows_par pixel rows x (C/4) channel quads; grid-strided over pixels.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            int relu, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, long long P, int C,
+                                                            double* sum_g, double* sum_gx, int cq_per_blk, int rows_par,
+                                                            long long rows_per_blk) {
+    extern __shared__ double red[];      // [rows_par][cq_per_blk*4][2]
+    const int tid = threadIdx.x;
+    const int cq = tid % cq_per_blk, row = tid / cq_per_blk;
+    const int c = (blockIdx.y * cq_per_blk + cq) * 4;
+    const bool active = row < rows_par && c < C;
+    double g1[4] = {0, 0, 0, 0}, g2[4] = {0, 0, 0, 0};
+    if (active) {
+        float4 s = ldg4(scale + c), t = ldg4(shift + c), mu = ldg4(mean + c), is = ldg4(invstd + c);
+        long long p0 = (long long)blockIdx.x * rows_per_blk;
+        long long p1 = p0 + rows_per_blk < P ? p0 + rows_per_blk : P;
+        float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
+        int cnt = 0;
+        for (long long p = p0 + row; p < p1; p += rows_par) {
+            float4 d = ldg4(dy + p * C + c);
+            float4 v = ldg4(z + p * C + c);
+            float gx = (relu && fmaf(v.x, s.x, t.x) <= 0.f) ? 0.f : d.x;
+            float gy = (relu && fmaf(v.y, s.y, t.y) <= 0.f) ? 0.f : d.y;
+            float gz = (relu && fmaf(v.z, s.z, t.z) <= 0.f) ? 0.f : d.z;
+            float gw = (relu && fmaf(v.w, s.w, t.w) <= 0.f) ? 0.f : d.w;
+            f1[0] += gx; f2[0] = fmaf(gx, (v.x - mu.x) * is.x, f2[0]);
+            f1[1] += gy; f2[1] = fmaf(gy, (v.y - mu.y) * is.y, f2[1]);
+            f1[2] += gz; f2[2] = fmaf(gz, (v.z - mu.z) * is.z, f2[2]);
+            f1[3] += gw; f2[3] = fmaf(gw, (v.w - mu.w) * is.w, f2[3]);
+            if (++cnt == 16) {           // flush short fp32 partials into fp64
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g1[j] += (double)f1[j]; g2[j] += (double)f2[j];
+                    f1[j] = 0.f; f2[j] = 0.f;
+                }
+                cnt = 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { g1[j] += (double)f1[j]; g2[j] += (double)f2[j]; }
+    }
+    if (row < rows_par) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[((row * cq_per_blk + cq) * 4 + j) * 2 + 0] = g1[j];
+            red[((row * cq_per_blk + cq) * 4 + j) * 2 + 1] = g2[j];
+        }
+    }
+    __syncthreads();
+    const int nch = cq_per_blk * 4;
+    if (tid < nch) {
+        int cc = blockIdx.y * nch + tid;
+        if (cc < C) {
+            double a = 0.0, b = 0.0;
+            for (int r = 0; r < rows_par; ++r) {
+                a += red[(r * nch + tid) * 2 + 0];
+                b += red[(r * nch + tid) * 2 + 1];
+            }
+            atomicAdd(sum_g + cc, a);
+            atomicAdd(sum_gx + cc, b);
+        }
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int training, float* dgamma, float* dbeta,
+                                       float* cA, float* cB, float* cC, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sg = sum_g[c], sgx = sum_gx[c];
+    if (dgamma != nullptr) dgamma[c] += (float)sgx;
+    if (dbeta != nullptr) dbeta[c] += (float)sg;
+    double A = (double)gamma[c] * (double)invstd[c];
+    if (training) {
+        double c1 = sg / count, c2 = sgx / count;
+        cA[c] = (float)A;
+        cB[c] = (float)(-A * (double)invstd[c] * c2);
+        cC[c] = (float)(-A * c1 + A * (double)mean[c] * (double)invstd[c] * c2);
+    } else {
+        cA[c] = (float)A;
+        cB[c] = 0.f;
+        cC[c] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           int relu, const float* __restrict__ cA, const float* __restrict__ cB,
+                                                           const float* __restrict__ cC, long long total4, int C4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        float4 d = ld4(dy + i * 4);
+        float4 v = ldg4(z + i * 4);
+        float4 s = ldg4(scale + c), t = ldg4(shift + c), a = ldg4(cA + c), b = ldg4(cB + c), cc = ldg4(cC + c);
+        float gx = (relu && fmaf(v.x, s.x, t.x) <= 0.f) ? 0.f : d.x;
+        float gy = (relu && fmaf(v.y, s.y, t.y) <= 0.f) ? 0.f : d.y;
+        float gz = (relu && fmaf(v.z, s.z, t.z) <= 0.f) ? 0.f : d.z;
+        float gw = (relu && fmaf(v.w, s.w, t.w) <= 0.f) ? 0.f : d.w;
+        float4 o;
+        o.x = fmaf(a.x, gx, fmaf(b.x, v.x, cc.x));
+        o.y = fmaf(a.y, gy, fmaf(b.y, v.y, cc.y));
+        o.z = fmaf(a.z, gz, fmaf(b.z, v.z, cc.z));
+        o.w = fmaf(a.w, gw, fmaf(b.w, v.w, cc.w));
+        st4(dy + i * 4, o);
+    }
+}
+
+}  // namespace hgk
+
+using namespace hgk;
+
+extern "C" int hgk_bn_finalize(const double* sum, const double* sq, long long count, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               float* scale, float* shift, float* save_mean, float* save_invstd, int C, void* stream) {
+    HGK_REQUIRE(sum && sq && gamma && beta && scale && shift && save_mean && save_invstd, "hgk_bn_finalize: null pointer");
+    HGK_REQUIRE(C > 0 && count > 0, "hgk_bn_finalize: C and count must be positive");
+    HGK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "hgk_bn_finalize: running stats must both be set");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sq, (double)count, gamma, beta, eps, momentum,
+                                                                           running_mean, running_var, scale, shift,
+                                                                           save_mean, save_invstd, C);
+    HGK_CHECK_LAUNCH("hgk_bn_finalize");
+    return HGK_OK;
+}
+
+extern "C" int hgk_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, float eps, float* scale, float* shift, float* save_mean,
+                                   float* save_invstd, int C, void* stream) {
+    HGK_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && save_mean && save_invstd,
+                "hgk_bn_eval_prepare: null pointer");
+    HGK_REQUIRE(C > 0, "hgk_bn_eval_prepare: C must be positive");
+    bn_eval_prepare_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps,
+                                                                               scale, shift, save_mean, save_invstd, C);
+    HGK_CHECK_LAUNCH("hgk_bn_eval_prepare");
+    return HGK_OK;
+}
+
+extern "C" int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                                 const float* mean, const float* invstd, long long P, int C, double* sum_g,
+                                 double* sum_gx, void* stream) {
+    HGK_REQUIRE(dy && z && scale && shift && mean && invstd && sum_g && sum_gx, "hgk_bn_bwd_reduce: null pointer");
+    HGK_REQUIRE(P > 0 && C > 0 && C % 4 == 0, "hgk_bn_bwd_reduce: need P > 0 and C %% 4 == 0 (P=%lld C=%d)", P, C);
+    int cq = C / 4;
+    int cq_per_blk = cq < 64 ? cq : 64;                   // up to 256 channels per block column
+    int ngrp = (cq + cq_per_blk - 1) / cq_per_blk;
+    int rows_par = 256 / cq_per_blk;
+    long long want_blocks = (4LL * kNumSMs + ngrp - 1) / ngrp;
+    long long rows_per_blk = (P + want_blocks - 1) / want_blocks;
+    if (rows_per_blk < 64) rows_per_blk = 64;
+    long long nblk = (P + rows_per_blk - 1) / rows_per_blk;
+    dim3 grid((unsigned)nblk, (unsigned)ngrp);
+    size_t smem = (size_t)rows_par * cq_per_blk * 4 * 2 * sizeof(double);
+    bn_bwd_reduce_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, mean, invstd, P, C, sum_g,
+                                                                    sum_gx, cq_per_blk, rows_par, rows_per_blk);
+    HGK_CHECK_LAUNCH("hgk_bn_bwd_reduce");
+    return HGK_OK;
+}
+
+extern "C" int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long count, const float* gamma,
+                                   const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
+                                   float* cA, float* cB, float* cC, int C, void* stream) {
+    HGK_REQUIRE(sum_g && sum_gx && gamma && mean && invstd && cA && cB && cC, "hgk_bn_bwd_finalize: null pointer");
+    HGK_REQUIRE(C > 0 && count > 0, "hgk_bn_bwd_finalize: C and count must be positive");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum_g, sum_gx, (double)count, gamma, mean,
+                                                                               invstd, training, dgamma, dbeta, cA, cB, cC, C);
+    HGK_CHECK_LAUNCH("hgk_bn_bwd_finalize");
+    return HGK_OK;
+}
+
+extern "C" int hgk_bn_bwd_apply(float* dy, const float* z, const float* scale, const float* shift, int relu,
+                                const float* cA, const float* cB, const float* cC, long long P, int C, void* stream) {
+    HGK_REQUIRE(dy && z && scale && shift && cA && cB && cC, "hgk_bn_bwd_apply: null pointer");
+    HGK_REQUIRE(P > 0 && C > 0 && C % 4 == 0, "hgk_bn_bwd_apply: need P > 0 and C %% 4 == 0");
+    long long total4 = P * (C / 4);
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+    bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, cA, cB, cC, total4, C / 4);
+    HGK_CHECK_LAUNCH("hgk_bn_bwd_apply");
+    return HGK_OK;
+}

@@ -1,0 +1,391 @@
+// Bandwidth-bound ladder ops of _Hourglass / ASN (reference models/asn_stacked_hg.py:69-70,
+// 140-157,192-203,407-417,431-435): 2x2 max-pool of a virtual activation (BN+ReLU applied on
+// load), nearest 2x up-sample + skip add, their backward passes, NCHW<->NHWC boundary
+// transposes, AvgPool2d and the tiny nn.Linear heads.  All are 128-bit coalesced NHWC streams.
+#include "common.cuh"
+
+namespace hgk {
+
+static inline unsigned stream_blocks(long long work_items) {
+    long long b = (work_items + 255) / 256;
+    long long cap = 16LL * kNumSMs;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(Act x, int N, int H, int W, int C4, float* __restrict__ y) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * OH * OW * C4;
+    const int C = C4 * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        int ow = (int)(q % OW);
+        long long r = q / OW;
+        int oh = (int)(r % OH);
+        int n = (int)(r / OH);
+        float4 s, t;
+        load_affine4(x.scale, x.shift, cq * 4, s, t);
+        const float* base = x.z + (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        float4 v00 = ldg4(base), v01 = ldg4(base + C), v10 = ldg4(base + (long long)W * C), v11 = ldg4(base + (long long)W * C + C);
+        if (x.scale != nullptr) {
+            v00 = act4(v00, s, t, x.relu); v01 = act4(v01, s, t, x.relu);
+            v10 = act4(v10, s, t, x.relu); v11 = act4(v11, s, t, x.relu);
+        }
+        float4 o;
+        o.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x));
+        o.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+        o.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z));
+        o.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+        st4(y + i * 4, o);
+    }
+}
+
+// first-maximum-in-scan-order wins (torch max_pool2d: `val > maxval`), so ties route like the reference
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+    int k = 0;
+    float m = a;
+    if (b > m) { m = b; k = 1; }
+    if (c > m) { m = c; k = 2; }
+    if (d > m) { m = d; k = 3; }
+    return k;
+}
+
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, int W, int C4,
+                                                           const float* __restrict__ dy, float* __restrict__ dx, int accumulate) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * OH * OW * C4;
+    const int C = C4 * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        int ow = (int)(q % OW);
+        long long r = q / OW;
+        int oh = (int)(r % OH);
+        int n = (int)(r / OH);
+        float4 s, t;
+        load_affine4(x.scale, x.shift, cq * 4, s, t);
+        const long long off = (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        const long long o01 = C, o10 = (long long)W * C, o11 = (long long)W * C + C;
+        float4 v00 = ldg4(x.z + off), v01 = ldg4(x.z + off + o01), v10 = ldg4(x.z + off + o10), v11 = ldg4(x.z + off + o11);
+        if (x.scale != nullptr) {
+            v00 = act4(v00, s, t, x.relu); v01 = act4(v01, s, t, x.relu);
+            v10 = act4(v10, s, t, x.relu); v11 = act4(v11, s, t, x.relu);
+        }
+        float4 g = ldg4(dy + i * 4);
+        int kx = argmax4(v00.x, v01.x, v10.x, v11.x);
+        int ky = argmax4(v00.y, v01.y, v10.y, v11.y);
+        int kz = argmax4(v00.z, v01.z, v10.z, v11.z);
+        int kw = argmax4(v00.w, v01.w, v10.w, v11.w);
+        float4 d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            d[k] = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f, kw == k ? g.w : 0.f);
+        const long long offs[4] = {0, o01, o10, o11};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float* p = dx + off + offs[k];
+            float4 o = d[k];
+            if (accumulate) {
+                float4 old = ld4(p);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            st4(p, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, int N, int H, int W, int C4, float* __restrict__ y) {
+    const long long total = (long long)N * H * W * C4;
+    const int C = C4 * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        float4 sa, ta, sb, tb;
+        load_affine4(a.scale, a.shift, cq * 4, sa, ta);
+        load_affine4(b.scale, b.shift, cq * 4, sb, tb);
+        long long ai = i * 4;
+        if (a_up) {
+            int w = (int)(q % W);
+            long long r = q / W;
+            int h = (int)(r % H);
+            int n = (int)(r / H);
+            ai = ((((long long)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C) + cq * 4;
+        }
+        float4 va = ldg4(a.z + ai);
+        float4 vb = ldg4(b.z + i * 4);
+        if (a.scale != nullptr) va = act4(va, sa, ta, a.relu);
+        if (b.scale != nullptr) vb = act4(vb, sb, tb, b.relu);
+        st4(y + i * 4, make_float4(va.x + vb.x, va.y + vb.y, va.z + vb.z, va.w + vb.w));
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C4,
+                                                            float* __restrict__ da, int accumulate) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * OH * OW * C4;
+    const int C = C4 * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        int ow = (int)(q % OW);
+        long long r = q / OW;
+        int oh = (int)(r % OH);
+        int n = (int)(r / OH);
+        const float* base = dy + (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        float4 a = ldg4(base), b = ldg4(base + C), c = ldg4(base + (long long)W * C), d = ldg4(base + (long long)W * C + C);
+        float4 o = make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
+        if (accumulate) {
+            float4 old = ld4(da + i * 4);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st4(da + i * 4, o);
+    }
+}
+
+__global__ void __launch_bounds__(256) add_into_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4,
+                                                       long long n, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = ldg4(src + i * 4);
+        if (accumulate) {
+            float4 o = ld4(dst + i * 4);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        st4(dst + i * 4, v);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = (accumulate ? dst[i] : 0.f) + src[i];
+    }
+}
+
+// [rows][cols] -> [cols][rows] per image, 32x32 smem tiles; optional affine(+relu) indexed by the
+// NHWC channel (which is `col` for nhwc->nchw)
+__global__ void transpose_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 int relu, int rows, int cols, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const long long img = (long long)blockIdx.z * rows * cols;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int r = r0 + j, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < rows && c < cols) {
+            v = __ldg(x + img + (long long)r * cols + c);
+            if (scale != nullptr) v = act1(v, __ldg(scale + c), __ldg(shift + c), relu);
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) y[img + (long long)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(Act x, int N, int H, int W, int C4, int k, float* __restrict__ y) {
+    const int OH = H / k, OW = W / k;
+    const long long total = (long long)N * OH * OW * C4;
+    const int C = C4 * 4;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        int ow = (int)(q % OW);
+        long long r = q / OW;
+        int oh = (int)(r % OH);
+        int n = (int)(r / OH);
+        float4 s, t;
+        load_affine4(x.scale, x.shift, cq * 4, s, t);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int dy = 0; dy < k; ++dy)
+            for (int dx = 0; dx < k; ++dx) {
+                float4 v = ldg4(x.z + (((long long)n * H + oh * k + dy) * W + ow * k + dx) * C + cq * 4);
+                if (x.scale != nullptr) v = act4(v, s, t, x.relu);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        st4(y + i * 4, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C4, int k,
+                                                          float* __restrict__ dx, int accumulate) {
+    const int OH = H / k, OW = W / k;
+    const long long total = (long long)N * H * W * C4;
+    const int C = C4 * 4;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cq = (int)(i % C4);
+        long long q = i / C4;
+        int w = (int)(q % W);
+        long long r = q / W;
+        int h = (int)(r % H);
+        int n = (int)(r / H);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h / k < OH && w / k < OW) {
+            float4 g = ldg4(dy + (((long long)n * OH + h / k) * OW + w / k) * C + cq * 4);
+            o = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
+        }
+        if (accumulate) {
+            float4 old = ld4(dx + i * 4);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st4(dx + i * 4, o);
+    }
+}
+
+// y[m][n] = b[n] + sum_k x[m][k] w[n][k]; one warp per output element
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int M,
+                                  int K, int Nout, float* __restrict__ y) {
+    int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= M * Nout) return;
+    int m = wid / Nout, n = wid - m * Nout;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(x + (size_t)m * K + k), __ldg(w + (size_t)n * K + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[wid] = acc + (b ? __ldg(b + n) : 0.f);
+}
+
+// dx[m][k] = sum_n dy[m][n] w[n][k];  dw[n][k] += sum_m dy[m][n] x[m][k];  db[n] += sum_m dy[m][n]
+__global__ void linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy, int M,
+                                  int K, int Nout, float* dx, float* dw, float* db) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dx != nullptr && i < M * K) {
+        int m = i / K, k = i - m * K;
+        float acc = 0.f;
+        for (int n = 0; n < Nout; ++n) acc = fmaf(__ldg(dy + m * Nout + n), __ldg(w + (size_t)n * K + k), acc);
+        dx[i] = acc;
+    }
+    if (dw != nullptr && i < Nout * K) {
+        int n = i / K, k = i - n * K;
+        float acc = 0.f;
+        for (int m = 0; m < M; ++m) acc = fmaf(__ldg(dy + m * Nout + n), __ldg(x + (size_t)m * K + k), acc);
+        dw[i] += acc;
+    }
+    if (db != nullptr && i < Nout) {
+        float acc = 0.f;
+        for (int m = 0; m < M; ++m) acc += __ldg(dy + m * Nout + i);
+        db[i] += acc;
+    }
+}
+
+}  // namespace hgk
+
+using namespace hgk;
+
+#define HGK_NHWC_CHECK(name)                                                                      \
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, name ": need positive dims and C %% 4 == 0 (C=%d)", C)
+
+extern "C" int hgk_maxpool2_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                                int C, float* y, void* stream) {
+    HGK_REQUIRE(x && y, "hgk_maxpool2_fwd: null pointer");
+    HGK_NHWC_CHECK("hgk_maxpool2_fwd");
+    HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_fwd: H and W must be even (H=%d W=%d)", H, W);
+    long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+    maxpool2_fwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
+    HGK_CHECK_LAUNCH("hgk_maxpool2_fwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_maxpool2_bwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                                int C, const float* dy, float* dx, int accumulate, void* stream) {
+    HGK_REQUIRE(x && dy && dx, "hgk_maxpool2_bwd: null pointer");
+    HGK_NHWC_CHECK("hgk_maxpool2_bwd");
+    HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_bwd: H and W must be even (H=%d W=%d)", H, W);
+    long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+    maxpool2_bwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
+                                                                                dy, dx, accumulate);
+    HGK_CHECK_LAUNCH("hgk_maxpool2_bwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_add_fwd(const float* a, const float* a_scale, const float* a_shift, int a_relu, int a_up, const float* b,
+                           const float* b_scale, const float* b_shift, int b_relu, int N, int H, int W, int C, float* y,
+                           void* stream) {
+    HGK_REQUIRE(a && b && y, "hgk_add_fwd: null pointer");
+    HGK_NHWC_CHECK("hgk_add_fwd");
+    HGK_REQUIRE(!a_up || (H % 2 == 0 && W % 2 == 0), "hgk_add_fwd: up-sampled output must have even H, W");
+    long long total = (long long)N * H * W * (C / 4);
+    add_fwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{a, a_scale, a_shift, a_relu}, a_up,
+                                                                           Act{b, b_scale, b_shift, b_relu}, N, H, W, C / 4, y);
+    HGK_CHECK_LAUNCH("hgk_add_fwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, int accumulate, void* stream) {
+    HGK_REQUIRE(dy && da, "hgk_upsample2_bwd: null pointer");
+    HGK_NHWC_CHECK("hgk_upsample2_bwd");
+    HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_upsample2_bwd: H and W must be even");
+    long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+    upsample2_bwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, N, H, W, C / 4, da, accumulate);
+    HGK_CHECK_LAUNCH("hgk_upsample2_bwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_add_into(const float* src, float* dst, long long n, int accumulate, void* stream) {
+    HGK_REQUIRE(src && dst && n > 0, "hgk_add_into: bad arguments");
+    HGK_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "hgk_add_into: pointers must be 16-byte aligned");
+    add_into_kernel<<<stream_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(src, dst, n / 4, n, accumulate);
+    HGK_CHECK_LAUNCH("hgk_add_into");
+    return HGK_OK;
+}
+
+extern "C" int hgk_nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, void* stream) {
+    HGK_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "hgk_nchw_to_nhwc: bad arguments");
+    HGK_REQUIRE(N <= 65535, "hgk_nchw_to_nhwc: batch too large");
+    int rows = C, cols = H * W;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, N), block(32, 8);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, 0, rows, cols, y);
+    HGK_CHECK_LAUNCH("hgk_nchw_to_nhwc");
+    return HGK_OK;
+}
+
+extern "C" int hgk_nhwc_to_nchw(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                                int C, float* y, void* stream) {
+    HGK_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "hgk_nhwc_to_nchw: bad arguments");
+    HGK_REQUIRE(N <= 65535, "hgk_nhwc_to_nchw: batch too large");
+    HGK_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "hgk_nhwc_to_nchw: scale/shift must both be set");
+    int rows = H * W, cols = C;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, N), block(32, 8);
+    HGK_REQUIRE(grid.y <= 65535, "hgk_nhwc_to_nchw: image too large");
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_scale, x_shift, x_relu, rows, cols, y);
+    HGK_CHECK_LAUNCH("hgk_nhwc_to_nchw");
+    return HGK_OK;
+}
+
+extern "C" int hgk_avgpool_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                               int C, int k, float* y, void* stream) {
+    HGK_REQUIRE(x && y, "hgk_avgpool_fwd: null pointer");
+    HGK_NHWC_CHECK("hgk_avgpool_fwd");
+    HGK_REQUIRE(k > 0 && H >= k && W >= k, "hgk_avgpool_fwd: kernel %d larger than input %dx%d", k, H, W);
+    long long total = (long long)N * (H / k) * (W / k) * (C / 4);
+    avgpool_fwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, k, y);
+    HGK_CHECK_LAUNCH("hgk_avgpool_fwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_avgpool_bwd(const float* dy, int N, int H, int W, int C, int k, float* dx, int accumulate, void* stream) {
+    HGK_REQUIRE(dy && dx, "hgk_avgpool_bwd: null pointer");
+    HGK_NHWC_CHECK("hgk_avgpool_bwd");
+    HGK_REQUIRE(k > 0 && H >= k && W >= k, "hgk_avgpool_bwd: kernel %d larger than input %dx%d", k, H, W);
+    long long total = (long long)N * H * W * (C / 4);
+    avgpool_bwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, N, H, W, C / 4, k, dx, accumulate);
+    HGK_CHECK_LAUNCH("hgk_avgpool_bwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_linear_fwd(const float* x, const float* w, const float* b, int M, int K, int Nout, float* y, void* stream) {
+    HGK_REQUIRE(x && w && y && M > 0 && K > 0 && Nout > 0, "hgk_linear_fwd: bad arguments");
+    long long threads = (long long)M * Nout * 32;
+    linear_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, M, K, Nout, y);
+    HGK_CHECK_LAUNCH("hgk_linear_fwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_linear_bwd(const float* x, const float* w, const float* dy, int M, int K, int Nout, float* dx, float* dw,
+                              float* db, void* stream) {
+    HGK_REQUIRE(x && w && dy && M > 0 && K > 0 && Nout > 0, "hgk_linear_bwd: bad arguments");
+    long long n = (long long)(M > Nout ? M : Nout) * K;
+    linear_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, dy, M, K, Nout, dx, dw, db);
+    HGK_CHECK_LAUNCH("hgk_linear_bwd");
+    return HGK_OK;
+}

@@ -1,0 +1,205 @@
+// Stem convolution nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3) of
+// _Hourglass_Wrapper (reference models/asn_stacked_hg.py:223,283): direct convolution that reads
+// the NCHW image the reference API is fed with and writes the NHWC pre-BN tensor + the batch
+// statistics of bn1 (:224).  Cin = 3 makes this an FFMA kernel (K = 147), 2 % of the step FLOPs.
+#include "common.cuh"
+
+namespace hgk {
+
+constexpr int ST_TH = 8, ST_TW = 16;                  // output tile (pixels)
+constexpr int ST_PH = 2 * ST_TH + 5, ST_PW = 2 * ST_TW + 5;   // input patch 21 x 37
+constexpr int ST_K = 147;                              // 3*7*7
+constexpr int ST_CO = 64;
+
+__device__ __forceinline__ void stem_load_patch(float* patch, const float* img, int n, int H, int W, int oy0,
+                                                int ox0, int tid) {
+    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+    for (int i = tid; i < 3 * ST_PH * ST_PW; i += 256) {
+        int c = i / (ST_PH * ST_PW);
+        int r = i - c * (ST_PH * ST_PW);
+        int py = r / ST_PW, px = r - py * ST_PW;
+        int iy = iy0 + py, ix = ix0 + px;
+        float v = 0.f;
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+            v = __ldg(img + ((size_t)(n * 3 + c) * H + iy) * W + ix);
+        patch[i] = v;
+    }
+}
+
+// grid: (tiles_x, tiles_y, N); 256 threads: tx = tid&15 -> 4 couts, ty = tid>>4 -> 8 pixels
+__global__ void __launch_bounds__(256) stem_conv7_fwd_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ y, double* stat_sum, double* stat_sq) {
+    __shared__ __align__(16) float Ws[ST_K * ST_CO];          // [k][co]
+    __shared__ float patch[3 * ST_PH * ST_PW];
+    const int tid = threadIdx.x;
+    const int OH = H / 2, OW = W / 2;
+    const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH, n = blockIdx.z;
+    for (int i = tid; i < ST_K * ST_CO; i += 256) {           // coalesced over k, transposed store
+        int co = i / ST_K, k = i - co * ST_K;
+        Ws[k * ST_CO + co] = __ldg(w + i);
+    }
+    stem_load_patch(patch, img, n, H, W, oy0, ox0, tid);
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    const int oy = ty >> 1, oxb = (ty & 1) * 8;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < 3; ++c)
+        for (int kh = 0; kh < 7; ++kh) {
+            const float* prow = patch + (c * ST_PH + oy * 2 + kh) * ST_PW + oxb * 2;
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+                float4 b = ld4(Ws + ((c * 7 + kh) * 7 + kw) * ST_CO + tx * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float av = prow[i * 2 + kw];
+                    acc[i][0] = fmaf(av, b.x, acc[i][0]);
+                    acc[i][1] = fmaf(av, b.y, acc[i][1]);
+                    acc[i][2] = fmaf(av, b.z, acc[i][2]);
+                    acc[i][3] = fmaf(av, b.w, acc[i][3]);
+                }
+            }
+        }
+    float4 bv = bias ? ldg4(bias + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int gy = oy0 + oy;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int gx = ox0 + oxb + i;
+        if (gy < OH && gx < OW) {
+            float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+            st4(y + (((size_t)n * OH + gy) * OW + gx) * ST_CO + tx * 4, v);
+            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+        }
+    }
+    if (stat_sum != nullptr) {
+        __syncthreads();
+        double* red = reinterpret_cast<double*>(Ws);          // [8 warps][64][2]
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double d1 = (double)s1[j], d2 = (double)s2[j];
+            d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, 16);
+            if (lane < 16) {
+                red[(warp * 64 + tx * 4 + j) * 2 + 0] = d1;
+                red[(warp * 64 + tx * 4 + j) * 2 + 1] = d2;
+            }
+        }
+        __syncthreads();
+        if (tid < 64) {
+            double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) {
+                d1 += red[(wv * 64 + tid) * 2 + 0];
+                d2 += red[(wv * 64 + tid) * 2 + 1];
+            }
+            atomicAdd(stat_sum + tid, d1);
+            atomicAdd(stat_sq + tid, d2);
+        }
+    }
+}
+
+// dW[co][k] += sum_p dz[p][co] * patch(p)[k];  persistent CTAs loop over output tiles and flush once.
+// thread -> 4 couts (tx) x 10 taps (ty*10 .. +9 of the 147, padded to 160)
+__global__ void __launch_bounds__(256) stem_conv7_wgrad_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                               const float* __restrict__ dz, float* dw, float* dbias,
+                                                               int tiles_x, int tiles_y) {
+    __shared__ __align__(16) float dzs[ST_TH * ST_TW * ST_CO];     // [pixel][co]
+    __shared__ float patch[3 * ST_PH * ST_PW];
+    const int tid = threadIdx.x;
+    const int OH = H / 2, OW = W / 2;
+    const int tx = tid & 15, ty = tid >> 4;
+    int koff[10];
+    bool kval[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        int k = ty * 10 + j;
+        kval[j] = k < ST_K;
+        int kk = kval[j] ? k : 0;
+        int c = kk / 49, r = kk - c * 49;
+        int kh = r / 7, kw = r - kh * 7;
+        koff[j] = (c * ST_PH + kh) * ST_PW + kw;
+    }
+    float acc[4][10];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    const int total = tiles_x * tiles_y * N;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int n = t / (tiles_x * tiles_y);
+        int r = t - n * (tiles_x * tiles_y);
+        int tyi = r / tiles_x, txi = r - tyi * tiles_x;
+        int oy0 = tyi * ST_TH, ox0 = txi * ST_TW;
+        __syncthreads();
+        stem_load_patch(patch, img, n, H, W, oy0, ox0, tid);
+        for (int i = tid; i < ST_TH * ST_TW * (ST_CO / 4); i += 256) {
+            int q = i >> 4, cv = i & 15;
+            int gy = oy0 + q / ST_TW, gx = ox0 + (q % ST_TW);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy < OH && gx < OW) v = ldg4(dz + (((size_t)n * OH + gy) * OW + gx) * ST_CO + cv * 4);
+            st4(dzs + q * ST_CO + cv * 4, v);
+        }
+        __syncthreads();
+        for (int q = 0; q < ST_TH * ST_TW; ++q) {
+            float4 a = ld4(dzs + q * ST_CO + tx * 4);
+            const float* pb = patch + (q / ST_TW) * 2 * ST_PW + (q % ST_TW) * 2;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                float b = pb[koff[j]];
+                acc[0][j] = fmaf(a.x, b, acc[0][j]);
+                acc[1][j] = fmaf(a.y, b, acc[1][j]);
+                acc[2][j] = fmaf(a.z, b, acc[2][j]);
+                acc[3][j] = fmaf(a.w, b, acc[3][j]);
+            }
+        }
+        if (dbias != nullptr && tid < ST_CO) {
+            for (int q = 0; q < ST_TH * ST_TW; ++q) bsum += dzs[q * ST_CO + tid];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+            if (kval[j]) atomicAdd(dw + (size_t)(tx * 4 + i) * ST_K + ty * 10 + j, acc[i][j]);
+    if (dbias != nullptr && tid < ST_CO) atomicAdd(dbias + tid, bsum);
+}
+
+}  // namespace hgk
+
+using namespace hgk;
+
+extern "C" int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const float* w, const float* bias, int Cout,
+                                  float* y, double* stat_sum, double* stat_sq, void* stream) {
+    HGK_REQUIRE(img && w && y, "hgk_stem_conv7_fwd: null pointer");
+    HGK_REQUIRE(Cout == ST_CO, "hgk_stem_conv7_fwd: Cout must be 64 (got %d)", Cout);
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hgk_stem_conv7_fwd: H, W must be even and positive");
+    HGK_REQUIRE((stat_sum == nullptr) == (stat_sq == nullptr), "hgk_stem_conv7_fwd: stat_sum/stat_sq must both be set");
+    HGK_REQUIRE(N <= 65535, "hgk_stem_conv7_fwd: batch too large");
+    dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
+    stem_conv7_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, w, bias, y, stat_sum, stat_sq);
+    HGK_CHECK_LAUNCH("hgk_stem_conv7_fwd");
+    return HGK_OK;
+}
+
+extern "C" int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const float* dz, int Cout,
+                                    float* dw, float* dbias, void* stream) {
+    HGK_REQUIRE(img && dz && dw, "hgk_stem_conv7_wgrad: null pointer");
+    HGK_REQUIRE(Cout == ST_CO, "hgk_stem_conv7_wgrad: Cout must be 64 (got %d)", Cout);
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hgk_stem_conv7_wgrad: H, W must be even and positive");
+    int tiles_x = (W / 2 + ST_TW - 1) / ST_TW, tiles_y = (H / 2 + ST_TH - 1) / ST_TH;
+    long long total = (long long)tiles_x * tiles_y * N;
+    int grid = (int)(total < 2 * kNumSMs ? total : 2 * kNumSMs);
+    stem_conv7_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, dz, dw, dbias, tiles_x, tiles_y);
+    HGK_CHECK_LAUNCH("hgk_stem_conv7_wgrad");
+    return HGK_OK;
+}

@@ -1,0 +1,752 @@
+"""Host-side plan builder / executor for the B200 hourglass path.
+
+The reference executes its graph op by op through torch-0.3 autograd (one THCUNN / cuDNN
+launch per nn.Module call).  Here a network forward is *planned once* per input shape into a
+static list of C-ABI kernel launches (include/hgk.h) over pre-allocated NHWC buffers; the
+backward list is derived from the same tape.  Activations that follow a BatchNorm are kept
+"virtual": the stored tensor is the pre-BN convolution output z and the consumers apply
+relu(z*scale+shift) on load (boundary shift).
+
+PyTorch is used for device memory, streams and autograd glue only; every arithmetic op of the
+path is a libhgk kernel.
+"""
+import ctypes
+
+import torch
+
+from ._lib import get_lib, HGKError
+
+BN_EPS = 1e-5        # nn.BatchNorm2d defaults used by the reference (models/asn_stacked_hg.py:19)
+BN_MOMENTUM = 0.1
+_ALIGN = 32          # elements; keeps every parameter 128-byte aligned inside the flat buffers
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------
+# Flat parameter / gradient storage
+# ------------------------------------------------------------------------------------------
+class ParamStore(object):
+    """All parameters of a root module as views into ONE flat fp32 buffer (+ one flat gradient
+    buffer, + flat BN running-stat buffers).  This is what the flat RMSprop kernel and the single
+    NCCL all-reduce operate on (the reference's nn.DataParallel reduce_add + ~2000 optimizer
+    launches, stack-hg.py:49,165)."""
+
+    def __init__(self, module, device):
+        self.device = device
+        self.params = []
+        seen = set()
+        for p in module.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = max(off, _ALIGN)
+        self.flat = torch.zeros(self.numel, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(self.numel, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data.to(device=device, dtype=torch.float32))
+                old_grad = p.grad
+                p.data = view
+                gview = self.grad[o:o + p.numel()].view(p.shape)
+                if old_grad is not None:
+                    gview.copy_(old_grad.to(device=device, dtype=torch.float32))
+                p.grad = gview
+        # buffers: fp32 running statistics and int64 num_batches_tracked
+        self.fbufs, self.ibufs = [], []
+        seen = set()
+        for name, b in module.named_buffers():
+            if id(b) in seen:
+                continue
+            seen.add(id(b))
+            (self.fbufs if b.dtype.is_floating_point else self.ibufs).append(b)
+        foff, self.fboff = 0, []
+        for b in self.fbufs:
+            self.fboff.append(foff)
+            foff += (b.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.fbuf_flat = torch.zeros(max(foff, _ALIGN), device=device, dtype=torch.float32)
+        self.ibuf_flat = torch.zeros(max(len(self.ibufs), 1), device=device, dtype=torch.long)
+        with torch.no_grad():
+            for b, o in zip(self.fbufs, self.fboff):
+                view = self.fbuf_flat[o:o + b.numel()].view(b.shape)
+                view.copy_(b.data.to(device=device, dtype=torch.float32))
+                b.data = view
+            for i, b in enumerate(self.ibufs):
+                view = self.ibuf_flat[i:i + 1].view(b.shape)
+                view.copy_(b.data.to(device))
+                b.data = view
+        self.index = dict((id(p), i) for i, p in enumerate(self.params))
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._bptrs = [b.data_ptr() for b in self.fbufs + self.ibufs]
+        self.version = 0
+
+    def grad_ptr(self, p_index):
+        return self.grad.data_ptr() + 4 * self.offsets[p_index]
+
+    def valid(self):
+        """True while every parameter / buffer is still the view this store created."""
+        for p, ptr in zip(self.params, self._ptrs):
+            if p.data_ptr() != ptr or p.dtype != torch.float32:
+                return False
+        for b, ptr in zip(self.fbufs + self.ibufs, self._bptrs):
+            if b.data_ptr() != ptr:
+                return False
+        return True
+
+    def attach_grads(self):
+        """Re-attach .grad views dropped by zero_grad(set_to_none=True) (zeroing their storage)."""
+        missing = [i for i, p in enumerate(self.params)
+                   if p.grad is None or p.grad.data_ptr() != self.grad_ptr(i)]
+        if not missing:
+            return
+        if len(missing) == len(self.params):
+            self.grad.zero_()
+        for i in missing:
+            p, o = self.params[i], self.offsets[i]
+            gview = self.grad[o:o + p.numel()].view(p.shape)
+            if len(missing) != len(self.params):
+                if p.grad is not None:
+                    gview.copy_(p.grad)
+                else:
+                    gview.zero_()
+            p.grad = gview
+
+    def index_of(self, p):
+        return self.index[id(p)]
+
+
+# ------------------------------------------------------------------------------------------
+# Plan
+# ------------------------------------------------------------------------------------------
+class T(object):
+    """A tensor node of the plan: NHWC buffer z [N,H,W,C] + optional on-load affine/ReLU."""
+    __slots__ = ("z", "N", "H", "W", "C", "scale", "shift", "relu", "needs_grad", "grad", "contribs",
+                 "producer", "name")
+
+    def __init__(self, z, N, H, W, C, scale=None, shift=None, relu=False, needs_grad=False, name=""):
+        self.z, self.N, self.H, self.W, self.C = z, N, H, W, C
+        self.scale, self.shift, self.relu = scale, shift, relu
+        self.needs_grad = needs_grad
+        self.grad = None          # buffer holding d loss / d (activated value) once initialised
+        self.contribs = []        # pending (buffer, donatable) gradient contributions
+        self.producer = None
+        self.name = name
+
+    @property
+    def P(self):
+        return self.N * self.H * self.W
+
+    def act_args(self):
+        return [_ptr(self.z), _ptr(self.scale), _ptr(self.shift), int(self.relu)]
+
+
+class BNRec(object):
+    __slots__ = ("gamma", "beta", "rmean", "rvar", "C", "scale", "shift", "mean", "invstd", "sum", "sq",
+                 "sum_g", "sum_gx", "cA", "cB", "cC", "training")
+
+
+class Plan(object):
+    """Static launch lists (forward, backward) for one module / input shape / mode."""
+
+    VEC_CAP = 1 << 22      # fp32 per-channel vectors (scale, shift, mean, invstd, cA, cB, cC)
+    STAT_CAP = 1 << 20     # fp64 per-channel accumulators
+
+    def __init__(self, stores, device, training, need_grad, conv_path=0):
+        self.lib = get_lib()
+        self.stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+        self.device = device
+        self.training = training       # current BN mode; builders may switch it between sub-modules
+        self.need_grad = need_grad
+        self.conv_path = conv_path
+        self.fwd = []              # [fn, args(list), name]
+        self.bwd = []
+        self.tape = []
+        self.keep = []             # tensors kept alive
+        self.vec = torch.zeros(self.VEC_CAP, device=device, dtype=torch.float32)
+        self.vec_used = 0
+        self.stat_f = torch.zeros(self.STAT_CAP, device=device, dtype=torch.float64)
+        self.stat_f_used = 0
+        self.stat_b = torch.zeros(self.STAT_CAP if need_grad else 1, device=device, dtype=torch.float64)
+        self.stat_b_used = 0
+        self.pack_entries = []     # (src param, dst offset, O, I, taps, mode)
+        self.pack_used = 0
+        self.pack_buf = None
+        self.pack_table = None
+        self.pack_launch = None
+        self.dyn = {}              # name -> list of (launch, arg index) patched at run time
+        self.inputs = []
+        self.outputs = []          # (kind, tensor node or torch tensor)
+        self.bn_recs = []
+        self.nbt_bufs = []
+        self.nbt_flat = []
+        self.fwd_count = 0
+        self.bytes_alloc = 0
+        self.finished = False
+
+    # ---- allocation helpers ----
+    def buf(self, *shape):
+        t = torch.empty(*shape, device=self.device, dtype=torch.float32)
+        self.bytes_alloc += t.numel() * 4
+        self.keep.append(t)
+        return t
+
+    def vec_alloc(self, C):
+        n = (C + 3) // 4 * 4
+        if self.vec_used + n > self.VEC_CAP:
+            raise HGKError("plan vector arena exhausted")
+        v = self.vec[self.vec_used:self.vec_used + C]
+        self.vec_used += n
+        return v
+
+    def _stat_alloc(self, which, C):
+        n = (C + 1) // 2 * 2
+        if which == "f":
+            if self.stat_f_used + n > self.STAT_CAP:
+                raise HGKError("plan statistics arena exhausted")
+            v = self.stat_f[self.stat_f_used:self.stat_f_used + C]
+            self.stat_f_used += n
+        else:
+            if self.stat_b_used + n > self.STAT_CAP:
+                raise HGKError("plan statistics arena exhausted")
+            v = self.stat_b[self.stat_b_used:self.stat_b_used + C]
+            self.stat_b_used += n
+        return v
+
+    def launch(self, lst, fn_name, *args):
+        fn = getattr(self.lib, fn_name)
+        rec = [fn, list(args), fn_name]
+        lst.append(rec)
+        return rec
+
+    def dynamic(self, key, rec, idx):
+        self.dyn.setdefault(key, []).append((rec, idx))
+
+    # ---- parameters ----
+    def param_ptr(self, p):
+        return p.data_ptr()
+
+    def param_grad_ptr(self, p):
+        for st in self.stores:
+            i = st.index.get(id(p))
+            if i is not None:
+                return st.grad_ptr(i)
+        raise KeyError("parameter is not part of any flat store of this plan")
+
+    def packed_weight(self, w, mode):
+        """Device pointer (resolved at finish()) of the repacked copy of OIHW weight `w`.
+        mode 0: [tap][I][O]  (forward operand), mode 1: [tap][O][I] (data-gradient operand)."""
+        O, I = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3]
+        for e in self.pack_entries:
+            if e[0] is w and e[5] == mode:
+                return e[1]
+        off = self.pack_used
+        self.pack_used += (O * I * taps + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.pack_entries.append((w, off, O, I, taps, mode))
+        return off
+
+    # ---- BN record ----
+    def bn_rec(self, bn):
+        r = BNRec()
+        r.gamma, r.beta, r.rmean, r.rvar = bn.weight, bn.bias, bn.running_mean, bn.running_var
+        r.training = self.training
+        C = r.C = bn.weight.numel()
+        r.scale, r.shift = self.vec_alloc(C), self.vec_alloc(C)
+        r.mean, r.invstd = self.vec_alloc(C), self.vec_alloc(C)
+        if self.training:
+            r.sum, r.sq = self._stat_alloc("f", C), self._stat_alloc("f", C)
+        else:
+            r.sum = r.sq = None
+        if self.need_grad:
+            r.sum_g, r.sum_gx = self._stat_alloc("b", C), self._stat_alloc("b", C)
+            r.cA, r.cB, r.cC = self.vec_alloc(C), self.vec_alloc(C), self.vec_alloc(C)
+        self.bn_recs.append(r)
+        if getattr(bn, "num_batches_tracked", None) is not None and self.training:
+            self.nbt_bufs.append(bn.num_batches_tracked)
+        if not self.training:
+            self.launch(self.fwd, "bn_eval_prepare", _ptr(r.gamma), _ptr(r.beta), _ptr(r.rmean), _ptr(r.rvar),
+                        BN_EPS, _ptr(r.scale), _ptr(r.shift), _ptr(r.mean), _ptr(r.invstd), C)
+        return r
+
+    # ---- gradient bookkeeping (resolved at plan-build time) ----
+    def contribute(self, t, buf, donatable):
+        if t is not None and t.needs_grad:
+            t.contribs.append((buf, donatable))
+
+    def grad_target(self, t, allow_res=True):
+        """(buffer, accumulate flag, residual buffer or None) for a kernel about to write d/d t."""
+        res = None
+        if t.grad is None:
+            for i, (b, don) in enumerate(t.contribs):
+                if don:
+                    t.grad = b
+                    t.contribs.pop(i)
+                    break
+            if t.grad is not None:
+                acc = 1
+            else:
+                t.grad = self.buf(t.N, t.H, t.W, t.C)
+                acc = 0
+        else:
+            acc = 1
+        if allow_res and t.contribs:
+            res = t.contribs.pop(0)[0]
+        return t.grad, acc, res
+
+    def finalize_grad(self, t):
+        """Flush pending contributions; returns the complete gradient buffer of t (or None)."""
+        if t.grad is None:
+            for i, (b, don) in enumerate(t.contribs):
+                if don:
+                    t.grad = b
+                    t.contribs.pop(i)
+                    break
+        n = t.P * t.C
+        while t.contribs:
+            b, _ = t.contribs.pop(0)
+            if t.grad is None:
+                t.grad = self.buf(t.N, t.H, t.W, t.C)
+                self.launch(self.bwd, "add_into", _ptr(b), _ptr(t.grad), n, 0)
+            else:
+                self.launch(self.bwd, "add_into", _ptr(b), _ptr(t.grad), n, 1)
+        return t.grad
+
+    # ---- ops ----
+    def input_image(self, N, H, W):
+        """Raw NCHW [N,3,H,W] user tensor (pointer patched per call); only the stem reads it."""
+        t = T(None, N, H, W, 3, name="image")
+        self.inputs.append(("image", t))
+        return t
+
+    def input_nchw(self, N, C, H, W, needs_grad):
+        """NCHW feature tensor at the module boundary -> NHWC plan tensor."""
+        z = self.buf(N, H, W, C)
+        t = T(z, N, H, W, C, needs_grad=needs_grad and self.need_grad, name="in%d" % len(self.inputs))
+        key = "in%d" % len(self.inputs)
+        rec = self.launch(self.fwd, "nchw_to_nhwc", 0, N, C, H, W, _ptr(z))
+        self.dynamic(key, rec, 0)
+        self.inputs.append((key, t))
+        op = _InputOp(self, t, key)
+        t.producer = op
+        self.tape.append(op)
+        return t
+
+    def stem(self, img, conv, bn):
+        op = _StemOp(self, img, conv, bn)
+        self.tape.append(op)
+        return op.out
+
+    def conv(self, x, conv, bn=None, res=None, relu=True):
+        op = _ConvOp(self, x, conv, bn, res, relu)
+        self.tape.append(op)
+        return op.out
+
+    def maxpool(self, x):
+        op = _PoolOp(self, x)
+        self.tape.append(op)
+        return op.out
+
+    def add(self, a, b, upsample_a=False):
+        op = _AddOp(self, a, b, upsample_a)
+        self.tape.append(op)
+        return op.out
+
+    def avgpool(self, x, k):
+        op = _AvgPoolOp(self, x, k)
+        self.tape.append(op)
+        return op.out
+
+    def linear(self, x, fc):
+        op = _LinearOp(self, x, fc)
+        self.tape.append(op)
+        return op.out
+
+    def detach(self, x):
+        """Same values, no gradient flow (x.detach(), models/asn_stacked_hg.py:161)."""
+        return T(x.z, x.N, x.H, x.W, x.C, x.scale, x.shift, x.relu, needs_grad=False, name=x.name + ".detached")
+
+    def target_nchw(self, N, C, H, W):
+        """NCHW ground-truth heat-maps (pointer patched per call) -> NHWC, no gradient."""
+        z = self.buf(N, H, W, C)
+        rec = self.launch(self.fwd, "nchw_to_nhwc", 0, N, C, H, W, _ptr(z))
+        self.dynamic("target", rec, 0)
+        t = T(z, N, H, W, C, name="target")
+        self.inputs.append(("target", t))
+        return t
+
+    def mse_loss(self, o, target, loss_acc, gscale=1.0):
+        """loss_acc (fp64 scalar) += mean((o - target)^2); the gradient 2(o-t)/numel is produced in
+        the same pass (inline loss of stack-hg.py:156-159)."""
+        op = _MSEOp(self, o, target, loss_acc, gscale)
+        self.tape.append(op)
+        return op
+
+    def output_nchw(self, x, no_grad=False):
+        """Materialise T(x) as a contiguous NCHW tensor handed to the caller."""
+        op = _OutputOp(self, x, len(self.outputs), no_grad=no_grad)
+        self.tape.append(op)
+        self.outputs.append(op)
+        return op
+
+    def output_rows(self, x):
+        """[N,1,1,C] plan tensor returned as an [N,C] torch tensor (ASN logits)."""
+        op = _OutputOp(self, x, len(self.outputs), rows=True)
+        self.tape.append(op)
+        self.outputs.append(op)
+        return op
+
+    # ---- finish / run ----
+    def finish(self):
+        if self.need_grad:
+            for op in reversed(self.tape):
+                op.emit_bwd()
+        if self.pack_entries:
+            self.pack_buf = torch.empty(self.pack_used, device=self.device, dtype=torch.float32)
+            self.bytes_alloc += self.pack_used * 4
+            base = min(st.flat.data_ptr() for st in self.stores)
+            rows = []
+            for (w, off, O, I, taps, mode) in self.pack_entries:
+                d = w.data_ptr() - base
+                assert d >= 0 and d % 4 == 0, "weight outside the flat stores"
+                rows.append([d // 4, off, O, I, taps, mode])
+            self.pack_table = torch.tensor(rows, dtype=torch.long, device=self.device)
+            self.pack_launch = [self.lib.pack_weights,
+                                [base, self.pack_buf.data_ptr(), self.pack_table.data_ptr(), len(rows)], "pack_weights"]
+            pb = self.pack_buf.data_ptr()
+            for lst in (self.fwd, self.bwd):
+                for rec in lst:
+                    rec[1] = [pb + 4 * a.off if isinstance(a, _PackRef) else a for a in rec[1]]
+        # num_batches_tracked: one flat add per store when every BN of that store is in training mode
+        ids = set(id(b) for b in self.nbt_bufs)
+        for st in self.stores:
+            if st.ibufs and all(id(b) in ids for b in st.ibufs):
+                self.nbt_flat.append(st.ibuf_flat)
+                mine = set(id(b) for b in st.ibufs)
+                self.nbt_bufs = [b for b in self.nbt_bufs if id(b) not in mine]
+        self.finished = True
+
+    def _run(self, lst, stream):
+        for fn, args, name in lst:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise HGKError("%s failed (%d): %s" % (name, rc, self.lib.last_error()))
+
+    def patch(self, key, ptr):
+        for rec, idx in self.dyn.get(key, ()):
+            rec[1][idx] = ptr
+
+    def run_forward(self, inputs):
+        """inputs: list of contiguous fp32 CUDA tensors in the order they were declared."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for (key, t), x in zip(self.inputs, inputs):
+            self.patch(key, x.data_ptr())
+        if self.stat_f_used:
+            self.stat_f[:self.stat_f_used].zero_()
+        if self.pack_launch is not None:
+            self._run([self.pack_launch], stream)
+        self._run(self.fwd, stream)
+        for f in self.nbt_flat:
+            f.add_(1)
+        for b in self.nbt_bufs:
+            b.add_(1)
+        self.fwd_count += 1
+        return [op.result for op in self.outputs]
+
+    def run_backward(self, inputs, gouts):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for (key, t), x in zip(self.inputs, inputs):
+            self.patch(key, x.data_ptr())
+        if self.stat_b_used:
+            self.stat_b[:self.stat_b_used].zero_()
+        held = []
+        for op, g in zip(self.outputs, gouts):
+            if op.no_grad:
+                continue
+            if g is None:
+                op.gsrc.zero_()
+                self.patch("gout%d" % op.index, op.gsrc.data_ptr())
+            else:
+                g = g.contiguous()
+                if g.dtype != torch.float32:
+                    g = g.float()
+                held.append(g)
+                self.patch("gout%d" % op.index, g.data_ptr())
+        self._run(self.bwd, stream)
+        return [op.gin for op in self.tape if isinstance(op, _InputOp)]
+
+
+class _PackRef(object):
+    __slots__ = ("off",)
+
+    def __init__(self, off):
+        self.off = off
+
+
+class _InputOp(object):
+    def __init__(self, plan, t, key):
+        self.plan, self.t, self.key = plan, t, key
+        self.gin = None
+
+    def emit_bwd(self):
+        p, t = self.plan, self.t
+        if not t.needs_grad:
+            return
+        g = p.finalize_grad(t)
+        if g is None:
+            return
+        self.gin = torch.empty(t.N, t.C, t.H, t.W, device=p.device, dtype=torch.float32)
+        p.launch(p.bwd, "nhwc_to_nchw", _ptr(g), 0, 0, 0, t.N, t.H, t.W, t.C, _ptr(self.gin))
+
+
+class _StemOp(object):
+    """conv1 7x7 s2 + bn1 (+relu on load), models/asn_stacked_hg.py:283-285."""
+
+    def __init__(self, plan, img, conv, bn):
+        self.plan, self.img, self.conv = plan, img, conv
+        p = plan
+        N, H, W = img.N, img.H, img.W
+        Cout = conv.weight.shape[0]
+        if H % 2 or W % 2:
+            raise ValueError("stem needs even H, W (got %dx%d)" % (H, W))
+        if tuple(conv.weight.shape[1:]) != (3, 7, 7) or Cout != 64:
+            raise ValueError("stem conv must be Conv2d(3,64,7,stride=2,padding=3)")
+        z = p.buf(N, H // 2, W // 2, Cout)
+        self.bn = r = p.bn_rec(bn)
+        rec = p.launch(p.fwd, "stem_conv7_fwd", 0, N, H, W, p.param_ptr(conv.weight), p.param_ptr(conv.bias), Cout,
+                       _ptr(z), _ptr(r.sum), _ptr(r.sq))
+        p.dynamic("image", rec, 0)
+        self.out = T(z, N, H // 2, W // 2, Cout, r.scale, r.shift, True, needs_grad=p.need_grad, name="stem")
+        self.out.producer = self
+        if r.training:
+            p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
+                     BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
+                     _ptr(r.invstd), Cout)
+
+    def emit_bwd(self):
+        p, o, r = self.plan, self.out, self.bn
+        g = p.finalize_grad(o)
+        if g is None:
+            return
+        _emit_bn_bwd(p, o, r, g)
+        rec = p.launch(p.bwd, "stem_conv7_wgrad", 0, self.img.N, self.img.H, self.img.W, _ptr(g), o.C,
+                       p.param_grad_ptr(self.conv.weight), p.param_grad_ptr(self.conv.bias))
+        p.dynamic("image", rec, 0)
+
+
+def _emit_bn_bwd(p, o, r, g):
+    """dY (buffer g, gradient w.r.t. relu(bn(z))) -> dz in place."""
+    p.launch(p.bwd, "bn_bwd_reduce", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean),
+             _ptr(r.invstd), o.P, o.C, _ptr(r.sum_g), _ptr(r.sum_gx))
+    p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
+             int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
+    p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.cA),
+             _ptr(r.cB), _ptr(r.cC), o.P, o.C)
+
+
+class _ConvOp(object):
+    """nn.Conv2d 1x1 / 3x3(p1) [+ `out += shortcut`] [+ nn.BatchNorm2d + ReLU applied by the consumers]."""
+
+    def __init__(self, plan, x, conv, bn, res, relu):
+        self.plan, self.x, self.conv, self.res = plan, x, conv, res
+        p = plan
+        w = conv.weight
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        if k not in (1, 3) or w.shape[3] != k:
+            raise ValueError("only 1x1 and 3x3 convolutions are supported (got %dx%d)" % (w.shape[2], w.shape[3]))
+        if Cin != x.C:
+            raise ValueError("conv expects %d input channels, got %d" % (Cin, x.C))
+        if Cin % 4 or Cout % 4:
+            raise ValueError("channel counts must be multiples of 4 (Cin=%d, Cout=%d)" % (Cin, Cout))
+        if res is not None and (res.C != Cout or res.P != x.P):
+            raise ValueError("shortcut shape mismatch")
+        self.k, self.Cin, self.Cout = k, Cin, Cout
+        z = p.buf(x.N, x.H, x.W, Cout)
+        self.bn = r = p.bn_rec(bn) if bn is not None else None
+        stats = r is not None and r.training
+        ra = res.act_args() if res is not None else [0, 0, 0, 0]
+        p.launch(p.fwd, "conv_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _PackRef(p.packed_weight(w, 0)), k, 0,
+                                                       p.param_ptr(conv.bias), Cout] + ra +
+                                       [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0,
+                                        p.conv_path]))
+        if r is not None:
+            self.out = T(z, x.N, x.H, x.W, Cout, r.scale, r.shift, relu, needs_grad=p.need_grad, name="conv")
+            if r.training:
+                p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
+                         BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
+                         _ptr(r.invstd), Cout)
+        else:
+            self.out = T(z, x.N, x.H, x.W, Cout, needs_grad=p.need_grad, name="conv")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, o, x = self.plan, self.out, self.x
+        g = p.finalize_grad(o)
+        if g is None:
+            return
+        if self.bn is not None:
+            _emit_bn_bwd(p, o, self.bn, g)
+        w = self.conv.weight
+        k, Cin, Cout = self.k, self.Cin, self.Cout
+        # weight / bias gradient straight into the OIHW .grad views
+        p.launch(p.bwd, "conv_wgrad_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k,
+                                                             p.param_grad_ptr(w), Cin * k * k, k * k, 1,
+                                                             p.param_grad_ptr(self.conv.bias)]))
+        # data gradient: same kernel on dz with the [tap][Cout][Cin] weights, taps flipped
+        if x.needs_grad:
+            gx, acc, extra = p.grad_target(x)
+            wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))
+            p.launch(p.bwd, "conv_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, wref, k, 1, 0, Cin,
+                     _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0, p.conv_path)
+        # shortcut: d/d res = dz (donated: this op never touches the buffer again)
+        if self.res is not None:
+            p.contribute(self.res, g, True)
+
+
+class _PoolOp(object):
+    """nn.MaxPool2d(2, 2) of a virtual activation, models/asn_stacked_hg.py:69,142-154,287."""
+
+    def __init__(self, plan, x):
+        self.plan, self.x = plan, x
+        if x.H % 2 or x.W % 2:
+            raise ValueError("max-pool input must have even H, W (got %dx%d)" % (x.H, x.W))
+        z = plan.buf(x.N, x.H // 2, x.W // 2, x.C)
+        plan.launch(plan.fwd, "maxpool2_fwd", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(z)]))
+        self.out = T(z, x.N, x.H // 2, x.W // 2, x.C, needs_grad=x.needs_grad, name="pool")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, x = self.plan, self.x
+        g = p.finalize_grad(self.out)
+        if g is None or not x.needs_grad:
+            return
+        gx, acc, _ = p.grad_target(x, allow_res=False)
+        p.launch(p.bwd, "maxpool2_bwd", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(g), _ptr(gx), acc]))
+
+
+class _AddOp(object):
+    """`upsample(x) + skip` (models/asn_stacked_hg.py:193-203) or a plain add (:408-417, :334)."""
+
+    def __init__(self, plan, a, b, up):
+        self.plan, self.a, self.b, self.up = plan, a, b, up
+        if a.C != b.C or a.N != b.N or (a.H * (2 if up else 1), a.W * (2 if up else 1)) != (b.H, b.W):
+            raise ValueError("add: shape mismatch")
+        z = plan.buf(b.N, b.H, b.W, b.C)
+        plan.launch(plan.fwd, "add_fwd", *(a.act_args() + [int(up)] + b.act_args() + [b.N, b.H, b.W, b.C, _ptr(z)]))
+        self.out = T(z, b.N, b.H, b.W, b.C, needs_grad=a.needs_grad or b.needs_grad, name="add")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, a, b = self.plan, self.a, self.b
+        g = p.finalize_grad(self.out)
+        if g is None:
+            return
+        if a.needs_grad:
+            ga, acc, _ = p.grad_target(a, allow_res=False)
+            if self.up:
+                p.launch(p.bwd, "upsample2_bwd", _ptr(g), b.N, b.H, b.W, b.C, _ptr(ga), acc)
+            else:
+                p.launch(p.bwd, "add_into", _ptr(g), _ptr(ga), a.P * a.C, acc)
+        p.contribute(b, g, True)
+
+
+class _AvgPoolOp(object):
+    """nn.AvgPool2d(k), models/asn_stacked_hg.py:375,431."""
+
+    def __init__(self, plan, x, k):
+        self.plan, self.x, self.k = plan, x, k
+        if x.H < k or x.W < k:
+            raise ValueError("avg-pool kernel %d larger than input %dx%d" % (k, x.H, x.W))
+        z = plan.buf(x.N, x.H // k, x.W // k, x.C)
+        plan.launch(plan.fwd, "avgpool_fwd", *(x.act_args() + [x.N, x.H, x.W, x.C, k, _ptr(z)]))
+        self.out = T(z, x.N, x.H // k, x.W // k, x.C, needs_grad=x.needs_grad, name="avgpool")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, x = self.plan, self.x
+        g = p.finalize_grad(self.out)
+        if g is None or not x.needs_grad:
+            return
+        gx, acc, _ = p.grad_target(x, allow_res=False)
+        p.launch(p.bwd, "avgpool_bwd", _ptr(g), x.N, x.H, x.W, x.C, self.k, _ptr(gx), acc)
+
+
+class _LinearOp(object):
+    """nn.Linear on [N, C] rows (fc_scale / fc_rotation, models/asn_stacked_hg.py:376-377,434-435)."""
+
+    def __init__(self, plan, x, fc):
+        self.plan, self.x, self.fc = plan, x, fc
+        if x.H != 1 or x.W != 1 or x.scale is not None:
+            raise ValueError("linear expects a plain [N,1,1,C] tensor")
+        Nout, K = fc.weight.shape
+        if K != x.C:
+            raise ValueError("linear expects %d features, got %d" % (K, x.C))
+        z = plan.buf(x.N, 1, 1, Nout)
+        plan.launch(plan.fwd, "linear_fwd", _ptr(x.z), plan.param_ptr(fc.weight), plan.param_ptr(fc.bias), x.N, K, Nout,
+                    _ptr(z))
+        self.out = T(z, x.N, 1, 1, Nout, needs_grad=plan.need_grad, name="linear")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, x, fc = self.plan, self.x, self.fc
+        g = p.finalize_grad(self.out)
+        if g is None:
+            return
+        Nout, K = fc.weight.shape
+        gx = 0
+        if x.needs_grad:
+            tmp = p.buf(x.N, 1, 1, K)
+            gx = _ptr(tmp)
+            p.contribute(x, tmp, True)
+        p.launch(p.bwd, "linear_bwd", _ptr(x.z), p.param_ptr(fc.weight), _ptr(g), x.N, K, Nout, gx,
+                 p.param_grad_ptr(fc.weight), p.param_grad_ptr(fc.bias))
+
+
+class _MSEOp(object):
+    def __init__(self, plan, o, target, loss_acc, gscale):
+        self.plan, self.o = plan, o
+        if o.scale is not None or (o.N, o.H, o.W, o.C) != (target.N, target.H, target.W, target.C):
+            raise ValueError("mse_loss expects a plain output and a target of the same shape")
+        n = o.P * o.C
+        self.g = plan.buf(o.N, o.H, o.W, o.C) if plan.need_grad else None
+        plan.launch(plan.fwd, "mse_fwd_bwd", _ptr(o.z), _ptr(target.z), n, 1.0 / n, gscale, _ptr(self.g), 0,
+                    _ptr(loss_acc))
+
+    def emit_bwd(self):
+        if self.g is not None:
+            self.plan.contribute(self.o, self.g, True)
+
+
+class _OutputOp(object):
+    def __init__(self, plan, x, index, rows=False, no_grad=False):
+        self.plan, self.x, self.index, self.rows, self.no_grad = plan, x, index, rows, no_grad
+        p = plan
+        if rows:
+            if x.H != 1 or x.W != 1 or x.scale is not None:
+                raise ValueError("row output expects a plain [N,1,1,C] tensor")
+            self.result = x.z.view(x.N, x.C)
+            self.gsrc = torch.zeros(x.N, x.C, device=p.device, dtype=torch.float32) if (p.need_grad and not no_grad) else None
+        else:
+            self.result = torch.empty(x.N, x.C, x.H, x.W, device=p.device, dtype=torch.float32)
+            p.bytes_alloc += self.result.numel() * 4
+            p.launch(p.fwd, "nhwc_to_nchw", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(self.result)]))
+            self.gsrc = torch.zeros_like(self.result) if (p.need_grad and not no_grad) else None
+
+    def emit_bwd(self):
+        p, x = self.plan, self.x
+        if not x.needs_grad or self.no_grad:
+            return
+        g = p.buf(x.N, x.H, x.W, x.C)
+        if self.rows:
+            rec = p.launch(p.bwd, "add_into", 0, _ptr(g), x.N * x.C, 0)
+        else:
+            rec = p.launch(p.bwd, "nchw_to_nhwc", 0, x.N, x.C, x.H, x.W, _ptr(g))
+        p.dynamic("gout%d" % self.index, rec, 0)
+        p.contribute(x, g, True)

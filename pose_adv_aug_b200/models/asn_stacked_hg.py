@@ -1,0 +1,444 @@
+"""Drop-in mirror of the reference module `models/asn_stacked_hg.py` (zhiqiangdon/pose-adv-aug):
+same constructors (`create_hg`, `create_asn`), class names, attribute names (hence identical
+`state_dict()` keys and shapes), forward signatures and return structures -- but `forward`
+plans and launches the hand-written sm_100a kernels of libhgk instead of torch ops.
+
+Reference lines cited as `ref:<line>` refer to /root/reference/models/asn_stacked_hg.py.
+torch.nn.Conv2d / BatchNorm2d / Linear objects are used only as *parameter containers* (their
+own forward is never called): that keeps parameter registration, state_dict schema and
+`isinstance` checks identical to the reference.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from ..engine import Plan, ParamStore, HGKError
+
+__all__ = ["_Residual", "_Hourglass", "_Hourglass_Wrapper", "ASN", "create_hg", "create_asn", "Hourglass"]
+
+# convolution kernel selection for newly built plans: 0 auto, 1 fp32 SIMT, 2 tcgen05
+CONV_PATH = 0
+
+
+def _reference_init(root):
+    """ref:258-270 / ref:381-393: conv W,b ~ U(+-1/sqrt(k*k*Cin)); BN gamma ~ U(0,1), beta = 0."""
+    for m in root.modules():
+        if isinstance(m, nn.Conv2d):
+            n = m.kernel_size[0] * m.kernel_size[1] * m.in_channels
+            stdv = 1 / math.sqrt(n)
+            m.weight.data.uniform_(-stdv, stdv)
+            if m.bias is not None:
+                m.bias.data.uniform_(-stdv, stdv)
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.uniform_()
+            m.bias.data.zero_()
+
+
+# ------------------------------------------------------------------------------------------
+# plan execution glue (autograd boundary)
+# ------------------------------------------------------------------------------------------
+class _PlanFn(torch.autograd.Function):
+    """One autograd node for a whole planned forward.  Parameter gradients are accumulated by the
+    kernels directly into the flat .grad views (ParamStore); input gradients are returned."""
+
+    @staticmethod
+    def forward(ctx, plan, n_in, *tensors):
+        inputs = tensors[:n_in]
+        outs = plan.run_forward(inputs)
+        ctx.plan = plan
+        ctx.inputs = inputs
+        ctx.count = plan.fwd_count
+        ctx.n_extra = len(tensors) - n_in
+        return tuple(o.clone() for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if plan.fwd_count != ctx.count:
+            raise HGKError("backward() after a newer forward of the same plan: the saved activations were "
+                           "overwritten (run backward before the next forward of this module/shape)")
+        for st in plan.stores:
+            st.attach_grads()
+        gins = plan.run_backward(ctx.inputs, gouts)
+        gins = list(gins) + [None] * (len(ctx.inputs) - len(gins))
+        return (None, None) + tuple(gins[:len(ctx.inputs)]) + (None,) * ctx.n_extra
+
+
+class _Root(object):
+    """Per-root-module state: flat parameter store + plan cache."""
+
+    def __init__(self):
+        self.store = None
+        self.plans = {}
+
+
+def _state(module):
+    st = module.__dict__.get("_hgk_root")
+    if st is None:
+        st = _Root()
+        module.__dict__["_hgk_root"] = st
+    return st
+
+
+def _ensure_store(module, device):
+    st = _state(module)
+    if st.store is None or st.store.device != device or not st.store.valid():
+        st.store = ParamStore(module, device)
+        st.plans = {}
+    return st.store
+
+
+def _check_input(x):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise HGKError("pose_adv_aug_b200 runs on CUDA (sm_100a) only; got a %s tensor -- there is no CPU fallback"
+                       % (x.device if isinstance(x, torch.Tensor) else type(x)))
+    if x.dtype != torch.float32:
+        raise ValueError("expected a float32 tensor, got %s" % x.dtype)
+    if x.dim() != 4:
+        raise ValueError("expected an NCHW tensor, got %d dims" % x.dim())
+
+
+def _run(root, extra_roots, key, inputs, build):
+    """Build (or fetch) the plan `key` of `root` and run it through autograd."""
+    for x in inputs:
+        _check_input(x)
+    device = inputs[0].device
+    stores = [_ensure_store(m, device) for m in [root] + list(extra_roots)]
+    mods = [root] + list(extra_roots)
+    need_grad = torch.is_grad_enabled() and (any(x.requires_grad for x in inputs) or
+                                             any(p.requires_grad for m in mods for p in m.parameters()))
+    shapes = tuple(tuple(x.shape) for x in inputs)
+    modes = tuple(m.training for m in mods)
+    ids = tuple(id(s) for s in stores)
+    pkey = (key, shapes, modes, need_grad, ids, CONV_PATH)
+    cache = _state(root).plans
+    plan = cache.get(pkey)
+    if plan is None:
+        plan = Plan(stores, device, root.training, need_grad, conv_path=CONV_PATH)
+        plan.in_requires_grad = [x.requires_grad for x in inputs]
+        plan.structure = build(plan)
+        plan.finish()
+        cache[pkey] = plan
+    inputs = [x.contiguous() for x in inputs]
+    if need_grad:
+        for st in stores:
+            st.attach_grads()
+        anchor = None
+        for m in mods:
+            for p in m.parameters():
+                if p.requires_grad:
+                    anchor = p
+                    break
+            if anchor is not None:
+                break
+        extra = (anchor,) if anchor is not None else ()
+        outs = _PlanFn.apply(plan, len(inputs), *(tuple(inputs) + extra))
+    else:
+        outs = tuple(o.clone() for o in plan.run_forward(inputs))
+    return plan, list(outs)
+
+
+# ------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------
+class _Residual(nn.Module):
+    """ref:11-49 -- post-activation bottleneck: c1(1x1) bn relu c2(3x3) bn relu c3(1x1) (+x | +adapter(x)) bn relu."""
+
+    def __init__(self, in_num, out_num, adapter=None):
+        super(_Residual, self).__init__()
+        self.in_num = in_num
+        self.out_num = out_num
+        self.conv1 = nn.Conv2d(in_num, out_num // 2, kernel_size=1, stride=1, bias=True)
+        self.bn1 = nn.BatchNorm2d(out_num // 2)
+        self.conv2 = nn.Conv2d(out_num // 2, out_num // 2, kernel_size=3, stride=1, padding=1, bias=True)
+        self.bn2 = nn.BatchNorm2d(out_num // 2)
+        self.conv3 = nn.Conv2d(out_num // 2, out_num, kernel_size=1, stride=1, bias=True)
+        self.bn3 = nn.BatchNorm2d(out_num)
+        self.relu = nn.ReLU(inplace=True)
+        self.adapter = adapter
+
+    def _build(self, plan, x):
+        if self.adapter is None:
+            if self.in_num != self.out_num:
+                raise ValueError("identity shortcut needs in_num == out_num (ref:31-32)")
+            shortcut = x
+        else:
+            shortcut = plan.conv(x, self.adapter)                       # ref:34
+        out = plan.conv(x, self.conv1, bn=self.bn1)                     # ref:36-38
+        out = plan.conv(out, self.conv2, bn=self.bn2)                   # ref:40-42
+        return plan.conv(out, self.conv3, bn=self.bn3, res=shortcut)    # ref:44-47
+
+    def forward(self, x):
+        def build(plan):
+            t = plan.input_nchw(*x.shape, needs_grad=x.requires_grad)
+            plan.output_nchw(self._build(plan, t))
+        return _run(self, (), "residual", [x], build)[1][0]
+
+
+def _build_stack(seq, plan, x):
+    for m in seq:
+        x = m._build(plan, x)
+    return x
+
+
+class _Hourglass(nn.Module):
+    """ref:51-213."""
+
+    def __init__(self, chan, num_modules):
+        super(_Hourglass, self).__init__()
+        self.num_modules = num_modules
+        self.chan = chan
+        self.down1 = self._stack_residual()
+        self.down2 = self._stack_residual()
+        self.down3 = self._stack_residual()
+        self.down4 = self._stack_residual()
+        self.up1 = self._stack_residual()
+        self.up2 = self._stack_residual()
+        self.up3 = self._stack_residual()
+        self.up4 = self._stack_residual()
+        self.skip1 = self._stack_residual()
+        self.skip2 = self._stack_residual()
+        self.skip3 = self._stack_residual()
+        self.skip4 = self._stack_residual()
+        self.neck = self._stack_residual()
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.upsample = nn.Upsample(scale_factor=2)
+        self.keys = ['neck', 'skip1', 'skip2', 'skip3', 'skip4']
+
+    def _stack_residual(self):
+        return nn.Sequential(*[_Residual(self.chan, self.chan) for _ in range(self.num_modules)])
+
+    def _build_down(self, plan, x):
+        """ref:140-157; returns (neck, skip1..4)."""
+        s1 = _build_stack(self.skip1, plan, x)
+        x = _build_stack(self.down1, plan, plan.maxpool(x))
+        s2 = _build_stack(self.skip2, plan, x)
+        x = _build_stack(self.down2, plan, plan.maxpool(x))
+        s3 = _build_stack(self.skip3, plan, x)
+        x = _build_stack(self.down3, plan, plan.maxpool(x))
+        s4 = _build_stack(self.skip4, plan, x)
+        x = _build_stack(self.down4, plan, plan.maxpool(x))
+        x = _build_stack(self.neck, plan, x)
+        return x, s1, s2, s3, s4
+
+    def _build_up(self, plan, x, s1, s2, s3, s4):
+        """ref:192-203: up residual -> nearest x2 -> + skip (one fused kernel per rung)."""
+        x = plan.add(_build_stack(self.up4, plan, x), s4, upsample_a=True)
+        x = plan.add(_build_stack(self.up3, plan, x), s3, upsample_a=True)
+        x = plan.add(_build_stack(self.up2, plan, x), s2, upsample_a=True)
+        x = plan.add(_build_stack(self.up1, plan, x), s1, upsample_a=True)
+        return x
+
+    def _build(self, plan, x, asn=None, is_half_hg=False):
+        """Returns (y or None, agent outputs or None)."""
+        neck, s1, s2, s3, s4 = self._build_down(plan, x)
+        agent = None
+        if asn is not None:
+            feats = {'neck': plan.detach(neck), 'skip1': plan.detach(s1), 'skip2': plan.detach(s2),
+                     'skip3': plan.detach(s3), 'skip4': plan.detach(s4)}           # ref:161-162
+            mode = plan.training
+            plan.training = asn.training
+            agent = asn._build(plan, feats)
+            plan.training = mode
+            if is_half_hg:
+                return None, agent                                                   # ref:169-171
+        return self._build_up(plan, neck, s1, s2, s3, s4), agent
+
+    def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False, dropout_masks=None):
+        if is_dropout or dropout_masks is not None:
+            raise NotImplementedError("ASN dropout mode (ref:172-190) is not invoked by any reference script "
+                                      "and is not built yet")
+        if asn is not None and not is_aug:
+            raise AssertionError("is_aug != is_dropout (ref:165)")
+
+        def build(plan):
+            t = plan.input_nchw(*x.shape, needs_grad=x.requires_grad)
+            y, agent = self._build(plan, t, asn, is_half_hg)
+            if y is not None:
+                plan.output_nchw(y)
+            if agent is not None:
+                plan.output_rows(agent[0])
+                plan.output_rows(agent[1])
+        extra = (asn,) if asn is not None else ()
+        outs = _run(self, extra, ("hourglass", asn is not None, is_half_hg), [x], build)[1]
+        if asn is None:
+            return outs[0]
+        if is_half_hg:
+            return outs[0], outs[1]
+        return outs[0], outs[1], outs[2]                                             # ref:208
+
+
+class _Hourglass_Wrapper(nn.Module):
+    """ref:215-342."""
+
+    def __init__(self, num_modules, num_stacks, chan=256, num_classes=16):
+        super(_Hourglass_Wrapper, self).__init__()
+        self.chan = chan
+        self.num_modules = num_modules
+        self.num_classes = num_classes
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=True)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.residual1 = self._make_adapter_residual(64, 128)
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.residual2 = _Residual(128, 128)
+        self.residual3 = self._make_adapter_residual(128, chan)
+        self.num_stacks = num_stacks
+        hg, post_res, linear, out_conv, forth_conv, in_conv = [], [], [], [], [], []
+        for i in range(0, num_stacks):
+            hg.append(_Hourglass(chan=chan, num_modules=num_modules))
+            post_res.append(self._stack_residual())
+            linear.append(nn.Sequential(nn.Conv2d(chan, chan, kernel_size=1, stride=1, bias=True),
+                                        nn.BatchNorm2d(chan), nn.ReLU(inplace=True)))
+            out_conv.append(nn.Conv2d(chan, num_classes, kernel_size=1, stride=1, bias=True))
+            if i < num_stacks - 1:
+                forth_conv.append(nn.Conv2d(chan, chan, kernel_size=1, stride=1, bias=True))
+                in_conv.append(nn.Conv2d(num_classes, chan, kernel_size=1, stride=1, bias=True))
+        self.hg = nn.ModuleList(hg)
+        self.post_res = nn.ModuleList(post_res)
+        self.linear = nn.ModuleList(linear)
+        self.out_conv = nn.ModuleList(out_conv)
+        self.forth_conv = nn.ModuleList(forth_conv)
+        self.in_conv = nn.ModuleList(in_conv)
+        _reference_init(self)
+
+    def _stack_residual(self):
+        return nn.Sequential(*[_Residual(self.chan, self.chan) for _ in range(self.num_modules)])
+
+    def _make_adapter_residual(self, in_num, out_num):
+        adapter = nn.Conv2d(in_num, out_num, kernel_size=1, stride=1, bias=True)
+        return _Residual(in_num, out_num, adapter)
+
+    def _build(self, plan, img, asn=None, is_half_hg=False):
+        """ref:282-342.  Returns (list of per-stack heat-map tensors, agent outputs or None)."""
+        x = plan.stem(img, self.conv1, self.bn1)                        # ref:283-285
+        x = self.residual1._build(plan, x)
+        x = plan.maxpool(x)
+        x = self.residual2._build(plan, x)
+        x = self.residual3._build(plan, x)
+        outs, agent = [], None
+        for i in range(self.num_stacks):
+            if i == 0 and asn is not None:
+                y, agent = self.hg[i]._build(plan, x, asn, is_half_hg)
+                if is_half_hg:
+                    return outs, agent                                  # ref:302-304
+            else:
+                y, _ = self.hg[i]._build(plan, x)
+            y = _build_stack(self.post_res[i], plan, y)                 # ref:327
+            y = plan.conv(y, self.linear[i][0], bn=self.linear[i][1])   # ref:328
+            o = plan.conv(y, self.out_conv[i])                          # ref:329
+            outs.append(o)
+            if i < self.num_stacks - 1:
+                t = plan.conv(y, self.forth_conv[i], res=x)             # ref:332,334
+                x = plan.conv(o, self.in_conv[i], res=t)                # ref:333-334
+        return outs, agent
+
+    def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False):
+        if is_dropout:
+            raise NotImplementedError("ASN dropout mode (ref:308-316) is not invoked by any reference script "
+                                      "and is not built yet")
+        if asn is not None and not is_aug:
+            raise AssertionError("is_aug != is_dropout (ref:297)")
+        _check_input(x)
+        if x.shape[1] != 3 or x.shape[2] % 64 or x.shape[3] % 64:
+            raise ValueError("expected [N,3,H,W] images with H, W multiples of 64 (got %s)" % (tuple(x.shape),))
+
+        def build(plan):
+            img = plan.input_image(x.shape[0], x.shape[2], x.shape[3])
+            outs, agent = self._build(plan, img, asn, is_half_hg)
+            for o in outs:
+                plan.output_nchw(o)
+            if agent is not None:
+                plan.output_rows(agent[0])
+                plan.output_rows(agent[1])
+            return len(outs)
+        extra = (asn,) if asn is not None else ()
+        plan, outs = _run(self, extra, ("wrapper", asn is not None, is_half_hg), [x], build)
+        n = plan.structure
+        if asn is None:
+            return outs[:n]                                             # ref:342
+        if is_half_hg:
+            return outs[n], outs[n + 1]                                 # ref:304
+        return outs[:n], outs[n], outs[n + 1]                           # ref:338
+
+
+def create_hg(num_stacks, num_modules, num_classes, chan):
+    """ref:344-347."""
+    return _Hourglass_Wrapper(num_stacks=num_stacks, num_modules=num_modules, num_classes=num_classes, chan=chan)
+
+
+def Hourglass(nStack, nFeat, num_modules=1, num_classes=16):
+    """north_star's `Hourglass(nStack, nFeat)` spelling of create_hg(nStack, 1, 16, nFeat)."""
+    return create_hg(nStack, num_modules, num_classes, nFeat)
+
+
+class ASN(nn.Module):
+    """ref:349-439 -- the adversarial augmentation agent."""
+
+    def __init__(self, chan_in, chan_out, scale_num, rotation_num, is_aug=False, is_dropout=False):
+        assert is_aug != is_dropout                                     # ref:351
+        super(ASN, self).__init__()
+        self.num_modules = 3
+        self.chan_in = chan_in
+        self.chan_out = chan_out
+        self.residual_skip1 = _Residual(chan_in, chan_out)
+        self.residual_skip2 = _Residual(chan_in, chan_out)
+        self.residual_skip3 = _Residual(chan_in, chan_out)
+        self.residual_skip4 = _Residual(chan_in, chan_out)
+        self.residual_neck = _Residual(chan_in, chan_out)
+        self.merge1 = _Residual(chan_out, chan_out)
+        self.merge2 = _Residual(chan_out, chan_out)
+        self.merge3 = _Residual(chan_out, chan_out)
+        self.merge4 = _Residual(chan_out, chan_out)
+        self.deep_merge = self._stack_residual()
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        if is_aug:
+            self.avgpool = nn.AvgPool2d(4)
+            self.fc_scale = nn.Linear(chan_out, scale_num)
+            self.fc_rotation = nn.Linear(chan_out, rotation_num)
+        if is_dropout:
+            self.out_conv = nn.Conv2d(chan_out, 1, kernel_size=1, stride=1, bias=True)
+        _reference_init(self)
+
+    def _stack_residual(self):
+        return nn.Sequential(*[_Residual(self.chan_out, self.chan_out) for _ in range(self.num_modules)])
+
+    def _build(self, plan, f):
+        """ref:401-436 (is_aug).  f: dict of plan tensors."""
+        if not hasattr(self, "fc_scale"):
+            raise NotImplementedError("ASN dropout head (ref:437-439) is not built yet")
+        skip1 = self.residual_skip1._build(plan, f['skip1'])
+        skip2 = self.residual_skip2._build(plan, f['skip2'])
+        skip3 = self.residual_skip3._build(plan, f['skip3'])
+        skip4 = self.residual_skip4._build(plan, f['skip4'])
+        neck = self.residual_neck._build(plan, f['neck'])
+        x = self.merge1._build(plan, plan.add(plan.maxpool(skip1), skip2))
+        x = self.merge2._build(plan, plan.add(plan.maxpool(x), skip3))
+        x = self.merge3._build(plan, plan.add(plan.maxpool(x), skip4))
+        x = self.merge4._build(plan, plan.add(plan.maxpool(x), neck))
+        x = _build_stack(self.deep_merge, plan, x)
+        x = plan.avgpool(x, 4)                                          # ref:431
+        if x.H != 1 or x.W != 1:
+            raise ValueError("ASN head needs a 4x4 neck (256x256 input); got %dx%d after AvgPool2d(4)" % (x.H, x.W))
+        return plan.linear(x, self.fc_scale), plan.linear(x, self.fc_rotation)   # ref:434-435
+
+    def forward(self, x, is_aug=False, is_dropout=False):
+        if is_dropout or not is_aug:
+            raise NotImplementedError("ASN dropout mode (ref:437-439) is not built yet")
+        keys = ['neck', 'skip1', 'skip2', 'skip3', 'skip4']
+        tensors = [x[k] for k in keys]
+
+        def build(plan):
+            f = dict((k, plan.input_nchw(*t.shape, needs_grad=t.requires_grad)) for k, t in zip(keys, tensors))
+            s, r = self._build(plan, f)
+            plan.output_rows(s)
+            plan.output_rows(r)
+        outs = _run(self, (), "asn", tensors, build)[1]
+        return outs[0], outs[1]
+
+
+def create_asn(chan_in, chan_out, scale_num=None, rotation_num=None, is_aug=False, is_dropout=False):
+    """ref:441-444."""
+    return ASN(chan_in=chan_in, chan_out=chan_out, scale_num=scale_num, rotation_num=rotation_num,
+               is_aug=is_aug, is_dropout=is_dropout)

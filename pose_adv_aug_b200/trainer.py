@@ -1,0 +1,108 @@
+"""The whole reference train step (stack-hg.py:153-165: forward -> sum over stacks of MSE ->
+zero_grad / backward / RMSprop.step) as one planned launch sequence, optionally captured in a
+single CUDA graph: weight repack, every conv / BN / pool / up-add kernel, the fused MSE
+forward+backward, the backward pass, the (optional) NCCL all-reduce of the flat gradient buffer
+and the flat RMSprop update."""
+import torch
+
+from ._lib import get_lib, HGKError
+from .engine import Plan
+from .models import asn_stacked_hg as M
+from . import dist as hdist
+
+
+class HourglassTrainer(object):
+    def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
+                 distributed=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
+        self.lr, self.alpha, self.eps = lr, alpha, eps
+        self.lib = get_lib()
+        self.world = hdist.world_size() if distributed is None else (hdist.world_size() if distributed else 1)
+        net.to(self.device)
+        net.train()
+        self.store = M._ensure_store(net, self.device)
+        if self.world > 1:
+            hdist.broadcast_flat_params(self.store.flat)
+        self.square_avg = torch.zeros_like(self.store.flat)
+        K = net.num_classes
+        self.x = torch.zeros(batch, 3, res, res, device=self.device)
+        self.t = torch.zeros(batch, K, res // 4, res // 4, device=self.device)
+        self.loss_acc = torch.zeros(1, device=self.device, dtype=torch.float64)
+        self.loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        plan = Plan([self.store], self.device, True, True, conv_path=M.CONV_PATH)
+        img = plan.input_image(batch, res, res)
+        tgt = plan.target_nchw(batch, K, res // 4, res // 4)
+        outs, _ = net._build(plan, img)
+        for o in outs:
+            plan.mse_loss(o, tgt, self.loss_acc)
+            plan.output_nchw(o, no_grad=True)
+        plan.finish()
+        self.plan = plan
+        self.graph = None
+        self.use_graph = use_graph
+        self.steps = 0
+
+    # number of libhgk kernel launches per step (for bench.py's gpu_launches)
+    @property
+    def launches_per_step(self):
+        return len(self.plan.fwd) + len(self.plan.bwd) + (1 if self.plan.pack_launch else 0) + 2
+
+    def _step_body(self):
+        st, plan = self.store, self.plan
+        self.loss_acc.zero_()
+        st.grad.zero_()
+        plan.run_forward([self.x, self.t])
+        plan.run_backward([self.x, self.t], [None] * len(plan.outputs))
+        if self.world > 1:
+            hdist.allreduce_flat_grads(st.grad)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.lib.check(self.lib.rmsprop_flat(st.flat.data_ptr(), st.grad.data_ptr(), self.square_avg.data_ptr(),
+                                             st.numel, self.lr, self.alpha, self.eps, 1.0 / self.world, stream),
+                       "hgk_rmsprop_flat")
+        self.lib.check(self.lib.f64_to_f32(self.loss_acc.data_ptr(), self.loss.data_ptr(), 1, 1.0, stream),
+                       "hgk_f64_to_f32")
+
+    def step_resident(self):
+        """One train step on the batch currently held in the static device buffers self.x / self.t."""
+        if not self.store.valid():
+            raise HGKError("parameters were re-allocated after the trainer was built")
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.steps += 1
+        return self.loss
+
+    def _capture(self):
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            saved = (self.store.flat.clone(), self.square_avg.clone(), self.store.fbuf_flat.clone(),
+                     self.store.ibuf_flat.clone())
+            self._step_body()            # warm-up outside capture (NCCL / lazy init)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        # restore the state consumed by the warm-up step
+        self.store.flat.copy_(saved[0])
+        self.square_avg.copy_(saved[1])
+        self.store.fbuf_flat.copy_(saved[2])
+        self.store.ibuf_flat.copy_(saved[3])
+        torch.cuda.synchronize(self.device)
+
+    def step(self, images, heatmaps):
+        """Public end-to-end step: images [N,3,R,R], heatmaps [N,K,R/4,R/4] (host pinned or device).
+        Returns the fp32 device scalar loss of this step (sum over stacks of per-stack MSE)."""
+        self.x.copy_(images, non_blocking=True)
+        self.t.copy_(heatmaps, non_blocking=True)
+        return self.step_resident()
+
+    def heatmaps(self):
+        """Per-stack NCHW heat-maps of the last step (views of the plan's static output buffers)."""
+        return [op.result for op in self.plan.outputs]

@@ -1,0 +1,366 @@
+"""Per-kernel parity (-m gpu): every libhgk entry point, called through the C-ABI, against a
+float64 CPU reference built from the same torch ops the oracle uses.  Tolerances are
+fp32-class (1e-5 relative to the tensor's max) unless stated."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hgk_testlib import (DEV, call, ptr, rnd, dev32, nhwc, from_nhwc, relerr, affine_act, pack_w)
+
+pytestmark = pytest.mark.gpu
+
+CONV_SHAPES = [
+    # N, H, W, Cin, Cout, k
+    (2, 16, 16, 64, 128, 1),
+    (2, 16, 16, 128, 64, 3),
+    (3, 5, 7, 12, 20, 3),        # ragged: nothing a multiple of the tile sizes
+    (3, 5, 7, 20, 12, 1),
+    (2, 1, 1, 256, 128, 1),      # 1x1 neck of config 1
+    (2, 1, 1, 64, 64, 3),
+    (1, 64, 64, 256, 16, 1),     # out_conv
+    (1, 64, 64, 16, 256, 1),     # in_conv
+    (2, 8, 8, 256, 256, 3),
+    (5, 4, 4, 128, 256, 1),
+]
+
+
+def _conv_ref(x, w, b, k):
+    return F.conv2d(x, w, b, padding=k // 2)
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "full"])
+def test_conv_fwd(shape, variant):
+    N, H, W, Ci, Co, k = shape
+    x = rnd("x", (N, Ci, H, W))
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    b = rnd("b", (Co,))
+    full = variant == "full"
+    xs, xt = (rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)) if full else (None, None)
+    res = rnd("res", (N, Co, H, W)) if full else None
+    rs, rt = (rnd("rs", (Co,), 0.5, 1.5), rnd("rt", (Co,), -0.3, 0.3)) if full else (None, None)
+    y0 = rnd("y0", (N, Co, H, W)) if full else None
+    ref = _conv_ref(affine_act(x, xs, xt, True), w, b, k)
+    if full:
+        ref = ref + affine_act(res, rs, rt, True) + y0
+    dx, dw, db = nhwc(x), pack_w(w, 0), dev32(b)
+    dxs, dxt = (dev32(xs), dev32(xt)) if full else (None, None)
+    dres = nhwc(res) if full else None
+    drs, drt = (dev32(rs), dev32(rt)) if full else (None, None)
+    y = nhwc(y0) if full else torch.empty(N, H, W, Co, device=DEV)
+    ssum = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    ssq = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    call("conv_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(dw), k, 0, ptr(db), Co,
+         ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), ptr(ssum), ptr(ssq), 1)
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(y), ref) < 1e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_and_wgrad(shape):
+    N, H, W, Ci, Co, k = shape
+    xs, xt = rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)
+    xin = rnd("x", (N, Ci, H, W))
+    a = affine_act(xin, xs, xt, True).requires_grad_(True)
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2).requires_grad_(True)
+    b = rnd("b", (Co,)).requires_grad_(True)
+    dz = rnd("dz", (N, Co, H, W))
+    _conv_ref(a, w, b, k).backward(dz)
+    # data gradient: same kernel, flipped taps, [tap][Cout][Cin] weights, plus residual + accumulate
+    extra = rnd("extra", (N, Ci, H, W))
+    g0 = rnd("g0", (N, Ci, H, W))
+    gx = nhwc(g0)
+    ddz, dextra = nhwc(dz), nhwc(extra)
+    wp = pack_w(w.detach(), 1)
+    call("conv_nhwc", ptr(ddz), 0, 0, 0, N, H, W, Co, ptr(wp), k, 1, 0, Ci, ptr(dextra), 0, 0, 0, ptr(gx), 1, 0, 0, 1)
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(gx), a.grad + extra + g0) < 1e-5
+    # weight / bias gradient written with OIHW strides, accumulating onto existing values
+    w0, b0 = rnd("w0", (Co, Ci, k, k)), rnd("b0", (Co,))
+    gw, gb = dev32(w0), dev32(b0)
+    dxin, dxs, dxt = nhwc(xin), dev32(xs), dev32(xt)
+    call("conv_wgrad_nhwc", ptr(dxin), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(ddz), Co, k, ptr(gw), Ci * k * k, k * k, 1,
+         ptr(gb))
+    torch.cuda.synchronize()
+    assert relerr(gw.cpu().double() - w0, w.grad) < 2e-5
+    assert relerr(gb.cpu().double() - b0, b.grad) < 2e-5
+
+
+def test_pack_weights():
+    ws = [rnd("w%d" % i, s) for i, s in enumerate([(8, 4, 3, 3), (16, 8, 1, 1), (4, 12, 3, 3)])]
+    flat = torch.cat([w.reshape(-1) for w in ws])
+    src = dev32(flat)
+    rows, off, so = [], 0, 0
+    for w in ws:
+        O, I, kh, kw = w.shape
+        for mode in (0, 1):
+            rows.append([so, off, O, I, kh * kw, mode])
+            off += w.numel()
+        so += w.numel()
+    dst = torch.zeros(off, device=DEV)
+    table = torch.tensor(rows, dtype=torch.long, device=DEV)
+    call("pack_weights", ptr(src), ptr(dst), ptr(table), len(rows))
+    torch.cuda.synchronize()
+    o = 0
+    for w in ws:
+        for mode in (0, 1):
+            got = dst[o:o + w.numel()].cpu()
+            assert torch.equal(got, pack_w(w, mode).cpu().reshape(-1))
+            o += w.numel()
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64), (3, 32, 48), (1, 256, 256)])
+def test_stem_fwd_and_wgrad(shape):
+    N, H, W = shape
+    x = rnd("img", (N, 3, H, W), 0.0, 1.0)
+    w = rnd("w", (64, 3, 7, 7), -0.1, 0.1).requires_grad_(True)
+    b = rnd("b", (64,)).requires_grad_(True)
+    ref = F.conv2d(x, w, b, stride=2, padding=3)
+    y = torch.empty(N, H // 2, W // 2, 64, device=DEV)
+    ssum = torch.zeros(64, device=DEV, dtype=torch.float64)
+    ssq = torch.zeros(64, device=DEV, dtype=torch.float64)
+    dimg, dw_, db_ = dev32(x), dev32(w.detach()), dev32(b.detach())
+    call("stem_conv7_fwd", ptr(dimg), N, H, W, ptr(dw_), ptr(db_), 64, ptr(y), ptr(ssum), ptr(ssq))
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(y), ref) < 1e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 1e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 1e-5
+    dz = rnd("dz", (N, 64, H // 2, W // 2))
+    ref.backward(dz)
+    gw = torch.zeros(64, 3, 7, 7, device=DEV)
+    gb = torch.zeros(64, device=DEV)
+    ddz = nhwc(dz)
+    call("stem_conv7_wgrad", ptr(dimg), N, H, W, ptr(ddz), 64, ptr(gw), ptr(gb))
+    torch.cuda.synchronize()
+    assert relerr(gw, w.grad) < 2e-5
+    assert relerr(gb, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64), (3, 5, 7, 12), (2, 1, 1, 128), (4, 16, 16, 256), (2, 4, 4, 320)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_fwd_bwd(shape, training):
+    N, H, W, C = shape
+    z = rnd("z", (N, C, H, W), -2.0, 3.0).requires_grad_(True)
+    gamma = rnd("gamma", (C,), 0.3, 1.2).requires_grad_(True)
+    beta = rnd("beta", (C,), -0.3, 0.3).requires_grad_(True)
+    rm, rv = rnd("rm", (C,), -0.2, 0.2), rnd("rv", (C,), 0.5, 1.5)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = F.relu(F.batch_norm(z, rm_ref, rv_ref, gamma, beta, training=training, momentum=0.1, eps=1e-5))
+    dy = rnd("dy", (N, C, H, W))
+    y.backward(dy)
+    P = N * H * W
+    dz_ = nhwc(z.detach())
+    dgamma, dbeta, drm, drv = dev32(gamma.detach()), dev32(beta.detach()), dev32(rm), dev32(rv)
+    scale, shift, mean, invstd = [torch.empty(C, device=DEV) for _ in range(4)]
+    if training:
+        ssum = z.detach().sum(dim=(0, 2, 3)).to(DEV)
+        ssq = (z.detach() ** 2).sum(dim=(0, 2, 3)).to(DEV)
+        call("bn_finalize", ptr(ssum), ptr(ssq), P, ptr(dgamma), ptr(dbeta), 1e-5, 0.1, ptr(drm), ptr(drv), ptr(scale),
+             ptr(shift), ptr(mean), ptr(invstd), C)
+        torch.cuda.synchronize()
+        if P > 1:
+            assert relerr(drm, rm_ref) < 1e-5 and relerr(drv, rv_ref) < 1e-5
+    else:
+        call("bn_eval_prepare", ptr(dgamma), ptr(dbeta), ptr(drm), ptr(drv), 1e-5, ptr(scale), ptr(shift), ptr(mean),
+             ptr(invstd), C)
+    # the consumers' on-load activation reproduces relu(bn(z))
+    act = torch.empty(N, C, H, W, device=DEV)
+    call("nhwc_to_nchw", ptr(dz_), ptr(scale), ptr(shift), 1, N, H, W, C, ptr(act))
+    torch.cuda.synchronize()
+    assert relerr(act, y) < 2e-5
+    # backward: reduce -> finalize -> apply (in place)
+    g = nhwc(dy)
+    sg = torch.zeros(C, device=DEV, dtype=torch.float64)
+    sgx = torch.zeros(C, device=DEV, dtype=torch.float64)
+    gg0, gb0 = rnd("gg0", (C,)), rnd("gb0", (C,))
+    ggamma, gbeta = dev32(gg0), dev32(gb0)
+    cA, cB, cC = [torch.empty(C, device=DEV) for _ in range(3)]
+    call("bn_bwd_reduce", ptr(g), ptr(dz_), ptr(scale), ptr(shift), 1, ptr(mean), ptr(invstd), P, C, ptr(sg), ptr(sgx))
+    call("bn_bwd_finalize", ptr(sg), ptr(sgx), P, ptr(dgamma), ptr(mean), ptr(invstd), int(training), ptr(ggamma),
+         ptr(gbeta), ptr(cA), ptr(cB), ptr(cC), C)
+    call("bn_bwd_apply", ptr(g), ptr(dz_), ptr(scale), ptr(shift), 1, ptr(cA), ptr(cB), ptr(cC), P, C)
+    torch.cuda.synchronize()
+    tol = 2e-4 if P <= 2 else 2e-5       # 2 samples: xhat = +-1, invstd ~ 1/|dz|: badly conditioned in any precision
+    assert relerr(from_nhwc(g), z.grad) < tol
+    assert relerr(ggamma.cpu().double() - gg0, gamma.grad) < 2e-5
+    assert relerr(gbeta.cpu().double() - gb0, beta.grad) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64), (3, 6, 10, 12), (1, 2, 2, 256)])
+def test_maxpool_fwd_bwd(shape):
+    N, H, W, C = shape
+    s, t = rnd("s", (C,), 0.5, 1.5), rnd("t", (C,), -0.3, 0.3)
+    x = rnd("x", (N, C, H, W))
+    a = affine_act(x, s, t, True).requires_grad_(True)
+    y = F.max_pool2d(a, 2, 2)
+    dy = rnd("dy", y.shape)
+    y.backward(dy)
+    dx, ds, dt = nhwc(x), dev32(s), dev32(t)
+    out = torch.empty(N, H // 2, W // 2, C, device=DEV)
+    call("maxpool2_fwd", ptr(dx), ptr(ds), ptr(dt), 1, N, H, W, C, ptr(out))
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(out), y) < 1e-6
+    g0 = rnd("g0", (N, C, H, W))
+    gx = nhwc(g0)
+    ddy = nhwc(dy)
+    call("maxpool2_bwd", ptr(dx), ptr(ds), ptr(dt), 1, N, H, W, C, ptr(ddy), ptr(gx), 1)
+    torch.cuda.synchronize()
+    # ties happen only where relu clamps to 0; there the reference's ReLU' = 0 kills the gradient, so
+    # compare the gradient w.r.t. the PRE-activation tensor
+    mask = (a > 0).double()
+    assert relerr((from_nhwc(gx) - g0) * mask, a.grad * mask) < 1e-6
+    gx2 = torch.empty(N, H, W, C, device=DEV)
+    call("maxpool2_bwd", ptr(dx), ptr(ds), ptr(dt), 1, N, H, W, C, ptr(ddy), ptr(gx2), 0)
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(gx2) * mask, a.grad * mask) < 1e-6
+
+
+@pytest.mark.parametrize("up", [1, 0])
+def test_add_upsample_fwd_bwd(up):
+    N, H, W, C = 2, 8, 12, 64
+    ha, wa = (H // 2, W // 2) if up else (H, W)
+    a, b = rnd("a", (N, C, ha, wa)), rnd("b", (N, C, H, W))
+    sa, ta, sb, tb = rnd("sa", (C,), 0.5, 1.5), rnd("ta", (C,), -0.3, 0.3), rnd("sb", (C,), 0.5, 1.5), rnd("tb", (C,), -0.3, 0.3)
+    ra = affine_act(a, sa, ta, True)
+    if up:
+        ra = ra.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    ref = ra + affine_act(b, sb, tb, True)
+    da, db_, dsa, dta, dsb, dtb = nhwc(a), nhwc(b), dev32(sa), dev32(ta), dev32(sb), dev32(tb)
+    y = torch.empty(N, H, W, C, device=DEV)
+    call("add_fwd", ptr(da), ptr(dsa), ptr(dta), 1, up, ptr(db_), ptr(dsb), ptr(dtb), 1, N, H, W, C, ptr(y))
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(y), ref) < 1e-6
+    # plain operands
+    call("add_fwd", ptr(da), 0, 0, 0, up, ptr(db_), 0, 0, 0, N, H, W, C, ptr(y))
+    torch.cuda.synchronize()
+    ra = a.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3) if up else a
+    assert relerr(from_nhwc(y), ra + b) < 1e-6
+    if up:
+        dy = rnd("dy", (N, C, H, W))
+        g0 = rnd("g0", (N, C, ha, wa))
+        ga = nhwc(g0)
+        ddy = nhwc(dy)
+        call("upsample2_bwd", ptr(ddy), N, H, W, C, ptr(ga), 1)
+        torch.cuda.synchronize()
+        ref_g = F.avg_pool2d(dy, 2) * 4 + g0
+        assert relerr(from_nhwc(ga), ref_g) < 1e-6
+
+
+def test_add_into_and_layout():
+    for n in (1024, 1030, 7):
+        a, b = rnd("a", (n,)), rnd("b", (n,))
+        da, db_ = dev32(a), dev32(b)
+        call("add_into", ptr(da), ptr(db_), n, 1)
+        torch.cuda.synchronize()
+        assert relerr(db_, a + b) < 1e-6
+        call("add_into", ptr(da), ptr(db_), n, 0)
+        torch.cuda.synchronize()
+        assert relerr(db_, a) == 0.0
+    for (N, C, H, W) in [(2, 16, 64, 64), (3, 20, 5, 7), (1, 3, 33, 65), (2, 256, 4, 4)]:
+        x = rnd("x", (N, C, H, W))
+        dx = dev32(x)
+        y = torch.empty(N, H, W, C, device=DEV)
+        call("nchw_to_nhwc", ptr(dx), N, C, H, W, ptr(y))
+        torch.cuda.synchronize()
+        assert torch.equal(y.cpu(), x.float().permute(0, 2, 3, 1).contiguous())
+        z = torch.empty(N, C, H, W, device=DEV)
+        call("nhwc_to_nchw", ptr(y), 0, 0, 0, N, H, W, C, ptr(z))
+        torch.cuda.synchronize()
+        assert torch.equal(z.cpu(), x.float())
+
+
+def test_avgpool_linear():
+    N, H, W, C, k = 3, 4, 4, 64, 4
+    s, t = rnd("s", (C,), 0.5, 1.5), rnd("t", (C,), -0.3, 0.3)
+    x = rnd("x", (N, C, H, W))
+    a = affine_act(x, s, t, True).requires_grad_(True)
+    pooled = F.avg_pool2d(a, k)
+    w = rnd("w", (7, C), -0.2, 0.2).requires_grad_(True)
+    b = rnd("b", (7,)).requires_grad_(True)
+    feat = pooled.view(N, C)
+    out = F.linear(feat, w, b)
+    dy = rnd("dy", (N, 7))
+    feat.retain_grad()
+    out.backward(dy)
+    dx, ds, dt = nhwc(x), dev32(s), dev32(t)
+    y = torch.empty(N, 1, 1, C, device=DEV)
+    call("avgpool_fwd", ptr(dx), ptr(ds), ptr(dt), 1, N, H, W, C, k, ptr(y))
+    o = torch.empty(N, 7, device=DEV)
+    dw_, db_ = dev32(w.detach()), dev32(b.detach())
+    call("linear_fwd", ptr(y), ptr(dw_), ptr(db_), N, C, 7, ptr(o))
+    torch.cuda.synchronize()
+    assert relerr(y.view(N, C), feat) < 1e-6
+    assert relerr(o, out) < 1e-5
+    gfeat = torch.empty(N, C, device=DEV)
+    gw, gb = torch.zeros(7, C, device=DEV), torch.zeros(7, device=DEV)
+    ddy = dev32(dy)
+    call("linear_bwd", ptr(y), ptr(dw_), ptr(ddy), N, C, 7, ptr(gfeat), ptr(gw), ptr(gb))
+    gx = torch.empty(N, H, W, C, device=DEV)
+    call("avgpool_bwd", ptr(gfeat), N, H, W, C, k, ptr(gx), 0)
+    torch.cuda.synchronize()
+    assert relerr(gfeat, feat.grad) < 1e-5
+    assert relerr(gw, w.grad) < 1e-5 and relerr(gb, b.grad) < 1e-5
+    assert relerr(from_nhwc(gx), a.grad) < 1e-5
+
+
+def test_mse_and_rmsprop_and_criterion():
+    from oracle import hg_oracle as O
+    o, t = rnd("o", (3, 16, 16, 16)), rnd("t", (3, 16, 16, 16), 0.0, 1.0)
+    n = o.numel()
+    do_, dt = dev32(o), dev32(t)
+    g = torch.empty_like(do_)
+    acc = torch.zeros(1, device=DEV, dtype=torch.float64)
+    call("mse_fwd_bwd", ptr(do_), ptr(dt), n, 1.0 / n, 1.0, ptr(g), 0, ptr(acc))
+    torch.cuda.synchronize()
+    ref = O.mse_loss([o], t)
+    assert abs(float(acc) - float(ref)) < 1e-6 * float(ref)
+    assert relerr(g, 2 * (o - t) / n) < 1e-6
+    # flat RMSprop == torch.optim.RMSprop semantics (oracle.rmsprop_step), two steps, odd length
+    for n in (1000, 1003):
+        p, gr = rnd("p", (n,)), rnd("g", (n,), -0.01, 0.01)
+        v = torch.zeros(n, dtype=torch.float64)
+        dp, dg, dv = dev32(p), dev32(gr), dev32(v)
+        params, grads, sq = {"p": p.clone()}, {"p": gr}, {"p": v}
+        for _ in range(2):
+            call("rmsprop_flat", ptr(dp), ptr(dg), ptr(dv), n, 2.5e-4, 0.99, 1e-8, 1.0)
+            O.rmsprop_step(params, grads, sq, lr=2.5e-4)
+        torch.cuda.synchronize()
+        assert relerr(dp, params["p"]) < 1e-6 and relerr(dv, sq["p"]) < 1e-5
+    # grad_scale folds the 1/world_size of the data-parallel mean
+    dp2, dv2 = dev32(p), dev32(v * 0)
+    dg2 = dev32(gr * 4)
+    call("rmsprop_flat", ptr(dp2), ptr(dg2), ptr(dv2), n, 2.5e-4, 0.99, 1e-8, 0.25)
+    dp3, dv3 = dev32(p), dev32(v * 0)
+    call("rmsprop_flat", ptr(dp3), ptr(dev32(gr)), ptr(dv3), n, 2.5e-4, 0.99, 1e-8, 1.0)
+    torch.cuda.synchronize()
+    assert relerr(dp2, dp3) < 1e-6
+    # pylib/Criterion.py
+    from pose_adv_aug_b200.pylib import Criterion as C
+    pred = torch.sigmoid(rnd("cp", (2, 4, 8, 8)))
+    gt = (rnd("cg", (2, 4, 8, 8)) > 0.5).double()
+    wt = 1.0 + 4.0 * gt
+    for fn_new, fn_ref in ((C.weighted_L2, O.weighted_L2), (C.weighted_sigmoid_crossentropy, O.weighted_sigmoid_crossentropy)):
+        p1 = pred.clone().requires_grad_(True)
+        l_ref = fn_ref(p1, gt, wt)
+        l_ref.backward()
+        p2 = dev32(pred).requires_grad_(True)
+        l_new = fn_new(p2, dev32(gt), dev32(wt))
+        (l_new * 3.0).backward()
+        assert abs(float(l_new) - float(l_ref)) < 1e-5 * abs(float(l_ref))
+        assert relerr(p2.grad, 3.0 * p1.grad) < 1e-5
+
+
+def test_error_paths():
+    from pose_adv_aug_b200._lib import get_lib
+    L = get_lib()
+    x = torch.zeros(4, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    rc = L.conv_nhwc(ptr(x), 0, 0, 0, 1, 1, 1, 6, ptr(x), 1, 0, 0, 4, 0, 0, 0, 0, ptr(x), 0, 0, 0, 1, s)
+    assert rc == -1 and "multiples of 4" in L.last_error()
+    rc = L.conv_nhwc(ptr(x), 0, 0, 0, 1, 1, 1, 4, ptr(x), 5, 0, 0, 4, 0, 0, 0, 0, ptr(x), 0, 0, 0, 1, s)
+    assert rc == -1 and "ksize" in L.last_error()
+    rc = L.maxpool2_fwd(ptr(x), 0, 0, 0, 1, 3, 3, 4, ptr(x), s)
+    assert rc == -1 and "even" in L.last_error()
+    assert L.cdll.hgk_device_ok() == 1

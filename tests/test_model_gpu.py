@@ -1,0 +1,311 @@
+"""Block- and whole-network parity (-m gpu) of the drop-in modules against the CPU oracle
+(oracle/hg_oracle.py, itself pinned to the reference by tests/golden) and directly against the
+committed golden outputs of the reference model.
+
+Tolerances (north_star): heat-maps and loss <= 1e-3 relative; gradients by the noise-floor rule
+of SURVEY.md 0.5 (fp32 vs fp64 of the reference itself differ by ~1e-2 whole-net)."""
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from hgk_testlib import DEV, relerr, rnd
+from oracle import hg_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+META = json.load(open(os.path.join(GOLD, "meta.json")))
+
+
+def _mods():
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    return M
+
+
+def _load(net, sd):
+    missing = net.load_state_dict(OrderedDict((k, v.float()) for k, v in sd.items()), strict=True)
+    return net
+
+
+def _grads64(sd64, fwd):
+    """fp64 oracle gradients of sum(outputs * weights) for a block test."""
+    leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd64.items() if O.is_trainable(k))
+    work = OrderedDict((k, leaves.get(k, v)) for k, v in sd64.items())
+    return leaves, work
+
+
+@pytest.mark.parametrize("cfg", [(64, 128, True, 2, 16), (128, 128, False, 3, 8), (256, 256, False, 2, 4),
+                                 (32, 32, False, 2, 1), (12, 24, True, 3, 6)])
+@pytest.mark.parametrize("training", [True, False])
+def test_residual_block(cfg, training):
+    M = _mods()
+    cin, cout, adapter, N, H = cfg
+    import torch.nn as nn
+    ad = nn.Conv2d(cin, cout, 1) if adapter else None
+    blk = M._Residual(cin, cout, ad)
+    schema = O.residual_schema("r", cin, cout, adapter)
+    sd64 = synth.make_state_dict(schema, seed=5, dtype=torch.float64)
+    _load(blk, OrderedDict((k[2:], v) for k, v in sd64.items()))
+    blk.to(DEV)
+    blk.train(training)
+    x64 = rnd("x", (N, cin, H, H), -1.0, 2.0)
+    leaves, work = _grads64(sd64, None)
+    xr = x64.clone().requires_grad_(True)
+    st = O.BNState(training)
+    yr = O.residual(work, "r", xr, st)
+    gy = rnd("gy", tuple(yr.shape))
+    yr.backward(gy)
+    x = x64.float().to(DEV).requires_grad_(True)
+    y = blk(x)
+    assert y.shape == yr.shape
+    tol = 5e-4 if (N * H * H <= 4 and training) else 2e-5
+    assert relerr(y, yr) < tol
+    y.backward(gy.float().to(DEV))
+    gtol = 5e-2 if (N * H * H <= 4 and training) else 2e-4
+    assert relerr(x.grad, xr.grad) < gtol
+    for k, p in blk.named_parameters():
+        ref = leaves["r." + k].grad
+        if training and k.endswith("bias") and "bn" not in k:
+            continue      # conv bias in front of a train-mode BN: true gradient is 0 (rounding noise on both sides)
+        assert relerr(p.grad, ref) < gtol, k
+    if training:
+        for k, v in st.updates.items():
+            if "num_batches" in k:
+                continue
+            assert relerr(blk.state_dict()[k[2:]], v) < 1e-5, k
+        assert int(blk.bn1.num_batches_tracked) == 1
+
+
+def _hg_case(case, dtype=torch.float32):
+    c = META["cases"][case]
+    S, Mo, K, C, N, R = c["stacks"], c["modules"], c["classes"], c["chan"], c["batch"], c["res"]
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=1, dtype=dtype)
+    x = synth.make_images(N, R, seed=2, dtype=dtype)
+    t = synth.make_heatmaps(N, R, K, seed=3, dtype=dtype)
+    return c, sd, x, t
+
+
+@pytest.mark.parametrize("case", [k for k in META["cases"] if k.startswith("hg_")])
+def test_whole_net_vs_reference_golden(case):
+    """Heat-maps / loss / gradients / running stats / RMSprop step against the REFERENCE's outputs."""
+    M = _mods()
+    c, sd, x, t = _hg_case(case)
+    g32 = np.load(os.path.join(GOLD, case + "_f32.npz"))
+    g64 = np.load(os.path.join(GOLD, case + "_f64.npz"))
+    net = _load(M.create_hg(c["stacks"], c["modules"], c["classes"], c["chan"]), sd).to(DEV)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    xd, td = x.to(DEV), t.to(DEV)
+    net.eval()
+    with torch.no_grad():
+        oe = net(xd)
+    assert isinstance(oe, list) and len(oe) == c["stacks"]
+    for i, o in enumerate(oe):
+        ref = torch.from_numpy(g32["eval_out%d" % i])
+        assert tuple(o.shape) == tuple(ref.shape)
+        assert relerr(o, ref) < 1e-3           # north_star: <= 1e-3 relative on fp32 heat-maps
+        assert relerr(o, ref) < 1e-4           # what fp32 arithmetic actually achieves
+    net.train()
+    outs = net(xd)
+    loss = 0
+    for o in outs:
+        tmp = (o - td) ** 2
+        loss = loss + tmp.sum() / tmp.numel()
+    opt = torch.optim.RMSprop(net.parameters(), lr=2.5e-4, alpha=0.99, eps=1e-8, momentum=0, weight_decay=0)
+    opt.zero_grad()
+    loss.backward()
+    for i, o in enumerate(outs):
+        ref64 = torch.from_numpy(g64["train_out%d" % i])
+        floor = relerr(torch.from_numpy(g32["train_out%d" % i]), ref64)
+        assert relerr(o, ref64) < 1e-3
+        assert relerr(o, ref64) < 3 * floor + 1e-4
+    assert abs(float(loss) - float(g64["loss"])) / float(g64["loss"]) < 1e-3
+    names = c["param_names"]
+    params = dict(net.named_parameters())
+    norms = np.array([float(params[k].grad.double().norm()) for k in names])
+    gn32, gn64 = g32["grad_norms"], g64["grad_norms"]
+    floor = np.abs(gn32 - gn64).max() / gn64.max()
+    assert np.abs(norms - gn64).max() / gn64.max() < 2 * floor + 2e-4
+    for k in g32.files:
+        if k.startswith("grad:"):
+            name = k[5:]
+            if name.endswith("bias") and "bn" not in name and "linear.0.1" not in name and "out_conv" not in name:
+                continue
+            assert relerr(params[name].grad, torch.from_numpy(g32[k])) < max(2e-2, 4 * floor), name
+        if k.startswith("stat:"):
+            assert relerr(net.state_dict()[k[5:]], torch.from_numpy(g32[k])) < 2e-3, k
+    opt.step()
+    for k in g32.files:
+        if k.startswith("step:"):
+            # RMSprop's first step is ~ lr*10*sign(g): robust except where g is at rounding-noise level
+            d = (net.state_dict()[k[5:]].cpu() - torch.from_numpy(g32[k])).abs()
+            assert float((d > 1e-5).float().mean()) < 0.02, k
+            assert float(d.max()) < 6e-3, k
+
+
+def test_whole_net_vs_oracle_two_stack_c64():
+    """A shape class the goldens do not hold (C=64, N=4, 128x128), oracle run live in fp64."""
+    M = _mods()
+    S, Mo, K, C, N, R = 2, 1, 16, 64, 4, 128
+    sd64 = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=31, dtype=torch.float64)
+    x64 = synth.make_images(N, R, seed=32, dtype=torch.float64)
+    t64 = synth.make_heatmaps(N, R, K, seed=33, dtype=torch.float64)
+    outs64, loss64, grads64, st = O.train_step(sd64, x64, t64, S, Mo)
+    sd32 = OrderedDict((k, v.float() if v.is_floating_point() else v) for k, v in sd64.items())
+    outs32, loss32, grads32, _ = O.train_step(sd32, x64.float(), t64.float(), S, Mo)
+    net = _load(M.create_hg(S, Mo, K, C), sd64).to(DEV)
+    net.train()
+    outs = net(x64.float().to(DEV))
+    loss = O.mse_loss(outs, t64.float().to(DEV))
+    loss.backward()
+    for o, r in zip(outs, outs64):
+        assert relerr(o, r) < 1e-3
+    assert abs(float(loss) - float(loss64)) / float(loss64) < 1e-4
+    names = [k for k in sd64 if O.is_trainable(k)]
+    params = dict(net.named_parameters())
+    num = sum(float((params[k].grad.cpu().double() - grads64[k]).pow(2).sum()) for k in names)
+    den = sum(float(grads64[k].pow(2).sum()) for k in names)
+    num32 = sum(float((grads32[k].double() - grads64[k]).pow(2).sum()) for k in names)
+    ours, floor = (num / den) ** 0.5, (num32 / den) ** 0.5
+    assert ours < 2 * floor + 1e-4, (ours, floor)
+    for k, v in st.updates.items():
+        if "num_batches" not in k:
+            assert relerr(net.state_dict()[k], v) < 1e-4, k
+
+
+def test_state_dict_schema_and_checkpoint_roundtrip():
+    M = _mods()
+    net = M.create_hg(2, 1, 16, 256)
+    got = [[k, list(v.shape)] for k, v in net.state_dict().items()]
+    assert got == META["schema_hg_s2_m1_k16_c256"]
+    asn = M.create_asn(256, 256, 7, 7, is_aug=True)
+    assert [[k, list(v.shape)] for k, v in asn.state_dict().items()] == META["schema_asn_aug_c256"]
+    # DataParallel-style `module.` prefix is a pure key rename (utils/checkpoint.py:57-67 copies by name)
+    small = M.create_hg(1, 1, 16, 32).to(DEV)
+    x = synth.make_images(2, 64, seed=4).to(DEV)
+    small.eval()
+    with torch.no_grad():
+        a = small(x)[0].clone()
+    sd = OrderedDict(("module." + k, v.clone()) for k, v in small.state_dict().items())
+    other = M.create_hg(1, 1, 16, 32).to(DEV)
+    own = other.state_dict()
+    for k, v in sd.items():                      # the reference loader's name-wise copy
+        own[k[len("module."):]].copy_(v)
+    other.eval()
+    with torch.no_grad():
+        b = other(x)[0]
+    assert torch.equal(a, b)
+
+
+def test_asn_half_hg_and_agent_update():
+    """half-hg + ASN (ref models/asn_stacked_hg.py:159-171) in both mode combinations the scripts use."""
+    M = _mods()
+    g = np.load(os.path.join(GOLD, "asn_c32_n2_r256_f32.npz"))
+    C, N, R = 32, 2, 256
+    sd = synth.make_state_dict(O.hg_schema(1, 1, 16, C), seed=11)
+    asd = synth.make_state_dict(O.asn_schema(C, C, 7, 7, is_aug=True), seed=12)
+    net = _load(M.create_hg(1, 1, 16, C), sd).to(DEV)
+    asn = _load(M.create_asn(C, C, 7, 7, is_aug=True), asd).to(DEV)
+    x = synth.make_images(N, R, seed=13).to(DEV)
+    # joint-train-pose-s-r-agent.py:207-208,250: hg.train(), agent.eval()
+    net.train()
+    asn.eval()
+    rm0 = net.state_dict()["bn1.running_mean"].clone()
+    ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
+    assert tuple(ps.shape) == (N, 7) and tuple(pr.shape) == (N, 7)
+    assert relerr(ps, torch.from_numpy(g["half_scale_asneval"])) < 1e-3
+    assert relerr(pr, torch.from_numpy(g["half_rot_asneval"])) < 1e-3
+    assert not torch.equal(rm0, net.state_dict()["bn1.running_mean"])     # train-mode half pass updates stats
+    # :323-324,342,399-410: hg.eval(), agent.train(); KL loss; gradients reach the ASN only
+    _load(net, sd)
+    net.eval()
+    asn.train()
+    ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
+    assert relerr(ps, torch.from_numpy(g["half_scale_asntrain"])) < 1e-3
+    assert relerr(pr, torch.from_numpy(g["half_rot_asntrain"])) < 1e-3
+    tgt = torch.softmax(synth.make_tensor("asn_target", (N, 7), seed=14), dim=1).to(DEV)
+    loss = O.agent_kl_loss(ps, tgt, 7) + O.agent_kl_loss(pr, tgt, 7)
+    assert abs(float(loss) - float(g["agent_loss"])) < 1e-3 * abs(float(g["agent_loss"])) + 1e-6
+    for p in list(net.parameters()) + list(asn.parameters()):
+        if p.grad is not None:
+            p.grad.zero_()
+    loss.backward()
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in net.parameters() if p.grad is not None)
+    assert relerr(asn.fc_scale.weight.grad, torch.from_numpy(g["grad:fc_scale.weight"])) < 1e-3
+    assert relerr(asn.merge1.conv2.weight.grad, torch.from_numpy(g["grad:merge1.conv2.weight"])) < 2e-2
+    assert relerr(asn.residual_skip1.conv1.weight.grad, torch.from_numpy(g["grad:residual_skip1.conv1.weight"])) < 2e-2
+    names = META["cases"]["asn_c32_n2_r256"]["param_names"]
+    params = dict(asn.named_parameters())
+    norms = np.array([float(params[k].grad.double().norm()) for k in names])
+    g64 = np.load(os.path.join(GOLD, "asn_c32_n2_r256_f64.npz"))["grad_norms"]
+    floor = np.abs(g["grad_norms"] - g64).max() / g64.max()
+    assert np.abs(norms - g64).max() / g64.max() < 2 * floor + 1e-3
+    # whole hg + ASN returns (outs, scale, rot) (ref :338)
+    net.train()
+    asn.eval()
+    outs, ps2, pr2 = net(x, asn, is_aug=True)
+    assert isinstance(outs, list) and len(outs) == 1 and tuple(outs[0].shape) == (N, 16, 64, 64)
+    # standalone ASN on NCHW feature dict (ref :401)
+    feats = {"neck": torch.rand(N, C, 4, 4, device=DEV), "skip1": torch.rand(N, C, 64, 64, device=DEV),
+             "skip2": torch.rand(N, C, 32, 32, device=DEV), "skip3": torch.rand(N, C, 16, 16, device=DEV),
+             "skip4": torch.rand(N, C, 8, 8, device=DEV)}
+    s1, r1 = asn(feats, is_aug=True)
+    (s_ref, r_ref), _ = O.asn_forward(OrderedDict((k, v.cpu().double()) for k, v in asn.state_dict().items()),
+                                      dict((k, v.cpu().double()) for k, v in feats.items()), training=False)
+    assert relerr(s1, s_ref) < 1e-3 and relerr(r1, r_ref) < 1e-3
+
+
+def test_trainer_matches_module_path_and_graph_replay():
+    """HourglassTrainer (fused step, CUDA graph) == module forward + torch loss + backward + RMSprop."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer, FlatRMSprop
+    S, Mo, K, C, N, R = 2, 1, 16, 32, 4, 64
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=41)
+    x = synth.make_images(N, R, seed=42)
+    t = synth.make_heatmaps(N, R, K, seed=43)
+    nets = [_load(M.create_hg(S, Mo, K, C), sd).to(DEV) for _ in range(3)]
+    # (a) module path + flat optimizer
+    a = nets[0]
+    a.train()
+    opt = FlatRMSprop(a, lr=2.5e-4)
+    losses_a = []
+    for _ in range(3):
+        outs = a(x.to(DEV))
+        loss = O.mse_loss(outs, t.to(DEV))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses_a.append(float(loss))
+    # (b) fused trainer without graph, (c) with graph
+    for net, use_graph in ((nets[1], False), (nets[2], True)):
+        tr = HourglassTrainer(net, N, R, lr=2.5e-4, use_graph=use_graph)
+        losses = [float(tr.step(x.pin_memory(), t.pin_memory())) for _ in range(3)]
+        for la, lb in zip(losses_a, losses):
+            assert abs(la - lb) < 2e-5 * abs(la), (losses_a, losses)
+        for (k, pa), (_, pb) in zip(a.state_dict().items(), net.state_dict().items()):
+            if pa.is_floating_point():
+                # RMSprop's first steps move a weight by up to ~lr*10 per step whatever |g| is, so elements whose
+                # gradient is rounding noise (atomics order) may differ; everything else agrees tightly
+                d = (pa - pb).abs()
+                assert float((d > 1e-5).float().mean()) < 0.02, k
+                assert float(d.max()) < 2e-2, k
+        hm = tr.heatmaps()
+        assert len(hm) == S and tuple(hm[0].shape) == (N, K, R // 4, R // 4)
+    # oracle: same three steps on CPU fp32
+    sdo = OrderedDict((k, v.clone()) for k, v in sd.items())
+    sq = OrderedDict((k, torch.zeros_like(v)) for k, v in sdo.items() if O.is_trainable(k))
+    for i in range(3):
+        _, lo, _, _ = O.train_step(sdo, x, t, S, Mo, square_avg=sq)
+        assert abs(float(lo) - losses_a[i]) < 1e-3 * abs(float(lo))
+
+
+def test_cpu_input_fails_loudly():
+    M = _mods()
+    from pose_adv_aug_b200 import HGKError
+    net = M.create_hg(1, 1, 16, 32)
+    with pytest.raises(HGKError):
+        net(torch.rand(1, 3, 64, 64))
