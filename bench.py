@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the 2-stack hourglass train step (BASELINE.json configs[1]:
+S=2, C=256, bs=24 per GPU, 256x256, fwd + sum-of-stacks MSE + bwd + RMSprop [+ grad all-reduce]).
+
+    python bench.py [--gpus N --steps K --warmup W]          our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [...]                   the reference's CPU implementation, host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec 2-stack HG bs24 256x256 train step"
+BYTES_PER_IMAGE_STEP = 0.892e9      # algorithmic HBM bytes / image / train step
+FLOP_PER_IMAGE_STEP = 50.0e9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), line.strip()))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(args, rank):
+    from oracle import synth
+    x = synth.make_images(args.batch, args.res, seed=100 + rank)
+    t = synth.make_heatmaps(args.batch, args.res, 16, seed=200 + rank)
+    return x, t
+
+
+def make_weights(args):
+    from oracle import synth
+    from oracle import hg_oracle as O
+    return synth.make_state_dict(O.hg_schema(args.stacks, 1, 16, args.chan), seed=1, perturb_bn=False)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref when present, else the oracle port)
+# ----------------------------------------------------------------------------------------------
+class CpuStep(object):
+    def __init__(self, args, sd):
+        import torch
+        from oracle import make_ref
+        from oracle import hg_oracle as O
+        self.torch, self.O, self.args = torch, O, args
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        ref, _ = make_ref.load()
+        self.kind = "reference" if ref is not None else "port"
+        if ref is not None:
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                self.net = ref.create_hg(num_stacks=args.stacks, num_modules=1, num_classes=16, chan=args.chan)
+            self.net.load_state_dict(sd)
+            self.net.train()
+            self.opt = torch.optim.RMSprop(self.net.parameters(), lr=2.5e-4, alpha=0.99, eps=1e-8, momentum=0,
+                                           weight_decay=0)
+        else:
+            from collections import OrderedDict
+            self.sd = OrderedDict((k, v.clone()) for k, v in sd.items())
+            self.sq = OrderedDict((k, torch.zeros_like(v)) for k, v in self.sd.items() if O.is_trainable(k))
+
+    def step(self, x, t):
+        """One reference train step (stack-hg.py:153-165) on CPU; returns (outputs, loss)."""
+        if self.kind == "reference":
+            outs = self.net(x)
+            loss = 0
+            for o in outs:
+                tmp = (o - t) ** 2
+                loss = loss + tmp.sum() / tmp.numel()
+            self.opt.zero_grad()
+            loss.backward()
+            self.opt.step()
+            return [o.detach() for o in outs], float(loss)
+        outs, loss, _, _ = self.O.train_step(self.sd, x, t, self.args.stacks, 1, square_avg=self.sq)
+        return outs, float(loss)
+
+
+def cpu_sample(args, sd, x, t, budget_s, steps, warmup):
+    """Times `steps` reference steps (after `warmup`) on a sample batch sized to fit budget_s."""
+    cpu = CpuStep(args, sd)
+    b = min(2, args.batch)
+    t0 = time.time()
+    cpu.step(x[:b], t[:b])
+    per_img = (time.time() - t0) / b
+    total = steps + warmup
+    sb = b
+    while sb * 2 <= args.batch and per_img * (sb * 2) * total <= budget_s:
+        sb *= 2
+    if sb == 16 and args.batch == 24 and per_img * 24 * total <= budget_s:
+        sb = 24
+    for _ in range(warmup):
+        cpu.step(x[:sb], t[:sb])
+    t0 = time.time()
+    outs = None
+    for _ in range(steps):
+        outs, loss = cpu.step(x[:sb], t[:sb])
+    dt = (time.time() - t0) / max(steps, 1)
+    return {"value": sb / dt, "unit": "images/s", "cores": cpu.cores, "kind": cpu.kind,
+            "sample": "%d timed train steps (fwd+MSE+bwd+RMSprop, %d warm-up) at batch %d of the same "
+                      "S=%d C=%d %dx%d workload, torch CPU fp32, %d threads" %
+                      (steps, warmup + 1, sb, args.stacks, args.chan, args.res, args.res, cpu.cores),
+            "s_per_step": dt, "sample_batch": sb}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sd = make_weights(args)
+    x, t = build_inputs(args, 0)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    r = cpu_sample(args, sd, x, t, budget_s=150.0, steps=steps, warmup=warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, 1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "torch": torch.__version__}
+    print(json.dumps(line))
+
+
+def config_dict(args, world):
+    return {"workload": "2-stack hourglass train step (fwd + sum-of-stacks MSE + bwd + RMSprop%s), S=%d C=%d, "
+                        "bs=%d/GPU, %dx%d synthetic MPII-shaped batch" %
+                        (" + 1 NCCL grad all-reduce" if world > 1 else "", args.stacks, args.chan, args.batch,
+                         args.res, args.res),
+            "stacks": args.stacks, "chan": args.chan, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "res": args.res, "parallelism": "dp%d" % world,
+            "l2": "no explicit flush: each step streams >5 GB of activations (>> 126 MB L2) between reuses"}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pose_adv_aug_b200 import dist as hdist
+    from pose_adv_aug_b200 import HourglassTrainer, get_lib
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    rank, world, local = hdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = get_lib()
+    assert lib.cdll.hgk_device_ok() == 1, "libhgk needs an sm_100 GPU"
+    pk = peaks()
+    sd = make_weights(args)
+    x, t = build_inputs(args, rank)
+    net = M.create_hg(args.stacks, 1, 16, args.chan)
+    net.load_state_dict(sd)
+    tr = HourglassTrainer(net, args.batch, args.res, device=dev, use_graph=not args.no_graph)
+    xp, tp = x.pin_memory(), t.pin_memory()
+    tr.x.copy_(xp)
+    tr.t.copy_(tp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- timed region: K device-resident steps ----
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        tr.step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    # ---- e2e: public API with host buffers (H2D of the batch + D2H of the loss every step) ----
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    last = 0.0
+    for _ in range(e2e_steps):
+        last = float(tr.step(xp, tp).item())
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.time() - t0
+    w2 = time.time()
+    sampler.stop()
+    tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    clocks = sampler.summary(w0, w1)
+    # ---- dominant kernel, timed live with CUDA events on the launching stream ----
+    roof = dominant_kernel_roofline(tr, pk, torch)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * args.batch * args.steps / (ms / 1e3)
+    ms_step = ms / args.steps
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
+            "roofline": roof,
+            "step_roofline": {"bound": "hbm", "achieved": args.batch * BYTES_PER_IMAGE_STEP / (ms_step / 1e3) / 1e9,
+                              "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "frac": args.batch * BYTES_PER_IMAGE_STEP / (ms_step / 1e3) / 1e9 / pk["hbm_gbs"],
+                              "note": "whole step, algorithmic 0.892 GB/image/step of the fused plan; peak %s" % pk["src"]},
+            "e2e": {"value": world * args.batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(xp.numel() * 4 + tp.numel() * 4), "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "api": "HourglassTrainer.step(images_pinned, heatmaps_pinned) -> loss.item()"},
+            "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
+            "cuda_graph": not args.no_graph, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_sample(args, sd, x, t, budget_s=25.0, steps=2, warmup=0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["parity"] = parity_vs_cpu(args, sd, x, t, torch, dev)
+        except Exception as e:      # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %s" % e}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parity_vs_cpu(args, sd, x, t, torch, dev):
+    """fp32 heat-map max-abs-err (BASELINE.json metric, second half) on a 2-image sample."""
+    from collections import OrderedDict
+    from oracle import hg_oracle as O
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    n = 2
+    outs_ref, loss_ref, _, _ = O.train_step(OrderedDict((k, v.clone()) for k, v in sd.items()), x[:n], t[:n],
+                                            args.stacks, 1)
+    net = M.create_hg(args.stacks, 1, 16, args.chan)
+    net.load_state_dict(sd)
+    net.to(dev).train()
+    with torch.no_grad():
+        outs = net(x[:n].to(dev))
+    err = max(float((a.cpu() - b).abs().max()) for a, b in zip(outs, outs_ref))
+    rel = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(outs, outs_ref))
+    return {"heatmap_max_abs_err": err, "heatmap_rel_to_max": rel, "sample": "train-mode forward, %d images" % n,
+            "oracle": "oracle/hg_oracle.py fp32 CPU"}
+
+
+def dominant_kernel_roofline(tr, pk, torch):
+    """Times the FLOP-dominant launch class of the step (3x3 conv, C/2 -> C/2 at the top resolution,
+    forward) with CUDA events, cycling over the plan's distinct launches of that class so that
+    inputs are not L2-resident between repetitions."""
+    plan = tr.plan
+    cand = []
+    for rec in plan.fwd:
+        if rec[2] == "conv_nhwc":
+            a = rec[1]
+            N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[9], a[12]
+            if k == 3:
+                cand.append((2.0 * N * H * W * Cin * Cout * 9, rec))
+    if not cand:
+        return None
+    top = max(c[0] for c in cand)
+    recs = [r for f, r in cand if f == top]
+    stream = torch.cuda.current_stream().cuda_stream
+    for r in recs:
+        r[0](*r[1], stream)
+    torch.cuda.synchronize()
+    reps = 4
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for r in recs:
+            r[0](*r[1], stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * len(recs))
+    a = recs[0][1]
+    N, H, W, Cin, Cout = a[4], a[5], a[6], a[7], a[12]
+    achieved = top / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"], "traffic": None,
+            "kernel": "conv_nhwc 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this class/step)" % (Cin, Cout, N, H, W, len(recs)),
+            "ms_per_launch": ms, "flop_per_launch": top, "algorithmic_bytes_per_launch": 4.0 * N * H * W * (Cin + Cout),
+            "peak_src": pk["src"] + " dense bf16 burst (tf32 runs at 1/2, 3xTF32 at 1/6 of it)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=24)
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--stacks", type=int, default=2)
+    ap.add_argument("--chan", type=int, default=256)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-path", type=int, default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 2 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args)
+        return
+    args.steps = 20 if args.steps is None else args.steps
+    args.warmup = 3 if args.warmup is None else args.warmup
+    if args.conv_path is not None:
+        from pose_adv_aug_b200.models import asn_stacked_hg as M
+        M.CONV_PATH = args.conv_path
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,14 +84,15 @@ int hgk_bn_eval_prepare(const float* gamma, const float* beta, const float* runn
 int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
                       const float* mean, const float* invstd, long long P, int C,
                       double* sum_g, double* sum_gx, void* stream);
-/* dgamma += sum_gx, dbeta += sum_g; coefficients of dz = cA*g + cB*z + cC  (training: full BN backward;
- * eval: cA = gamma*invstd, cB = cC = 0) */
+/* dgamma += sum_gx, dbeta += sum_g; coefficients of dz = cA*(g - cC - (z-mean)*cB)  (training: full BN
+ * backward, cA = gamma*invstd, cB = mean(g*xhat)*invstd, cC = mean(g); eval: cB = cC = 0) */
 int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long count, const float* gamma,
                         const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
                         float* cA, float* cB, float* cC, int C, void* stream);
-/* in place: dy <- dz = cA*(dy*mask) + cB*z + cC */
+/* in place: dy <- dz = cA*((dy*mask) - cC - (z-mean)*cB) */
 int hgk_bn_bwd_apply(float* dy, const float* z, const float* scale, const float* shift, int relu,
-                     const float* cA, const float* cB, const float* cC, long long P, int C, void* stream);
+                     const float* mean, const float* cA, const float* cB, const float* cC, long long P, int C,
+                     void* stream);
 
 /* ---- nn.MaxPool2d(2,2) (:69,227,371) on a virtual activation; backward recomputes the argmax ---- */
 int hgk_maxpool2_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu,

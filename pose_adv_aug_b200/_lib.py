@@ -22,7 +22,7 @@ SIGNATURES = {
     "hgk_bn_eval_prepare": [P, P, P, P, F, P, P, P, P, I, P],
     "hgk_bn_bwd_reduce": [P, P, P, P, I, P, P, L, I, P, P, P],
     "hgk_bn_bwd_finalize": [P, P, L, P, P, P, I, P, P, P, P, P, I, P],
-    "hgk_bn_bwd_apply": [P, P, P, P, I, P, P, P, L, I, P],
+    "hgk_bn_bwd_apply": [P, P, P, P, I, P, P, P, P, L, I, P],
     "hgk_maxpool2_fwd": [P, P, P, I, I, I, I, I, P, P],
     "hgk_maxpool2_bwd": [P, P, P, I, I, I, I, I, P, P, I, P],
     "hgk_add_fwd": [P, P, P, I, I, P, P, P, I, I, I, I, I, P, P],

@@ -116,10 +116,12 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
     if (dbeta != nullptr) dbeta[c] += (float)sg;
     double A = (double)gamma[c] * (double)invstd[c];
     if (training) {
+        // dz = cA * (g - cC - (z - mean) * cB): the centred form keeps the fp32 rounding error of the
+        // projection term proportional to |z - mean| instead of |mean| (no cancellation)
         double c1 = sg / count, c2 = sgx / count;
         cA[c] = (float)A;
-        cB[c] = (float)(-A * (double)invstd[c] * c2);
-        cC[c] = (float)(-A * c1 + A * (double)mean[c] * (double)invstd[c] * c2);
+        cB[c] = (float)(c2 * (double)invstd[c]);
+        cC[c] = (float)c1;
     } else {
         cA[c] = (float)A;
         cB[c] = 0.f;
@@ -129,7 +131,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           int relu, const float* __restrict__ cA, const float* __restrict__ cB,
+                                                           int relu, const float* __restrict__ mean,
+                                                           const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, long long total4, int C4) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -137,15 +140,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
         float4 d = ld4(dy + i * 4);
         float4 v = ldg4(z + i * 4);
         float4 s = ldg4(scale + c), t = ldg4(shift + c), a = ldg4(cA + c), b = ldg4(cB + c), cc = ldg4(cC + c);
+        float4 mu = ldg4(mean + c);
         float gx = (relu && fmaf(v.x, s.x, t.x) <= 0.f) ? 0.f : d.x;
         float gy = (relu && fmaf(v.y, s.y, t.y) <= 0.f) ? 0.f : d.y;
         float gz = (relu && fmaf(v.z, s.z, t.z) <= 0.f) ? 0.f : d.z;
         float gw = (relu && fmaf(v.w, s.w, t.w) <= 0.f) ? 0.f : d.w;
         float4 o;
-        o.x = fmaf(a.x, gx, fmaf(b.x, v.x, cc.x));
-        o.y = fmaf(a.y, gy, fmaf(b.y, v.y, cc.y));
-        o.z = fmaf(a.z, gz, fmaf(b.z, v.z, cc.z));
-        o.w = fmaf(a.w, gw, fmaf(b.w, v.w, cc.w));
+        o.x = a.x * ((gx - cc.x) - (v.x - mu.x) * b.x);
+        o.y = a.y * ((gy - cc.y) - (v.y - mu.y) * b.y);
+        o.z = a.z * ((gz - cc.z) - (v.z - mu.z) * b.z);
+        o.w = a.w * ((gw - cc.w) - (v.w - mu.w) * b.w);
         st4(dy + i * 4, o);
     }
 }
@@ -212,13 +216,14 @@ extern "C" int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, lo
 }
 
 extern "C" int hgk_bn_bwd_apply(float* dy, const float* z, const float* scale, const float* shift, int relu,
-                                const float* cA, const float* cB, const float* cC, long long P, int C, void* stream) {
-    HGK_REQUIRE(dy && z && scale && shift && cA && cB && cC, "hgk_bn_bwd_apply: null pointer");
+                                const float* mean, const float* cA, const float* cB, const float* cC, long long P, int C,
+                                void* stream) {
+    HGK_REQUIRE(dy && z && scale && shift && mean && cA && cB && cC, "hgk_bn_bwd_apply: null pointer");
     HGK_REQUIRE(P > 0 && C > 0 && C % 4 == 0, "hgk_bn_bwd_apply: need P > 0 and C %% 4 == 0");
     long long total4 = P * (C / 4);
     long long blocks = (total4 + 255) / 256;
     if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
-    bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, cA, cB, cC, total4, C / 4);
+    bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, mean, cA, cB, cC, total4, C / 4);
     HGK_CHECK_LAUNCH("hgk_bn_bwd_apply");
     return HGK_OK;
 }

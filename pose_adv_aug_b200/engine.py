@@ -547,7 +547,7 @@ def _emit_bn_bwd(p, o, r, g):
              _ptr(r.invstd), o.P, o.C, _ptr(r.sum_g), _ptr(r.sum_gx))
     p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
              int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
-    p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.cA),
+    p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA),
              _ptr(r.cB), _ptr(r.cC), o.P, o.C)
 
 

@@ -169,7 +169,7 @@ def test_batchnorm_fwd_bwd(shape, training):
     act = torch.empty(N, C, H, W, device=DEV)
     call("nhwc_to_nchw", ptr(dz_), ptr(scale), ptr(shift), 1, N, H, W, C, ptr(act))
     torch.cuda.synchronize()
-    assert relerr(act, y) < 2e-5
+    assert relerr(act, y) < (2e-4 if P <= 2 else 2e-5)     # 2 samples: xhat = +-1 exactly, ill-conditioned
     # backward: reduce -> finalize -> apply (in place)
     g = nhwc(dy)
     sg = torch.zeros(C, device=DEV, dtype=torch.float64)
@@ -180,7 +180,7 @@ def test_batchnorm_fwd_bwd(shape, training):
     call("bn_bwd_reduce", ptr(g), ptr(dz_), ptr(scale), ptr(shift), 1, ptr(mean), ptr(invstd), P, C, ptr(sg), ptr(sgx))
     call("bn_bwd_finalize", ptr(sg), ptr(sgx), P, ptr(dgamma), ptr(mean), ptr(invstd), int(training), ptr(ggamma),
          ptr(gbeta), ptr(cA), ptr(cB), ptr(cC), C)
-    call("bn_bwd_apply", ptr(g), ptr(dz_), ptr(scale), ptr(shift), 1, ptr(cA), ptr(cB), ptr(cC), P, C)
+    call("bn_bwd_apply", ptr(g), ptr(dz_), ptr(scale), ptr(shift), 1, ptr(mean), ptr(cA), ptr(cB), ptr(cC), P, C)
     torch.cuda.synchronize()
     tol = 2e-4 if P <= 2 else 2e-5       # 2 samples: xhat = +-1, invstd ~ 1/|dz|: badly conditioned in any precision
     assert relerr(from_nhwc(g), z.grad) < tol
@@ -257,7 +257,7 @@ def test_add_into_and_layout():
         assert relerr(db_, a + b) < 1e-6
         call("add_into", ptr(da), ptr(db_), n, 0)
         torch.cuda.synchronize()
-        assert relerr(db_, a) == 0.0
+        assert torch.equal(db_.cpu(), a.float())
     for (N, C, H, W) in [(2, 16, 64, 64), (3, 20, 5, 7), (1, 3, 33, 65), (2, 256, 4, 4)]:
         x = rnd("x", (N, C, H, W))
         dx = dev32(x)
