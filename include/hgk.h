@@ -42,13 +42,31 @@ int hgk_device_ok(void);
  * flipped taps and the [tap][Cout_fwd][Cin_fwd] weight array);  bias/res optional (NULL);
  * stat_sum/stat_sq optional fp64 [Cout] accumulators (+=) of y and y^2 over all pixels: the
  * batch statistics of the following nn.BatchNorm2d (:19,22,25,243), fused into the epilogue.
- * path: 0 = auto, 1 = force fp32 SIMT kernel, 2 = force tcgen05 tensor-core kernel.          */
+ * This entry point is the exact-fp32 SIMT kernel (any C % 4 == 0); path must be 0 or 1.       */
 int hgk_conv_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
                   int N, int H, int W, int Cin,
                   const float* w, int ksize, int flip, const float* bias, int Cout,
                   const float* res, const float* res_scale, const float* res_shift, int res_relu,
                   float* y, int accumulate, double* stat_sum, double* stat_sq,
                   int path, void* stream);
+
+/* The same convolution on the tcgen05 tensor cores (TF32 operands, fp32 accumulate in TMEM).
+ * Weights come pre-packed by hgk_pack_weights_tc in the UMMA operand layout; w_lo != NULL selects the
+ * error-compensated 3xTF32 product (fp32-class accuracy, used for the forward pass), w_lo == NULL
+ * plain TF32 (used for data gradients; taps are pre-flipped by the packer).  Shapes:
+ * hgk_conv_tc_supported(Cin, Cout, ksize) -> Cin % 32 == 0, Cout in {64,128,256}, ksize in {1,3}. */
+int hgk_conv_tc_supported(int Cin, int Cout, int ksize);
+int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                     int N, int H, int W, int Cin,
+                     const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                     const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                     float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream);
+/* table: n_entries x 8 int64 {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN};
+ * mode 0 (forward operand): B[n][k;tap] = W[o=n][i=k][tap];  mode 1 (data-gradient operand):
+ * B[n][k;tap] = W[o=k][i=n][taps-1-tap].  Destination: [n-tile][tap][k/32] blocks of [8][BN][4] floats,
+ * hi = tf32(w), lo = w - hi. */
+int hgk_pack_weights_tc(const float* src_base, float* dst_base, const long long* table, int n_entries,
+                        void* stream);
 
 /* weight / bias gradient of the same convolutions (autograd of nn.Conv2d):
  * dw[co*s_co + ci*s_ci + tap*s_tap] += sum_p dz[p,co] * T(x)[p+off(tap),ci];  dbias[co] += sum_p dz[p,co]

@@ -6,23 +6,9 @@
 // Replaces: nn.Conv2d + nn.BatchNorm2d(batch statistics) + nn.ReLU + `out += shortcut`
 // of _Residual.forward (reference models/asn_stacked_hg.py:30-49) and their autograd.
 #include "common.cuh"
+#include "conv_args.cuh"
 
 namespace hgk {
-
-struct ConvArgs {
-    Act x;
-    int N, H, W, Cin;
-    const float* w;
-    int ksize, flip;
-    const float* bias;
-    int Cout;
-    Act res;
-    float* y;
-    int accumulate;
-    double* stat_sum;
-    double* stat_sq;
-    long long P;
-};
 
 constexpr int CBM = 128, CBK = 16, CNT = 256;
 
@@ -390,11 +376,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, float* __rest
 
 using namespace hgk;
 
-// implemented in conv_tc.cu (tcgen05 path); returns 1 if it took the launch, 0 if the shape is
-// not covered, <0 on error
-extern "C" int hgk_conv_tc_try(const ConvArgs* a, void* stream);
-__attribute__((weak)) int hgk_conv_tc_try(const ConvArgs*, void*) { return 0; }
-
 extern "C" int hgk_conv_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
                              int N, int H, int W, int Cin,
                              const float* w, int ksize, int flip, const float* bias, int Cout,
@@ -417,12 +398,7 @@ extern "C" int hgk_conv_nhwc(const float* x, const float* x_scale, const float* 
     a.y = y; a.accumulate = accumulate; a.stat_sum = stat_sum; a.stat_sq = stat_sq;
     a.P = (long long)N * H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (path != 1) {
-        int r = hgk_conv_tc_try(&a, stream);
-        if (r < 0) return r;
-        if (r == 1) return HGK_OK;
-        HGK_REQUIRE(path != 2, "hgk_conv_nhwc: shape not covered by the tcgen05 path (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
-    }
+    HGK_REQUIRE(path == 0 || path == 1, "hgk_conv_nhwc: this entry point is the fp32 SIMT kernel; use hgk_conv_tc_nhwc for tcgen05");
     long long mt = (a.P + CBM - 1) / CBM;
     HGK_REQUIRE(mt < 2147483647LL, "hgk_conv_nhwc: too many pixels");
     if (Cout > 64) {

@@ -1,0 +1,448 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: 1x1 / 3x3(p1) NHWC with the
+// same contract as the SIMT kernel (BN+ReLU applied on load, bias / residual / accumulate /
+// BN-statistics epilogue), TF32 operands with fp32 accumulation in TMEM.
+//
+//   forward  : 3xTF32 error-compensated split  x*w ~= xh*wh + xh*wl + xl*wh  (fp32-class accuracy,
+//              heat-map parity <= 1e-3 needs it: plain TF32 is 2.6e-2 off)
+//   backward : data gradient with 1xTF32 (w_lo == NULL)
+//
+// CTA = 128 output pixels x BN (= Cout) channels, K streamed in 32-channel stages:
+//   * all 8 warps load the activation tile from global (coalesced 128-bit), apply BN+ReLU, split
+//     hi/lo and write the UMMA canonical K-major (no-swizzle) operand tile to shared memory;
+//   * the weight stage is one contiguous pre-packed block fetched with cp.async.bulk (TMA bulk
+//     copy) that completes on an mbarrier;
+//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator and
+//     commits to the stage's mbarrier, which frees the stage for the producers;
+//   * epilogue: tcgen05.ld -> shared staging tile -> coalesced bias/residual/accumulate/store and
+//     fp64 per-channel statistics.
+#include "common.cuh"
+#include "conv_args.cuh"
+
+namespace hgk {
+
+struct TcArgs {
+    ConvArgs c;
+    const float* w_hi;
+    const float* w_lo;
+};
+
+constexpr int TBM = 128, TBK = 32, TNT = 256;
+constexpr int T_A_BYTES = TBM * TBK * 4;      // 16 KB per (hi|lo) activation stage
+constexpr int T_SMEM_BUDGET = 196 * 1024;
+
+__host__ __device__ constexpr int tc_stage_bytes(int BN, bool split) { return (split ? 2 : 1) * (T_A_BYTES + BN * TBK * 4); }
+__host__ __device__ constexpr int tc_num_stages(int BN, bool split) {
+    int n = T_SMEM_BUDGET / tc_stage_bytes(BN, split);
+    return n > 4 ? 4 : n;
+}
+__host__ __device__ constexpr int tc_staging_bytes(int BN) { return TBM * (BN + 4) * 4 + 16384; }
+__host__ __device__ constexpr int tc_smem_bytes(int BN, bool split) {
+    int p = tc_num_stages(BN, split) * tc_stage_bytes(BN, split);
+    int s = tc_staging_bytes(BN);
+    return (p > s ? p : s) + 256;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B (rows 16 B apart);
+// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;     // descriptor version 1 (Blackwell)
+    return d;
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
+    constexpr int NST = tc_num_stages(BN, SPLIT);
+    constexpr int B_BYTES = BN * TBK * 4;
+    constexpr int STAGE = tc_stage_bytes(BN, SPLIT);
+    constexpr uint32_t LBO_A = TBM * 16, LBO_B = BN * 16, SBO = 128;
+    // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    const ConvArgs& a = args.c;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 4];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * TBM;
+    const int n0 = blockIdx.y * BN;
+    const int taps = a.ksize * a.ksize;
+    const int KC = a.Cin / TBK;
+    const int T = taps * KC;
+    const int HW = a.H * a.W;
+    const uint32_t bar_mma = smem_u32(&bars[0]), bar_b = smem_u32(&bars[4]);
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_mma + 8 * s, 1);
+            mbar_init(bar_b + 8 * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    // packed weights: [n-tile][tap][k-chunk] blocks of BN*32 floats in UMMA canonical layout
+    const size_t wblk = (size_t)BN * TBK;
+    const float* whi = args.w_hi + (size_t)blockIdx.y * T * wblk;
+    const float* wlo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
+    auto issue_b = [&](int it) {
+        const int s = it % NST;
+        const uint32_t bb = bar_b + 8 * s;
+        const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * T_A_BYTES;
+        mbar_expect_tx(bb, (SPLIT ? 2 : 1) * B_BYTES);
+        bulk_g2s(dst, whi + (size_t)it * wblk, B_BYTES, bb);
+        if (SPLIT) bulk_g2s(dst + B_BYTES, wlo + (size_t)it * wblk, B_BYTES, bb);
+    };
+    if (tid == 0) issue_b(0);
+
+    // ---- activation loader: thread -> 4 pixels x one channel quad of the 32-channel stage ----
+    const int p_low = lane & 7, q_low = lane >> 3;
+    const int quad = (warp & 1) * 4 + q_low;
+    int a_h[4], a_w[4], a_row[4];
+    long long a_p[4];
+    bool a_ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a_row[j] = (j * 4 + (warp >> 1)) * 8 + p_low;
+        long long p = m0 + a_row[j];
+        a_ok[j] = p < a.P;
+        long long pp = a_ok[j] ? p : 0;
+        int rem = (int)(pp % HW);
+        a_h[j] = rem / a.W;
+        a_w[j] = rem - a_h[j] * a.W;
+        a_p[j] = pp;
+    }
+    float4 a_reg[4];
+    auto load_a = [&](int it) {
+        const int tap = it / KC;
+        const int c = (it - tap * KC) * TBK + quad * 4;
+        int dh = 0, dw = 0;
+        if (a.ksize == 3) {
+            dh = tap / 3 - 1;
+            dw = tap - (tap / 3) * 3 - 1;
+        }
+        float4 s, t;
+        load_affine4(a.x.scale, a.x.shift, c, s, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bool ok = a_ok[j] && (unsigned)(a_h[j] + dh) < (unsigned)a.H && (unsigned)(a_w[j] + dw) < (unsigned)a.W;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                v = ldg4(a.x.z + (a_p[j] + dh * a.W + dw) * a.Cin + c);
+                if (a.x.scale != nullptr) v = act4(v, s, t, a.x.relu);
+            }
+            a_reg[j] = v;
+        }
+    };
+    auto store_a = [&](int s) {
+        uint8_t* base = sgen + s * STAGE + quad * LBO_A;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 v = a_reg[j];
+            float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+            *reinterpret_cast<float4*>(base + a_row[j] * 16) = hi;
+            if (SPLIT) {
+                float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                *reinterpret_cast<float4*>(base + T_A_BYTES + a_row[j] * 16) = lo;
+            }
+        }
+    };
+
+    load_a(0);
+    for (int it = 0; it < T; ++it) {
+        const int s = it % NST, u = it / NST;
+        if (it >= NST) mbar_wait(bar_mma + 8 * s, (u - 1) & 1);          // stage s drained by the tensor core
+        store_a(s);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
+        if (it + 1 < T) load_a(it + 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(bar_b + 8 * s, u & 1);                             // weight stage landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = sbase + s * STAGE;
+            const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * T_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TBK / 8; ++k) {
+                const uint64_t da = umma_desc(a_hi + k * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO);
+                if (SPLIT) {
+                    const uint64_t dal = umma_desc(a_hi + T_A_BYTES + k * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dbl = umma_desc(b_hi + B_BYTES + k * 2 * LBO_B, LBO_B, SBO);
+                    umma_tf32(tmem, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);     // small terms first
+                    umma_tf32(tmem, da, dbl, IDESC, 1u);
+                    umma_tf32(tmem, da, db, IDESC, 1u);
+                } else {
+                    umma_tf32(tmem, da, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_mma + 8 * s);
+            if (it + 1 < T) {
+                const int s1 = (it + 1) % NST;
+                if (it + 1 >= NST) mbar_wait(bar_mma + 8 * s1, (((it + 1) / NST) - 1) & 1);
+                issue_b(it + 1);
+            }
+        }
+    }
+    // all MMAs retired?
+    mbar_wait(bar_mma + 8 * ((T - 1) % NST), ((T - 1) / NST) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue 1: TMEM -> registers -> staging tile (row stride BN+4 floats) ----
+    float* stg = reinterpret_cast<float*>(sgen);
+    constexpr int SROW = BN + 4;
+    {
+        const int lq = warp & 3;
+        const int row = lq * 32 + lane;
+        const int cbeg = (warp >> 2) * (BN / 2);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* dst = stg + row * SROW + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+
+    // ---- epilogue 2: coalesced bias / residual / accumulate / store + BN statistics ----
+    constexpr int CG = BN / 4;           // float4 column groups
+    constexpr int RL = TNT / CG;         // row lanes (4 for BN=256, 8 for 128, 16 for 64)
+    const int cg = tid % CG, r0 = tid / CG;
+    const int n = n0 + cg * 4;
+    const bool do_stats = a.stat_sum != nullptr;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias != nullptr) bv = ldg4(a.bias + n);
+    float4 rs, rt;
+    load_affine4(a.res.scale, a.res.shift, n, rs, rt);
+    double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int r = r0; r < TBM; r += RL) {
+        const long long p = m0 + r;
+        if (p >= a.P) break;
+        float4 v = ld4(stg + r * SROW + cg * 4);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        if (a.res.z != nullptr) {
+            float4 rr = ldg4(a.res.z + p * a.Cout + n);
+            if (a.res.scale != nullptr) rr = act4(rr, rs, rt, a.res.relu);
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        float* yp = a.y + p * a.Cout + n;
+        if (a.accumulate) {
+            float4 o = ld4(yp);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        st4(yp, v);
+        if (do_stats) {
+            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+            if (++cnt == 8) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+                cnt = 0;
+            }
+        }
+    }
+    if (do_stats) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
+        double* red = reinterpret_cast<double*>(sgen + TBM * SROW * 4);     // [RL][BN][2], behind the staging tile
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[((r0 * BN) + cg * 4 + j) * 2 + 0] = d1[j];
+            red[((r0 * BN) + cg * 4 + j) * 2 + 1] = d2[j];
+        }
+        __syncthreads();
+        if (tid < BN) {
+            double x1 = 0.0, x2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                x1 += red[((q * BN) + tid) * 2 + 0];
+                x2 += red[((q * BN) + tid) * 2 + 1];
+            }
+            atomicAdd(a.stat_sum + n0 + tid, x1);
+            atomicAdd(a.stat_sq + n0 + tid, x2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing into the UMMA operand layout (+ hi/lo TF32 split)
+// table rows (8 x int64): {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN}
+//   mode 0 (forward) : B[n][k; tap] = W[o=n][i=k][tap]              (OIHW source, O=N, I=K)
+//   mode 1 (dgrad)   : B[n][k; tap] = W[o=k][i=n][taps-1-tap]       (O=K, I=N; taps pre-flipped)
+// destination: [n-tile][tap][k/32] blocks, each block [quad(8)][n(BN)][4]
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                       const long long* __restrict__ table, int n_entries) {
+    const int e = blockIdx.y;
+    if (e >= n_entries) return;
+    const long long* t = table + (size_t)e * 8;
+    const long long so = t[0], dhi = t[1], dlo = t[2];
+    const int N = (int)t[3], K = (int)t[4], taps = (int)t[5], mode = (int)t[6], BN = (int)t[7];
+    const long long total = (long long)N * K * taps;
+    const int KC = K / 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int el = (int)(i & 3);
+        long long r = i >> 2;
+        int nn = (int)(r % BN);
+        r /= BN;
+        int q = (int)(r & 7);
+        long long blk = r >> 3;
+        int kc = (int)(blk % KC);
+        blk /= KC;
+        int tap = (int)(blk % taps);
+        int ntile = (int)(blk / taps);
+        int n = ntile * BN + nn, k = kc * 32 + q * 4 + el;
+        float v;
+        if (mode == 0) v = __ldg(src + so + ((long long)n * K + k) * taps + tap);
+        else v = __ldg(src + so + ((long long)k * N + n) * taps + (taps - 1 - tap));
+        float hi = tf32_rna(v);
+        dst[dhi + i] = hi;
+        if (dlo >= 0) dst[dlo + i] = v - hi;
+    }
+}
+
+template <int BN, bool SPLIT>
+static int launch_tc(const TcArgs& ta, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = tc_smem_bytes(BN, SPLIT);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("hgk_conv_tc_nhwc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+            return HGK_ECUDA;
+        }
+        configured = true;
+    }
+    long long mt = (ta.c.P + TBM - 1) / TBM;
+    dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN));
+    conv_tc_kernel<BN, SPLIT><<<grid, TNT, smem, st>>>(ta);
+    return HGK_OK;
+}
+
+}  // namespace hgk
+
+using namespace hgk;
+
+extern "C" int hgk_conv_tc_supported(int Cin, int Cout, int ksize) {
+    return (Cin > 0 && Cin % 32 == 0 && (Cout == 64 || Cout == 128 || Cout == 256) && (ksize == 1 || ksize == 3)) ? 1 : 0;
+}
+
+extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                int N, int H, int W, int Cin,
+                                const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                                const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                                float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream) {
+    HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
+    HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
+                "(need Cin %% 32 == 0, Cout in {64,128,256}, k in {1,3})", Cin, Cout, ksize);
+    HGK_REQUIRE((stat_sum == nullptr) == (stat_sq == nullptr), "hgk_conv_tc_nhwc: stat_sum/stat_sq must both be set");
+    HGK_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "hgk_conv_tc_nhwc: x scale/shift must both be set");
+    HGK_REQUIRE((res_scale == nullptr) == (res_shift == nullptr), "hgk_conv_tc_nhwc: res scale/shift must both be set");
+    HGK_REQUIRE(((uintptr_t)w_hi % 16 == 0) && ((uintptr_t)w_lo % 16 == 0), "hgk_conv_tc_nhwc: packed weights must be 16-byte aligned");
+    TcArgs ta;
+    ta.c.x = Act{x, x_scale, x_shift, x_relu};
+    ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin;
+    ta.c.w = nullptr; ta.c.ksize = ksize; ta.c.flip = 0; ta.c.bias = bias; ta.c.Cout = Cout;
+    ta.c.res = Act{res, res_scale, res_shift, res_relu};
+    ta.c.y = y; ta.c.accumulate = accumulate; ta.c.stat_sum = stat_sum; ta.c.stat_sq = stat_sq;
+    ta.c.P = (long long)N * H * W;
+    ta.w_hi = w_hi; ta.w_lo = w_lo;
+    HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const bool split = w_lo != nullptr;
+    if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
+    else if (Cout == 128) rc = split ? launch_tc<128, true>(ta, st) : launch_tc<128, false>(ta, st);
+    else rc = split ? launch_tc<256, true>(ta, st) : launch_tc<256, false>(ta, st);
+    if (rc != HGK_OK) return rc;
+    HGK_CHECK_LAUNCH("hgk_conv_tc_nhwc");
+    return HGK_OK;
+}
+
+extern "C" int hgk_pack_weights_tc(const float* src_base, float* dst_base, const long long* table, int n_entries,
+                                   void* stream) {
+    HGK_REQUIRE(src_base && dst_base && table, "hgk_pack_weights_tc: null pointer");
+    if (n_entries <= 0) return HGK_OK;
+    HGK_REQUIRE(n_entries <= 65535, "hgk_pack_weights_tc: too many entries");
+    dim3 grid(16, (unsigned)n_entries);
+    pack_weights_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_base, dst_base, table, n_entries);
+    HGK_CHECK_LAUNCH("hgk_pack_weights_tc");
+    return HGK_OK;
+}

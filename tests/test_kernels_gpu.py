@@ -364,3 +364,83 @@ def test_error_paths():
     rc = L.maxpool2_fwd(ptr(x), 0, 0, 0, 1, 3, 3, 4, ptr(x), s)
     assert rc == -1 and "even" in L.last_error()
     assert L.cdll.hgk_device_ok() == 1
+
+
+TC_SHAPES = [
+    # N, H, W, Cin, Cout, k
+    (2, 16, 16, 64, 128, 1),
+    (2, 16, 16, 128, 64, 3),
+    (3, 5, 7, 32, 64, 3),        # ragged pixel count (105 px: one partial tile)
+    (2, 1, 1, 256, 128, 1),
+    (1, 64, 64, 256, 256, 1),
+    (2, 8, 8, 128, 128, 3),
+    (5, 12, 12, 128, 256, 1),
+    (1, 20, 24, 256, 128, 3),
+]
+
+
+def _pack_tc(w, mode, BN):
+    """OIHW fp64 cpu -> (hi, lo) fp32 device arrays in the UMMA operand layout via hgk_pack_weights_tc."""
+    O, I, kh, kw = w.shape
+    taps = kh * kw
+    N, K = (O, I) if mode == 0 else (I, O)
+    src = dev32(w.reshape(-1))
+    dst = torch.zeros(2 * w.numel(), device=DEV)
+    table = torch.tensor([[0, 0, w.numel(), N, K, taps, mode, BN]], dtype=torch.long, device=DEV)
+    call("pack_weights_tc", ptr(src), ptr(dst), ptr(table), 1)
+    torch.cuda.synchronize()
+    hi, lo = dst[:w.numel()], dst[w.numel():]
+    # hi + lo reproduces w exactly in fp32 and hi is a TF32 number
+    assert torch.equal((hi.double() + lo.double()).float().sort().values, src.sort().values)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    return hi, lo
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "full"])
+def test_conv_tc_fwd_3xtf32(shape, variant):
+    N, H, W, Ci, Co, k = shape
+    x = rnd("x", (N, Ci, H, W))
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    b = rnd("b", (Co,))
+    full = variant == "full"
+    xs, xt = (rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)) if full else (None, None)
+    res = rnd("res", (N, Co, H, W)) if full else None
+    rs, rt = (rnd("rs", (Co,), 0.5, 1.5), rnd("rt", (Co,), -0.3, 0.3)) if full else (None, None)
+    y0 = rnd("y0", (N, Co, H, W)) if full else None
+    ref = _conv_ref(affine_act(x, xs, xt, True), w, b, k)
+    if full:
+        ref = ref + affine_act(res, rs, rt, True) + y0
+    hi, lo = _pack_tc(w, 0, Co)
+    dx, db = nhwc(x), dev32(b)
+    dxs, dxt = (dev32(xs), dev32(xt)) if full else (None, None)
+    dres = nhwc(res) if full else None
+    drs, drt = (dev32(rs), dev32(rt)) if full else (None, None)
+    y = nhwc(y0) if full else torch.empty(N, H, W, Co, device=DEV)
+    ssum = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    ssq = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    call("conv_tc_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(db), Co,
+         ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), ptr(ssum), ptr(ssq))
+    torch.cuda.synchronize()
+    # 3xTF32: dropped lo*lo term ~2^-22 per product -> fp32-class result
+    assert relerr(from_nhwc(y), ref) < 2e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 2e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_dgrad_1xtf32(shape):
+    N, H, W, Ci, Co, k = shape
+    a = rnd("x", (N, Ci, H, W)).requires_grad_(True)
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    dz = rnd("dz", (N, Co, H, W))
+    _conv_ref(a, w, None, k).backward(dz)
+    if Ci not in (64, 128, 256) or Co % 32:
+        pytest.skip("data-gradient shape not covered by the tcgen05 path")
+    extra, g0 = rnd("extra", (N, Ci, H, W)), rnd("g0", (N, Ci, H, W))
+    gx, ddz, dextra = nhwc(g0), nhwc(dz), nhwc(extra)
+    hi, _ = _pack_tc(w, 1, Ci)
+    call("conv_tc_nhwc", ptr(ddz), 0, 0, 0, N, H, W, Co, ptr(hi), 0, k, 0, Ci, ptr(dextra), 0, 0, 0, ptr(gx), 1, 0, 0)
+    torch.cuda.synchronize()
+    # plain TF32 operands (10-bit mantissa): ~1e-3 relative
+    assert relerr(from_nhwc(gx) - extra - g0, a.grad) < 3e-3
