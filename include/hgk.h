@@ -76,6 +76,18 @@ int hgk_conv_wgrad_nhwc(const float* x, const float* x_scale, const float* x_shi
                         float* dw, long long s_co, long long s_ci, long long s_tap,
                         float* dbias, void* stream);
 
+/* Weight gradient on the tcgen05 tensor cores (plain TF32 operands, fp32 accumulate): accumulates (+=, vector
+ * atomics) into a TAP-MAJOR destination dw[tap][Cout][Cin] -- for 1x1 convolutions that is the OIHW .grad itself;
+ * 3x3 gradients go to a scratch buffer that hgk_unpack_add_grads adds into the OIHW .grad views
+ * (table: n_entries x 5 int64 {src_off, dst_off, O, I, taps}).  dbias[co] += sum_p dz[p,co] (optional).
+ * hgk_conv_wgrad_tc_supported(Cin, Cout, ksize): Cin in {64,128,256}, Cout % 4 == 0, ksize in {1,3}. */
+int hgk_conv_wgrad_tc_supported(int Cin, int Cout, int ksize);
+int hgk_conv_wgrad_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                           int N, int H, int W, int Cin, const float* dz, int Cout, int ksize,
+                           float* dw_tap_major, float* dbias, void* stream);
+int hgk_unpack_add_grads(const float* src_base, float* dst_base, const long long* table, int n_entries,
+                         void* stream);
+
 /* repack many OIHW conv weights in one launch.  table: n_entries x 6 int64 on the device:
  * {src_offset, dst_offset, O, I, taps, mode}; mode 0: dst[tap][i][o] = src[o][i][tap],
  * mode 1: dst[tap][o][i] = src[o][i][tap].  Offsets in elements from src_base / dst_base.    */

@@ -18,6 +18,8 @@ SIGNATURES = {
     "hgk_pack_weights": [P, P, P, I, P],
     "hgk_conv_tc_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P, P],
     "hgk_pack_weights_tc": [P, P, P, I, P],
+    "hgk_conv_wgrad_tc_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, P, P],
+    "hgk_unpack_add_grads": [P, P, P, I, P],
     "hgk_stem_conv7_fwd": [P, I, I, I, P, P, I, P, P, P, P],
     "hgk_stem_conv7_wgrad": [P, I, I, I, P, I, P, P, P],
     "hgk_bn_finalize": [P, P, L, P, P, F, F, P, P, P, P, P, P, I, P],
@@ -62,6 +64,8 @@ class _Lib(object):
         self.cdll.hgk_device_ok.restype = I
         self.cdll.hgk_conv_tc_supported.restype = I
         self.cdll.hgk_conv_tc_supported.argtypes = [I, I, I]
+        self.cdll.hgk_conv_wgrad_tc_supported.restype = I
+        self.cdll.hgk_conv_wgrad_tc_supported.argtypes = [I, I, I]
         for name, args in SIGNATURES.items():
             fn = getattr(self.cdll, name)      # AttributeError if the symbol is not exported
             fn.argtypes = args
@@ -70,6 +74,9 @@ class _Lib(object):
 
     def conv_tc_supported(self, cin, cout, k):
         return bool(self.cdll.hgk_conv_tc_supported(cin, cout, k))
+
+    def conv_wgrad_tc_supported(self, cin, cout, k):
+        return bool(self.cdll.hgk_conv_wgrad_tc_supported(cin, cout, k))
 
     def last_error(self):
         return self.cdll.hgk_last_error().decode()

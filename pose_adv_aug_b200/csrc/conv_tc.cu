@@ -341,6 +341,280 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
 }
 
 // ------------------------------------------------------------------------------------------
+// weight gradient on tcgen05:  dW[tap][co][ci] += sum_p dz[p][co] * T(x)[p+off(tap)][ci]
+// GEMM with M = co (128-row tile), N = ci (= Cin), K = pixels.  tcgen05 takes 32-bit operands
+// K-major only without swizzle, so every producer thread loads a 4-pixel x 4-channel block
+// (four coalesced 128-bit loads), transposes it in registers and stores four 16-byte rows
+// [channel][4 pixels] of the UMMA canonical K-major tile (LBO = rows*16+16 bytes between 4-pixel
+// chunks -- the +16 spreads the chunks over the banks --, SBO = 128).
+// Warp-specialised: warps 0-7 produce (BN+ReLU on x, TF32 rounding, smem stores, fence, mbarrier
+// arrive, 2-stage register prefetch), warp 8 issues the MMAs and commits each stage back to the
+// producers.  Split over pixel ranges (grid.z); partial tiles are reduced with coalesced vector
+// atomics (red.global.add.v4.f32) into the [tap][Cout][Cin] destination.
+// ------------------------------------------------------------------------------------------
+struct WgTcArgs {
+    Act x;
+    int N, H, W, Cin;
+    const float* dz;
+    int Cout, ksize;
+    float* dw;
+    float* dbias;
+    long long P, chunk;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 tf32_rna4(float4 v) {
+    return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+}
+
+constexpr int WG_THREADS = 288;       // 8 producer/epilogue warps + 1 MMA warp
+__host__ __device__ constexpr int wg_a_bytes() { return 8 * (TBM * 16 + 16); }
+__host__ __device__ constexpr int wg_b_bytes(int BN) { return 8 * (BN * 16 + 16); }
+__host__ __device__ constexpr int wg_stage_bytes(int BN) { return (wg_a_bytes() + wg_b_bytes(BN) + 127) / 128 * 128; }
+__host__ __device__ constexpr int wg_smem_bytes(int BN) {
+    int p = 4 * wg_stage_bytes(BN);
+    int s = tc_staging_bytes(BN);
+    return (p > s ? p : s) + 256;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs a) {
+    constexpr int NST = 4;
+    constexpr int A_BYTES = wg_a_bytes(), STAGE = wg_stage_bytes(BN);
+    constexpr uint32_t LBO_A = TBM * 16 + 16, LBO_B = BN * 16 + 16, SBO = 128;
+    constexpr int NBLK = BN > 128 ? 2 : 1;      // 4x4 x-blocks per producer thread per stage
+    // D=f32, A=B=tf32, both K-major, N>>3 at 17, M>>4 at 24
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * NST];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int co0 = blockIdx.x * TBM, tap = blockIdx.y;
+    const long long p_begin = (long long)blockIdx.z * a.chunk;
+    const long long p_end = (p_begin + a.chunk < a.P) ? (p_begin + a.chunk) : a.P;
+    const int T = (int)((p_end - p_begin + 31) / 32);      // host guarantees p_begin < P
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]);
+    int dh = 0, dw_ = 0;
+    if (a.ksize == 3) {
+        dh = tap / 3 - 1;
+        dw_ = tap - (tap / 3) * 3 - 1;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_full + 8 * s, 256);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== producers: thread -> (4-pixel chunk c_low, channel quad) block of each operand =====
+        const int c_low = lane & 7, q_low = lane >> 3;
+        const int HW = a.H * a.W;
+        const int a_quad = warp * 4 + q_low;              // 32 quads = 128 dz channels
+        const int a_c = co0 + a_quad * 4;
+        const bool a_cok = a_c < a.Cout;
+        const bool b_on = (BN >= 128) || (warp < 4);      // BN = 64: 16 quads, warps 0-3 only
+        int b_quad[NBLK];
+        float4 xs[NBLK], xt[NBLK];
+#pragma unroll
+        for (int v = 0; v < NBLK; ++v) {
+            b_quad[v] = (v * 8 + warp) * 4 + q_low;
+            load_affine4(a.x.scale, a.x.shift, b_on ? b_quad[v] * 4 : 0, xs[v], xt[v]);
+        }
+        float4 ra[2][4], rb[2][NBLK][4];
+        float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool do_bias = a.dbias != nullptr && tap == 0;
+        auto load = [&](int it, int set) {
+            const long long p0 = p_begin + (long long)it * 32 + c_low * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p0 + j < p_end && a_cok) v = ldg4(a.dz + (p0 + j) * a.Cout + a_c);
+                ra[set][j] = v;
+            }
+            if (b_on) {
+                int rem = (int)(p0 % HW);
+                int h = rem / a.W, w = rem - h * a.W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = p0 + j < p_end && (unsigned)(h + dh) < (unsigned)a.H && (unsigned)(w + dw_) < (unsigned)a.W;
+#pragma unroll
+                    for (int v = 0; v < NBLK; ++v) {
+                        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) {
+                            x4 = ldg4(a.x.z + (p0 + j + dh * a.W + dw_) * a.Cin + b_quad[v] * 4);
+                            if (a.x.scale != nullptr) x4 = act4(x4, xs[v], xt[v], a.x.relu);
+                        }
+                        rb[set][v][j] = x4;
+                    }
+                    if (++w == a.W) {
+                        w = 0;
+                        if (++h == a.H) h = 0;
+                    }
+                }
+            }
+        };
+        auto store = [&](int s, int set) {
+            uint8_t* sa = sgen + s * STAGE + c_low * LBO_A + a_quad * 64;
+            const float4 r0 = ra[set][0], r1 = ra[set][1], r2 = ra[set][2], r3 = ra[set][3];
+            if (do_bias) {
+                bsum[0] += (r0.x + r1.x) + (r2.x + r3.x);
+                bsum[1] += (r0.y + r1.y) + (r2.y + r3.y);
+                bsum[2] += (r0.z + r1.z) + (r2.z + r3.z);
+                bsum[3] += (r0.w + r1.w) + (r2.w + r3.w);
+            }
+            // register transpose: row = channel, 4 consecutive pixels per 16-byte store
+            *reinterpret_cast<float4*>(sa + 0) = tf32_rna4(make_float4(r0.x, r1.x, r2.x, r3.x));
+            *reinterpret_cast<float4*>(sa + 16) = tf32_rna4(make_float4(r0.y, r1.y, r2.y, r3.y));
+            *reinterpret_cast<float4*>(sa + 32) = tf32_rna4(make_float4(r0.z, r1.z, r2.z, r3.z));
+            *reinterpret_cast<float4*>(sa + 48) = tf32_rna4(make_float4(r0.w, r1.w, r2.w, r3.w));
+            if (b_on) {
+#pragma unroll
+                for (int v = 0; v < NBLK; ++v) {
+                    uint8_t* sb = sgen + s * STAGE + A_BYTES + c_low * LBO_B + b_quad[v] * 64;
+                    const float4 x0 = rb[set][v][0], x1 = rb[set][v][1], x2 = rb[set][v][2], x3 = rb[set][v][3];
+                    *reinterpret_cast<float4*>(sb + 0) = tf32_rna4(make_float4(x0.x, x1.x, x2.x, x3.x));
+                    *reinterpret_cast<float4*>(sb + 16) = tf32_rna4(make_float4(x0.y, x1.y, x2.y, x3.y));
+                    *reinterpret_cast<float4*>(sb + 32) = tf32_rna4(make_float4(x0.z, x1.z, x2.z, x3.z));
+                    *reinterpret_cast<float4*>(sb + 48) = tf32_rna4(make_float4(x0.w, x1.w, x2.w, x3.w));
+                }
+            }
+        };
+        load(0, 0);
+        if (T > 1) load(1, 1);
+        for (int it = 0; it < T; ++it) {
+            const int s = it % NST, u = it / NST;
+            if (it >= NST) mbar_wait(bar_empty + 8 * s, (u - 1) & 1);
+            if (it & 1) store(s, 1); else store(s, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_full + 8 * s);
+            if (it + 2 < T) { if (it & 1) load(it + 2, 1); else load(it + 2, 0); }
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = bsum[j];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (c_low == 0 && a_cok) atomicAdd(a.dbias + a_c + j, v);
+            }
+        }
+        // all MMAs retired?
+        mbar_wait(bar_empty + 8 * ((T - 1) % NST), ((T - 1) / NST) & 1);
+    } else if (lane == 0) {
+        // ===== MMA issuer =====
+        for (int it = 0; it < T; ++it) {
+            const int s = it % NST, u = it / NST;
+            mbar_wait(bar_full + 8 * s, u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = sbase + s * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_tf32(tmem, umma_desc(sa + k * 2 * LBO_A, LBO_A, SBO), umma_desc(sb + k * 2 * LBO_B, LBO_B, SBO), IDESC,
+                          (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit(bar_empty + 8 * s);
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();       // producers have observed the last commit: accumulator complete, smem reusable
+
+    // ---- epilogue: TMEM -> staging tile -> coalesced vector atomics ----
+    float* stg = reinterpret_cast<float*>(sgen);
+    constexpr int SROW = BN + 4;
+    if (warp < 8) {
+        const int lq = warp & 3;
+        const int row = lq * 32 + lane;
+        const int cbeg = (warp >> 2) * (BN / 2);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* dst = stg + row * SROW + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+    if (tid < 256) {
+        constexpr int CG = BN / 4, RL = 256 / CG;
+        const int cg = tid % CG, r0 = tid / CG;
+        for (int r = r0; r < TBM; r += RL) {
+            const int co = co0 + r;
+            if (co >= a.Cout) break;
+            float4 v = ld4(stg + r * SROW + cg * 4);
+            red_add_v4(a.dw + ((size_t)tap * a.Cout + co) * a.Cin + cg * 4, v);
+        }
+    }
+}
+
+// grads of 3x3 convs are accumulated tap-major ([tap][O][I]) by the tensor-core kernel; this adds them
+// into the OIHW-shaped .grad views.  table rows (5 x int64): {src_off, dst_off, O, I, taps}
+__global__ void unpack_add_grads_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                        const long long* __restrict__ table, int n_entries) {
+    const int e = blockIdx.y;
+    if (e >= n_entries) return;
+    const long long* t = table + (size_t)e * 5;
+    const long long so = t[0], d0 = t[1];
+    const int O = (int)t[2], I = (int)t[3], taps = (int)t[4];
+    const long long total = (long long)O * I * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long tap = i % taps, oi = i / taps;           // destination order (OIHW): stores coalesced
+        dst[d0 + i] += __ldg(src + so + tap * (long long)O * I + oi);
+    }
+}
+
+template <int BN>
+static int launch_wg(const WgTcArgs& a, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = wg_smem_bytes(BN);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("hgk_conv_wgrad_tc_nhwc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+            return HGK_ECUDA;
+        }
+        configured = true;
+    }
+    wgrad_tc_kernel<BN><<<grid, WG_THREADS, smem, st>>>(a);
+    return HGK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // weight packing into the UMMA operand layout (+ hi/lo TF32 split)
 // table rows (8 x int64): {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN}
 //   mode 0 (forward) : B[n][k; tap] = W[o=n][i=k][tap]              (OIHW source, O=N, I=K)
@@ -444,5 +718,55 @@ extern "C" int hgk_pack_weights_tc(const float* src_base, float* dst_base, const
     dim3 grid(16, (unsigned)n_entries);
     pack_weights_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_base, dst_base, table, n_entries);
     HGK_CHECK_LAUNCH("hgk_pack_weights_tc");
+    return HGK_OK;
+}
+
+extern "C" int hgk_conv_wgrad_tc_supported(int Cin, int Cout, int ksize) {
+    return ((Cin == 64 || Cin == 128 || Cin == 256) && Cout > 0 && Cout % 4 == 0 && (ksize == 1 || ksize == 3)) ? 1 : 0;
+}
+
+extern "C" int hgk_conv_wgrad_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                      int N, int H, int W, int Cin, const float* dz, int Cout, int ksize,
+                                      float* dw_tap_major, float* dbias, void* stream) {
+    HGK_REQUIRE(x && dz && dw_tap_major, "hgk_conv_wgrad_tc_nhwc: null pointer");
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_wgrad_tc_nhwc: empty tensor");
+    HGK_REQUIRE(hgk_conv_wgrad_tc_supported(Cin, Cout, ksize), "hgk_conv_wgrad_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
+                "(need Cin in {64,128,256}, Cout %% 4 == 0, k in {1,3})", Cin, Cout, ksize);
+    HGK_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "hgk_conv_wgrad_tc_nhwc: x scale/shift must both be set");
+    HGK_REQUIRE((uintptr_t)dw_tap_major % 16 == 0, "hgk_conv_wgrad_tc_nhwc: dw must be 16-byte aligned");
+    WgTcArgs a;
+    a.x = Act{x, x_scale, x_shift, x_relu};
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.dz = dz; a.Cout = Cout; a.ksize = ksize;
+    a.dw = dw_tap_major; a.dbias = dbias;
+    a.P = (long long)N * H * W;
+    const int taps = ksize * ksize;
+    const int mtiles = (Cout + TBM - 1) / TBM;
+    // split the pixel range so that ~1 CTA per SM runs, but keep >= 16 stages (512 pixels) per CTA so the
+    // atomics epilogue stays small against the main loop
+    long long want = kNumSMs / (mtiles * taps);
+    if (want < 1) want = 1;
+    long long max_splits = (a.P + 511) / 512;
+    long long splits = want > max_splits ? max_splits : want;
+    if (splits > 65535) splits = 65535;
+    long long chunk = (a.P + splits - 1) / splits;
+    chunk = (chunk + 31) / 32 * 32;
+    splits = (a.P + chunk - 1) / chunk;
+    a.chunk = chunk;
+    dim3 grid((unsigned)mtiles, (unsigned)taps, (unsigned)splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = Cin == 64 ? launch_wg<64>(a, grid, st) : (Cin == 128 ? launch_wg<128>(a, grid, st) : launch_wg<256>(a, grid, st));
+    if (rc != HGK_OK) return rc;
+    HGK_CHECK_LAUNCH("hgk_conv_wgrad_tc_nhwc");
+    return HGK_OK;
+}
+
+extern "C" int hgk_unpack_add_grads(const float* src_base, float* dst_base, const long long* table, int n_entries,
+                                    void* stream) {
+    HGK_REQUIRE(src_base && dst_base && table, "hgk_unpack_add_grads: null pointer");
+    if (n_entries <= 0) return HGK_OK;
+    HGK_REQUIRE(n_entries <= 65535, "hgk_unpack_add_grads: too many entries");
+    dim3 grid(8, (unsigned)n_entries);
+    unpack_add_grads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_base, dst_base, table, n_entries);
+    HGK_CHECK_LAUNCH("hgk_unpack_add_grads");
     return HGK_OK;
 }

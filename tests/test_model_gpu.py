@@ -42,8 +42,10 @@ def _grads64(sd64, fwd):
 @pytest.mark.parametrize("cfg", [(64, 128, True, 2, 16), (128, 128, False, 3, 8), (256, 256, False, 2, 4),
                                  (32, 32, False, 2, 1), (12, 24, True, 3, 6)])
 @pytest.mark.parametrize("training", [True, False])
-def test_residual_block(cfg, training):
+@pytest.mark.parametrize("conv_path", [1, 0])      # 1: fp32 SIMT kernels, 0: tcgen05 where the shape is covered
+def test_residual_block(cfg, training, conv_path, monkeypatch):
     M = _mods()
+    monkeypatch.setattr(M, "CONV_PATH", conv_path)
     cin, cout, adapter, N, H = cfg
     import torch.nn as nn
     ad = nn.Conv2d(cin, cout, 1) if adapter else None
@@ -63,10 +65,12 @@ def test_residual_block(cfg, training):
     x = x64.float().to(DEV).requires_grad_(True)
     y = blk(x)
     assert y.shape == yr.shape
-    tol = 5e-4 if (N * H * H <= 4 and training) else 1e-5
+    tc = conv_path == 0
+    tol = 5e-4 if (N * H * H <= 4 and training) else (3e-5 if tc else 1e-5)     # 3xTF32 forward: fp32-class
     assert relerr(y, yr) < tol
     y.backward(gy.float().to(DEV))
-    gtol = 5e-2 if (N * H * H <= 4 and training) else 5e-5
+    # data gradients run on plain TF32 operands on the tcgen05 path (10-bit mantissa)
+    gtol = 5e-2 if (N * H * H <= 4 and training) else (5e-3 if tc else 5e-5)
     assert relerr(x.grad, xr.grad) < gtol
     for k, p in blk.named_parameters():
         ref = leaves["r." + k].grad
