@@ -325,11 +325,15 @@ def dominant_kernel_roofline(tr, pk, torch):
     plan = tr.plan
     cand = []
     for rec in plan.fwd:
+        a = rec[1]
         if rec[2] == "conv_nhwc":
-            a = rec[1]
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[9], a[12]
-            if k == 3:
-                cand.append((2.0 * N * H * W * Cin * Cout * 9, rec))
+        elif rec[2] == "conv_tc_nhwc":
+            N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[10], a[12]
+        else:
+            continue
+        if k == 3:
+            cand.append((2.0 * N * H * W * Cin * Cout * 9, rec))
     if not cand:
         return None
     top = max(c[0] for c in cand)
@@ -349,12 +353,17 @@ def dominant_kernel_roofline(tr, pk, torch):
     ms = e0.elapsed_time(e1) / (reps * len(recs))
     a = recs[0][1]
     N, H, W, Cin, Cout = a[4], a[5], a[6], a[7], a[12]
+    tc = recs[0][2] == "conv_tc_nhwc"
     achieved = top / (ms / 1e3) / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"], "traffic": None,
-            "kernel": "conv_nhwc 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this class/step)" % (Cin, Cout, N, H, W, len(recs)),
+            "kernel": "%s 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this FLOP class/step)" %
+                      ("conv_tc_kernel (tcgen05, 3xTF32)" if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
             "ms_per_launch": ms, "flop_per_launch": top, "algorithmic_bytes_per_launch": 4.0 * N * H * W * (Cin + Cout),
-            "peak_src": pk["src"] + " dense bf16 burst (tf32 runs at 1/2, 3xTF32 at 1/6 of it)"}
+            "mma_flop_per_launch": top * (3 if tc else 1),
+            "frac_of_3xtf32_ceiling": achieved / (pk["bf16_tflops"] / 6.0) if tc else None,
+            "peak_src": pk["src"] + " dense bf16 burst; achieved counts algorithmic fp32 FLOPs (the kernel issues 3 TF32 MMAs "
+                        "per product at 1/2 the bf16 rate, so its own ceiling is peak/6)"}
 
 
 def main():

@@ -24,7 +24,20 @@ struct TcArgs {
     ConvArgs c;
     const float* w_hi;
     const float* w_lo;
+    long long* dbg;      // optional timeline buffer (developer diagnostics): [cta][16] globaltimer stamps
 };
+
+static long long* g_dbg_buf = nullptr;
+
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define HGK_STAMP(slot)                                                                   \
+    do {                                                                                  \
+        if (args.dbg != nullptr && blockIdx.x < 512) args.dbg[blockIdx.x * 16 + (slot)] = gtimer(); \
+    } while (0)
 
 constexpr int TBM = 128, TBK = 32, TNT = 256;
 constexpr int T_A_BYTES = TBM * TBK * 4;      // 16 KB per (hi|lo) activation stage
@@ -93,18 +106,30 @@ __device__ __forceinline__ float tf32_rna(float v) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
+__global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args) {
     constexpr int NST = tc_num_stages(BN, SPLIT);
     constexpr int B_BYTES = BN * TBK * 4;
     constexpr int STAGE = tc_stage_bytes(BN, SPLIT);
     constexpr uint32_t LBO_A = TBM * 16, LBO_B = BN * 16, SBO = 128;
     // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    // The tensor core accumulates in fp32 with truncation: a chain of n dependent accumulations carries a
+    // systematic ~n*2^-25 relative shrink (1.3e-5 at K = 9*256 with all three 3xTF32 terms in one chain).
+    // So the big hi*hi products go to NMAIN accumulators used round-robin by stage, the two small
+    // cross terms to their own accumulator, and the epilogue adds them with round-to-nearest fp32 adds.
+    constexpr int NMAIN = (SPLIT && BN <= 128) ? 2 : 1;
+    constexpr int NACC = SPLIT ? NMAIN + 1 : 1;
+    constexpr int TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
+    static_assert(NACC * BN <= 512, "TMEM capacity");
     const ConvArgs& a = args.c;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * 4];
+    __shared__ __align__(8) uint64_t bars[3 * 4];
     __shared__ uint32_t tmem_slot;
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -116,17 +141,20 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
     const int KC = a.Cin / TBK;
     const int T = taps * KC;
     const int HW = a.H * a.W;
-    const uint32_t bar_mma = smem_u32(&bars[0]), bar_b = smem_u32(&bars[4]);
+    // full_a: 256 producer arrivals; full_b: weight bulk copy (expect_tx); empty: tcgen05.commit
+    const uint32_t bar_fa = smem_u32(&bars[0]), bar_fb = smem_u32(&bars[4]), bar_em = smem_u32(&bars[8]);
+    if (tid == 0) HGK_STAMP(0);
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(bar_mma + 8 * s, 1);
-            mbar_init(bar_b + 8 * s, 1);
+            mbar_init(bar_fa + 8 * s, 256);
+            mbar_init(bar_fb + 8 * s, 1);
+            mbar_init(bar_em + 8 * s, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(BN)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -134,84 +162,141 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (tid == 0) HGK_STAMP(1);
 
-    // packed weights: [n-tile][tap][k-chunk] blocks of BN*32 floats in UMMA canonical layout
-    const size_t wblk = (size_t)BN * TBK;
-    const float* whi = args.w_hi + (size_t)blockIdx.y * T * wblk;
-    const float* wlo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
-    auto issue_b = [&](int it) {
-        const int s = it % NST;
-        const uint32_t bb = bar_b + 8 * s;
-        const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * T_A_BYTES;
-        mbar_expect_tx(bb, (SPLIT ? 2 : 1) * B_BYTES);
-        bulk_g2s(dst, whi + (size_t)it * wblk, B_BYTES, bb);
-        if (SPLIT) bulk_g2s(dst + B_BYTES, wlo + (size_t)it * wblk, B_BYTES, bb);
-    };
-    if (tid == 0) issue_b(0);
-
-    // ---- activation loader: thread -> 4 pixels x one channel quad of the 32-channel stage ----
-    const int p_low = lane & 7, q_low = lane >> 3;
-    const int quad = (warp & 1) * 4 + q_low;
-    int a_h[4], a_w[4], a_row[4];
-    long long a_p[4];
-    bool a_ok[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        a_row[j] = (j * 4 + (warp >> 1)) * 8 + p_low;
-        long long p = m0 + a_row[j];
-        a_ok[j] = p < a.P;
-        long long pp = a_ok[j] ? p : 0;
-        int rem = (int)(pp % HW);
-        a_h[j] = rem / a.W;
-        a_w[j] = rem - a_h[j] * a.W;
-        a_p[j] = pp;
-    }
-    float4 a_reg[4];
-    auto load_a = [&](int it) {
-        const int tap = it / KC;
-        const int c = (it - tap * KC) * TBK + quad * 4;
-        int dh = 0, dw = 0;
-        if (a.ksize == 3) {
-            dh = tap / 3 - 1;
-            dw = tap - (tap / 3) * 3 - 1;
-        }
-        float4 s, t;
-        load_affine4(a.x.scale, a.x.shift, c, s, t);
+    if (warp < 8) {
+        // ===== producers (activation transform + weight bulk copies) =====
+        // packed weights: [n-tile][tap][k-chunk] blocks of BN*32 floats in UMMA canonical layout
+        const size_t wblk = (size_t)BN * TBK;
+        const float* whi = args.w_hi + (size_t)blockIdx.y * T * wblk;
+        const float* wlo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
+        // thread -> 4 pixels x one channel quad of the 32-channel stage
+        const int p_low = lane & 7, q_low = lane >> 3;
+        const int quad = (warp & 1) * 4 + q_low;
+        // per-pixel state, computed once: element offset of the pixel and the 9-bit mask of taps whose
+        // source pixel lies inside the image (padding = 1); the main loop only does shifts and adds
+        int a_row[4];
+        unsigned a_off[4], a_vm[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            bool ok = a_ok[j] && (unsigned)(a_h[j] + dh) < (unsigned)a.H && (unsigned)(a_w[j] + dw) < (unsigned)a.W;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            a_row[j] = (j * 4 + (warp >> 1)) * 8 + p_low;
+            const long long p = m0 + a_row[j];
+            const bool ok = p < a.P;
+            const long long pp = ok ? p : 0;
+            const int rem = (int)(pp % HW);
+            const int h = rem / a.W, w = rem - h * a.W;
+            unsigned vm = 0;
             if (ok) {
-                v = ldg4(a.x.z + (a_p[j] + dh * a.W + dw) * a.Cin + c);
-                if (a.x.scale != nullptr) v = act4(v, s, t, a.x.relu);
-            }
-            a_reg[j] = v;
-        }
-    };
-    auto store_a = [&](int s) {
-        uint8_t* base = sgen + s * STAGE + quad * LBO_A;
+                if (a.ksize == 3) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 v = a_reg[j];
-            float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-            *reinterpret_cast<float4*>(base + a_row[j] * 16) = hi;
-            if (SPLIT) {
-                float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                *reinterpret_cast<float4*>(base + T_A_BYTES + a_row[j] * 16) = lo;
+                    for (int t = 0; t < 9; ++t) {
+                        const int dh = t / 3 - 1, dw = t % 3 - 1;
+                        if ((unsigned)(h + dh) < (unsigned)a.H && (unsigned)(w + dw) < (unsigned)a.W) vm |= 1u << t;
+                    }
+                } else {
+                    vm = 1u;
+                }
             }
+            a_vm[j] = vm;
+            a_off[j] = (unsigned)(pp * a.Cin) + quad * 4;
         }
-    };
-
-    load_a(0);
-    for (int it = 0; it < T; ++it) {
-        const int s = it % NST, u = it / NST;
-        if (it >= NST) mbar_wait(bar_mma + 8 * s, (u - 1) & 1);          // stage s drained by the tensor core
-        store_a(s);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
-        if (it + 1 < T) load_a(it + 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(bar_b + 8 * s, u & 1);                             // weight stage landed
+        const float* xz = a.x.z;
+        const bool has_aff = a.x.scale != nullptr;
+        // raw loads only (no dependent math): PF register sets give PF stages of latency cover
+        constexpr int PF = 2;
+        float4 a_reg[PF][4];
+        unsigned a_msk[PF];
+        // running (tap, k-chunk) counters of the load stream (two stages ahead) and of the store stream
+        int l_tap = 0, l_kc = 0, l_toff = (a.ksize == 3) ? -(a.W + 1) * a.Cin : 0;
+        int s_kc = 0;
+        auto load_a = [&](int set) {
+            const int coff = l_toff + l_kc * TBK;
+            unsigned m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((a_vm[j] >> l_tap) & 1u) {
+                    v = ldg4(xz + (a_off[j] + coff));
+                    m |= 1u << j;
+                }
+                a_reg[set][j] = v;
+            }
+            a_msk[set] = m;
+            if (++l_kc == KC) {            // next tap: offsets advance by one pixel, or by a row at the end of a tap row
+                l_kc = 0;
+                ++l_tap;
+                l_toff += (l_tap == 3 || l_tap == 6) ? (a.W - 2) * a.Cin : a.Cin;
+            }
+        };
+        auto store_a = [&](int s, int set) {
+            float4 sc, sh;
+            load_affine4(a.x.scale, a.x.shift, s_kc * TBK + quad * 4, sc, sh);
+            if (++s_kc == KC) s_kc = 0;
+            uint8_t* base = sgen + s * STAGE + quad * LBO_A;
+            const unsigned msk = a_msk[set];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = a_reg[set][j];
+                // zero padding is a zero of the ACTIVATED tensor: transform only valid pixels
+                if (has_aff && ((msk >> j) & 1u)) v = act4(v, sc, sh, a.x.relu);
+                float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                *reinterpret_cast<float4*>(base + a_row[j] * 16) = hi;
+                if (SPLIT) {
+                    float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                    *reinterpret_cast<float4*>(base + T_A_BYTES + a_row[j] * 16) = lo;
+                }
+            }
+        };
+#define HGK_SEL4(idx, fn, ...)                                     \
+    switch ((idx) & 3) {                                           \
+        case 0: fn(__VA_ARGS__ 0); break;                          \
+        case 1: fn(__VA_ARGS__ 1); break;                          \
+        case 2: fn(__VA_ARGS__ 2); break;                          \
+        default: fn(__VA_ARGS__ 3); break;                         \
+    }
+        load_a(0);
+        if (T > 1) load_a(1);
+        if (PF == 4) {
+            if (T > 2) load_a(2);
+            if (T > 3) load_a(3);
+        }
+        if (tid == 0) HGK_STAMP(2);
+        int s = 0;
+        unsigned em_par = 1;               // parity of the previous use of the stage (toggles when s wraps)
+        const float* wsrc_hi = whi;
+        const float* wsrc_lo = wlo;
+        for (int it = 0; it < T; ++it) {
+            if (it >= NST) mbar_wait(bar_em + 8 * s, em_par);          // stage s drained by the tensor core
+            if (tid == 0) {
+                const uint32_t bb = bar_fb + 8 * s;
+                const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * T_A_BYTES;
+                mbar_expect_tx(bb, (SPLIT ? 2 : 1) * B_BYTES);
+                bulk_g2s(dst, wsrc_hi, B_BYTES, bb);
+                if (SPLIT) bulk_g2s(dst + B_BYTES, wsrc_lo, B_BYTES, bb);
+            }
+            wsrc_hi += wblk;
+            if (SPLIT) wsrc_lo += wblk;
+            if (PF == 4) { HGK_SEL4(it, store_a, s, ); } else { if (it & 1) store_a(s, 1); else store_a(s, 0); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
+            mbar_arrive(bar_fa + 8 * s);
+            if (tid == 0 && it == 0) HGK_STAMP(3);
+            if (it + PF < T) {
+                if (PF == 4) { HGK_SEL4(it, load_a, ); } else { if (it & 1) load_a(1); else load_a(0); }
+            }
+            if (++s == NST) { s = 0; em_par ^= 1u; }
+        }
+        if (tid == 0) HGK_STAMP(4);
+        // all MMAs retired?
+        mbar_wait(bar_em + 8 * ((T - 1) % NST), ((T - 1) / NST) & 1);
+        if (tid == 0) HGK_STAMP(5);
+    } else if (lane == 0) {
+        // ===== MMA issuer =====
+        for (int it = 0; it < T; ++it) {
+            const int s = it % NST, u = it / NST;
+            mbar_wait(bar_fa + 8 * s, u & 1);
+            if (it == 0) HGK_STAMP(8);
+            mbar_wait(bar_fb + 8 * s, u & 1);
+            if (it == 0) HGK_STAMP(9);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = sbase + s * STAGE;
             const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * T_A_BYTES;
@@ -222,29 +307,25 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
                 if (SPLIT) {
                     const uint64_t dal = umma_desc(a_hi + T_A_BYTES + k * 2 * LBO_A, LBO_A, SBO);
                     const uint64_t dbl = umma_desc(b_hi + B_BYTES + k * 2 * LBO_B, LBO_B, SBO);
-                    umma_tf32(tmem, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);     // small terms first
-                    umma_tf32(tmem, da, dbl, IDESC, 1u);
-                    umma_tf32(tmem, da, db, IDESC, 1u);
+                    const uint32_t t_small = tmem + NMAIN * BN;
+                    const uint32_t t_main = tmem + (NMAIN > 1 ? (it & 1) * BN : 0);
+                    umma_tf32(t_small, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(t_small, da, dbl, IDESC, 1u);
+                    umma_tf32(t_main, da, db, IDESC, (it >= NMAIN || k > 0) ? 1u : 0u);
                 } else {
                     umma_tf32(tmem, da, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
                 }
             }
-            umma_commit(bar_mma + 8 * s);
-            if (it + 1 < T) {
-                const int s1 = (it + 1) % NST;
-                if (it + 1 >= NST) mbar_wait(bar_mma + 8 * s1, (((it + 1) / NST) - 1) & 1);
-                issue_b(it + 1);
-            }
+            umma_commit(bar_em + 8 * s);
         }
     }
-    // all MMAs retired?
-    mbar_wait(bar_mma + 8 * ((T - 1) % NST), ((T - 1) / NST) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();       // every producer has observed the last commit: accumulator complete, smem reusable
 
     // ---- epilogue 1: TMEM -> registers -> staging tile (row stride BN+4 floats) ----
     float* stg = reinterpret_cast<float*>(sgen);
     constexpr int SROW = BN + 4;
-    {
+    if (warp < 8) {
         const int lq = warp & 3;
         const int row = lq * 32 + lane;
         const int cbeg = (warp >> 2) * (BN / 2);
@@ -263,23 +344,47 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float acc[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(r[q]);
+            // remaining accumulators (second hi*hi chain, cross terms): fp32 round-to-nearest adds.  With a
+            // single stage the second main accumulator was never written.
+#pragma unroll
+            for (int e = 1; e < NACC; ++e) {
+                if (NMAIN > 1 && e == 1 && T < 2) continue;
+                const uint32_t ta2 = taddr + (uint32_t)(e * BN);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(ta2)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(r[q]);
+            }
             float* dst = stg + row * SROW + c0;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+                st4(dst + q * 4, make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) HGK_STAMP(6);
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 
     // ---- epilogue 2: coalesced bias / residual / accumulate / store + BN statistics ----
     constexpr int CG = BN / 4;           // float4 column groups
     constexpr int RL = TNT / CG;         // row lanes (4 for BN=256, 8 for 128, 16 for 64)
-    const int cg = tid % CG, r0 = tid / CG;
+    const bool epi = tid < TNT;          // the MMA warp only takes part in the barriers below
+    const int cg = (epi ? tid : 0) % CG, r0 = (epi ? tid : 0) / CG;
     const int n = n0 + cg * 4;
     const bool do_stats = a.stat_sum != nullptr;
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,43 +393,60 @@ __global__ void __launch_bounds__(TNT, 1) conv_tc_kernel(const TcArgs args) {
     load_affine4(a.res.scale, a.res.shift, n, rs, rt);
     double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    int cnt = 0;
-    for (int r = r0; r < TBM; r += RL) {
-        const long long p = m0 + r;
-        if (p >= a.P) break;
-        float4 v = ld4(stg + r * SROW + cg * 4);
-        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-        if (a.res.z != nullptr) {
-            float4 rr = ldg4(a.res.z + p * a.Cout + n);
-            if (a.res.scale != nullptr) rr = act4(rr, rs, rt, a.res.relu);
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-        }
-        float* yp = a.y + p * a.Cout + n;
-        if (a.accumulate) {
-            float4 o = ld4(yp);
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        st4(yp, v);
-        if (do_stats) {
-            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
-            if (++cnt == 8) {
+    // rows are processed 8 at a time with all global loads (residual / previous output) issued first,
+    // so their latency is paid once per batch instead of once per row
+    constexpr int ROWS = TBM / RL;       // rows per thread (32 / 16 / 8)
+    const bool has_res = a.res.z != nullptr, has_aff = a.res.scale != nullptr;
+#pragma unroll 1
+    for (int g = 0; epi && g < ROWS; g += 8) {
+        float4 rr[8], oo[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
-                cnt = 0;
+        for (int i = 0; i < 8; ++i) {
+            const long long p = m0 + r0 + (g + i) * RL;
+            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < a.P) {
+                if (has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n);
+                if (a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + (g + i) * RL;
+            const long long p = m0 + r;
+            if (p >= a.P) break;
+            float4 v = ld4(stg + r * SROW + cg * 4);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (has_res) {
+                float4 q = rr[i];
+                if (has_aff) q = act4(q, rs, rt, a.res.relu);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
+            st4(a.y + p * a.Cout + n, v);
+            if (do_stats) {
+                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+            }
+        }
+        if (do_stats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+        }
     }
+    if (tid == 0) HGK_STAMP(7);
     if (do_stats) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
         double* red = reinterpret_cast<double*>(sgen + TBM * SROW * 4);     // [RL][BN][2], behind the staging tile
+        if (epi) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            red[((r0 * BN) + cg * 4 + j) * 2 + 0] = d1[j];
-            red[((r0 * BN) + cg * 4 + j) * 2 + 1] = d2[j];
+            for (int j = 0; j < 4; ++j) {
+                red[((r0 * BN) + cg * 4 + j) * 2 + 0] = d1[j];
+                red[((r0 * BN) + cg * 4 + j) * 2 + 1] = d2[j];
+            }
         }
         __syncthreads();
         if (tid < BN) {
@@ -362,9 +484,6 @@ struct WgTcArgs {
     long long P, chunk;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -438,30 +557,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
             b_quad[v] = (v * 8 + warp) * 4 + q_low;
             load_affine4(a.x.scale, a.x.shift, b_on ? b_quad[v] * 4 : 0, xs[v], xt[v]);
         }
-        float4 ra[2][4], rb[2][NBLK][4];
+        constexpr int PF = 2;                       // register sets = stages of load latency cover
+        float4 ra[PF][4], rb[PF][NBLK][4];          // raw loads only: no dependent math until the stage is stored
+        unsigned bmsk[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) bmsk[i] = 0u;
         float bsum[4] = {0.f, 0.f, 0.f, 0.f};
         const bool do_bias = a.dbias != nullptr && tap == 0;
-        auto load = [&](int it, int set) {
-            const long long p0 = p_begin + (long long)it * 32 + c_low * 4;
+        // running position of this thread's 4-pixel chunk in the load stream (two stages ahead of the stores)
+        long long l_p = p_begin + c_low * 4;
+        int l_h, l_w;
+        {
+            const int rem = (int)(l_p % HW);
+            l_h = rem / a.W;
+            l_w = rem - l_h * a.W;
+        }
+        const int toff = (dh * a.W + dw_) * a.Cin;
+        const float* dzp = a.dz + a_c;
+        const float* xzp = a.x.z;
+        auto load = [&](int set) {
+            const unsigned pe = (unsigned)(p_end - l_p > 4 ? 4 : (p_end - l_p < 0 ? 0 : p_end - l_p));   // valid pixels of the chunk
+            const unsigned o_dz = (unsigned)(l_p * a.Cout);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p0 + j < p_end && a_cok) v = ldg4(a.dz + (p0 + j) * a.Cout + a_c);
+                if ((unsigned)j < pe && a_cok) v = ldg4(dzp + (o_dz + j * a.Cout));
                 ra[set][j] = v;
             }
             if (b_on) {
-                int rem = (int)(p0 % HW);
-                int h = rem / a.W, w = rem - h * a.W;
+                int h = l_h, w = l_w;
+                const unsigned o_x = (unsigned)(l_p * a.Cin + toff);
+                unsigned m = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const bool ok = p0 + j < p_end && (unsigned)(h + dh) < (unsigned)a.H && (unsigned)(w + dw_) < (unsigned)a.W;
+                    const bool ok = (unsigned)j < pe && (unsigned)(h + dh) < (unsigned)a.H && (unsigned)(w + dw_) < (unsigned)a.W;
+                    if (ok) m |= 1u << j;
 #pragma unroll
                     for (int v = 0; v < NBLK; ++v) {
                         float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok) {
-                            x4 = ldg4(a.x.z + (p0 + j + dh * a.W + dw_) * a.Cin + b_quad[v] * 4);
-                            if (a.x.scale != nullptr) x4 = act4(x4, xs[v], xt[v], a.x.relu);
-                        }
+                        if (ok) x4 = ldg4(xzp + (o_x + j * a.Cin + b_quad[v] * 4));
                         rb[set][v][j] = x4;
                     }
                     if (++w == a.W) {
@@ -469,6 +603,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
                         if (++h == a.H) h = 0;
                     }
                 }
+                bmsk[set] = m;
+            }
+            l_p += 32;
+            l_w += 32;
+            while (l_w >= a.W) {
+                l_w -= a.W;
+                if (++l_h == a.H) l_h = 0;
             }
         };
         auto store = [&](int s, int set) {
@@ -489,7 +630,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
 #pragma unroll
                 for (int v = 0; v < NBLK; ++v) {
                     uint8_t* sb = sgen + s * STAGE + A_BYTES + c_low * LBO_B + b_quad[v] * 64;
-                    const float4 x0 = rb[set][v][0], x1 = rb[set][v][1], x2 = rb[set][v][2], x3 = rb[set][v][3];
+                    float4 x0 = rb[set][v][0], x1 = rb[set][v][1], x2 = rb[set][v][2], x3 = rb[set][v][3];
+                    if (a.x.scale != nullptr) {      // BN+ReLU on valid pixels only (padding = zero of the activated tensor)
+                        const unsigned m = bmsk[set];
+                        if (m & 1u) x0 = act4(x0, xs[v], xt[v], a.x.relu);
+                        if (m & 2u) x1 = act4(x1, xs[v], xt[v], a.x.relu);
+                        if (m & 4u) x2 = act4(x2, xs[v], xt[v], a.x.relu);
+                        if (m & 8u) x3 = act4(x3, xs[v], xt[v], a.x.relu);
+                    }
                     *reinterpret_cast<float4*>(sb + 0) = tf32_rna4(make_float4(x0.x, x1.x, x2.x, x3.x));
                     *reinterpret_cast<float4*>(sb + 16) = tf32_rna4(make_float4(x0.y, x1.y, x2.y, x3.y));
                     *reinterpret_cast<float4*>(sb + 32) = tf32_rna4(make_float4(x0.z, x1.z, x2.z, x3.z));
@@ -497,15 +645,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
                 }
             }
         };
-        load(0, 0);
-        if (T > 1) load(1, 1);
+        load(0);
+        if (T > 1) load(1);
+        if (PF == 4) {
+            if (T > 2) load(2);
+            if (T > 3) load(3);
+        }
+        int s = 0;
+        unsigned em_par = 1;               // parity of the previous use of the stage (toggles when s wraps)
         for (int it = 0; it < T; ++it) {
-            const int s = it % NST, u = it / NST;
-            if (it >= NST) mbar_wait(bar_empty + 8 * s, (u - 1) & 1);
-            if (it & 1) store(s, 1); else store(s, 0);
+            if (it >= NST) mbar_wait(bar_empty + 8 * s, em_par);
+            if (PF == 4) { HGK_SEL4(it, store, s, ); } else { if (it & 1) store(s, 1); else store(s, 0); }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_full + 8 * s);
-            if (it + 2 < T) { if (it & 1) load(it + 2, 1); else load(it + 2, 0); }
+            if (it + PF < T) {
+                if (PF == 4) { HGK_SEL4(it, load, ); } else { if (it & 1) load(1); else load(0); }
+            }
+            if (++s == NST) { s = 0; em_par ^= 1u; }
         }
         if (do_bias) {
 #pragma unroll
@@ -665,7 +821,7 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     }
     long long mt = (ta.c.P + TBM - 1) / TBM;
     dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN));
-    conv_tc_kernel<BN, SPLIT><<<grid, TNT, smem, st>>>(ta);
+    conv_tc_kernel<BN, SPLIT><<<grid, TNT + 32, smem, st>>>(ta);
     return HGK_OK;
 }
 
@@ -697,7 +853,7 @@ extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const floa
     ta.c.res = Act{res, res_scale, res_shift, res_relu};
     ta.c.y = y; ta.c.accumulate = accumulate; ta.c.stat_sum = stat_sum; ta.c.stat_sq = stat_sq;
     ta.c.P = (long long)N * H * W;
-    ta.w_hi = w_hi; ta.w_lo = w_lo;
+    ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
@@ -707,6 +863,12 @@ extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const floa
     else rc = split ? launch_tc<256, true>(ta, st) : launch_tc<256, false>(ta, st);
     if (rc != HGK_OK) return rc;
     HGK_CHECK_LAUNCH("hgk_conv_tc_nhwc");
+    return HGK_OK;
+}
+
+/* developer diagnostics: per-CTA globaltimer stamps of conv_tc_kernel ([512][16] int64), NULL disables */
+extern "C" int hgk_debug_set_timeline(long long* buf) {
+    g_dbg_buf = buf;
     return HGK_OK;
 }
 

@@ -159,7 +159,7 @@ class Plan(object):
     VEC_CAP = 1 << 22      # fp32 per-channel vectors (scale, shift, mean, invstd, cA, cB, cC)
     STAT_CAP = 1 << 20     # fp64 per-channel accumulators
 
-    def __init__(self, stores, device, training, need_grad, conv_path=0):
+    def __init__(self, stores, device, training, need_grad, conv_path=0, precise_grads=False):
         self.lib = get_lib()
         self.stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
         self.device = device
@@ -177,6 +177,9 @@ class Plan(object):
         self.stat_b = torch.zeros(self.STAT_CAP if need_grad else 1, device=device, dtype=torch.float64)
         self.stat_b_used = 0
         self.use_tc = conv_path != 1   # tcgen05 convolutions where the shape is covered
+        # gradients: plain TF32 operands by default (error below the fp32-vs-fp64 noise floor of the
+        # whole net); precise_grads -> 3xTF32 data gradients + fp32 SIMT weight gradients
+        self.precise_grads = precise_grads
         self.tc_entries = []       # (src param, mode, BN, hi offset, lo offset or -1)
         self.tc_used = 0
         self.tc_buf = None
@@ -687,7 +690,7 @@ class _ConvOp(object):
             _emit_bn_bwd(p, o, self.bn, g)
         w = self.conv.weight
         k, Cin, Cout = self.k, self.Cin, self.Cout
-        if p.use_tc and p.lib.conv_wgrad_tc_supported(Cin, Cout, k):
+        if p.use_tc and not p.precise_grads and p.lib.conv_wgrad_tc_supported(Cin, Cout, k):
             # tensor cores; 1x1: tap-major == OIHW, accumulate straight into .grad; 3x3: via the tap-major scratch
             dst = p.param_grad_ptr(w) if k == 1 else p.wgrad_scratch(w)
             p.launch(p.bwd, "conv_wgrad_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k, dst,
@@ -701,8 +704,8 @@ class _ConvOp(object):
         if x.needs_grad:
             gx, acc, extra = p.grad_target(x)
             if p.use_tc and p.lib.conv_tc_supported(Cout, Cin, k):
-                hi, _ = p.packed_weight_tc(w, 1, False)          # plain TF32 is enough for gradients
-                p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, 0, k, 0, Cin,
+                hi, lo = p.packed_weight_tc(w, 1, p.precise_grads)   # plain TF32 is enough for gradients
+                p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, lo, k, 0, Cin,
                          _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0)
             else:
                 wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))

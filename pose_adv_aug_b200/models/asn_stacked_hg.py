@@ -17,8 +17,12 @@ from ..engine import Plan, ParamStore, HGKError
 
 __all__ = ["_Residual", "_Hourglass", "_Hourglass_Wrapper", "ASN", "create_hg", "create_asn", "Hourglass"]
 
-# convolution kernel selection for newly built plans: 0 auto, 1 fp32 SIMT, 2 tcgen05
+# convolution kernel selection for newly built plans: 0 = tcgen05 tensor cores where the shape is covered
+# (3xTF32 forward), 1 = fp32 SIMT kernels everywhere
 CONV_PATH = 0
+# False: gradients use plain TF32 operands on the tensor cores (fast; error below the whole-net fp32 noise
+# floor).  True: 3xTF32 data gradients + fp32 weight gradients (fp32-class gradients, slower).
+PRECISE_GRADS = False
 
 
 def _reference_init(root):
@@ -111,11 +115,11 @@ def _run(root, extra_roots, key, inputs, build):
     shapes = tuple(tuple(x.shape) for x in inputs)
     modes = tuple(m.training for m in mods)
     ids = tuple(id(s) for s in stores)
-    pkey = (key, shapes, modes, need_grad, ids, CONV_PATH)
+    pkey = (key, shapes, modes, need_grad, ids, CONV_PATH, PRECISE_GRADS)
     cache = _state(root).plans
     plan = cache.get(pkey)
     if plan is None:
-        plan = Plan(stores, device, root.training, need_grad, conv_path=CONV_PATH)
+        plan = Plan(stores, device, root.training, need_grad, conv_path=CONV_PATH, precise_grads=PRECISE_GRADS)
         plan.in_requires_grad = [x.requires_grad for x in inputs]
         plan.structure = build(plan)
         plan.finish()

@@ -31,7 +31,7 @@ class HourglassTrainer(object):
         self.t = torch.zeros(batch, K, res // 4, res // 4, device=self.device)
         self.loss_acc = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.loss = torch.zeros(1, device=self.device, dtype=torch.float32)
-        plan = Plan([self.store], self.device, True, True, conv_path=M.CONV_PATH)
+        plan = Plan([self.store], self.device, True, True, conv_path=M.CONV_PATH, precise_grads=M.PRECISE_GRADS)
         img = plan.input_image(batch, res, res)
         tgt = plan.target_nchw(batch, K, res // 4, res // 4)
         outs, _ = net._build(plan, img)

@@ -422,11 +422,12 @@ def test_conv_tc_fwd_3xtf32(shape, variant):
     call("conv_tc_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(db), Co,
          ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), ptr(ssum), ptr(ssq))
     torch.cuda.synchronize()
-    # 3xTF32: dropped lo*lo term ~2^-22 per product -> fp32-class result; the tensor core accumulates in
-    # fp32 with truncation, which shows as a ~1e-5 systematic shrink at K = 9*256 (BN renormalises it away)
-    assert relerr(from_nhwc(y), ref) < 3e-5
-    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 5e-5
-    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 5e-5
+    # 3xTF32: dropped lo*lo term ~2^-22 per product -> fp32-class result.  (The tensor core accumulates in
+    # fp32 with truncation; the kernel splits the chain over several TMEM accumulators to keep that bias
+    # at the 1e-6 level even at K = 9*256.)
+    assert relerr(from_nhwc(y), ref) < 2e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 2e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)

@@ -1,0 +1,85 @@
+"""Per-launch CUDA-event timing of one real train step (no profiler, real clocks).
+usage: python tools/time_plan.py [--batch 24] [--top 25]"""
+import argparse
+import collections
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import hg_oracle as O, synth                      # noqa: E402
+from pose_adv_aug_b200.models import asn_stacked_hg as M      # noqa: E402
+from pose_adv_aug_b200 import HourglassTrainer                # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=24)
+ap.add_argument("--res", type=int, default=256)
+ap.add_argument("--chan", type=int, default=256)
+ap.add_argument("--stacks", type=int, default=2)
+ap.add_argument("--top", type=int, default=25)
+ap.add_argument("--conv-path", type=int, default=0)
+args = ap.parse_args()
+M.CONV_PATH = args.conv_path
+dev = torch.device("cuda", 0)
+net = M.create_hg(args.stacks, 1, 16, args.chan)
+net.load_state_dict(synth.make_state_dict(O.hg_schema(args.stacks, 1, 16, args.chan), seed=1, perturb_bn=False))
+tr = HourglassTrainer(net, args.batch, args.res, device=dev, use_graph=False)
+tr.x.copy_(synth.make_images(args.batch, args.res, seed=100))
+tr.t.copy_(synth.make_heatmaps(args.batch, args.res, 16, seed=200))
+for _ in range(3):
+    tr.step_resident()
+torch.cuda.synchronize()
+plan = tr.plan
+stream = torch.cuda.current_stream().cuda_stream
+recs = []
+if plan.pack_launch:
+    recs.append(plan.pack_launch)
+if plan.tc_launch:
+    recs.append(plan.tc_launch)
+recs += plan.fwd + plan.bwd
+plan.stat_f[:plan.stat_f_used].zero_()
+plan.stat_b[:plan.stat_b_used].zero_()
+tr.store.grad.zero_()
+if plan.wg_buf is not None:
+    plan.wg_buf.zero_()
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(recs) + 1)]
+evs[0].record()
+for i, (fn, a, name) in enumerate(recs):
+    rc = fn(*a, stream)
+    assert rc == 0, name
+    evs[i + 1].record()
+torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+rows = []
+for i, (fn, a, name) in enumerate(recs):
+    ms = evs[i].elapsed_time(evs[i + 1])
+    key = name
+    if name in ("conv_nhwc", "conv_tc_nhwc"):
+        N, H, W, Cin = a[4:8]
+        if name == "conv_tc_nhwc":
+            k, Cout, split = a[10], a[12], a[9] != 0
+            key = "%s k%d %s" % (name, k, "3xtf32" if split else "tf32")
+        else:
+            k, Cout = a[9], a[12]
+            key = "%s k%d" % (name, k)
+        desc = "%dx%d %d->%d" % (H, W, Cin, Cout)
+    elif name in ("conv_wgrad_nhwc", "conv_wgrad_tc_nhwc"):
+        N, H, W, Cin = a[4:8]
+        Cout, k = a[9], a[10]
+        key = "%s k%d" % (name, k)
+        desc = "%dx%d %d->%d" % (H, W, Cin, Cout)
+    else:
+        desc = ""
+    agg[key][0] += 1
+    agg[key][1] += ms
+    rows.append((ms, key, desc))
+tot = sum(v[1] for v in agg.values())
+print("step (event-timed, launches serialized on one stream): %.2f ms, %d launches" % (tot, len(recs)))
+for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:args.top]:
+    print("%-34s %4d %9.3f ms %5.1f%%" % (k, c, t, 100 * t / tot))
+print("--- slowest launches")
+rows.sort(reverse=True)
+for r in rows[:20]:
+    print("%8.3f ms  %-30s %s" % r)
