@@ -100,10 +100,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     d |= (uint64_t)1 << 46;     // descriptor version 1 (Blackwell)
     return d;
 }
+// round-to-nearest (ties away) to TF32 = add half an ulp of the 10-bit mantissa and clear the low 13 bits.
+// (cvt.rna.tf32.f32 has no single-instruction lowering on sm_100a: ptxas expands it to ~8 integer ops,
+// which made the producers issue-bound; inf stays inf, NaN stays NaN.)
 __device__ __forceinline__ float tf32_rna(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+// BN+ReLU on load with the ReLU expressed as a clamp value (0 or -inf): one FFMA + one FMNMX per element
+__device__ __forceinline__ float4 actc4(float4 v, float4 s, float4 t, float clampv) {
+    return make_float4(fmaxf(fmaf(v.x, s.x, t.x), clampv), fmaxf(fmaf(v.y, s.y, t.y), clampv),
+                       fmaxf(fmaf(v.z, s.z, t.z), clampv), fmaxf(fmaf(v.w, s.w, t.w), clampv));
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
         }
         const float* xz = a.x.z;
         const bool has_aff = a.x.scale != nullptr;
+        const float x_clamp = a.x.relu ? 0.f : -INFINITY;
         // raw loads only (no dependent math): PF register sets give PF stages of latency cover
         constexpr int PF = 2;
         float4 a_reg[PF][4];
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
             for (int j = 0; j < 4; ++j) {
                 float4 v = a_reg[set][j];
                 // zero padding is a zero of the ACTIVATED tensor: transform only valid pixels
-                if (has_aff && ((msk >> j) & 1u)) v = act4(v, sc, sh, a.x.relu);
+                if (has_aff && ((msk >> j) & 1u)) v = actc4(v, sc, sh, x_clamp);
                 float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
                 *reinterpret_cast<float4*>(base + a_row[j] * 16) = hi;
                 if (SPLIT) {
@@ -575,6 +582,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
         const int toff = (dh * a.W + dw_) * a.Cin;
         const float* dzp = a.dz + a_c;
         const float* xzp = a.x.z;
+        const bool has_aff = a.x.scale != nullptr;
+        const float x_clamp = a.x.relu ? 0.f : -INFINITY;
         auto load = [&](int set) {
             const unsigned pe = (unsigned)(p_end - l_p > 4 ? 4 : (p_end - l_p < 0 ? 0 : p_end - l_p));   // valid pixels of the chunk
             const unsigned o_dz = (unsigned)(l_p * a.Cout);
@@ -631,12 +640,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
                 for (int v = 0; v < NBLK; ++v) {
                     uint8_t* sb = sgen + s * STAGE + A_BYTES + c_low * LBO_B + b_quad[v] * 64;
                     float4 x0 = rb[set][v][0], x1 = rb[set][v][1], x2 = rb[set][v][2], x3 = rb[set][v][3];
-                    if (a.x.scale != nullptr) {      // BN+ReLU on valid pixels only (padding = zero of the activated tensor)
+                    if (has_aff) {      // BN+ReLU on valid pixels only (padding = zero of the activated tensor)
                         const unsigned m = bmsk[set];
-                        if (m & 1u) x0 = act4(x0, xs[v], xt[v], a.x.relu);
-                        if (m & 2u) x1 = act4(x1, xs[v], xt[v], a.x.relu);
-                        if (m & 4u) x2 = act4(x2, xs[v], xt[v], a.x.relu);
-                        if (m & 8u) x3 = act4(x3, xs[v], xt[v], a.x.relu);
+                        if (m & 1u) x0 = actc4(x0, xs[v], xt[v], x_clamp);
+                        if (m & 2u) x1 = actc4(x1, xs[v], xt[v], x_clamp);
+                        if (m & 4u) x2 = actc4(x2, xs[v], xt[v], x_clamp);
+                        if (m & 8u) x3 = actc4(x3, xs[v], xt[v], x_clamp);
                     }
                     *reinterpret_cast<float4*>(sb + 0) = tf32_rna4(make_float4(x0.x, x1.x, x2.x, x3.x));
                     *reinterpret_cast<float4*>(sb + 16) = tf32_rna4(make_float4(x0.y, x1.y, x2.y, x3.y));
