@@ -41,6 +41,7 @@ class HourglassTrainer(object):
         plan.finish()
         self.plan = plan
         self.graph = None
+        self.graph_update = None
         self.use_graph = use_graph
         self.steps = 0
 
@@ -50,20 +51,29 @@ class HourglassTrainer(object):
         return (len(self.plan.fwd) + len(self.plan.bwd) + (1 if self.plan.pack_launch else 0)
                 + (1 if self.plan.tc_launch else 0) + 2)
 
-    def _step_body(self):
+    def _body_grads(self):
+        """zero grads/loss -> forward -> fused MSE -> backward (local gradients in the flat buffer)."""
         st, plan = self.store, self.plan
         self.loss_acc.zero_()
         st.grad.zero_()
         plan.run_forward([self.x, self.t])
         plan.run_backward([self.x, self.t], [None] * len(plan.outputs))
-        if self.world > 1:
-            hdist.allreduce_flat_grads(st.grad)
+
+    def _body_update(self):
+        """flat RMSprop (1/world folded in) + loss accumulator -> fp32 scalar."""
+        st = self.store
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.lib.check(self.lib.rmsprop_flat(st.flat.data_ptr(), st.grad.data_ptr(), self.square_avg.data_ptr(),
                                              st.numel, self.lr, self.alpha, self.eps, 1.0 / self.world, stream),
                        "hgk_rmsprop_flat")
         self.lib.check(self.lib.f64_to_f32(self.loss_acc.data_ptr(), self.loss.data_ptr(), 1, 1.0, stream),
                        "hgk_f64_to_f32")
+
+    def _step_body(self):
+        self._body_grads()
+        if self.world > 1:
+            hdist.allreduce_flat_grads(self.store.grad)      # the ONE collective of the step (NCCL, NVLink)
+        self._body_update()
 
     def step_resident(self):
         """One train step on the batch currently held in the static device buffers self.x / self.t."""
@@ -72,7 +82,14 @@ class HourglassTrainer(object):
         if self.use_graph:
             if self.graph is None:
                 self._capture()
-            self.graph.replay()
+            if self.world > 1:
+                # two graphs around the eager NCCL call: NCCL's watchdog thread makes stream-capture of the
+                # collective fragile, and one extra graph launch per step costs a few microseconds
+                self.graph.replay()
+                hdist.allreduce_flat_grads(self.store.grad)
+                self.graph_update.replay()
+            else:
+                self.graph.replay()
         else:
             self._step_body()
         self.steps += 1
@@ -84,12 +101,19 @@ class HourglassTrainer(object):
         with torch.cuda.stream(s):
             saved = (self.store.flat.clone(), self.square_avg.clone(), self.store.fbuf_flat.clone(),
                      self.store.ibuf_flat.clone())
-            self._step_body()            # warm-up outside capture (NCCL / lazy init)
+            self._step_body()            # warm-up outside capture (lazy init, NCCL communicator)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._step_body()
+        if self.world > 1:
+            with torch.cuda.graph(self.graph):
+                self._body_grads()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update):
+                self._body_update()
+        else:
+            with torch.cuda.graph(self.graph):
+                self._step_body()
         # restore the state consumed by the warm-up step
         self.store.flat.copy_(saved[0])
         self.square_avg.copy_(saved[1])
