@@ -39,21 +39,8 @@ __device__ __forceinline__ long long gtimer() {
         if (args.dbg != nullptr && blockIdx.x < 512) args.dbg[blockIdx.x * 16 + (slot)] = gtimer(); \
     } while (0)
 
-constexpr int TBM = 128, TBK = 32, TNT = 256;
-constexpr int T_A_BYTES = TBM * TBK * 4;      // 16 KB per (hi|lo) activation stage
-constexpr int T_SMEM_BUDGET = 196 * 1024;
-
-__host__ __device__ constexpr int tc_stage_bytes(int BN, bool split) { return (split ? 2 : 1) * (T_A_BYTES + BN * TBK * 4); }
-__host__ __device__ constexpr int tc_num_stages(int BN, bool split) {
-    int n = T_SMEM_BUDGET / tc_stage_bytes(BN, split);
-    return n > 4 ? 4 : n;
-}
+constexpr int TBM = 128, TNT = 256;
 __host__ __device__ constexpr int tc_staging_bytes(int BN) { return TBM * (BN + 4) * 4 + 16384; }
-__host__ __device__ constexpr int tc_smem_bytes(int BN, bool split) {
-    int p = tc_num_stages(BN, split) * tc_stage_bytes(BN, split);
-    int s = tc_staging_bytes(BN);
-    return (p > s ? p : s) + 256;
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -116,22 +103,55 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Per-instantiation configuration.  Everything is sized so that TWO CTAs fit on one SM (<= ~97 KB of shared
+// memory, <= 256 TMEM columns, <= 112 registers): while one CTA is in its prologue (TMEM alloc, first loads)
+// or epilogue, the other one keeps the tensor pipe and the memory system busy.
 template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args) {
-    constexpr int NST = tc_num_stages(BN, SPLIT);
-    constexpr int B_BYTES = BN * TBK * 4;
-    constexpr int STAGE = tc_stage_bytes(BN, SPLIT);
+struct TcCfg {
+    static constexpr int BK = (SPLIT && BN >= 128) ? 16 : 32;              // channels per pipeline stage
+    static constexpr int QP = BK / 4;                                       // 16-byte channel quads per pixel per stage
+    static constexpr int NJ = QP / 2;                                       // (pixel, quad) items per producer thread
+    static constexpr int A_BYTES = TBM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int NST = (96 * 1024 / STAGE) > 4 ? 4 : (96 * 1024 / STAGE);
+    // The tensor core accumulates in fp32 with truncation: a chain of n dependent accumulations carries a
+    // systematic ~n*2^-25 relative shrink (1.3e-5 measured at K = 9*256 with all three 3xTF32 terms in one
+    // chain).  So the hi*hi products and the two small cross terms get separate TMEM accumulators (BN = 64:
+    // two alternating hi*hi accumulators), added with round-to-nearest fp32 adds in the epilogue.  BN = 256
+    // only occurs with K <= 256 (1x1 convolutions): one 96-step chain, bias ~1.5e-6.
+    static constexpr int NMAIN = (SPLIT && BN <= 64) ? 2 : 1;
+    static constexpr int NACC = !SPLIT ? 1 : (BN >= 256 ? 1 : NMAIN + 1);
+    static constexpr int TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : 256;
+    static constexpr int CH = BN > 128 ? 128 : BN;                          // epilogue column chunk
+    static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
+    static constexpr int SMEM = (NST * STAGE > STG_BYTES ? NST * STAGE : STG_BYTES) + 256;
+    static_assert(NACC * BN <= 256, "two CTAs per SM share the 512 TMEM columns");
+    static_assert(NST >= 2, "pipeline needs two stages");
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args) {
+    using Cfg = TcCfg<BN, SPLIT>;
+    constexpr int BK = Cfg::BK, NJ = Cfg::NJ, NST = Cfg::NST, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE = Cfg::STAGE, TMEM_COLS = Cfg::TMEM_COLS;
     constexpr uint32_t LBO_A = TBM * 16, LBO_B = BN * 16, SBO = 128;
     // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-    // The tensor core accumulates in fp32 with truncation: a chain of n dependent accumulations carries a
-    // systematic ~n*2^-25 relative shrink (1.3e-5 at K = 9*256 with all three 3xTF32 terms in one chain).
-    // So the big hi*hi products go to NMAIN accumulators used round-robin by stage, the two small
-    // cross terms to their own accumulator, and the epilogue adds them with round-to-nearest fp32 adds.
-    constexpr int NMAIN = (SPLIT && BN <= 128) ? 2 : 1;
-    constexpr int NACC = SPLIT ? NMAIN + 1 : 1;
-    constexpr int TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
-    static_assert(NACC * BN <= 512, "TMEM capacity");
     const ConvArgs& a = args.c;
 
     extern __shared__ uint8_t smem_raw[];
@@ -144,7 +164,7 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
     const long long m0 = (long long)blockIdx.x * TBM;
     const int n0 = blockIdx.y * BN;
     const int taps = a.ksize * a.ksize;
-    const int KC = a.Cin / TBK;
+    const int KC = a.Cin / BK;
     const int T = taps * KC;
     const int HW = a.H * a.W;
     // full_a: 256 producer arrivals; full_b: weight bulk copy (expect_tx); empty: tcgen05.commit
@@ -172,20 +192,22 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
 
     if (warp < 8) {
         // ===== producers (activation transform + weight bulk copies) =====
-        // packed weights: [n-tile][tap][k-chunk] blocks of BN*32 floats in UMMA canonical layout
-        const size_t wblk = (size_t)BN * TBK;
-        const float* whi = args.w_hi + (size_t)blockIdx.y * T * wblk;
-        const float* wlo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
-        // thread -> 4 pixels x one channel quad of the 32-channel stage
+        // packed weights: [n-tile][tap][k] blocks in UMMA canonical layout; one stage = BN*BK contiguous floats
+        const size_t wblk = (size_t)BN * BK;
+        const float* wsrc_hi = args.w_hi + (size_t)blockIdx.y * T * wblk;
+        const float* wsrc_lo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
+        // thread -> NJ pixels x one 4-channel quad of the stage; a warp covers 8 pixels x 4 quads so that global
+        // loads are full 32-byte sectors and shared stores are conflict-free 128-byte runs
         const int p_low = lane & 7, q_low = lane >> 3;
-        const int quad = (warp & 1) * 4 + q_low;
+        constexpr int QH = Cfg::QP / 4;
+        const int quad = (warp % QH) * 4 + q_low;
         // per-pixel state, computed once: element offset of the pixel and the 9-bit mask of taps whose
         // source pixel lies inside the image (padding = 1); the main loop only does shifts and adds
-        int a_row[4];
-        unsigned a_off[4], a_vm[4];
+        int a_row[NJ];
+        unsigned a_off[NJ], a_vm[NJ];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            a_row[j] = (j * 4 + (warp >> 1)) * 8 + p_low;
+        for (int j = 0; j < NJ; ++j) {
+            a_row[j] = ((j * 8 + warp) / QH) * 8 + p_low;
             const long long p = m0 + a_row[j];
             const bool ok = p < a.P;
             const long long pp = ok ? p : 0;
@@ -209,18 +231,17 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
         const float* xz = a.x.z;
         const bool has_aff = a.x.scale != nullptr;
         const float x_clamp = a.x.relu ? 0.f : -INFINITY;
-        // raw loads only (no dependent math): PF register sets give PF stages of latency cover
-        constexpr int PF = 2;
-        float4 a_reg[PF][4];
-        unsigned a_msk[PF];
+        // raw loads only (no dependent math): two register sets give two stages of latency cover
+        float4 a_reg[2][NJ];
+        unsigned a_msk[2];
         // running (tap, k-chunk) counters of the load stream (two stages ahead) and of the store stream
         int l_tap = 0, l_kc = 0, l_toff = (a.ksize == 3) ? -(a.W + 1) * a.Cin : 0;
         int s_kc = 0;
         auto load_a = [&](int set) {
-            const int coff = l_toff + l_kc * TBK;
+            const int coff = l_toff + l_kc * BK;
             unsigned m = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((a_vm[j] >> l_tap) & 1u) {
                     v = ldg4(xz + (a_off[j] + coff));
@@ -237,12 +258,12 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
         };
         auto store_a = [&](int s, int set) {
             float4 sc, sh;
-            load_affine4(a.x.scale, a.x.shift, s_kc * TBK + quad * 4, sc, sh);
+            load_affine4(a.x.scale, a.x.shift, s_kc * BK + quad * 4, sc, sh);
             if (++s_kc == KC) s_kc = 0;
             uint8_t* base = sgen + s * STAGE + quad * LBO_A;
             const unsigned msk = a_msk[set];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 float4 v = a_reg[set][j];
                 // zero padding is a zero of the ACTIVATED tensor: transform only valid pixels
                 if (has_aff && ((msk >> j) & 1u)) v = actc4(v, sc, sh, x_clamp);
@@ -250,46 +271,31 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
                 *reinterpret_cast<float4*>(base + a_row[j] * 16) = hi;
                 if (SPLIT) {
                     float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                    *reinterpret_cast<float4*>(base + T_A_BYTES + a_row[j] * 16) = lo;
+                    *reinterpret_cast<float4*>(base + A_BYTES + a_row[j] * 16) = lo;
                 }
             }
         };
-#define HGK_SEL4(idx, fn, ...)                                     \
-    switch ((idx) & 3) {                                           \
-        case 0: fn(__VA_ARGS__ 0); break;                          \
-        case 1: fn(__VA_ARGS__ 1); break;                          \
-        case 2: fn(__VA_ARGS__ 2); break;                          \
-        default: fn(__VA_ARGS__ 3); break;                         \
-    }
         load_a(0);
         if (T > 1) load_a(1);
-        if (PF == 4) {
-            if (T > 2) load_a(2);
-            if (T > 3) load_a(3);
-        }
         if (tid == 0) HGK_STAMP(2);
         int s = 0;
         unsigned em_par = 1;               // parity of the previous use of the stage (toggles when s wraps)
-        const float* wsrc_hi = whi;
-        const float* wsrc_lo = wlo;
         for (int it = 0; it < T; ++it) {
             if (it >= NST) mbar_wait(bar_em + 8 * s, em_par);          // stage s drained by the tensor core
             if (tid == 0) {
                 const uint32_t bb = bar_fb + 8 * s;
-                const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * T_A_BYTES;
+                const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * A_BYTES;
                 mbar_expect_tx(bb, (SPLIT ? 2 : 1) * B_BYTES);
                 bulk_g2s(dst, wsrc_hi, B_BYTES, bb);
                 if (SPLIT) bulk_g2s(dst + B_BYTES, wsrc_lo, B_BYTES, bb);
             }
             wsrc_hi += wblk;
             if (SPLIT) wsrc_lo += wblk;
-            if (PF == 4) { HGK_SEL4(it, store_a, s, ); } else { if (it & 1) store_a(s, 1); else store_a(s, 0); }
+            if (it & 1) store_a(s, 1); else store_a(s, 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
             mbar_arrive(bar_fa + 8 * s);
             if (tid == 0 && it == 0) HGK_STAMP(3);
-            if (it + PF < T) {
-                if (PF == 4) { HGK_SEL4(it, load_a, ); } else { if (it & 1) load_a(1); else load_a(0); }
-            }
+            if (it + 2 < T) { if (it & 1) load_a(1); else load_a(0); }
             if (++s == NST) { s = 0; em_par ^= 1u; }
         }
         if (tid == 0) HGK_STAMP(4);
@@ -306,19 +312,25 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
             if (it == 0) HGK_STAMP(9);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = sbase + s * STAGE;
-            const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * T_A_BYTES;
+            const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_BYTES;
 #pragma unroll
-            for (int k = 0; k < TBK / 8; ++k) {
+            for (int k = 0; k < BK / 8; ++k) {
                 const uint64_t da = umma_desc(a_hi + k * 2 * LBO_A, LBO_A, SBO);
                 const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO);
                 if (SPLIT) {
-                    const uint64_t dal = umma_desc(a_hi + T_A_BYTES + k * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dal = umma_desc(a_hi + A_BYTES + k * 2 * LBO_A, LBO_A, SBO);
                     const uint64_t dbl = umma_desc(b_hi + B_BYTES + k * 2 * LBO_B, LBO_B, SBO);
-                    const uint32_t t_small = tmem + NMAIN * BN;
-                    const uint32_t t_main = tmem + (NMAIN > 1 ? (it & 1) * BN : 0);
-                    umma_tf32(t_small, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(t_small, da, dbl, IDESC, 1u);
-                    umma_tf32(t_main, da, db, IDESC, (it >= NMAIN || k > 0) ? 1u : 0u);
+                    if (NACC == 1) {
+                        umma_tf32(tmem, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem, da, dbl, IDESC, 1u);
+                        umma_tf32(tmem, da, db, IDESC, 1u);
+                    } else {
+                        const uint32_t t_small = tmem + NMAIN * BN;
+                        const uint32_t t_main = tmem + (NMAIN > 1 ? (it & 1) * BN : 0);
+                        umma_tf32(t_small, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(t_small, da, dbl, IDESC, 1u);
+                        umma_tf32(t_main, da, db, IDESC, (it >= NMAIN || k > 0) ? 1u : 0u);
+                    }
                 } else {
                     umma_tf32(tmem, da, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
                 }
@@ -329,144 +341,125 @@ __global__ void __launch_bounds__(TNT + 32, 1) conv_tc_kernel(const TcArgs args)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // every producer has observed the last commit: accumulator complete, smem reusable
 
-    // ---- epilogue 1: TMEM -> registers -> staging tile (row stride BN+4 floats) ----
+    // ---- epilogue, in column chunks of CH: TMEM -> registers -> staging tile -> coalesced
+    //      bias / residual / accumulate / store + BN statistics ----
+    constexpr int CH = Cfg::CH, SROW = CH + 4;
+    constexpr int CG = CH / 4;           // float4 column groups of a chunk
+    constexpr int RL = TNT / CG;         // row lanes (8 for CH=128, 16 for CH=64)
+    constexpr int ROWS = TBM / RL;       // rows per thread (16 / 8)
     float* stg = reinterpret_cast<float*>(sgen);
-    constexpr int SROW = BN + 4;
-    if (warp < 8) {
-        const int lq = warp & 3;
-        const int row = lq * 32 + lane;
-        const int cbeg = (warp >> 2) * (BN / 2);
-#pragma unroll 1
-        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float acc[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(r[q]);
-            // remaining accumulators (second hi*hi chain, cross terms): fp32 round-to-nearest adds.  With a
-            // single stage the second main accumulator was never written.
-#pragma unroll
-            for (int e = 1; e < NACC; ++e) {
-                if (NMAIN > 1 && e == 1 && T < 2) continue;
-                const uint32_t ta2 = taddr + (uint32_t)(e * BN);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(ta2)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(r[q]);
-            }
-            float* dst = stg + row * SROW + c0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                st4(dst + q * 4, make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) HGK_STAMP(6);
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-    }
-
-    // ---- epilogue 2: coalesced bias / residual / accumulate / store + BN statistics ----
-    constexpr int CG = BN / 4;           // float4 column groups
-    constexpr int RL = TNT / CG;         // row lanes (4 for BN=256, 8 for 128, 16 for 64)
+    double* red = reinterpret_cast<double*>(sgen + TBM * SROW * 4);     // [RL][CH][2], behind the staging tile
     const bool epi = tid < TNT;          // the MMA warp only takes part in the barriers below
     const int cg = (epi ? tid : 0) % CG, r0 = (epi ? tid : 0) / CG;
-    const int n = n0 + cg * 4;
     const bool do_stats = a.stat_sum != nullptr;
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.bias != nullptr) bv = ldg4(a.bias + n);
-    float4 rs, rt;
-    load_affine4(a.res.scale, a.res.shift, n, rs, rt);
-    double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    // rows are processed 8 at a time with all global loads (residual / previous output) issued first,
-    // so their latency is paid once per batch instead of once per row
-    constexpr int ROWS = TBM / RL;       // rows per thread (32 / 16 / 8)
-    const bool has_res = a.res.z != nullptr, has_aff = a.res.scale != nullptr;
+    const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
 #pragma unroll 1
-    for (int g = 0; epi && g < ROWS; g += 8) {
-        float4 rr[8], oo[8];
+    for (int ch = 0; ch < BN / CH; ++ch) {
+        if (warp < 8) {
+            const int lq = warp & 3;
+            const int row = lq * 32 + lane;
+            const int cbeg = (warp >> 2) * (CH / 2);
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + CH / 2; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * CH + c0);
+                tmem_ld32(taddr, r);
+                float acc[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long p = m0 + r0 + (g + i) * RL;
-            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p < a.P) {
-                if (has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n);
-                if (a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n);
+                for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(r[q]);
+                // remaining accumulators (second hi*hi chain, cross terms): fp32 round-to-nearest adds.
+                // With a single stage the second main accumulator was never written.
+#pragma unroll
+                for (int e = 1; e < NACC; ++e) {
+                    if (NMAIN > 1 && e == 1 && T < 2) continue;
+                    tmem_ld32(taddr + (uint32_t)(e * BN), r);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(r[q]);
+                }
+                float* dst = stg + row * SROW + c0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    st4(dst + q * 4, make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (ch == BN / CH - 1) {
+            if (tid == 0) HGK_STAMP(6);
+            if (warp == 0)
+                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        }
+        const int n = n0 + ch * CH + cg * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias != nullptr) bv = ldg4(a.bias + n);
+        float4 rs, rt;
+        load_affine4(a.res.scale, a.res.shift, n, rs, rt);
+        double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+        float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+        // rows are processed 4 at a time with all global loads (residual / previous output) issued first,
+        // so their latency is paid once per batch instead of once per row
+#pragma unroll 1
+        for (int g = 0; epi && g < ROWS; g += 4) {
+            float4 rr[4], oo[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + (g + i) * RL;
-            const long long p = m0 + r;
-            if (p >= a.P) break;
-            float4 v = ld4(stg + r * SROW + cg * 4);
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if (has_res) {
-                float4 q = rr[i];
-                if (has_aff) q = act4(q, rs, rt, a.res.relu);
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            for (int i = 0; i < 4; ++i) {
+                const long long p = m0 + r0 + (g + i) * RL;
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p < a.P) {
+                    if (has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n);
+                    if (a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n);
+                }
             }
-            v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
-            st4(a.y + p * a.Cout + n, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + (g + i) * RL;
+                const long long p = m0 + r;
+                if (p >= a.P) break;
+                float4 v = ld4(stg + r * SROW + cg * 4);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                if (has_res) {
+                    float4 q = rr[i];
+                    if (res_aff) q = act4(q, rs, rt, a.res.relu);
+                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                }
+                v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
+                st4(a.y + p * a.Cout + n, v);
+                if (do_stats) {
+                    s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                    s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                    s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                    s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                }
+            }
             if (do_stats) {
-                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
             }
         }
         if (do_stats) {
+            if (epi) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+                for (int j = 0; j < 4; ++j) {
+                    red[((r0 * CH) + cg * 4 + j) * 2 + 0] = d1[j];
+                    red[((r0 * CH) + cg * 4 + j) * 2 + 1] = d2[j];
+                }
+            }
+            __syncthreads();
+            if (tid < CH) {
+                double x1 = 0.0, x2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    x1 += red[((q * CH) + tid) * 2 + 0];
+                    x2 += red[((q * CH) + tid) * 2 + 1];
+                }
+                atomicAdd(a.stat_sum + n0 + ch * CH + tid, x1);
+                atomicAdd(a.stat_sq + n0 + ch * CH + tid, x2);
+            }
         }
+        if (ch + 1 < BN / CH) __syncthreads();       // staging tile is rewritten by the next chunk
     }
     if (tid == 0) HGK_STAMP(7);
-    if (do_stats) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
-        double* red = reinterpret_cast<double*>(sgen + TBM * SROW * 4);     // [RL][BN][2], behind the staging tile
-        if (epi) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                red[((r0 * BN) + cg * 4 + j) * 2 + 0] = d1[j];
-                red[((r0 * BN) + cg * 4 + j) * 2 + 1] = d2[j];
-            }
-        }
-        __syncthreads();
-        if (tid < BN) {
-            double x1 = 0.0, x2 = 0.0;
-#pragma unroll
-            for (int q = 0; q < RL; ++q) {
-                x1 += red[((q * BN) + tid) * 2 + 0];
-                x2 += red[((q * BN) + tid) * 2 + 1];
-            }
-            atomicAdd(a.stat_sum + n0 + tid, x1);
-            atomicAdd(a.stat_sq + n0 + tid, x2);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -656,20 +649,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
         };
         load(0);
         if (T > 1) load(1);
-        if (PF == 4) {
-            if (T > 2) load(2);
-            if (T > 3) load(3);
-        }
         int s = 0;
         unsigned em_par = 1;               // parity of the previous use of the stage (toggles when s wraps)
         for (int it = 0; it < T; ++it) {
             if (it >= NST) mbar_wait(bar_empty + 8 * s, em_par);
-            if (PF == 4) { HGK_SEL4(it, store, s, ); } else { if (it & 1) store(s, 1); else store(s, 0); }
+            if (it & 1) store(s, 1); else store(s, 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_full + 8 * s);
-            if (it + PF < T) {
-                if (PF == 4) { HGK_SEL4(it, load, ); } else { if (it & 1) load(1); else load(0); }
-            }
+            if (it + PF < T) { if (it & 1) load(1); else load(0); }
             if (++s == NST) { s = 0; em_par ^= 1u; }
         }
         if (do_bias) {
@@ -819,7 +806,7 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
 template <int BN, bool SPLIT>
 static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
-    constexpr int smem = tc_smem_bytes(BN, SPLIT);
+    constexpr int smem = TcCfg<BN, SPLIT>::SMEM;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
