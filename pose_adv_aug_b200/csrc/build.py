@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libhgk.so")
-SOURCES = ["conv_simt.cu", "conv_tc.cu", "stem.cu", "bn.cu", "pointwise.cu", "loss_optim.cu"]
+SOURCES = ["conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "stem.cu", "bn.cu", "pointwise.cu", "loss_optim.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 
@@ -41,9 +41,10 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if (not force) and os.path.exists(o) and os.path.getmtime(o) > max(
-                os.path.getmtime(s), os.path.getmtime(os.path.join(HERE, "common.cuh")),
-                os.path.getmtime(os.path.join(os.path.dirname(PKG), "include", "hgk.h"))):
+        hdrs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))]
+        hdrs.append(os.path.join(os.path.dirname(PKG), "include", "hgk.h"))
+        if (not force) and os.path.exists(o) and os.path.getmtime(o) > max([os.path.getmtime(s)] +
+                                                                           [os.path.getmtime(h) for h in hdrs]):
             continue
         cmd = [_nvcc()] + flags + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

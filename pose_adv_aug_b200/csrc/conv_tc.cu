@@ -15,93 +15,14 @@
 //     commits to the stage's mbarrier, which frees the stage for the producers;
 //   * epilogue: tcgen05.ld -> shared staging tile -> coalesced bias/residual/accumulate/store and
 //     fp64 per-channel statistics.
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_args.cuh"
+#include "tc_common.cuh"
 
 namespace hgk {
 
-struct TcArgs {
-    ConvArgs c;
-    const float* w_hi;
-    const float* w_lo;
-    long long* dbg;      // optional timeline buffer (developer diagnostics): [cta][16] globaltimer stamps
-};
-
-static long long* g_dbg_buf = nullptr;
-
-__device__ __forceinline__ long long gtimer() {
-    long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define HGK_STAMP(slot)                                                                   \
-    do {                                                                                  \
-        if (args.dbg != nullptr && blockIdx.x < 512) args.dbg[blockIdx.x * 16 + (slot)] = gtimer(); \
-    } while (0)
-
-constexpr int TBM = 128, TNT = 256;
-__host__ __device__ constexpr int tc_staging_bytes(int BN) { return TBM * (BN + 4) * 4 + 16384; }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B (rows 16 B apart);
-// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;     // descriptor version 1 (Blackwell)
-    return d;
-}
-// round-to-nearest (ties away) to TF32 = add half an ulp of the 10-bit mantissa and clear the low 13 bits.
-// (cvt.rna.tf32.f32 has no single-instruction lowering on sm_100a: ptxas expands it to ~8 integer ops,
-// which made the producers issue-bound; inf stays inf, NaN stays NaN.)
-__device__ __forceinline__ float tf32_rna(float v) {
-    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-}
-// BN+ReLU on load with the ReLU expressed as a clamp value (0 or -inf): one FFMA + one FMNMX per element
-__device__ __forceinline__ float4 actc4(float4 v, float4 s, float4 t, float clampv) {
-    return make_float4(fmaxf(fmaf(v.x, s.x, t.x), clampv), fmaxf(fmaf(v.y, s.y, t.y), clampv),
-                       fmaxf(fmaf(v.z, s.z, t.z), clampv), fmaxf(fmaf(v.w, s.w, t.w), clampv));
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
+long long* g_dbg_buf = nullptr;
 
 // Per-instantiation configuration.  Everything is sized so that TWO CTAs fit on one SM (<= ~97 KB of shared
 // memory, <= 256 TMEM columns, <= 112 registers): while one CTA is in its prologue (TMEM alloc, first loads)
@@ -129,20 +50,6 @@ struct TcCfg {
     static_assert(NACC * BN <= 256, "two CTAs per SM share the 512 TMEM columns");
     static_assert(NST >= 2, "pipeline needs two stages");
 };
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args) {
@@ -495,15 +402,18 @@ constexpr int WG_THREADS = 288;       // 8 producer/epilogue warps + 1 MMA warp
 __host__ __device__ constexpr int wg_a_bytes() { return 8 * (TBM * 16 + 16); }
 __host__ __device__ constexpr int wg_b_bytes(int BN) { return 8 * (BN * 16 + 16); }
 __host__ __device__ constexpr int wg_stage_bytes(int BN) { return (wg_a_bytes() + wg_b_bytes(BN) + 127) / 128 * 128; }
+// one CTA per SM, four stages (two CTAs per SM were tried: the 112-register cap spills the producers)
+__host__ __device__ constexpr int wg_num_stages(int BN) { return 4; }
+__host__ __device__ constexpr int wg_stg_bytes(int BN) { return TBM * ((BN > 128 ? 128 : BN) + 4) * 4; }
 __host__ __device__ constexpr int wg_smem_bytes(int BN) {
-    int p = 4 * wg_stage_bytes(BN);
-    int s = tc_staging_bytes(BN);
+    int p = wg_num_stages(BN) * wg_stage_bytes(BN);
+    int s = wg_stg_bytes(BN);
     return (p > s ? p : s) + 256;
 }
 
 template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs a) {
-    constexpr int NST = 4;
+    constexpr int NST = wg_num_stages(BN);
     constexpr int A_BYTES = wg_a_bytes(), STAGE = wg_stage_bytes(BN);
     constexpr uint32_t LBO_A = TBM * 16 + 16, LBO_B = BN * 16 + 16, SBO = 128;
     constexpr int NBLK = BN > 128 ? 2 : 1;      // 4x4 x-blocks per producer thread per stage
@@ -688,49 +598,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // producers have observed the last commit: accumulator complete, smem reusable
 
-    // ---- epilogue: TMEM -> staging tile -> coalesced vector atomics ----
+    // ---- epilogue, in column chunks of CH: TMEM -> staging tile -> coalesced vector atomics ----
     float* stg = reinterpret_cast<float*>(sgen);
-    constexpr int SROW = BN + 4;
-    if (warp < 8) {
-        const int lq = warp & 3;
-        const int row = lq * 32 + lane;
-        const int cbeg = (warp >> 2) * (BN / 2);
+    constexpr int CH = BN > 128 ? 128 : BN, SROW = CH + 4;
 #pragma unroll 1
-        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float* dst = stg + row * SROW + c0;
+    for (int ch = 0; ch < BN / CH; ++ch) {
+        if (warp < 8) {
+            const int lq = warp & 3;
+            const int row = lq * 32 + lane;
+            const int cbeg = (warp >> 2) * (CH / 2);
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + CH / 2; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * CH + c0), r);
+                float* dst = stg + row * SROW + c0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+                for (int q = 0; q < 8; ++q)
+                    st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                                 __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+            }
         }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
-    }
-    if (tid < 256) {
-        constexpr int CG = BN / 4, RL = 256 / CG;
-        const int cg = tid % CG, r0 = tid / CG;
-        for (int r = r0; r < TBM; r += RL) {
-            const int co = co0 + r;
-            if (co >= a.Cout) break;
-            float4 v = ld4(stg + r * SROW + cg * 4);
-            red_add_v4(a.dw + ((size_t)tap * a.Cout + co) * a.Cin + cg * 4, v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (ch == BN / CH - 1 && warp == 0) {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
         }
+        if (tid < 256) {
+            constexpr int CG = CH / 4, RL = 256 / CG;
+            const int cg = tid % CG, r0 = tid / CG;
+            for (int r = r0; r < TBM; r += RL) {
+                const int co = co0 + r;
+                if (co >= a.Cout) break;
+                float4 v = ld4(stg + r * SROW + cg * 4);
+                red_add_v4(a.dw + ((size_t)tap * a.Cout + co) * a.Cin + ch * CH + cg * 4, v);
+            }
+        }
+        if (ch + 1 < BN / CH) __syncthreads();
     }
 }
 
@@ -823,7 +726,22 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
 
 }  // namespace hgk
 
+namespace hgk {
+int conv_tcp_launch(const TcArgs& ta, bool split, void* stream);      // conv_tcp.cu (persistent kernel)
+}
+
 using namespace hgk;
+
+// HGK_TC_PERSIST=1 selects the persistent warp-specialised kernel of conv_tcp.cu (experimental: its
+// 4-warp epilogue is currently the bottleneck, so the two-CTAs-per-SM kernel above is the default)
+static bool use_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HGK_TC_PERSIST");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 extern "C" int hgk_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin > 0 && Cin % 32 == 0 && (Cout == 64 || Cout == 128 || Cout == 256) && (ksize == 1 || ksize == 3)) ? 1 : 0;
@@ -854,7 +772,8 @@ extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const floa
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool split = w_lo != nullptr;
-    if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
+    if (use_persistent()) rc = conv_tcp_launch(ta, split, stream);
+    else if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
     else if (Cout == 128) rc = split ? launch_tc<128, true>(ta, st) : launch_tc<128, false>(ta, st);
     else rc = split ? launch_tc<256, true>(ta, st) : launch_tc<256, false>(ta, st);
     if (rc != HGK_OK) return rc;
