@@ -559,6 +559,64 @@ class Plan(object):
         return [op.gin for op in self.tape if isinstance(op, _InputOp)]
 
 
+def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads")):
+    """Assign each launch of a static list to one of `n_streams` streams.
+
+    Dependencies are derived conservatively from the launch arguments: two launches that share ANY
+    device pointer are ordered (read-read sharing only costs a little parallelism, never correctness);
+    launches named in `barrier_names` take base pointers of whole arenas and are ordered against
+    everything.  Returns (stream index per launch, list of predecessor indices per launch that live on
+    another stream and therefore need an event).  The hourglass has coarse branch parallelism (skip
+    residuals vs the down/up chain, weight- vs data-gradients): this lets the latency-bound 4x4 / 8x8 /
+    16x16 layers run under the large 64x64 ones inside one CUDA graph."""
+    PTR_MIN = 1 << 32
+    last_touch = {}
+    tail = [-1] * n_streams            # last launch index per stream
+    stream_of, cross = [], []
+    barrier = -1
+    lru = list(range(n_streams))
+    waited = [[-1] * n_streams for _ in range(n_streams)]   # waited[k][kd]: newest launch of stream kd that k already waits for
+    for i, (fn, args, name) in enumerate(launches):
+        ptrs = [a for a in args if isinstance(a, int) and a >= PTR_MIN]
+        if name in barrier_names:
+            deps = set(t for t in tail if t >= 0)
+        else:
+            deps = set(last_touch[p] for p in ptrs if p in last_touch)
+            if barrier >= 0:
+                deps.add(barrier)
+        k = None
+        for d in sorted(deps, reverse=True):       # continue on the stream of the most recent dependency
+            if tail[stream_of[d]] == d:
+                k = stream_of[d]
+                break
+        if k is None:
+            free = [q for q in lru if tail[q] < 0]
+            k = free[0] if free else lru[0]
+        lru.remove(k)
+        lru.append(k)
+        need = []
+        for d in deps:
+            kd = stream_of[d]
+            if kd != k and not any(stream_of[e] == kd and e > d for e in need):
+                need.append(d)
+        # a later event on the same foreign stream covers earlier ones
+        best = {}
+        for d in need:
+            kd = stream_of[d]
+            if d > waited[k][kd]:
+                best[kd] = max(best.get(kd, -1), d)
+        for kd, d in best.items():
+            waited[k][kd] = d
+        cross.append(sorted(best.values()))
+        stream_of.append(k)
+        tail[k] = i
+        for p in ptrs:
+            last_touch[p] = i
+        if name in barrier_names:
+            barrier = i
+    return stream_of, cross
+
+
 class _PackRef(object):
     __slots__ = ("off",)
 

@@ -13,7 +13,7 @@ from . import dist as hdist
 
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None):
+                 distributed=None, n_streams=4):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
@@ -42,6 +42,8 @@ class HourglassTrainer(object):
         self.plan = plan
         self.graph = None
         self.graph_update = None
+        self._sched = None
+        self.n_streams = n_streams
         self.use_graph = use_graph
         self.steps = 0
 
@@ -58,6 +60,65 @@ class HourglassTrainer(object):
         st.grad.zero_()
         plan.run_forward([self.x, self.t])
         plan.run_backward([self.x, self.t], [None] * len(plan.outputs))
+
+    def _body_grads_multistream(self, n_streams=4):
+        """Same work as _body_grads, but the static launch list is spread over several streams according to
+        its data dependencies (engine.schedule_streams).  Only used under CUDA-graph capture, where the
+        fork/join events become graph edges."""
+        from .engine import schedule_streams
+        st, plan = self.store, self.plan
+        main = torch.cuda.current_stream(self.device)
+        self.loss_acc.zero_()
+        st.grad.zero_()
+        for (key, t), x in zip(plan.inputs, [self.x, self.t]):
+            plan.patch(key, x.data_ptr())
+        if plan.stat_f_used:
+            plan.stat_f[:plan.stat_f_used].zero_()
+        if plan.stat_b_used:
+            plan.stat_b[:plan.stat_b_used].zero_()
+        if plan.wg_buf is not None:
+            plan.wg_buf.zero_()
+        for op in plan.outputs:
+            if not op.no_grad and op.gsrc is not None:
+                op.gsrc.zero_()
+                plan.patch("gout%d" % op.index, op.gsrc.data_ptr())
+        launches = []
+        if plan.pack_launch is not None:
+            launches.append(plan.pack_launch)
+        if plan.tc_launch is not None:
+            launches.append(plan.tc_launch)
+        launches += plan.fwd + plan.bwd
+        if self._sched is None:
+            self._sched = schedule_streams(launches, n_streams)
+        stream_of, cross = self._sched
+        side = [torch.cuda.Stream(self.device) for _ in range(n_streams - 1)]
+        streams = [main] + side
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for s_ in side:
+            s_.wait_event(fork)
+        events = {}
+        users = set(d for c in cross for d in c)
+        for i, (fn, args, name) in enumerate(launches):
+            sk = streams[stream_of[i]]
+            for d in cross[i]:
+                sk.wait_event(events[d])
+            rc = fn(*args, sk.cuda_stream)
+            if rc != 0:
+                raise HGKError("%s failed (%d): %s" % (name, rc, self.lib.last_error()))
+            if i in users:
+                ev = torch.cuda.Event()
+                ev.record(sk)
+                events[i] = ev
+        for s_ in side:                      # join
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            main.wait_event(ev)
+        for f in plan.nbt_flat:
+            f.add_(1)
+        for b in plan.nbt_bufs:
+            b.add_(1)
+        plan.fwd_count += 1
 
     def _body_update(self):
         """flat RMSprop (1/world folded in) + loss accumulator -> fp32 scalar."""
@@ -105,15 +166,17 @@ class HourglassTrainer(object):
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
+        grads = self._body_grads if self.n_streams <= 1 else (lambda: self._body_grads_multistream(self.n_streams))
         if self.world > 1:
             with torch.cuda.graph(self.graph):
-                self._body_grads()
+                grads()
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_update):
                 self._body_update()
         else:
             with torch.cuda.graph(self.graph):
-                self._step_body()
+                grads()
+                self._body_update()
         # restore the state consumed by the warm-up step
         self.store.flat.copy_(saved[0])
         self.square_avg.copy_(saved[1])

@@ -20,6 +20,7 @@ ap.add_argument("--chan", type=int, default=256)
 ap.add_argument("--stacks", type=int, default=2)
 ap.add_argument("--top", type=int, default=25)
 ap.add_argument("--conv-path", type=int, default=0)
+ap.add_argument("--filter", default="")
 args = ap.parse_args()
 M.CONV_PATH = args.conv_path
 dev = torch.device("cuda", 0)
@@ -79,6 +80,14 @@ tot = sum(v[1] for v in agg.values())
 print("step (event-timed, launches serialized on one stream): %.2f ms, %d launches" % (tot, len(recs)))
 for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:args.top]:
     print("%-34s %4d %9.3f ms %5.1f%%" % (k, c, t, 100 * t / tot))
+if args.filter:
+    print("--- launches matching", args.filter)
+    seen = collections.OrderedDict()
+    for ms, key, desc in rows:
+        if args.filter in key:
+            seen.setdefault((key, desc), []).append(ms)
+    for (key, desc), v in seen.items():
+        print("%-30s %-22s n=%2d avg %7.1f us" % (key, desc, len(v), 1e3 * sum(v) / len(v)))
 print("--- slowest launches")
 rows.sort(reverse=True)
 for r in rows[:20]:
