@@ -379,7 +379,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-path", type=int, default=None)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=6)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 2 if args.steps is None else args.steps

@@ -559,31 +559,57 @@ class Plan(object):
         return [op.gin for op in self.tape if isinstance(op, _InputOp)]
 
 
+# argument positions written by each entry point (everything else is read-only); used by schedule_streams
+_WRITES = {
+    "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20),
+    "conv_wgrad_nhwc": (11, 15), "conv_wgrad_tc_nhwc": (11, 12),
+    "bn_finalize": (7, 8, 9, 10, 11, 12), "bn_eval_prepare": (5, 6, 7, 8),
+    "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
+    "maxpool2_fwd": (8,), "maxpool2_bwd": (9,), "add_fwd": (13,), "upsample2_bwd": (5,), "add_into": (1,),
+    "nchw_to_nhwc": (5,), "nhwc_to_nchw": (8,),
+    "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7),
+    "mse_fwd_bwd": (5, 7), "avgpool_fwd": (9,), "avgpool_bwd": (6,), "linear_fwd": (6,), "linear_bwd": (6, 7, 8),
+}
+
+
 def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads")):
     """Assign each launch of a static list to one of `n_streams` streams.
 
-    Dependencies are derived conservatively from the launch arguments: two launches that share ANY
-    device pointer are ordered (read-read sharing only costs a little parallelism, never correctness);
-    launches named in `barrier_names` take base pointers of whole arenas and are ordered against
-    everything.  Returns (stream index per launch, list of predecessor indices per launch that live on
-    another stream and therefore need an event).  The hourglass has coarse branch parallelism (skip
-    residuals vs the down/up chain, weight- vs data-gradients): this lets the latency-bound 4x4 / 8x8 /
-    16x16 layers run under the large 64x64 ones inside one CUDA graph."""
+    Dependencies are derived from the launch arguments (device pointers; `_WRITES` says which positions
+    an entry point writes): read-after-write, write-after-write and write-after-read orderings are kept,
+    read-read sharing is free.  Launches named in `barrier_names` take base pointers of whole arenas and are
+    ordered against everything.  Returns (stream index per launch, for each launch the launches on OTHER
+    streams it has to wait for).  The hourglass has coarse branch parallelism (skip residuals vs the down/up
+    chain, weight- vs data-gradients): this lets the latency-bound 4x4 / 8x8 / 16x16 layers run under the
+    large 64x64 ones inside one CUDA graph."""
     PTR_MIN = 1 << 32
-    last_touch = {}
+    last_write = {}                    # ptr -> launch index of the last writer
+    readers = {}                       # ptr -> launch indices that read it since that write
     tail = [-1] * n_streams            # last launch index per stream
     stream_of, cross = [], []
     barrier = -1
     lru = list(range(n_streams))
     waited = [[-1] * n_streams for _ in range(n_streams)]   # waited[k][kd]: newest launch of stream kd that k already waits for
     for i, (fn, args, name) in enumerate(launches):
-        ptrs = [a for a in args if isinstance(a, int) and a >= PTR_MIN]
+        wpos = _WRITES.get(name)
+        rd, wr = [], []
+        for j, a in enumerate(args):
+            if isinstance(a, int) and a >= PTR_MIN:
+                (wr if (wpos is None or j in wpos) else rd).append(a)
         if name in barrier_names:
             deps = set(t for t in tail if t >= 0)
         else:
-            deps = set(last_touch[p] for p in ptrs if p in last_touch)
+            deps = set()
+            for p in rd:
+                if p in last_write:
+                    deps.add(last_write[p])
+            for p in wr:
+                if p in last_write:
+                    deps.add(last_write[p])
+                deps.update(readers.get(p, ()))
             if barrier >= 0:
                 deps.add(barrier)
+        deps.discard(i)
         k = None
         for d in sorted(deps, reverse=True):       # continue on the stream of the most recent dependency
             if tail[stream_of[d]] == d:
@@ -594,24 +620,21 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
             k = free[0] if free else lru[0]
         lru.remove(k)
         lru.append(k)
-        need = []
+        best = {}
         for d in deps:
             kd = stream_of[d]
-            if kd != k and not any(stream_of[e] == kd and e > d for e in need):
-                need.append(d)
-        # a later event on the same foreign stream covers earlier ones
-        best = {}
-        for d in need:
-            kd = stream_of[d]
-            if d > waited[k][kd]:
+            if kd != k and d > waited[k][kd]:
                 best[kd] = max(best.get(kd, -1), d)
         for kd, d in best.items():
             waited[k][kd] = d
         cross.append(sorted(best.values()))
         stream_of.append(k)
         tail[k] = i
-        for p in ptrs:
-            last_touch[p] = i
+        for p in rd:
+            readers.setdefault(p, []).append(i)
+        for p in wr:
+            last_write[p] = i
+            readers[p] = []
         if name in barrier_names:
             barrier = i
     return stream_of, cross

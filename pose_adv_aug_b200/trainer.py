@@ -13,7 +13,7 @@ from . import dist as hdist
 
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None, n_streams=4):
+                 distributed=None, n_streams=6):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)

@@ -1,0 +1,87 @@
+"""CPU check of engine.schedule_streams: for the full config-2 step, every data dependency between two
+launches (RAW / WAW / WAR on any device pointer) is enforced by stream order or by a chain of event waits."""
+import torch
+
+from pose_adv_aug_b200.engine import Plan, ParamStore, schedule_streams, _WRITES
+from pose_adv_aug_b200.models import asn_stacked_hg as M
+
+
+def _plan():
+    net = M.create_hg(2, 1, 16, 256)
+    dev = torch.device("cpu")
+    st = ParamStore(net, dev)
+    plan = Plan([st], dev, True, True)
+    img = plan.input_image(2, 256, 256)
+    tgt = plan.target_nchw(2, 16, 64, 64)
+    acc = torch.zeros(1, dtype=torch.float64)
+    outs, _ = net._build(plan, img)
+    for o in outs:
+        plan.mse_loss(o, tgt, acc)
+        plan.output_nchw(o, no_grad=True)
+    plan.finish()
+    keep = (torch.zeros(2, 3, 256, 256), torch.zeros(2, 16, 64, 64))
+    plan.patch("image", keep[0].data_ptr())
+    plan.patch("target", keep[1].data_ptr())
+    return plan, keep, [plan.pack_launch, plan.tc_launch] + plan.fwd + plan.bwd
+
+
+def test_schedule_respects_every_dependency():
+    plan, keep, L = _plan()
+    for ns in (2, 4):
+        so, cross = schedule_streams(L, ns)
+        assert len(so) == len(L) and max(so) < ns
+        # vector clocks: vc[i][k] = newest launch on stream k that is ordered before (or is) launch i
+        vc, tail = [], [-1] * ns
+        for i in range(len(L)):
+            k = so[i]
+            c = list(vc[tail[k]]) if tail[k] >= 0 else [-1] * ns
+            for d in cross[i]:
+                assert so[d] != k and d < i
+                c = [max(x, y) for x, y in zip(c, vc[d])]
+            c[k] = i
+            vc.append(c)
+            tail[k] = i
+        # recompute true dependencies independently of the scheduler
+        PTR_MIN = 1 << 32
+        last_write, readers, barrier = {}, {}, -1
+        barriers = ("pack_weights", "pack_weights_tc", "unpack_add_grads")
+        n_dep = 0
+        for i, (fn, args, name) in enumerate(L):
+            wpos = _WRITES.get(name)
+            rd = [a for j, a in enumerate(args) if isinstance(a, int) and a >= PTR_MIN and wpos is not None and j not in wpos]
+            wr = [a for j, a in enumerate(args) if isinstance(a, int) and a >= PTR_MIN and (wpos is None or j in wpos)]
+            deps = set()
+            if name in barriers:
+                deps = set(range(i))
+            else:
+                for p in rd:
+                    if p in last_write:
+                        deps.add(last_write[p])
+                for p in wr:
+                    if p in last_write:
+                        deps.add(last_write[p])
+                    deps.update(readers.get(p, ()))
+                if barrier >= 0:
+                    deps.add(barrier)
+            for d in deps:
+                if d == i:
+                    continue
+                n_dep += 1
+                assert vc[i][so[d]] >= d, "launch %d (%s) not ordered after %d (%s)" % (i, name, d, L[d][2])
+            for p in rd:
+                readers.setdefault(p, []).append(i)
+            for p in wr:
+                last_write[p] = i
+                readers[p] = []
+            if name in barriers:
+                barrier = i
+        assert n_dep > 1000
+        # and there is real parallelism: no stream holds more than 60 % of the launches
+        assert max(so.count(k) for k in range(ns)) < 0.6 * len(L) or ns == 2
+
+
+def test_write_table_covers_plan_entry_points():
+    plan, keep, L = _plan()
+    names = set(r[2] for r in L)
+    for n in names:
+        assert n in _WRITES or n in ("pack_weights", "pack_weights_tc", "unpack_add_grads"), n

@@ -88,6 +88,39 @@ if args.filter:
             seen.setdefault((key, desc), []).append(ms)
     for (key, desc), v in seen.items():
         print("%-30s %-22s n=%2d avg %7.1f us" % (key, desc, len(v), 1e3 * sum(v) / len(v)))
+# critical path of the dependency DAG with these per-launch times (what infinitely many streams could reach)
+from pose_adv_aug_b200.engine import _WRITES
+PTR_MIN = 1 << 32
+last_write, readers, barrier = {}, {}, -1
+finish = []
+for i, (fn, a, name) in enumerate(recs):
+    ms = evs[i].elapsed_time(evs[i + 1])
+    wpos = _WRITES.get(name)
+    rd = [x for j, x in enumerate(a) if isinstance(x, int) and x >= PTR_MIN and wpos is not None and j not in wpos]
+    wr = [x for j, x in enumerate(a) if isinstance(x, int) and x >= PTR_MIN and (wpos is None or j in wpos)]
+    deps = set()
+    if wpos is None:
+        deps = set(range(i))
+    else:
+        for p_ in rd:
+            if p_ in last_write:
+                deps.add(last_write[p_])
+        for p_ in wr:
+            if p_ in last_write:
+                deps.add(last_write[p_])
+            deps.update(readers.get(p_, ()))
+        if barrier >= 0:
+            deps.add(barrier)
+    start = max([finish[d] for d in deps], default=0.0)
+    finish.append(start + ms)
+    for p_ in rd:
+        readers.setdefault(p_, []).append(i)
+    for p_ in wr:
+        last_write[p_] = i
+        readers[p_] = []
+    if wpos is None:
+        barrier = i
+print("critical path of the launch DAG: %.2f ms (sum of launches %.2f ms)" % (max(finish), tot))
 print("--- slowest launches")
 rows.sort(reverse=True)
 for r in rows[:20]:
