@@ -61,6 +61,16 @@ int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const float* x_shift,
                      const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
                      const float* res, const float* res_scale, const float* res_shift, int res_relu,
                      float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream);
+/* Data gradient of a convolution whose INPUT was relu(bn(bz)), with the reduction pass of that BatchNorm's
+ * backward fused into the epilogue:  dy = [accumulate ? dy : 0] + conv^T(dz) + extra;
+ * sum_g += sum_p g, sum_gx += sum_p g*xhat,  g = dy*[bz*bscale+bshift > 0], xhat = (bz-bmean)*binvstd.
+ * Only valid when this launch produces the COMPLETE gradient of that activation (single consumer). */
+int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int W, int Cin,
+                                   const float* w_hi, const float* w_lo, int ksize, int Cout,
+                                   const float* extra, float* dy, int accumulate,
+                                   const float* bz, const float* bscale, const float* bshift, int brelu,
+                                   const float* bmean, const float* binvstd,
+                                   double* sum_g, double* sum_gx, void* stream);
 /* table: n_entries x 8 int64 {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN};
  * mode 0 (forward operand): B[n][k;tap] = W[o=n][i=k][tap];  mode 1 (data-gradient operand):
  * B[n][k;tap] = W[o=k][i=n][taps-1-tap].  Destination: [n-tile][tap][k/32] blocks of [8][BN][4] floats,

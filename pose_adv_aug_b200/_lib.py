@@ -17,6 +17,7 @@ SIGNATURES = {
     "hgk_conv_wgrad_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, L, L, L, P, P],
     "hgk_pack_weights": [P, P, P, I, P],
     "hgk_conv_tc_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P, P],
+    "hgk_conv_tc_dgrad_bnstats_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P, P],
     "hgk_pack_weights_tc": [P, P, P, I, P],
     "hgk_conv_wgrad_tc_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, P, P],
     "hgk_unpack_add_grads": [P, P, P, I, P],

@@ -17,6 +17,15 @@ struct ConvArgs {
     double* stat_sum;
     double* stat_sq;
     long long P;
+    // BN-backward statistics mode (tcgen05 kernel only): the output is dL/d relu(bn(bz)); instead of sum(y), sum(y^2)
+    // the epilogue accumulates stat_sum += sum g, stat_sq += sum g*xhat with g = y*[bz*bscale+bshift > 0],
+    // xhat = (bz - bmean)*binvstd  (the reduction pass of nn.BatchNorm2d's backward, fused)
+    const float* bz;
+    const float* bscale;
+    const float* bshift;
+    const float* bmean;
+    const float* binvstd;
+    int brelu;
 };
 
 }  // namespace hgk

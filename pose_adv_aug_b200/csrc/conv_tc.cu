@@ -51,7 +51,7 @@ struct TcCfg {
     static_assert(NST >= 2, "pipeline needs two stages");
 };
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool BWDSTATS>
 __global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args) {
     using Cfg = TcCfg<BN, SPLIT>;
     constexpr int BK = Cfg::BK, NJ = Cfg::NJ, NST = Cfg::NST, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
@@ -301,21 +301,26 @@ __global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args)
         if (a.bias != nullptr) bv = ldg4(a.bias + n);
         float4 rs, rt;
         load_affine4(a.res.scale, a.res.shift, n, rs, rt);
+        constexpr bool bwd_stats = BWDSTATS;      // separate instantiation: keeps the common kernels lean
+        float4 bsc = make_float4(1.f, 1.f, 1.f, 1.f), bsh = make_float4(0.f, 0.f, 0.f, 0.f), bmu = bsh, biv = bsc;
+        if (bwd_stats) { bsc = ldg4(a.bscale + n); bsh = ldg4(a.bshift + n); bmu = ldg4(a.bmean + n); biv = ldg4(a.binvstd + n); }
         double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
         float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-        // rows are processed 4 at a time with all global loads (residual / previous output) issued first,
-        // so their latency is paid once per batch instead of once per row
+        // rows are processed 4 at a time with all global loads (residual / previous output / BN input) issued
+        // first, so their latency is paid once per batch instead of once per row
 #pragma unroll 1
         for (int g = 0; epi && g < ROWS; g += 4) {
-            float4 rr[4], oo[4];
+            float4 rr[4], oo[4], zz[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const long long p = m0 + r0 + (g + i) * RL;
                 rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                zz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p < a.P) {
                     if (has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n);
                     if (a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n);
+                    if (bwd_stats) zz[i] = ldg4(a.bz + p * a.Cout + n);
                 }
             }
 #pragma unroll
@@ -333,10 +338,22 @@ __global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args)
                 v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
                 st4(a.y + p * a.Cout + n, v);
                 if (do_stats) {
-                    s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-                    s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-                    s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-                    s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                    if (bwd_stats) {
+                        const float4 z = zz[i];
+                        const float gx = (a.brelu && fmaf(z.x, bsc.x, bsh.x) <= 0.f) ? 0.f : v.x;
+                        const float gy = (a.brelu && fmaf(z.y, bsc.y, bsh.y) <= 0.f) ? 0.f : v.y;
+                        const float gz = (a.brelu && fmaf(z.z, bsc.z, bsh.z) <= 0.f) ? 0.f : v.z;
+                        const float gw = (a.brelu && fmaf(z.w, bsc.w, bsh.w) <= 0.f) ? 0.f : v.w;
+                        s1[0] += gx; s2[0] = fmaf(gx, (z.x - bmu.x) * biv.x, s2[0]);
+                        s1[1] += gy; s2[1] = fmaf(gy, (z.y - bmu.y) * biv.y, s2[1]);
+                        s1[2] += gz; s2[2] = fmaf(gz, (z.z - bmu.z) * biv.z, s2[2]);
+                        s1[3] += gw; s2[3] = fmaf(gw, (z.w - bmu.w) * biv.w, s2[3]);
+                    } else {
+                        s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                        s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                        s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                        s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                    }
                 }
             }
             if (do_stats) {
@@ -706,12 +723,12 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
     }
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool BWDSTATS = false>
 static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
     constexpr int smem = TcCfg<BN, SPLIT>::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, BWDSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
@@ -720,7 +737,7 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     }
     long long mt = (ta.c.P + TBM - 1) / TBM;
     dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN));
-    conv_tc_kernel<BN, SPLIT><<<grid, TNT + 32, smem, st>>>(ta);
+    conv_tc_kernel<BN, SPLIT, BWDSTATS><<<grid, TNT + 32, smem, st>>>(ta);
     return HGK_OK;
 }
 
@@ -747,11 +764,13 @@ extern "C" int hgk_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin > 0 && Cin % 32 == 0 && (Cout == 64 || Cout == 128 || Cout == 256) && (ksize == 1 || ksize == 3)) ? 1 : 0;
 }
 
-extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
-                                int N, int H, int W, int Cin,
-                                const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
-                                const float* res, const float* res_scale, const float* res_shift, int res_relu,
-                                float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream) {
+static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                        int N, int H, int W, int Cin,
+                        const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                        const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                        float* y, int accumulate, double* stat_sum, double* stat_sq,
+                        const float* bz, const float* bscale, const float* bshift, const float* bmean,
+                        const float* binvstd, int brelu, void* stream) {
     HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
     HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
     HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
@@ -767,18 +786,43 @@ extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const floa
     ta.c.res = Act{res, res_scale, res_shift, res_relu};
     ta.c.y = y; ta.c.accumulate = accumulate; ta.c.stat_sum = stat_sum; ta.c.stat_sq = stat_sq;
     ta.c.P = (long long)N * H * W;
+    ta.c.bz = bz; ta.c.bscale = bscale; ta.c.bshift = bshift; ta.c.bmean = bmean; ta.c.binvstd = binvstd; ta.c.brelu = brelu;
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool split = w_lo != nullptr;
-    if (use_persistent()) rc = conv_tcp_launch(ta, split, stream);
+    if (bz != nullptr) {
+        HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
+        rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
+                        : (Cout == 128 ? launch_tc<128, false, true>(ta, st) : launch_tc<256, false, true>(ta, st));
+    } else if (use_persistent()) rc = conv_tcp_launch(ta, split, stream);
     else if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
     else if (Cout == 128) rc = split ? launch_tc<128, true>(ta, st) : launch_tc<128, false>(ta, st);
     else rc = split ? launch_tc<256, true>(ta, st) : launch_tc<256, false>(ta, st);
     if (rc != HGK_OK) return rc;
     HGK_CHECK_LAUNCH("hgk_conv_tc_nhwc");
     return HGK_OK;
+}
+
+extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                int N, int H, int W, int Cin,
+                                const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                                const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                                float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream) {
+    return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_lo, ksize, bias, Cout, res, res_scale, res_shift,
+                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int W, int Cin,
+                                              const float* w_hi, const float* w_lo, int ksize, int Cout,
+                                              const float* extra, float* dy, int accumulate,
+                                              const float* bz, const float* bscale, const float* bshift, int brelu,
+                                              const float* bmean, const float* binvstd,
+                                              double* sum_g, double* sum_gx, void* stream) {
+    HGK_REQUIRE(bz && bscale && bshift && bmean && binvstd && sum_g && sum_gx, "hgk_conv_tc_dgrad_bnstats_nhwc: null pointer");
+    return conv_tc_impl(dz, nullptr, nullptr, 0, N, H, W, Cin, w_hi, w_lo, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
+                        dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, stream);
 }
 
 /* developer diagnostics: per-CTA globaltimer stamps of conv_tc_kernel ([512][16] int64), NULL disables */

@@ -11,6 +11,7 @@ PyTorch is used for device memory, streams and autograd glue only; every arithme
 path is a libhgk kernel.
 """
 import ctypes
+import os
 
 import torch
 
@@ -129,7 +130,7 @@ class ParamStore(object):
 class T(object):
     """A tensor node of the plan: NHWC buffer z [N,H,W,C] + optional on-load affine/ReLU."""
     __slots__ = ("z", "N", "H", "W", "C", "scale", "shift", "relu", "needs_grad", "grad", "contribs",
-                 "producer", "name")
+                 "producer", "name", "bn", "n_cons", "bwd_stats_fused")
 
     def __init__(self, z, N, H, W, C, scale=None, shift=None, relu=False, needs_grad=False, name=""):
         self.z, self.N, self.H, self.W, self.C = z, N, H, W, C
@@ -139,6 +140,13 @@ class T(object):
         self.contribs = []        # pending (buffer, donatable) gradient contributions
         self.producer = None
         self.name = name
+        self.bn = None            # BNRec whose (scale, shift) this tensor carries
+        self.n_cons = 0           # number of ops that consume this tensor
+        self.bwd_stats_fused = False   # the BN-backward reduction was produced by the consumer's data-gradient kernel
+
+    def use(self):
+        self.n_cons += 1
+        return self
 
     @property
     def P(self):
@@ -180,6 +188,7 @@ class Plan(object):
         # gradients: plain TF32 operands by default (error below the fp32-vs-fp64 noise floor of the
         # whole net); precise_grads -> 3xTF32 data gradients + fp32 SIMT weight gradients
         self.precise_grads = precise_grads
+        self.fuse_bn_bwd = os.environ.get("HGK_FUSE_BN_BWD", "1") == "1"   # fold BN-backward reductions into single-consumer data-gradient epilogues
         self.tc_entries = []       # (src param, mode, BN, hi offset, lo offset or -1)
         self.tc_used = 0
         self.tc_buf = None
@@ -411,6 +420,7 @@ class Plan(object):
 
     def detach(self, x):
         """Same values, no gradient flow (x.detach(), models/asn_stacked_hg.py:161)."""
+        x.use()      # a detached reader still means "more than one consumer" for fusion decisions
         return T(x.z, x.N, x.H, x.W, x.C, x.scale, x.shift, x.relu, needs_grad=False, name=x.name + ".detached")
 
     def target_nchw(self, N, C, H, W):
@@ -561,7 +571,7 @@ class Plan(object):
 
 # argument positions written by each entry point (everything else is read-only); used by schedule_streams
 _WRITES = {
-    "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20),
+    "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20), "conv_tc_dgrad_bnstats_nhwc": (10, 18, 19),
     "conv_wgrad_nhwc": (11, 15), "conv_wgrad_tc_nhwc": (11, 12),
     "bn_finalize": (7, 8, 9, 10, 11, 12), "bn_eval_prepare": (5, 6, 7, 8),
     "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
@@ -696,6 +706,7 @@ class _StemOp(object):
         p.dynamic("image", rec, 0)
         self.out = T(z, N, H // 2, W // 2, Cout, r.scale, r.shift, True, needs_grad=p.need_grad, name="stem")
         self.out.producer = self
+        self.out.bn = r
         if r.training:
             p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
                      BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
@@ -714,8 +725,9 @@ class _StemOp(object):
 
 def _emit_bn_bwd(p, o, r, g):
     """dY (buffer g, gradient w.r.t. relu(bn(z))) -> dz in place."""
-    p.launch(p.bwd, "bn_bwd_reduce", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean),
-             _ptr(r.invstd), o.P, o.C, _ptr(r.sum_g), _ptr(r.sum_gx))
+    if not o.bwd_stats_fused:      # otherwise the consumer's data-gradient kernel already accumulated sum_g / sum_gx
+        p.launch(p.bwd, "bn_bwd_reduce", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean),
+                 _ptr(r.invstd), o.P, o.C, _ptr(r.sum_g), _ptr(r.sum_gx))
     p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
              int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
     p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA),
@@ -727,6 +739,9 @@ class _ConvOp(object):
 
     def __init__(self, plan, x, conv, bn, res, relu):
         self.plan, self.x, self.conv, self.res = plan, x, conv, res
+        x.use()
+        if res is not None:
+            res.use()
         p = plan
         w = conv.weight
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
@@ -754,6 +769,7 @@ class _ConvOp(object):
                                            [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0, 0]))
         if r is not None:
             self.out = T(z, x.N, x.H, x.W, Cout, r.scale, r.shift, relu, needs_grad=p.need_grad, name="conv")
+            self.out.bn = r
             if r.training:
                 p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
                          BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
@@ -786,8 +802,18 @@ class _ConvOp(object):
             gx, acc, extra = p.grad_target(x)
             if p.use_tc and p.lib.conv_tc_supported(Cout, Cin, k):
                 hi, lo = p.packed_weight_tc(w, 1, p.precise_grads)   # plain TF32 is enough for gradients
-                p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, lo, k, 0, Cin,
-                         _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0)
+                if (x.bn is not None and x.n_cons == 1 and acc == 0 and not x.contribs and p.fuse_bn_bwd
+                        and not p.precise_grads):
+                    # this launch produces the complete dL/d relu(bn(z)) of the previous layer: fuse that
+                    # BatchNorm's backward reduction (sum g, sum g*xhat) into the epilogue
+                    r = x.bn
+                    p.launch(p.bwd, "conv_tc_dgrad_bnstats_nhwc", _ptr(g), x.N, x.H, x.W, Cout, hi, lo, k, Cin,
+                             _ptr(extra), _ptr(gx), acc, _ptr(x.z), _ptr(x.scale), _ptr(x.shift), int(x.relu),
+                             _ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g), _ptr(r.sum_gx))
+                    x.bwd_stats_fused = True
+                else:
+                    p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, lo, k, 0, Cin,
+                             _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0)
             else:
                 wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))
                 p.launch(p.bwd, "conv_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, wref, k, 1, 0, Cin,
@@ -802,6 +828,7 @@ class _PoolOp(object):
 
     def __init__(self, plan, x):
         self.plan, self.x = plan, x
+        x.use()
         if x.H % 2 or x.W % 2:
             raise ValueError("max-pool input must have even H, W (got %dx%d)" % (x.H, x.W))
         z = plan.buf(x.N, x.H // 2, x.W // 2, x.C)
@@ -823,6 +850,8 @@ class _AddOp(object):
 
     def __init__(self, plan, a, b, up):
         self.plan, self.a, self.b, self.up = plan, a, b, up
+        a.use()
+        b.use()
         if a.C != b.C or a.N != b.N or (a.H * (2 if up else 1), a.W * (2 if up else 1)) != (b.H, b.W):
             raise ValueError("add: shape mismatch")
         z = plan.buf(b.N, b.H, b.W, b.C)
@@ -849,6 +878,7 @@ class _AvgPoolOp(object):
 
     def __init__(self, plan, x, k):
         self.plan, self.x, self.k = plan, x, k
+        x.use()
         if x.H < k or x.W < k:
             raise ValueError("avg-pool kernel %d larger than input %dx%d" % (k, x.H, x.W))
         z = plan.buf(x.N, x.H // k, x.W // k, x.C)
@@ -870,6 +900,7 @@ class _LinearOp(object):
 
     def __init__(self, plan, x, fc):
         self.plan, self.x, self.fc = plan, x, fc
+        x.use()
         if x.H != 1 or x.W != 1 or x.scale is not None:
             raise ValueError("linear expects a plain [N,1,1,C] tensor")
         Nout, K = fc.weight.shape
@@ -899,6 +930,7 @@ class _LinearOp(object):
 class _MSEOp(object):
     def __init__(self, plan, o, target, loss_acc, gscale):
         self.plan, self.o = plan, o
+        o.use()
         if o.scale is not None or (o.N, o.H, o.W, o.C) != (target.N, target.H, target.W, target.C):
             raise ValueError("mse_loss expects a plain output and a target of the same shape")
         n = o.P * o.C
@@ -914,6 +946,8 @@ class _MSEOp(object):
 class _OutputOp(object):
     def __init__(self, plan, x, index, rows=False, no_grad=False):
         self.plan, self.x, self.index, self.rows, self.no_grad = plan, x, index, rows, no_grad
+        if not no_grad:
+            x.use()
         p = plan
         if rows:
             if x.H != 1 or x.W != 1 or x.scale is not None:
