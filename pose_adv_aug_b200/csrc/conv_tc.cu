@@ -654,6 +654,247 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 3x3 weight gradient, three taps (one kernel row dh, dw = -1,0,+1) per CTA: the dz tile is staged once and
+// shared by three MMAs, and the three column-shifted x tiles are built in registers from ONE 6-pixel load
+// (pixels p-1 .. p+4 of the row shifted by dh).  Per tap this needs 3.3 instead of 8 global loads and a
+// third of the barrier hand-shakes of wgrad_tc_kernel.  Requires W % 4 == 0 (4-pixel chunks never straddle
+// image rows) and Cin <= 128 (3 accumulators of BN columns in TMEM).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int wg3_stage_bytes(int BN) { return (wg_a_bytes() + 3 * wg_b_bytes(BN) + 127) / 128 * 128; }
+__host__ __device__ constexpr int wg3_num_stages(int BN) { return BN > 64 ? 3 : 4; }
+__host__ __device__ constexpr int wg3_smem_bytes(int BN) {
+    int p = wg3_num_stages(BN) * wg3_stage_bytes(BN);
+    int s = wg_stg_bytes(BN);
+    return (p > s ? p : s) + 256;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad3_tc_kernel(const WgTcArgs a) {
+    constexpr int NST = wg3_num_stages(BN);
+    constexpr int A_BYTES = wg_a_bytes(), B_BYTES = wg_b_bytes(BN), STAGE = wg3_stage_bytes(BN);
+    constexpr uint32_t LBO_A = TBM * 16 + 16, LBO_B = BN * 16 + 16, SBO = 128;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    constexpr int TMEM_COLS = 3 * BN <= 256 ? 256 : 512;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 4];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int co0 = blockIdx.x * TBM, dhg = blockIdx.y;          // dhg = tap row: taps 3*dhg .. 3*dhg+2
+    const int dh = dhg - 1;
+    const long long p_begin = (long long)blockIdx.z * a.chunk;
+    const long long p_end = (p_begin + a.chunk < a.P) ? (p_begin + a.chunk) : a.P;
+    const int T = (int)((p_end - p_begin + 31) / 32);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[4]);
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_full + 8 * s, 256);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== producers =====
+        const int c_low = lane & 7, q_low = lane >> 3;
+        const int HW = a.H * a.W;
+        const int a_quad = warp * 4 + q_low;
+        const int a_c = co0 + a_quad * 4;
+        const bool a_cok = a_c < a.Cout;
+        const bool b_on = (BN >= 128) || (warp < 4);
+        const int b_quad = warp * 4 + q_low;
+        float4 xs, xt;
+        load_affine4(a.x.scale, a.x.shift, b_on ? b_quad * 4 : 0, xs, xt);
+        const bool has_aff = a.x.scale != nullptr;
+        const float x_clamp = a.x.relu ? 0.f : -INFINITY;
+        float4 ra[2][4], rb[2][6];
+        unsigned bmsk[2] = {0u, 0u};
+        float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool do_bias = a.dbias != nullptr && dhg == 0;
+        long long l_p = p_begin + c_low * 4;
+        int l_h, l_w;
+        {
+            const int rem = (int)(l_p % HW);
+            l_h = rem / a.W;
+            l_w = rem - l_h * a.W;
+        }
+        const float* dzp = a.dz + a_c;
+        const float* xzp = a.x.z + b_quad * 4;
+        auto load = [&](int set) {
+            const bool pv = l_p < p_end;                              // chunks are all-valid or all-invalid (W % 4 == 0)
+            const unsigned o_dz = (unsigned)(l_p * a.Cout);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pv && a_cok) v = ldg4(dzp + (o_dz + j * a.Cout));
+                ra[set][j] = v;
+            }
+            unsigned m = 0;
+            if (b_on) {
+                const bool hv = pv && (unsigned)(l_h + dh) < (unsigned)a.H;
+                const long long src0 = (l_p + (long long)dh * a.W - 1) * a.Cin;       // pixel p0-1 of the shifted row
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const bool ok = hv && (unsigned)(l_w - 1 + i) < (unsigned)a.W;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        v = ldg4(xzp + (src0 + (long long)i * a.Cin));
+                        m |= 1u << i;
+                    }
+                    rb[set][i] = v;
+                }
+            }
+            bmsk[set] = m;
+            l_p += 32;
+            l_w += 32;
+            while (l_w >= a.W) {
+                l_w -= a.W;
+                if (++l_h == a.H) l_h = 0;
+            }
+        };
+        auto store = [&](int s, int set) {
+            uint8_t* sa = sgen + s * STAGE + c_low * LBO_A + a_quad * 64;
+            const float4 r0 = ra[set][0], r1 = ra[set][1], r2 = ra[set][2], r3 = ra[set][3];
+            if (do_bias) {
+                bsum[0] += (r0.x + r1.x) + (r2.x + r3.x);
+                bsum[1] += (r0.y + r1.y) + (r2.y + r3.y);
+                bsum[2] += (r0.z + r1.z) + (r2.z + r3.z);
+                bsum[3] += (r0.w + r1.w) + (r2.w + r3.w);
+            }
+            *reinterpret_cast<float4*>(sa + 0) = tf32_rna4(make_float4(r0.x, r1.x, r2.x, r3.x));
+            *reinterpret_cast<float4*>(sa + 16) = tf32_rna4(make_float4(r0.y, r1.y, r2.y, r3.y));
+            *reinterpret_cast<float4*>(sa + 32) = tf32_rna4(make_float4(r0.z, r1.z, r2.z, r3.z));
+            *reinterpret_cast<float4*>(sa + 48) = tf32_rna4(make_float4(r0.w, r1.w, r2.w, r3.w));
+            if (b_on) {
+                float4 x[6];
+                const unsigned m = bmsk[set];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float4 v = rb[set][i];
+                    if (has_aff && ((m >> i) & 1u)) v = actc4(v, xs, xt, x_clamp);     // padding = zero of the activated tensor
+                    x[i] = tf32_rna4(v);
+                }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {                     // tap dw = t-1: output pixel j reads source pixel j+t
+                    uint8_t* sb = sgen + s * STAGE + A_BYTES + t * B_BYTES + c_low * LBO_B + b_quad * 64;
+                    *reinterpret_cast<float4*>(sb + 0) = make_float4(x[t].x, x[t + 1].x, x[t + 2].x, x[t + 3].x);
+                    *reinterpret_cast<float4*>(sb + 16) = make_float4(x[t].y, x[t + 1].y, x[t + 2].y, x[t + 3].y);
+                    *reinterpret_cast<float4*>(sb + 32) = make_float4(x[t].z, x[t + 1].z, x[t + 2].z, x[t + 3].z);
+                    *reinterpret_cast<float4*>(sb + 48) = make_float4(x[t].w, x[t + 1].w, x[t + 2].w, x[t + 3].w);
+                }
+            }
+        };
+        load(0);
+        if (T > 1) load(1);
+        int s = 0;
+        unsigned em_par = 1;
+        for (int it = 0; it < T; ++it) {
+            if (it >= NST) mbar_wait(bar_empty + 8 * s, em_par);
+            if (it & 1) store(s, 1); else store(s, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_full + 8 * s);
+            if (it + 2 < T) { if (it & 1) load(1); else load(0); }
+            if (++s == NST) { s = 0; em_par ^= 1u; }
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = bsum[j];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (c_low == 0 && a_cok) atomicAdd(a.dbias + a_c + j, v);
+            }
+        }
+        mbar_wait(bar_empty + 8 * ((T - 1) % NST), ((T - 1) / NST) & 1);
+    } else if (lane == 0) {
+        // ===== MMA issuer: 3 taps x 4 k-steps per stage =====
+        for (int it = 0; it < T; ++it) {
+            const int s = it % NST, u = it / NST;
+            mbar_wait(bar_full + 8 * s, u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = sbase + s * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_desc(sa + k * 2 * LBO_A, LBO_A, SBO);
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    umma_tf32(tmem + t * BN, da, umma_desc(sb + t * B_BYTES + k * 2 * LBO_B, LBO_B, SBO), IDESC,
+                              (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * s);
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // ---- epilogue: per tap, TMEM -> staging tile -> coalesced vector atomics ----
+    float* stg = reinterpret_cast<float*>(sgen);
+    constexpr int SROW = BN + 4;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        if (warp < 8) {
+            const int lq = warp & 3;
+            const int row = lq * 32 + lane;
+            const int cbeg = (warp >> 2) * (BN / 2);
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * BN + c0), r);
+                float* dst = stg + row * SROW + c0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    st4(dst + q * 4, make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                                 __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 2 && warp == 0) {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        }
+        if (tid < 256) {
+            constexpr int CG = BN / 4, RL = 256 / CG;
+            const int cg = tid % CG, r0 = tid / CG;
+            const int tap = dhg * 3 + t;
+            for (int r = r0; r < TBM; r += RL) {
+                const int co = co0 + r;
+                if (co >= a.Cout) break;
+                float4 v = ld4(stg + r * SROW + cg * 4);
+                red_add_v4(a.dw + ((size_t)tap * a.Cout + co) * a.Cin + cg * 4, v);
+            }
+        }
+        if (t < 2) __syncthreads();
+    }
+}
+
+template <int BN>
+static int launch_wg3(const WgTcArgs& a, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = wg3_smem_bytes(BN);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("hgk_conv_wgrad_tc_nhwc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+            return HGK_ECUDA;
+        }
+        configured = true;
+    }
+    wgrad3_tc_kernel<BN><<<grid, WG_THREADS, smem, st>>>(a);
+    return HGK_OK;
+}
+
 // grads of 3x3 convs are accumulated tap-major ([tap][O][I]) by the tensor-core kernel; this adds them
 // into the OIHW-shaped .grad views.  table rows (5 x int64): {src_off, dst_off, O, I, taps}
 __global__ void unpack_add_grads_kernel(const float* __restrict__ src, float* __restrict__ dst,
@@ -860,8 +1101,24 @@ extern "C" int hgk_conv_wgrad_tc_nhwc(const float* x, const float* x_scale, cons
     a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.dz = dz; a.Cout = Cout; a.ksize = ksize;
     a.dw = dw_tap_major; a.dbias = dbias;
     a.P = (long long)N * H * W;
-    const int taps = ksize * ksize;
     const int mtiles = (Cout + TBM - 1) / TBM;
+    if (ksize == 3 && W % 4 == 0 && Cin <= 128 && getenv("HGK_WGRAD3_OFF") == nullptr) {
+        // three taps per CTA (wgrad3_tc_kernel)
+        long long want3 = kNumSMs / (mtiles * 3);
+        if (want3 < 1) want3 = 1;
+        long long max3 = (a.P + 511) / 512;
+        long long sp = want3 > max3 ? max3 : want3;
+        long long ck = (a.P + sp - 1) / sp;
+        ck = (ck + 31) / 32 * 32;
+        sp = (a.P + ck - 1) / ck;
+        a.chunk = ck;
+        dim3 grid3((unsigned)mtiles, 3u, (unsigned)sp);
+        int rc3 = Cin == 64 ? launch_wg3<64>(a, grid3, (cudaStream_t)stream) : launch_wg3<128>(a, grid3, (cudaStream_t)stream);
+        if (rc3 != HGK_OK) return rc3;
+        HGK_CHECK_LAUNCH("hgk_conv_wgrad_tc_nhwc");
+        return HGK_OK;
+    }
+    const int taps = ksize * ksize;
     // split the pixel range so that ~1 CTA per SM runs, but keep >= 16 stages (512 pixels) per CTA so the
     // atomics epilogue stays small against the main loop
     long long want = kNumSMs / (mtiles * taps);
