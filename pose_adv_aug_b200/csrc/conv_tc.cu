@@ -27,15 +27,18 @@ long long* g_dbg_buf = nullptr;
 // Per-instantiation configuration.  Everything is sized so that TWO CTAs fit on one SM (<= ~97 KB of shared
 // memory, <= 256 TMEM columns, <= 112 registers): while one CTA is in its prologue (TMEM alloc, first loads)
 // or epilogue, the other one keeps the tensor pipe and the memory system busy.
-template <int BN, bool SPLIT>
+// BIG = one CTA per SM with 32-channel stages and the whole shared memory: used when the grid has at most one
+// CTA per SM anyway (the 4x4 .. 32x32 layers), where fewer, larger stages shorten the latency-bound pipeline.
+template <int BN, bool SPLIT, bool BIG = false>
 struct TcCfg {
-    static constexpr int BK = (SPLIT && BN >= 128) ? 16 : 32;              // channels per pipeline stage
+    static constexpr int BK = (!BIG && SPLIT && BN >= 128) ? 16 : 32;      // channels per pipeline stage
     static constexpr int QP = BK / 4;                                       // 16-byte channel quads per pixel per stage
     static constexpr int NJ = QP / 2;                                       // (pixel, quad) items per producer thread
     static constexpr int A_BYTES = TBM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int NST = (96 * 1024 / STAGE) > 4 ? 4 : (96 * 1024 / STAGE);
+    static constexpr int SMEM_BUDGET = BIG ? 196 * 1024 : 96 * 1024;
+    static constexpr int NST = (SMEM_BUDGET / STAGE) > 4 ? 4 : (SMEM_BUDGET / STAGE);
     // The tensor core accumulates in fp32 with truncation: a chain of n dependent accumulations carries a
     // systematic ~n*2^-25 relative shrink (1.3e-5 measured at K = 9*256 with all three 3xTF32 terms in one
     // chain).  So the hi*hi products and the two small cross terms get separate TMEM accumulators (BN = 64:
@@ -51,9 +54,9 @@ struct TcCfg {
     static_assert(NST >= 2, "pipeline needs two stages");
 };
 
-template <int BN, bool SPLIT, bool BWDSTATS>
-__global__ void __launch_bounds__(TNT + 32, 2) conv_tc_kernel(const TcArgs args) {
-    using Cfg = TcCfg<BN, SPLIT>;
+template <int BN, bool SPLIT, bool BWDSTATS, bool BIG>
+__global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const TcArgs args) {
+    using Cfg = TcCfg<BN, SPLIT, BIG>;
     constexpr int BK = Cfg::BK, NJ = Cfg::NJ, NST = Cfg::NST, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE = Cfg::STAGE, TMEM_COLS = Cfg::TMEM_COLS;
     constexpr uint32_t LBO_A = TBM * 16, LBO_B = BN * 16, SBO = 128;
@@ -964,12 +967,12 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
     }
 }
 
-template <int BN, bool SPLIT, bool BWDSTATS = false>
-static int launch_tc(const TcArgs& ta, cudaStream_t st) {
+template <int BN, bool SPLIT, bool BWDSTATS, bool BIG>
+static int launch_tc_cfg(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
-    constexpr int smem = TcCfg<BN, SPLIT>::SMEM;
+    constexpr int smem = TcCfg<BN, SPLIT, BIG>::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, BWDSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
@@ -978,8 +981,16 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     }
     long long mt = (ta.c.P + TBM - 1) / TBM;
     dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN));
-    conv_tc_kernel<BN, SPLIT, BWDSTATS><<<grid, TNT + 32, smem, st>>>(ta);
+    conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG><<<grid, TNT + 32, smem, st>>>(ta);
     return HGK_OK;
+}
+
+template <int BN, bool SPLIT, bool BWDSTATS = false>
+static int launch_tc(const TcArgs& ta, cudaStream_t st) {
+    // at most one CTA per SM anyway -> the large-stage single-CTA configuration
+    const long long ctas = ((ta.c.P + TBM - 1) / TBM) * (ta.c.Cout / BN);
+    if (ctas <= kNumSMs) return launch_tc_cfg<BN, SPLIT, BWDSTATS, true>(ta, st);
+    return launch_tc_cfg<BN, SPLIT, BWDSTATS, false>(ta, st);
 }
 
 }  // namespace hgk

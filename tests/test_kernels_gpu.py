@@ -376,6 +376,9 @@ TC_SHAPES = [
     (2, 8, 8, 128, 128, 3),
     (5, 12, 12, 128, 256, 1),
     (1, 20, 24, 256, 128, 3),
+    (8, 64, 64, 64, 128, 1),     # 256 tiles > 148 SMs: the two-CTAs-per-SM configuration
+    (5, 64, 64, 128, 128, 3),    # 160 tiles, 3x3
+    (5, 64, 64, 128, 256, 1),
 ]
 
 

@@ -92,7 +92,7 @@ if args.filter:
 from pose_adv_aug_b200.engine import _WRITES
 PTR_MIN = 1 << 32
 last_write, readers, barrier = {}, {}, -1
-finish = []
+finish, pred = [], []
 for i, (fn, a, name) in enumerate(recs):
     ms = evs[i].elapsed_time(evs[i + 1])
     wpos = _WRITES.get(name)
@@ -112,6 +112,7 @@ for i, (fn, a, name) in enumerate(recs):
         if barrier >= 0:
             deps.add(barrier)
     start = max([finish[d] for d in deps], default=0.0)
+    pred.append(max(deps, key=lambda d: finish[d]) if deps else -1)
     finish.append(start + ms)
     for p_ in rd:
         readers.setdefault(p_, []).append(i)
@@ -121,6 +122,15 @@ for i, (fn, a, name) in enumerate(recs):
     if wpos is None:
         barrier = i
 print("critical path of the launch DAG: %.2f ms (sum of launches %.2f ms)" % (max(finish), tot))
+cp = collections.defaultdict(lambda: [0, 0.0])
+i = max(range(len(finish)), key=lambda j: finish[j])
+while i >= 0:
+    cp[recs[i][2]][0] += 1
+    cp[recs[i][2]][1] += evs[i].elapsed_time(evs[i + 1])
+    i = pred[i]
+print("--- critical path by entry point")
+for k, (c, t) in sorted(cp.items(), key=lambda x: -x[1][1]):
+    print("  %-32s %4d %8.3f ms" % (k, c, t))
 print("--- slowest launches")
 rows.sort(reverse=True)
 for r in rows[:20]:
