@@ -340,16 +340,28 @@ def test_multistream_graph_equals_single_stream():
     for ns in (1, 4):
         net = _load(M.create_hg(S, Mo, K, C), sd).to(DEV)
         tr = HourglassTrainer(net, N, R, use_graph=True, n_streams=ns)
-        losses = [float(tr.step(x, t)) for _ in range(4)]
-        res.append((losses, [h.clone() for h in tr.heatmaps()], tr.store.flat.clone()))
-    # steps 0-1 agree to rounding; later steps inherit the float-atomics ordering noise of the weight gradients
-    # through RMSprop's sign-like first updates (the same spread exists between two single-stream runs)
-    for i, (la, lb) in enumerate(zip(res[0][0], res[1][0])):
-        assert abs(la - lb) < (2e-6 if i < 2 else 2e-3) * abs(la), (res[0][0], res[1][0])
-    for ha, hb in zip(res[0][1], res[1][1]):
-        assert relerr(ha, hb) < 5e-2
-    # forward is order-independent up to fp64-atomic BN statistics; the step-0 loss must match to fp32 rounding
-    assert abs(res[0][0][0] - res[1][0][0]) < 1e-6 * abs(res[0][0][0])
+        losses, hms, grads = [], [], []
+        for _ in range(4):
+            losses.append(float(tr.step(x, t)))
+            hms.append([h.clone() for h in tr.heatmaps()])
+            grads.append(tr.store.grad.clone())
+        res.append((losses, hms, grads))
+    (la, ha, ga), (lb, hb, gb) = res
+    # step 0 sees identical parameters: the forward is order-independent up to the fp64-atomic BN statistics and the
+    # gradients up to the order of the float atomics of the weight-gradient reduction
+    assert abs(la[0] - lb[0]) < 1e-6 * abs(la[0])
+    for a, b in zip(ha[0], hb[0]):
+        assert relerr(a, b) < 1e-5
+    assert float((ga[0] - gb[0]).norm() / ga[0].norm()) < 1e-4
+    # step 1 runs on parameters updated from those gradients (a missing dependency edge would show here)
+    assert abs(la[1] - lb[1]) < 2e-6 * abs(la[1]), (la, lb)
+    for a, b in zip(ha[1], hb[1]):
+        assert relerr(a, b) < 5e-3
+    # later steps inherit the atomics ordering noise through RMSprop's sign-like first updates (lr * g / sqrt(0.01 g^2):
+    # a sign flip of a near-zero gradient moves a weight by 2 * 10 * lr); the same spread exists between two
+    # single-stream runs, so only the loss is compared from here on
+    for i in (2, 3):
+        assert abs(la[i] - lb[i]) < 2e-3 * abs(la[i]), (la, lb)
 
 
 def test_cpu_input_fails_loudly():
