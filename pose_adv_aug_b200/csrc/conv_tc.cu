@@ -414,9 +414,6 @@ struct WgTcArgs {
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ float4 tf32_rna4(float4 v) {
-    return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-}
 
 constexpr int WG_THREADS = 288;       // 8 producer/epilogue warps + 1 MMA warp
 __host__ __device__ constexpr int wg_a_bytes() { return 8 * (TBM * 16 + 16); }
@@ -997,6 +994,10 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
 
 namespace hgk {
 int conv_tcp_launch(const TcArgs& ta, bool split, void* stream);      // conv_tcp.cu (persistent kernel)
+bool conv_tc2_eligible(const TcArgs& ta);                             // conv_tc2.cu (16x16 image-tile kernel)
+int wgrad_tc2_try(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W, int Cin,
+                  const float* dz, int Cout, int ksize, float* dw, float* dbias, void* stream);   // wgrad_tc2.cu (MN-major)
+int conv_tc2_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream);
 }
 
 using namespace hgk;
@@ -1014,6 +1015,16 @@ static bool use_persistent() {
 
 extern "C" int hgk_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin > 0 && Cin % 32 == 0 && (Cout == 64 || Cout == 128 || Cout == 256) && (ksize == 1 || ksize == 3)) ? 1 : 0;
+}
+
+// HGK_TC2_OFF=1 disables the image-tile kernel of conv_tc2.cu (every shape then takes conv_tc_kernel)
+static bool use_tile_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HGK_TC2_OFF");
+        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shift, int x_relu,
@@ -1044,8 +1055,10 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const bool split = w_lo != nullptr;
-    if (bz != nullptr) {
+    if (bz != nullptr)
         HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
+    if (use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
+    else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
                         : (Cout == 128 ? launch_tc<128, false, true>(ta, st) : launch_tc<256, false, true>(ta, st));
     } else if (use_persistent()) rc = conv_tcp_launch(ta, split, stream);
@@ -1107,6 +1120,14 @@ extern "C" int hgk_conv_wgrad_tc_nhwc(const float* x, const float* x_scale, cons
                 "(need Cin in {64,128,256}, Cout %% 4 == 0, k in {1,3})", Cin, Cout, ksize);
     HGK_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "hgk_conv_wgrad_tc_nhwc: x scale/shift must both be set");
     HGK_REQUIRE((uintptr_t)dw_tap_major % 16 == 0, "hgk_conv_wgrad_tc_nhwc: dw must be 16-byte aligned");
+    {
+        const int r2 = wgrad_tc2_try(x, x_scale, x_shift, x_relu, N, H, W, Cin, dz, Cout, ksize, dw_tap_major, dbias, stream);
+        if (r2 < 0) return r2;
+        if (r2 == 1) {
+            HGK_CHECK_LAUNCH("hgk_conv_wgrad_tc_nhwc");
+            return HGK_OK;
+        }
+    }
     WgTcArgs a;
     a.x = Act{x, x_scale, x_shift, x_relu};
     a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.dz = dz; a.Cout = Cout; a.ksize = ksize;

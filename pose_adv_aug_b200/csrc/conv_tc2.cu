@@ -1,0 +1,424 @@
+// tcgen05 implicit-GEMM convolution over 16x16-pixel IMAGE TILES (M = 256 output pixels per CTA) -- the
+// kernel for every layer whose H and W are multiples of 16 (16x16 .. 128x128).  Same contract as
+// conv_tc_kernel (conv_tc.cu): BN+ReLU on load, 3xTF32 (forward) or plain TF32 (data gradient), bias /
+// shortcut / accumulate / BN-statistics (or fused BN-backward reduction) epilogue.
+//
+// Why tiles: the 128-linear-pixel kernel re-reads its activation tile once per 3x3 tap and re-streams the
+// whole packed weight matrix per 128 pixels; at 64x64 both flows go through L2 at ~10x the compulsory HBM
+// bytes and L2 -> SM bandwidth (about the HBM bandwidth on B200) becomes the bound (profiles/r1b_tc_summary.md).
+// Here
+//   * the activation HALO tile (18x18 pixels x 16 channels for 3x3; 16x16 for 1x1) is loaded, transformed
+//     (BN+ReLU, TF32 hi/lo split) and stored to shared memory ONCE per 16-channel chunk, in a layout where
+//     pixel (hh, ww) of channel quad q sits at q*LBO + (hh*HW + ww)*16 bytes: an 8-pixel run of one image row
+//     is one UMMA core matrix (8 rows x 16 B, K-major, no swizzle), the next row is SBO = HW*16 bytes further.
+//     The nine taps are nine MMAs on the SAME tile with the descriptor start address shifted by
+//     (dh*HW + dw)*16 bytes -- no im2col, no re-load;
+//   * each weight stage (one tap x 16 channels x Cout, hi and lo) arrives by cp.async.bulk (TMA bulk copy) and
+//     is used by both 128-pixel halves of the tile (columns 0-7 and 8-15), halving the weight stream per pixel;
+//   * roles: warps 0-7 load/transform/store the halo tiles (two chunks of register prefetch), warp 8 issues
+//     tcgen05.mma.kind::tf32 into TMEM and commits stages back, warp 9 streams the weights; all 8 producer
+//     warps then run the epilogue (tcgen05.ld -> smem tile -> coalesced stores + fp64 channel statistics).
+#include "common.cuh"
+#include "conv_args.cuh"
+#include "tc_common.cuh"
+
+namespace hgk {
+
+constexpr int T2_THREADS = 320;      // 8 producer/epilogue warps + MMA warp + weight-copy warp
+
+template <int BN, bool SPLIT, int KS>
+struct T2Cfg {
+    static constexpr int TH = 16, TW = 16;
+    static constexpr int PAD = KS / 2;
+    static constexpr int HH = TH + 2 * PAD, HWD = TW + 2 * PAD;           // halo tile
+    static constexpr int NPIX = HH * HWD;
+    static constexpr int TAPS = KS * KS;
+    static constexpr int BK = 16, QP = 4;                                  // channels / 16-byte quads per chunk
+    static constexpr int NITEM = NPIX * QP;                                // (pixel, quad) items per chunk
+    static constexpr int NJ = (NITEM + 255) / 256;                         // items per producer thread
+    // quad stride: pixels*16 rounded to 128 plus 32 -> the four quads of a pixel pair fall into distinct banks
+    static constexpr int LBO_A = (NPIX * 16 + 127) / 128 * 128 + 32;
+    static constexpr int SBO_A = HWD * 16;
+    static constexpr int A_HALF = QP * LBO_A;
+    static constexpr int A_STAGE = (SPLIT ? 2 : 1) * A_HALF;
+    static constexpr int B_HALF = BN * BK * 4;
+    static constexpr int B_STAGE = (SPLIT ? 2 : 1) * B_HALF;
+    static constexpr int NSA = KS == 3 ? 2 : 3;                            // activation stages (one per chunk)
+    static constexpr int NSB = KS == 3 ? 8 : 3;                            // weight stages (one per chunk x tap)
+    static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
+    // accumulators per 128-pixel half, see conv_tc.cu (fp32 accumulator truncation of the tensor core)
+    static constexpr int NMAIN = (SPLIT && BN <= 64) ? 2 : 1;
+    static constexpr int NACC = !SPLIT ? 1 : (BN >= 256 ? 1 : NMAIN + 1);
+    static constexpr int SUBCOLS = NACC * BN;
+    static constexpr int TMEM_COLS = (2 * SUBCOLS <= 128) ? 128 : (2 * SUBCOLS <= 256) ? 256 : 512;
+    static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
+    static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
+    static constexpr int SMEM = (PIPE > STG_BYTES ? PIPE : STG_BYTES) + 256;
+    static_assert(2 * SUBCOLS <= 512, "TMEM capacity");
+    static_assert(A_HALF % 128 == 0 && B_HALF % 128 == 0, "stage alignment");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <int BN, bool SPLIT, int KS, bool BWDSTATS>
+__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs args) {
+    using Cfg = T2Cfg<BN, SPLIT, KS>;
+    constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
+    constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
+    constexpr uint32_t LBO_A = Cfg::LBO_A, SBO_A = Cfg::SBO_A, LBO_B = BN * 16, SBO_B = 128;
+    constexpr uint32_t A_HALF = Cfg::A_HALF, A_STAGE = Cfg::A_STAGE, B_HALF = Cfg::B_HALF, B_STAGE = Cfg::B_STAGE;
+    constexpr uint32_t B_OFF = NSA * A_STAGE;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    const ConvArgs& a = args.c;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * NSA + 2 * NSB + 1];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_w = a.W >> 4, tiles_hw = (a.H >> 4) * tiles_w;
+    const int n_img = blockIdx.x / tiles_hw;
+    const int trem = blockIdx.x - n_img * tiles_hw;
+    const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) << 4;
+    const int KC = a.Cin >> 4;
+    const uint32_t bar_fa = smem_u32(&bars[0]), bar_ea = smem_u32(&bars[NSA]);
+    const uint32_t bar_fb = smem_u32(&bars[2 * NSA]), bar_eb = smem_u32(&bars[2 * NSA + NSB]);
+    const uint32_t bar_done = smem_u32(&bars[2 * NSA + 2 * NSB]);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSA; ++s) {
+            mbar_init(bar_fa + 8 * s, 256);
+            mbar_init(bar_ea + 8 * s, 1);
+        }
+        for (int s = 0; s < NSB; ++s) {
+            mbar_init(bar_fb + 8 * s, 1);
+            mbar_init(bar_eb + 8 * s, 1);
+        }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== producers: halo tile of one 16-channel chunk -> registers -> BN+ReLU, hi/lo -> shared memory =====
+        // item idx = tid + 256*j: halo pixel idx>>2, channel quad idx&3 (= tid&3 for every j)
+        const int quad = tid & 3;
+        unsigned a_off[NJ], s_off[NJ];
+        unsigned vmask = 0, smask = 0;          // pixel inside the image / item inside the tile
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int idx = tid + 256 * j;
+            const int hp = idx >> 2;
+            const int hh = hp / HWD, ww = hp - hh * HWD;
+            const int h = th0 - PAD + hh, w = tw0 - PAD + ww;
+            const bool in_tile = idx < Cfg::NITEM;
+            const bool in_img = in_tile && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W;
+            a_off[j] = in_img ? (unsigned)((((long long)n_img * a.H + h) * a.W + w) * a.Cin) + quad * 4 : 0u;
+            s_off[j] = (unsigned)quad * LBO_A + (unsigned)hp * 16u;
+            if (in_img) vmask |= 1u << j;
+            if (in_tile) smask |= 1u << j;
+        }
+        const float* xz = a.x.z;
+        const bool has_aff = a.x.scale != nullptr;
+        const float x_clamp = a.x.relu ? 0.f : -INFINITY;
+        float4 a_reg[2][NJ];
+        auto load_a = [&](int set, int kc) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((vmask >> j) & 1u) v = ldg4(xz + (a_off[j] + (unsigned)kc * 16u));
+                a_reg[set][j] = v;
+            }
+        };
+        auto store_a = [&](int s, int set, int kc) {
+            float4 sc, sh;
+            load_affine4(a.x.scale, a.x.shift, kc * 16 + quad * 4, sc, sh);
+            uint8_t* base = sgen + s * A_STAGE;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (!((smask >> j) & 1u)) continue;
+                float4 v = a_reg[set][j];
+                // zero padding is a zero of the ACTIVATED tensor: transform only pixels inside the image
+                if (has_aff && ((vmask >> j) & 1u)) v = actc4(v, sc, sh, x_clamp);
+                const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                *reinterpret_cast<float4*>(base + s_off[j]) = hi;
+                if (SPLIT) {
+                    const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                    *reinterpret_cast<float4*>(base + A_HALF + s_off[j]) = lo;
+                }
+            }
+        };
+        load_a(0, 0);
+        if (KC > 1) load_a(1, 1);
+        int sa = 0;
+        unsigned ea_par = 1;                 // parity of the previous use of the stage (toggles when sa wraps)
+        for (int kc = 0; kc < KC; ++kc) {
+            if (kc >= NSA) mbar_wait(bar_ea + 8 * sa, ea_par);            // stage drained by the tensor core
+            if (kc & 1) store_a(sa, 1, kc); else store_a(sa, 0, kc);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+            mbar_arrive(bar_fa + 8 * sa);
+            if (kc + 2 < KC) { if (kc & 1) load_a(1, kc + 2); else load_a(0, kc + 2); }
+            if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
+        }
+        mbar_wait(bar_done, 0);              // every MMA retired: accumulators complete, shared memory reusable
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int sa = 0, sb = 0, it = 0;
+            unsigned fa_par = 0, fb_par = 0;
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(bar_fa + 8 * sa, fa_par);
+                const uint32_t a_stage = sbase + sa * A_STAGE;
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap, ++it) {
+                    mbar_wait(bar_fb + 8 * sb, fb_par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 16u : 0u);
+                    const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const uint32_t t_sub = tmem + sub * SUBCOLS;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t da = umma_desc(a_tap + sub * 128 + k * 2 * LBO_A, LBO_A, SBO_A);
+                            const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO_B);
+                            if (SPLIT) {
+                                const uint64_t dal = umma_desc(a_tap + A_HALF + sub * 128 + k * 2 * LBO_A, LBO_A, SBO_A);
+                                const uint64_t dbl = umma_desc(b_hi + B_HALF + k * 2 * LBO_B, LBO_B, SBO_B);
+                                if (NACC == 1) {
+                                    umma_tf32(t_sub, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                                    umma_tf32(t_sub, da, dbl, IDESC, 1u);
+                                    umma_tf32(t_sub, da, db, IDESC, 1u);
+                                } else {
+                                    const uint32_t t_small = t_sub + NMAIN * BN;
+                                    const uint32_t t_main = t_sub + (NMAIN > 1 ? (it & 1) * BN : 0);
+                                    umma_tf32(t_small, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                                    umma_tf32(t_small, da, dbl, IDESC, 1u);
+                                    umma_tf32(t_main, da, db, IDESC, (it >= NMAIN || k > 0) ? 1u : 0u);
+                                }
+                            } else {
+                                umma_tf32(t_sub, da, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(bar_eb + 8 * sb);                          // weight stage free
+                    if (++sb == NSB) { sb = 0; fb_par ^= 1u; }
+                }
+                umma_commit(bar_ea + 8 * sa);                              // activation stage free
+                if (++sa == NSA) { sa = 0; fa_par ^= 1u; }
+            }
+            umma_commit(bar_done);
+        }
+    } else {
+        // ===== weight stream: one cp.async.bulk per (chunk, tap) stage; packed blocks are [tap][Cin/32][8 quads][BN][4] =====
+        if (lane == 0) {
+            const int KC32 = a.Cin >> 5;
+            int sb = 0, it = 0;
+            unsigned eb_par = 1;
+            for (int kc = 0; kc < KC; ++kc) {
+                for (int tap = 0; tap < TAPS; ++tap, ++it) {
+                    if (it >= NSB) mbar_wait(bar_eb + 8 * sb, eb_par);
+                    const size_t off = ((size_t)tap * KC32 + (kc >> 1)) * (size_t)(BN * 32) + (size_t)(kc & 1) * (BN * 16);
+                    const uint32_t bb = bar_fb + 8 * sb;
+                    const uint32_t dst = sbase + B_OFF + sb * B_STAGE;
+                    mbar_expect_tx(bb, B_STAGE);
+                    bulk_g2s(dst, args.w_hi + off, B_HALF, bb);
+                    if (SPLIT) bulk_g2s(dst + B_HALF, args.w_lo + off, B_HALF, bb);
+                    if (++sb == NSB) { sb = 0; eb_par ^= 1u; }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // ---- epilogue: per column chunk of CH and per 128-pixel half: TMEM -> registers -> staging tile -> coalesced
+    //      bias / shortcut / accumulate / store + BN statistics (row r of half `sub` = pixel (th0 + r/8, tw0 + 8 sub + r%8)) ----
+    constexpr int CH = Cfg::CH, SROW = CH + 4;
+    constexpr int CG = CH / 4;           // float4 column groups of a chunk
+    constexpr int RL = TNT / CG;         // row lanes (8 for CH=128, 16 for CH=64)
+    constexpr int ROWS = TBM / RL;       // rows per thread (16 / 8)
+    float* stg = reinterpret_cast<float*>(sgen);
+    double* red = reinterpret_cast<double*>(sgen + TBM * SROW * 4);     // [RL][CH][2], behind the staging tile
+    const bool epi = tid < TNT;
+    const int cg = (epi ? tid : 0) % CG, r0 = (epi ? tid : 0) / CG;
+    const bool do_stats = a.stat_sum != nullptr;
+    const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
+    const long long pix0 = ((long long)n_img * a.H + th0) * a.W + tw0;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / CH; ++ch) {
+        const int n = ch * CH + cg * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias != nullptr) bv = ldg4(a.bias + n);
+        float4 rs, rt;
+        load_affine4(a.res.scale, a.res.shift, n, rs, rt);
+        float4 bsc = make_float4(1.f, 1.f, 1.f, 1.f), bsh = make_float4(0.f, 0.f, 0.f, 0.f), bmu = bsh, biv = bsc;
+        if (BWDSTATS) { bsc = ldg4(a.bscale + n); bsh = ldg4(a.bshift + n); bmu = ldg4(a.bmean + n); biv = ldg4(a.binvstd + n); }
+        double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+            if (warp < 8) {
+                const int lq = warp & 3;
+                const int row = lq * 32 + lane;
+                const int cbeg = (warp >> 2) * (CH / 2);
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + CH / 2; c0 += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(sub * SUBCOLS + ch * CH + c0);
+                    tmem_ld32(taddr, r);
+                    float acc[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(r[q]);
+#pragma unroll
+                    for (int e = 1; e < NACC; ++e) {
+                        tmem_ld32(taddr + (uint32_t)(e * BN), r);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(r[q]);
+                    }
+                    float* dst = stg + row * SROW + c0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        st4(dst + q * 4, make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (ch == BN / CH - 1 && sub == 1 && warp == 0)
+                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+            float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+            // rows are processed 4 at a time with all global loads (shortcut / previous output / BN input) issued first
+#pragma unroll 1
+            for (int g = 0; epi && g < ROWS; g += 4) {
+                float4 rr[4], oo[4], zz[4];
+                long long pp[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + (g + i) * RL;
+                    pp[i] = (pix0 + (long long)(r >> 3) * a.W + (sub * 8 + (r & 7))) * a.Cout + n;
+                    rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    zz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_res) rr[i] = ldg4(a.res.z + pp[i]);
+                    if (a.accumulate) oo[i] = ld4(a.y + pp[i]);
+                    if (BWDSTATS) zz[i] = ldg4(a.bz + pp[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + (g + i) * RL;
+                    float4 v = ld4(stg + r * SROW + cg * 4);
+                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    if (has_res) {
+                        float4 q = rr[i];
+                        if (res_aff) q = act4(q, rs, rt, a.res.relu);
+                        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    }
+                    v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
+                    st4(a.y + pp[i], v);
+                    if (do_stats) {
+                        if (BWDSTATS) {
+                            const float4 z = zz[i];
+                            const float gx = (a.brelu && fmaf(z.x, bsc.x, bsh.x) <= 0.f) ? 0.f : v.x;
+                            const float gy = (a.brelu && fmaf(z.y, bsc.y, bsh.y) <= 0.f) ? 0.f : v.y;
+                            const float gz = (a.brelu && fmaf(z.z, bsc.z, bsh.z) <= 0.f) ? 0.f : v.z;
+                            const float gw = (a.brelu && fmaf(z.w, bsc.w, bsh.w) <= 0.f) ? 0.f : v.w;
+                            s1[0] += gx; s2[0] = fmaf(gx, (z.x - bmu.x) * biv.x, s2[0]);
+                            s1[1] += gy; s2[1] = fmaf(gy, (z.y - bmu.y) * biv.y, s2[1]);
+                            s1[2] += gz; s2[2] = fmaf(gz, (z.z - bmu.z) * biv.z, s2[2]);
+                            s1[3] += gw; s2[3] = fmaf(gw, (z.w - bmu.w) * biv.w, s2[3]);
+                        } else {
+                            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                        }
+                    }
+                }
+                if (do_stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+                }
+            }
+            if (!(ch == BN / CH - 1 && sub == 1)) __syncthreads();       // staging tile is rewritten by the next half / chunk
+        }
+        if (do_stats) {
+            if (epi) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    red[((r0 * CH) + cg * 4 + j) * 2 + 0] = d1[j];
+                    red[((r0 * CH) + cg * 4 + j) * 2 + 1] = d2[j];
+                }
+            }
+            __syncthreads();
+            if (tid < CH) {
+                double x1 = 0.0, x2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    x1 += red[((q * CH) + tid) * 2 + 0];
+                    x2 += red[((q * CH) + tid) * 2 + 1];
+                }
+                atomicAdd(a.stat_sum + ch * CH + tid, x1);
+                atomicAdd(a.stat_sq + ch * CH + tid, x2);
+            }
+            if (ch + 1 < BN / CH) __syncthreads();                       // `red` is rewritten by the next chunk
+        }
+    }
+}
+
+template <int BN, bool SPLIT, int KS, bool BWDSTATS>
+static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = T2Cfg<BN, SPLIT, KS>::SMEM;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("hgk_conv_tc_nhwc (tile kernel): cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
+            return HGK_ECUDA;
+        }
+        configured = true;
+    }
+    const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 4));
+    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS><<<grid, T2_THREADS, smem, st>>>(ta);
+    return HGK_OK;
+}
+
+template <int BN, int KS>
+static int launch_tc2_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream_t st) {
+    if (bwdstats) return launch_tc2_cfg<BN, false, KS, true>(ta, st);
+    if (split) return launch_tc2_cfg<BN, true, KS, false>(ta, st);
+    return launch_tc2_cfg<BN, false, KS, false>(ta, st);
+}
+
+// true when the tile kernel covers this problem (the caller falls back to conv_tc_kernel otherwise)
+bool conv_tc2_eligible(const TcArgs& ta) {
+    const ConvArgs& c = ta.c;
+    if (c.H % 16 || c.W % 16) return false;
+    if (c.ksize == 3 && c.Cout > 128) return false;                       // 3x3 with 256 outputs: no instantiation
+    const long long cmax = c.Cin > c.Cout ? c.Cin : c.Cout;
+    if (c.P * cmax >= (1LL << 32)) return false;                          // 32-bit element offsets in the producers
+    if ((long long)c.N * (c.H >> 4) * (c.W >> 4) >= (1LL << 31)) return false;
+    return true;
+}
+
+int conv_tc2_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BN = ta.c.Cout;
+    if (ta.c.ksize == 3) {
+        if (BN == 64) return launch_tc2_bn<64, 3>(ta, split, bwdstats, st);
+        return launch_tc2_bn<128, 3>(ta, split, bwdstats, st);
+    }
+    if (BN == 64) return launch_tc2_bn<64, 1>(ta, split, bwdstats, st);
+    if (BN == 128) return launch_tc2_bn<128, 1>(ta, split, bwdstats, st);
+    return launch_tc2_bn<256, 1>(ta, split, bwdstats, st);
+}
+
+}  // namespace hgk

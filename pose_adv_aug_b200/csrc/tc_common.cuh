@@ -78,6 +78,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ float tf32_rna(float v) {
     return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
+__device__ __forceinline__ float4 tf32_rna4(float4 v) {
+    return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+}
 // BN+ReLU on load with the ReLU expressed as a clamp value (0 or -inf): one FFMA + one FMNMX per element
 __device__ __forceinline__ float4 actc4(float4 v, float4 s, float4 t, float clampv) {
     return make_float4(fmaxf(fmaf(v.x, s.x, t.x), clampv), fmaxf(fmaf(v.y, s.y, t.y), clampv),

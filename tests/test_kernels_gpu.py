@@ -379,6 +379,17 @@ TC_SHAPES = [
     (8, 64, 64, 64, 128, 1),     # 256 tiles > 148 SMs: the two-CTAs-per-SM configuration
     (5, 64, 64, 128, 128, 3),    # 160 tiles, 3x3
     (5, 64, 64, 128, 256, 1),
+    # 16x16-pixel image-tile kernel (conv_tc2.cu: H, W multiples of 16): every instantiation
+    (1, 128, 128, 64, 64, 3),
+    (1, 128, 128, 64, 64, 1),
+    (2, 32, 32, 256, 128, 1),
+    (3, 32, 48, 128, 128, 3),    # non-square, borders on every side of a tile
+    (1, 16, 32, 64, 64, 1),
+    (2, 16, 16, 256, 256, 1),
+    (1, 48, 16, 128, 64, 1),
+    # the same layer classes just off the 16-pixel grid: conv_tc_kernel, two-CTAs-per-SM configuration
+    (6, 60, 60, 128, 128, 3),
+    (8, 60, 60, 64, 128, 1),
 ]
 
 
@@ -451,10 +462,48 @@ def test_conv_tc_dgrad_1xtf32(shape):
     assert relerr(from_nhwc(gx) - extra - g0, a.grad) < 3e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (3, 32, 48, 128, 128, 3), (2, 32, 32, 128, 256, 1),
+                                   (1, 64, 64, 64, 64, 3), (2, 8, 8, 128, 128, 3), (3, 5, 7, 64, 64, 3),
+                                   (1, 16, 32, 256, 256, 1), (1, 64, 64, 128, 64, 1)])
+@pytest.mark.parametrize("acc", [0, 1])
+def test_conv_tc_dgrad_bnstats(shape, acc):
+    """Data gradient + fused BN-backward reduction (sum g, sum g*xhat) of the producer's BatchNorm."""
+    N, H, W, Ci, Co, k = shape           # the convolution maps Ci -> Co; the gradient flows Co -> Ci
+    a = rnd("x", (N, Ci, H, W)).requires_grad_(True)
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    dz = rnd("dz", (N, Co, H, W))
+    _conv_ref(a, w, None, k).backward(dz)
+    extra, g0 = rnd("extra", (N, Ci, H, W)), rnd("g0", (N, Ci, H, W))
+    bz = rnd("bz", (N, Ci, H, W))
+    bsc, bsh = rnd("bsc", (Ci,), 0.5, 1.5), rnd("bsh", (Ci,), -0.3, 0.3)
+    bmu, biv = rnd("bmu", (Ci,), -0.2, 0.2), rnd("biv", (Ci,), 0.5, 2.0)
+    dy_ref = a.grad + extra + (g0 if acc else 0)
+    mask = (bz * bsc.view(1, -1, 1, 1) + bsh.view(1, -1, 1, 1) > 0).double()
+    g = dy_ref * mask
+    xhat = (bz - bmu.view(1, -1, 1, 1)) * biv.view(1, -1, 1, 1)
+    gx, ddz, dextra, dbz = nhwc(g0), nhwc(dz), nhwc(extra), nhwc(bz)
+    hi, _ = _pack_tc(w, 1, Ci)
+    sg = torch.zeros(Ci, device=DEV, dtype=torch.float64)
+    sgx = torch.zeros(Ci, device=DEV, dtype=torch.float64)
+    dbsc, dbsh, dbmu, dbiv = dev32(bsc), dev32(bsh), dev32(bmu), dev32(biv)
+    call("conv_tc_dgrad_bnstats_nhwc", ptr(ddz), N, H, W, Co, ptr(hi), 0, k, Ci, ptr(dextra), ptr(gx), acc,
+         ptr(dbz), ptr(dbsc), ptr(dbsh), 1, ptr(dbmu), ptr(dbiv), ptr(sg), ptr(sgx))
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(gx) - extra - (g0 if acc else 0), a.grad) < 3e-3      # plain TF32 operands
+    # the sums are taken over the kernel's own (TF32-accurate) dy: compare against sums of the exact gradient
+    # relative to the sum of magnitudes
+    scale_g = g.abs().sum(dim=(0, 2, 3))
+    assert float(((sg.cpu() - g.sum(dim=(0, 2, 3))).abs() / scale_g).max()) < 2e-3
+    scale_gx = (g * xhat).abs().sum(dim=(0, 2, 3))
+    assert float(((sgx.cpu() - (g * xhat).sum(dim=(0, 2, 3))).abs() / scale_gx).max()) < 2e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128, 1), (2, 16, 16, 128, 64, 3), (3, 5, 7, 64, 20, 3),
                                    (2, 1, 1, 256, 128, 1), (1, 64, 64, 256, 256, 1), (2, 8, 8, 128, 128, 3),
                                    (5, 12, 12, 128, 256, 1), (1, 20, 24, 256, 128, 3), (1, 64, 64, 256, 16, 1),
-                                   (4, 64, 64, 128, 128, 3)])
+                                   (4, 64, 64, 128, 128, 3), (2, 32, 32, 128, 256, 1), (1, 128, 128, 64, 64, 3),
+                                   (1, 64, 64, 64, 128, 1), (2, 16, 16, 256, 128, 1), (3, 16, 8, 64, 64, 1),
+                                   (3, 8, 32, 64, 128, 3), (1, 64, 64, 128, 64, 3), (7, 4, 4, 128, 256, 1)])
 def test_conv_wgrad_tc(shape):
     N, H, W, Ci, Co, k = shape
     xs, xt = rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)
