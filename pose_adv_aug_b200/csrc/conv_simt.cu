@@ -374,6 +374,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, float* __rest
 
 }  // namespace hgk
 
+namespace hgk {
+int conv_skinny_try(const ConvArgs& a, cudaStream_t st);      // conv_skinny.cu
+}
 using namespace hgk;
 
 extern "C" int hgk_conv_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
@@ -402,6 +405,10 @@ extern "C" int hgk_conv_nhwc(const float* x, const float* x_scale, const float* 
     HGK_REQUIRE(path == 0 || path == 1, "hgk_conv_nhwc: this entry point is the fp32 SIMT kernel; use hgk_conv_tc_nhwc for tcgen05");
     long long mt = (a.P + CBM - 1) / CBM;
     HGK_REQUIRE(mt < 2147483647LL, "hgk_conv_nhwc: too many pixels");
+    if (conv_skinny_try(a, st) == 1) {            // 16-channel heads: streaming kernels of conv_skinny.cu
+        HGK_CHECK_LAUNCH("hgk_conv_nhwc");
+        return HGK_OK;
+    }
     if (Cout > 64) {
         dim3 grid((unsigned)mt, (unsigned)((Cout + 127) / 128));
         conv_igemm_simt<128><<<grid, CNT, 0, st>>>(a);

@@ -1,0 +1,190 @@
+// fp32 1x1 convolutions with a 16-channel side: the heat-map head out_conv (C -> 16,
+// models/asn_stacked_hg.py:248,329), in_conv (16 -> C, :279,333) and their data gradients.  Both are pure
+// HBM streams (100 MB of activations against <1 GFLOP): the generic implicit-GEMM tiles (128 x 64) spend their
+// time on padding.  Same contract as hgk_conv_nhwc (BN+ReLU on load, bias, shortcut, accumulate); no
+// statistics epilogue (no BatchNorm follows these layers).
+//
+//   conv_n16_kernel : y[p][0:16] = sum_k T(x)[p][k] w[k][0:16]   -- a warp per pixel group, lane = 4-channel
+//                     quad of x with its 4x16 weights in registers, 512-byte coalesced loads, 16 warp-shuffle
+//                     reduce-scatter steps per pixel, one 64-byte store.
+//   conv_k16_kernel : y[p][n] = sum_{k<16} T(x)[p][k] w[k][n]    -- lane = 4 output channels with its 16x4
+//                     weights in registers; x rows are warp-uniform (broadcast) loads; 512-byte stores.
+#include "common.cuh"
+#include "conv_args.cuh"
+
+namespace hgk {
+
+// ---- C -> 16.  CQ = warps cooperating on one pixel (Cin = 128 * CQ) ----
+template <int CQ>
+__global__ void __launch_bounds__(256) conv_n16_kernel(const ConvArgs a) {
+    __shared__ float part[8][4][16];               // [warp][pixel of the batch][output]: partial sums when CQ > 1
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cq = warp % CQ;                       // which 128-channel slice of the pixel this warp owns
+    const int wp = warp / CQ;                       // pixel-group slot of the warp inside the CTA
+    constexpr int WPB = 8 / CQ;                     // pixel groups per CTA per iteration
+    const int c0 = cq * 128 + lane * 4;
+    // weights of this lane's four input channels: w[k][0:16], k = c0 .. c0+3
+    float4 wr[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wr[k][q] = ldg4(a.w + (size_t)(c0 + k) * 16 + q * 4);
+    float4 sc, sh;
+    load_affine4(a.x.scale, a.x.shift, c0, sc, sh);
+    const bool has_aff = a.x.scale != nullptr;
+    const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
+    const long long groups = (a.P + 3) / 4;         // 4 pixels per warp iteration
+    // the trip count is CTA-uniform (barriers inside): warps past the end run on masked pixels
+    for (long long gb = (long long)blockIdx.x * WPB; gb < groups; gb += (long long)gridDim.x * WPB) {
+        const long long p0 = (gb + wp) * 4;
+        float4 xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p0 + i < a.P) {
+                xv[i] = ldg4(a.x.z + (p0 + i) * a.Cin + c0);
+                if (has_aff) xv[i] = act4(xv[i], sc, sh, a.x.relu);
+            }
+        }
+        float out[4];                                // after the reduce-scatter: output (lane & 15) of pixel i, half-summed
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float acc[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q * 4 + 0] = xv[i].x * wr[0][q].x + xv[i].y * wr[1][q].x + xv[i].z * wr[2][q].x + xv[i].w * wr[3][q].x;
+                acc[q * 4 + 1] = xv[i].x * wr[0][q].y + xv[i].y * wr[1][q].y + xv[i].z * wr[2][q].y + xv[i].w * wr[3][q].y;
+                acc[q * 4 + 2] = xv[i].x * wr[0][q].z + xv[i].y * wr[1][q].z + xv[i].z * wr[2][q].z + xv[i].w * wr[3][q].z;
+                acc[q * 4 + 3] = xv[i].x * wr[0][q].w + xv[i].y * wr[1][q].w + xv[i].z * wr[2][q].w + xv[i].w * wr[3][q].w;
+            }
+            // reduce-scatter over the 32 lanes: the step with offset h keeps outputs [h, 2h) on lanes with bit h set and
+            // [0, h) on the others; after offsets 8, 4, 2, 1 lane l holds output (l & 15) summed over its 16-lane half;
+            // the last step adds the two halves
+#pragma unroll
+            for (int half = 8; half >= 1; half >>= 1) {
+                const bool up = (lane & half) != 0;
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    const float mine = up ? acc[j + half] : acc[j];
+                    const float give = up ? acc[j] : acc[j + half];
+                    acc[j] = mine + __shfl_xor_sync(0xffffffffu, give, half);
+                }
+            }
+            out[i] = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 16);
+        }
+        // lane l now holds output (l & 15) of pixels 0..3 (each step keeps the half selected by the lane bit it crosses)
+        const int o = lane & 15;
+        if (CQ > 1) {
+            if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[warp][i][o] = out[i];
+            }
+            __syncthreads();
+        }
+        if (cq == 0 && lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (p0 + i >= a.P) break;
+                float v = out[i];
+                if (CQ > 1) {
+                    v = part[warp][i][o];
+#pragma unroll
+                    for (int c = 1; c < CQ; ++c) v += part[warp + c][i][o];
+                }
+                if (a.bias != nullptr) v += __ldg(a.bias + o);
+                const long long idx = (p0 + i) * 16 + o;
+                if (has_res) {
+                    float r = __ldg(a.res.z + idx);
+                    if (res_aff) r = act1(r, __ldg(a.res.scale + o), __ldg(a.res.shift + o), a.res.relu);
+                    v += r;
+                }
+                if (a.accumulate) v += a.y[idx];
+                a.y[idx] = v;
+            }
+        }
+        if (CQ > 1) __syncthreads();                 // `part` is rewritten by the next iteration
+    }
+}
+
+// ---- 16 -> C.  A warp covers 128 output channels of one pixel per step; CTA = 8 warps ----
+__global__ void __launch_bounds__(256) conv_k16_kernel(const ConvArgs a) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nq = a.Cout >> 7;                      // 128-channel slices per pixel
+    const int slice = warp % nq;                     // host guarantees 8 % nq == 0
+    const int wp = warp / nq, WPB = 8 / nq;
+    const int n0 = slice * 128 + lane * 4;
+    float4 wr[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wr[k] = ldg4(a.w + (size_t)k * a.Cout + n0);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias != nullptr) bv = ldg4(a.bias + n0);
+    float4 rs, rt;
+    load_affine4(a.res.scale, a.res.shift, n0, rs, rt);
+    const bool has_aff = a.x.scale != nullptr;
+    const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
+    float4 xsc[4], xsh[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) load_affine4(a.x.scale, a.x.shift, q * 4, xsc[q], xsh[q]);
+    constexpr int PB = 2;                            // pixels per warp iteration
+    for (long long p0 = ((long long)blockIdx.x * WPB + wp) * PB; p0 < a.P; p0 += (long long)gridDim.x * WPB * PB) {
+        float4 xv[PB][4], rr[PB], oo[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            const bool ok = p0 + i < a.P;
+            const long long p = ok ? p0 + i : p0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xv[i][q] = ldg4(a.x.z + p * 16 + q * 4);         // warp-uniform address: one broadcast transaction
+                if (has_aff) xv[i][q] = act4(xv[i][q], xsc[q], xsh[q], a.x.relu);
+            }
+            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n0);
+            if (ok && a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n0);
+        }
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            if (p0 + i >= a.P) break;
+            float4 v = bv;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x4 = xv[i][q];
+                const float4 w0 = wr[q * 4 + 0], w1 = wr[q * 4 + 1], w2 = wr[q * 4 + 2], w3 = wr[q * 4 + 3];
+                v.x += x4.x * w0.x + x4.y * w1.x + x4.z * w2.x + x4.w * w3.x;
+                v.y += x4.x * w0.y + x4.y * w1.y + x4.z * w2.y + x4.w * w3.y;
+                v.z += x4.x * w0.z + x4.y * w1.z + x4.z * w2.z + x4.w * w3.z;
+                v.w += x4.x * w0.w + x4.y * w1.w + x4.z * w2.w + x4.w * w3.w;
+            }
+            if (has_res) {
+                float4 q = rr[i];
+                if (res_aff) q = act4(q, rs, rt, a.res.relu);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
+            st4(a.y + (p0 + i) * a.Cout + n0, v);
+        }
+    }
+}
+
+// returns 1 when one of the skinny kernels took the launch, 0 when the shape is not covered
+int conv_skinny_try(const ConvArgs& a, cudaStream_t st) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("HGK_SKINNY_OFF");
+        off = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (off || a.ksize != 1 || a.stat_sum != nullptr) return 0;
+    const int grid = kNumSMs * 4;
+    if (a.Cout == 16 && (a.Cin == 128 || a.Cin == 256)) {
+        if (a.Cin == 128) conv_n16_kernel<1><<<grid, 256, 0, st>>>(a);
+        else conv_n16_kernel<2><<<grid, 256, 0, st>>>(a);
+        return 1;
+    }
+    if (a.Cin == 16 && (a.Cout == 128 || a.Cout == 256)) {
+        conv_k16_kernel<<<grid, 256, 0, st>>>(a);
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace hgk

@@ -8,11 +8,14 @@
 // bytes and L2 -> SM bandwidth (about the HBM bandwidth on B200) becomes the bound (profiles/r1b_tc_summary.md).
 // Here
 //   * the activation HALO tile (18x18 pixels x 16 channels for 3x3; 16x16 for 1x1) is loaded, transformed
-//     (BN+ReLU, TF32 hi/lo split) and stored to shared memory ONCE per 16-channel chunk, in a layout where
-//     pixel (hh, ww) of channel quad q sits at q*LBO + (hh*HW + ww)*16 bytes: an 8-pixel run of one image row
-//     is one UMMA core matrix (8 rows x 16 B, K-major, no swizzle), the next row is SBO = HW*16 bytes further.
-//     The nine taps are nine MMAs on the SAME tile with the descriptor start address shifted by
-//     (dh*HW + dw)*16 bytes -- no im2col, no re-load;
+//     (BN+ReLU, TF32 hi/lo split) and stored to shared memory ONCE per 16-channel chunk in the K-major
+//     64-byte-swizzle UMMA layout: halo pixel (hh, ww) is one 64-byte row at (hh*HW + ww)*64, its four 16-byte
+//     channel quads XOR-swizzled with address bits [7,9).  An 8-pixel run of one image row is one 8-row group,
+//     the next image row is SBO = HW*64 bytes further.  The nine taps are nine MMAs on the SAME tile with the
+//     descriptor start address shifted by (dh*HW + dw)*64 bytes -- no im2col, no re-load.  (The swizzle is a
+//     function of the absolute shared-memory address, so row-shifted starts stay consistent; the first version
+//     used the no-swizzle layout with 16-byte pixel rows, whose shifted core matrices straddle 128-byte lines:
+//     ncu showed every 3x3 MMA occupying the tensor pipe for 128 instead of 64 cycles.)
 //   * each weight stage (one tap x 16 channels x Cout, hi and lo) arrives by cp.async.bulk (TMA bulk copy) and
 //     is used by both 128-pixel halves of the tile (columns 0-7 and 8-15), halving the weight stream per pixel;
 //   * roles: warps 0-7 load/transform/store the halo tiles (two chunks of register prefetch), warp 8 issues
@@ -23,6 +26,12 @@
 #include "tc_common.cuh"
 
 namespace hgk {
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B (layout type 4 in bits 61-63): rows of 64 bytes, 8-row groups
+// SBO bytes apart; LBO is not used by swizzled K-major layouts (canonical value 1)
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t saddr, uint32_t sbo) {
+    return umma_desc(saddr, 16u, sbo) | ((uint64_t)4 << 61);
+}
 
 constexpr int T2_THREADS = 320;      // 8 producer/epilogue warps + MMA warp + weight-copy warp
 
@@ -36,10 +45,8 @@ struct T2Cfg {
     static constexpr int BK = 16, QP = 4;                                  // channels / 16-byte quads per chunk
     static constexpr int NITEM = NPIX * QP;                                // (pixel, quad) items per chunk
     static constexpr int NJ = (NITEM + 255) / 256;                         // items per producer thread
-    // quad stride: pixels*16 rounded to 128 plus 32 -> the four quads of a pixel pair fall into distinct banks
-    static constexpr int LBO_A = (NPIX * 16 + 127) / 128 * 128 + 32;
-    static constexpr int SBO_A = HWD * 16;
-    static constexpr int A_HALF = QP * LBO_A;
+    static constexpr int SBO_A = HWD * 64;                                 // 8-pixel row group -> next image row
+    static constexpr int A_HALF = (NPIX * 64 + 1023) / 1024 * 1024;        // hi (or lo) part of a stage
     static constexpr int A_STAGE = (SPLIT ? 2 : 1) * A_HALF;
     static constexpr int B_HALF = BN * BK * 4;
     static constexpr int B_STAGE = (SPLIT ? 2 : 1) * B_HALF;
@@ -53,9 +60,9 @@ struct T2Cfg {
     static constexpr int TMEM_COLS = (2 * SUBCOLS <= 128) ? 128 : (2 * SUBCOLS <= 256) ? 256 : 512;
     static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
     static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
-    static constexpr int SMEM = (PIPE > STG_BYTES ? PIPE : STG_BYTES) + 256;
+    static constexpr int SMEM = (PIPE > STG_BYTES ? PIPE : STG_BYTES) + 1024;
     static_assert(2 * SUBCOLS <= 512, "TMEM capacity");
-    static_assert(A_HALF % 128 == 0 && B_HALF % 128 == 0, "stage alignment");
+    static_assert(A_HALF % 1024 == 0 && B_HALF % 1024 == 0, "stage alignment (swizzle atoms)");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
     using Cfg = T2Cfg<BN, SPLIT, KS>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
     constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
-    constexpr uint32_t LBO_A = Cfg::LBO_A, SBO_A = Cfg::SBO_A, LBO_B = BN * 16, SBO_B = 128;
+    constexpr uint32_t SBO_A = Cfg::SBO_A, LBO_B = BN * 16, SBO_B = 128;
     constexpr uint32_t A_HALF = Cfg::A_HALF, A_STAGE = Cfg::A_STAGE, B_HALF = Cfg::B_HALF, B_STAGE = Cfg::B_STAGE;
     constexpr uint32_t B_OFF = NSA * A_STAGE;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
@@ -73,7 +80,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * NSA + 2 * NSB + 1];
     __shared__ uint32_t tmem_slot;
-    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
             const bool in_tile = idx < Cfg::NITEM;
             const bool in_img = in_tile && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W;
             a_off[j] = in_img ? (unsigned)((((long long)n_img * a.H + h) * a.W + w) * a.Cin) + quad * 4 : 0u;
-            s_off[j] = (unsigned)quad * LBO_A + (unsigned)hp * 16u;
+            // 64-byte swizzle: 16-byte chunk index ^= address bits [7,9) = (pixel >> 1) & 3 (stage bases are 1024-aligned)
+            s_off[j] = (unsigned)hp * 64u + (((unsigned)quad ^ (((unsigned)hp >> 1) & 3u)) << 4);
             if (in_img) vmask |= 1u << j;
             if (in_tile) smask |= 1u << j;
         }
@@ -183,17 +191,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
                 for (int tap = 0; tap < TAPS; ++tap, ++it) {
                     mbar_wait(bar_fb + 8 * sb, fb_par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 16u : 0u);
+                    const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
                     const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const uint32_t t_sub = tmem + sub * SUBCOLS;
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
-                            const uint64_t da = umma_desc(a_tap + sub * 128 + k * 2 * LBO_A, LBO_A, SBO_A);
+                            const uint64_t da = umma_desc_k64(a_tap + sub * 512 + k * 32, SBO_A);
                             const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO_B);
                             if (SPLIT) {
-                                const uint64_t dal = umma_desc(a_tap + A_HALF + sub * 128 + k * 2 * LBO_A, LBO_A, SBO_A);
+                                const uint64_t dal = umma_desc_k64(a_tap + A_HALF + sub * 512 + k * 32, SBO_A);
                                 const uint64_t dbl = umma_desc(b_hi + B_HALF + k * 2 * LBO_B, LBO_B, SBO_B);
                                 if (NACC == 1) {
                                     umma_tf32(t_sub, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);

@@ -58,6 +58,36 @@ def test_conv_fwd(shape, variant):
     assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 64, 256, 16, 1), (1, 64, 64, 16, 256, 1), (2, 5, 7, 128, 16, 1),
+                                   (3, 5, 5, 16, 128, 1), (2, 9, 3, 256, 16, 1)])
+@pytest.mark.parametrize("variant", ["plain", "full"])
+def test_conv_skinny_heads(shape, variant):
+    """out_conv / in_conv (16-channel side) without a statistics epilogue: the streaming kernels of conv_skinny.cu."""
+    N, H, W, Ci, Co, k = shape
+    x = rnd("x", (N, Ci, H, W))
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    b = rnd("b", (Co,))
+    full = variant == "full"
+    xs, xt = (rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)) if full else (None, None)
+    res = rnd("res", (N, Co, H, W)) if full else None
+    rs, rt = (rnd("rs", (Co,), 0.5, 1.5), rnd("rt", (Co,), -0.3, 0.3)) if full else (None, None)
+    y0 = rnd("y0", (N, Co, H, W)) if full else None
+    ref = _conv_ref(affine_act(x, xs, xt, True), w, b, k)
+    if full:
+        ref = ref + affine_act(res, rs, rt, True) + y0
+    dx, dw, db = nhwc(x), pack_w(w, 0), dev32(b)
+    dxs, dxt = (dev32(xs), dev32(xt)) if full else (None, None)
+    dres = nhwc(res) if full else None
+    drs, drt = (dev32(rs), dev32(rt)) if full else (None, None)
+    y = nhwc(y0) if full else torch.empty(N, H, W, Co, device=DEV)
+    call("conv_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(dw), k, 0, ptr(db) if full else 0, Co,
+         ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), 0, 0, 1)
+    torch.cuda.synchronize()
+    if not full:
+        ref = ref - b.view(1, -1, 1, 1)
+    assert relerr(from_nhwc(y), ref) < 1e-5
+
+
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_conv_dgrad_and_wgrad(shape):
     N, H, W, Ci, Co, k = shape
