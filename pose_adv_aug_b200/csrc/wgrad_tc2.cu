@@ -33,7 +33,7 @@ struct Wg2Args {
     float* dbias;
     long long units;          // P / 8
     long long units_per_cta;  // multiple of 4
-    int lw8;                  // log2(W / 8) (3x3 only)
+    int lw8;                  // log2(W / 8) (3x3 only; W and H are powers of two there)
 };
 
 __device__ __forceinline__ void red_add_v4_g(float* p, float4 v) {
@@ -127,14 +127,17 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args
         const float* xzp = a.x.z + qb * 4;
         float4 ra[2][NJA], rb[2][NJB];
         unsigned bm[2] = {0u, 0u};
-        long long l_u = u_begin;                                // first unit of the stage the next load() fetches
+        // all index arithmetic in 32 bits (host guarantees P * max(Cin, Cout) < 2^31); H and W are powers of two for 3x3
+        int l_u = (int)u_begin;                                  // first unit of the stage the next load() fetches
+        const int i_end = (int)u_end;
+        const int hmask = a.H - 1, umask = (1 << a.lw8) - 1;
         auto load = [&](int set) {
 #pragma unroll
             for (int j = 0; j < NJA; ++j) {
                 const int slot = (tid + 256 * j) / QA;           // pixel of the stage
-                const long long u = l_u + (slot >> 3);
+                const int u = l_u + (slot >> 3);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (u < u_end && qa_ok) v = ldg4(dzp + (u * 8 + (slot & 7)) * a.Cout);
+                if (u < i_end && qa_ok) v = ldg4(dzp + (unsigned)(u * 8 + (slot & 7)) * (unsigned)a.Cout);
                 ra[set][j] = v;
             }
             unsigned m = 0;
@@ -143,21 +146,21 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args
                 const int idx = tid + 256 * j;
                 const int slot = idx / QB;                       // x pixel slot of the stage: unit slot / UPX, offset slot % UPX
                 const int us = slot / UPX, i = slot - us * UPX;
-                const long long u = l_u + us;
+                const int u = l_u + us;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool ok = idx < Cfg::NPB * QB && u < u_end;
-                long long p;
+                bool ok = idx < Cfg::NPB * QB && u < i_end;
+                int p;
                 if (TAPS == 3) {
-                    const long long r = u >> a.lw8;              // global image row n*H + h
-                    const int w = (int)(u - (r << a.lw8)) * 8 - 1 + i;
-                    const int h = (int)(r % a.H) + dh;
+                    const int r = u >> a.lw8;                    // global image row n*H + h
+                    const int w = (u & umask) * 8 - 1 + i;
+                    const int h = (r & hmask) + dh;
                     ok = ok && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W;
                     p = (r + dh) * a.W + w;
                 } else {
                     p = u * 8 + i;
                 }
                 if (ok) {
-                    v = ldg4(xzp + p * a.Cin);
+                    v = ldg4(xzp + (unsigned)p * (unsigned)a.Cin);
                     m |= 1u << j;
                 }
                 rb[set][j] = v;
@@ -316,11 +319,11 @@ int wgrad_tc2_try(const float* x, const float* x_scale, const float* x_shift, in
     const long long P = (long long)N * H * W;
     if (P % 8) return 0;
     if (!(Cout == 64 || Cout == 128 || Cout == 256)) return 0;
-    if (P * (long long)(Cin > Cout ? Cin : Cout) >= (1LL << 40)) return 0;
+    if (P * (long long)(Cin > Cout ? Cin : Cout) >= (1LL << 31)) return 0;       // 32-bit index arithmetic in the producers
     const int MT = Cout > 128 ? 2 : 1;
     int lw8 = 0;
     if (ksize == 3) {
-        if (W < 8 || (W & (W - 1)) || Cout > 128 || Cin > 128) return 0;      // 3 x MT x Cin accumulator columns
+        if (W < 8 || (W & (W - 1)) || (H & (H - 1)) || Cout > 128 || Cin > 128) return 0;   // 3 x MT x Cin accumulator columns
         while ((8 << lw8) < W) ++lw8;
     } else if (MT * Cin > 512) {
         return 0;
