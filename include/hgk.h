@@ -71,6 +71,27 @@ int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int W, int Cin
                                    const float* bz, const float* bscale, const float* bshift, int brelu,
                                    const float* bmean, const float* binvstd,
                                    double* sum_g, double* sum_gx, void* stream);
+/* hgk_conv_tc_nhwc + the nn.BatchNorm2d finaliser of its statistics (hgk_bn_finalize) executed by the LAST CTA of the
+ * convolution (ticket counter, re-armed by the kernel: `ticket` must be zero before the first launch).  Requires
+ * stat_sum / stat_sq; count = N*H*W.  Replaces nn.Conv2d + the batch-statistics half of nn.BatchNorm2d
+ * (models/asn_stacked_hg.py:36-47) in one launch. */
+int hgk_conv_tc_bn_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                        int N, int H, int W, int Cin,
+                        const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                        const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                        float* y, int accumulate, double* stat_sum, double* stat_sq,
+                        const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, float* scale, float* shift,
+                        float* save_mean, float* save_invstd, unsigned int* ticket, void* stream);
+/* hgk_conv_tc_dgrad_bnstats_nhwc + hgk_bn_bwd_finalize of that BatchNorm executed by the last CTA. */
+int hgk_conv_tc_dgrad_bnfin_nhwc(const float* dz, int N, int H, int W, int Cin,
+                                 const float* w_hi, const float* w_lo, int ksize, int Cout,
+                                 const float* extra, float* dy, int accumulate,
+                                 const float* bz, const float* bscale, const float* bshift, int brelu,
+                                 const float* bmean, const float* binvstd,
+                                 double* sum_g, double* sum_gx,
+                                 const float* gamma, int training, float* dgamma, float* dbeta,
+                                 float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
 /* table: n_entries x 8 int64 {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN};
  * mode 0 (forward operand): B[n][k;tap] = W[o=n][i=k][tap];  mode 1 (data-gradient operand):
  * B[n][k;tap] = W[o=k][i=n][taps-1-tap].  Destination: [n-tile][tap][k/32] blocks of [8][BN][4] floats,
@@ -124,6 +145,11 @@ int hgk_bn_eval_prepare(const float* gamma, const float* beta, const float* runn
 int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
                       const float* mean, const float* invstd, long long P, int C,
                       double* sum_g, double* sum_gx, void* stream);
+/* hgk_bn_bwd_reduce + hgk_bn_bwd_finalize executed by the last CTA of the reduction (`ticket` zero before the first launch) */
+int hgk_bn_bwd_reduce_fin(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                          const float* mean, const float* invstd, long long P, int C,
+                          double* sum_g, double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                          float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
 /* dgamma += sum_gx, dbeta += sum_g; coefficients of dz = cA*(g - cC - (z-mean)*cB)  (training: full BN
  * backward, cA = gamma*invstd, cB = mean(g*xhat)*invstd, cC = mean(g); eval: cB = cC = 0) */
 int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long count, const float* gamma,

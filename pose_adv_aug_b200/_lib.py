@@ -18,6 +18,11 @@ SIGNATURES = {
     "hgk_pack_weights": [P, P, P, I, P],
     "hgk_conv_tc_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P, P],
     "hgk_conv_tc_dgrad_bnstats_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P, P],
+    "hgk_conv_tc_bn_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P,
+                            P, P, F, F, P, P, P, P, P, P, P, P],
+    "hgk_conv_tc_dgrad_bnfin_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P,
+                                     P, I, P, P, P, P, P, P, P],
+    "hgk_bn_bwd_reduce_fin": [P, P, P, P, I, P, P, L, I, P, P, P, I, P, P, P, P, P, P, P],
     "hgk_pack_weights_tc": [P, P, P, I, P],
     "hgk_conv_wgrad_tc_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, P, P],
     "hgk_unpack_add_grads": [P, P, P, I, P],

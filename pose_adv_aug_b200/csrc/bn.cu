@@ -3,6 +3,7 @@
 // (fp64 accumulators), `bn_finalize` turns them into (scale, shift) that the *consumers* apply on
 // load, and the backward is reduce -> finalize -> apply over the stored pre-BN tensor.
 #include "common.cuh"
+#include "bn_fin.cuh"
 
 namespace hgk {
 
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             int relu, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, long long P, int C,
                                                             double* sum_g, double* sum_gx, int cq_per_blk, int rows_par,
-                                                            long long rows_per_blk) {
+                                                            long long rows_per_blk, BnBwdFin fin) {
     extern __shared__ double red[];      // [rows_par][cq_per_blk*4][2]
     const int tid = threadIdx.x;
     const int cq = tid % cq_per_blk, row = tid / cq_per_blk;
@@ -102,6 +103,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
             atomicAdd(sum_g + cc, a);
             atomicAdd(sum_gx + cc, b);
         }
+    }
+    if (fin.ticket != nullptr) {          // fused bn_bwd_finalize: run by the CTA that arrives last
+        if (last_cta_arrives(fin.ticket, gridDim.x * gridDim.y)) bn_bwd_finalize_cta(fin, sum_g, sum_gx, (double)P, C);
     }
 }
 
@@ -183,9 +187,9 @@ extern "C" int hgk_bn_eval_prepare(const float* gamma, const float* beta, const 
     return HGK_OK;
 }
 
-extern "C" int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
-                                 const float* mean, const float* invstd, long long P, int C, double* sum_g,
-                                 double* sum_gx, void* stream) {
+static int bn_bwd_reduce_impl(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                              const float* mean, const float* invstd, long long P, int C, double* sum_g,
+                              double* sum_gx, const BnBwdFin& fin, void* stream) {
     HGK_REQUIRE(dy && z && scale && shift && mean && invstd && sum_g && sum_gx, "hgk_bn_bwd_reduce: null pointer");
     HGK_REQUIRE(P > 0 && C > 0 && C % 4 == 0, "hgk_bn_bwd_reduce: need P > 0 and C %% 4 == 0 (P=%lld C=%d)", P, C);
     int cq = C / 4;
@@ -199,9 +203,24 @@ extern "C" int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* s
     dim3 grid((unsigned)nblk, (unsigned)ngrp);
     size_t smem = (size_t)rows_par * cq_per_blk * 4 * 2 * sizeof(double);
     bn_bwd_reduce_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, mean, invstd, P, C, sum_g,
-                                                                    sum_gx, cq_per_blk, rows_par, rows_per_blk);
+                                                                    sum_gx, cq_per_blk, rows_par, rows_per_blk, fin);
     HGK_CHECK_LAUNCH("hgk_bn_bwd_reduce");
     return HGK_OK;
+}
+
+extern "C" int hgk_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                                 const float* mean, const float* invstd, long long P, int C, double* sum_g,
+                                 double* sum_gx, void* stream) {
+    return bn_bwd_reduce_impl(dy, z, scale, shift, relu, mean, invstd, P, C, sum_g, sum_gx, BnBwdFin{}, stream);
+}
+
+extern "C" int hgk_bn_bwd_reduce_fin(const float* dy, const float* z, const float* scale, const float* shift, int relu,
+                                     const float* mean, const float* invstd, long long P, int C, double* sum_g,
+                                     double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                                     float* cA, float* cB, float* cC, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(gamma && cA && cB && cC && ticket, "hgk_bn_bwd_reduce_fin: null pointer");
+    BnBwdFin f{gamma, mean, invstd, dgamma, dbeta, cA, cB, cC, ticket, training};
+    return bn_bwd_reduce_impl(dy, z, scale, shift, relu, mean, invstd, P, C, sum_g, sum_gx, f, stream);
 }
 
 extern "C" int hgk_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long count, const float* gamma,

@@ -4,6 +4,32 @@
 
 namespace hgk {
 
+// optional finalisers executed by the last CTA (bn_fin.cuh); ticket == nullptr disables them
+struct BnFwdFin {
+    const float* gamma;
+    const float* beta;
+    float* rmean;        // running statistics (nullptr: not updated)
+    float* rvar;
+    float* scale;
+    float* shift;
+    float* mean;
+    float* invstd;
+    unsigned int* ticket;
+    float eps, momentum;
+};
+struct BnBwdFin {
+    const float* gamma;
+    const float* mean;
+    const float* invstd;
+    float* dgamma;       // += (nullptr: skipped)
+    float* dbeta;
+    float* cA;
+    float* cB;
+    float* cC;
+    unsigned int* ticket;
+    int training;
+};
+
 struct ConvArgs {
     Act x;
     int N, H, W, Cin;
@@ -26,6 +52,8 @@ struct ConvArgs {
     const float* bmean;
     const float* binvstd;
     int brelu;
+    BnFwdFin ffin;       // forward: (stat_sum, stat_sq) -> scale/shift/running stats
+    BnBwdFin bfin;       // BN-backward statistics mode: (stat_sum, stat_sq) = (sum g, sum g*xhat) -> dgamma/dbeta/cA/cB/cC
 };
 
 }  // namespace hgk

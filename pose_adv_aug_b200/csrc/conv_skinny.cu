@@ -14,14 +14,21 @@
 
 namespace hgk {
 
-// ---- C -> 16.  CQ = warps cooperating on one pixel (Cin = 128 * CQ) ----
+// named barrier of the CQ warps that share a pixel group (immediate barrier ids: a register id reserves all 16)
 template <int CQ>
-__global__ void __launch_bounds__(256) conv_n16_kernel(const ConvArgs a) {
-    __shared__ float part[8][4][16];               // [warp][pixel of the batch][output]: partial sums when CQ > 1
+__device__ __forceinline__ void pair_sync(int wp) {
+    if (wp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * CQ) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(32 * CQ) : "memory");
+}
+
+// ---- C -> 16.  CQ = warps cooperating on one pixel (Cin = 128 * CQ); CTA = 4 warps, 2 pixels per warp step ----
+template <int CQ>
+__global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
+    __shared__ float part[4][2][16];                // [warp][pixel of the step][output]: partial sums when CQ > 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cq = warp % CQ;                       // which 128-channel slice of the pixel this warp owns
     const int wp = warp / CQ;                       // pixel-group slot of the warp inside the CTA
-    constexpr int WPB = 8 / CQ;                     // pixel groups per CTA per iteration
+    constexpr int WPB = 4 / CQ;                     // pixel groups per CTA per step
     const int c0 = cq * 128 + lane * 4;
     // weights of this lane's four input channels: w[k][0:16], k = c0 .. c0+3
     float4 wr[4][4];
@@ -33,22 +40,29 @@ __global__ void __launch_bounds__(256) conv_n16_kernel(const ConvArgs a) {
     load_affine4(a.x.scale, a.x.shift, c0, sc, sh);
     const bool has_aff = a.x.scale != nullptr;
     const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
-    const long long groups = (a.P + 3) / 4;         // 4 pixels per warp iteration
-    // the trip count is CTA-uniform (barriers inside): warps past the end run on masked pixels
-    for (long long gb = (long long)blockIdx.x * WPB; gb < groups; gb += (long long)gridDim.x * WPB) {
-        const long long p0 = (gb + wp) * 4;
-        float4 xv[4];
+    const long long groups = (a.P + 1) / 2;         // 2 pixels per warp step
+    const long long gstride = (long long)gridDim.x * WPB;
+    const float* xz = a.x.z + c0;
+    auto load2 = [&](long long g, float4 (&xv)[2]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p0 + i < a.P) {
-                xv[i] = ldg4(a.x.z + (p0 + i) * a.Cin + c0);
-                if (has_aff) xv[i] = act4(xv[i], sc, sh, a.x.relu);
-            }
+            const long long p = g * 2 + i;
+            if (p < a.P) xv[i] = ldg4(xz + p * a.Cin);
         }
-        float out[4];                                // after the reduce-scatter: output (lane & 15) of pixel i, half-summed
+    };
+    float4 xn[2];
+    long long g = (long long)blockIdx.x * WPB + wp;
+    load2(g, xn);
+    // the warps of a pixel group run the same number of steps (same g): named barriers pair them up
+    for (; g < groups; g += gstride) {
+        float4 xv[2] = {xn[0], xn[1]};
+        load2(g + gstride, xn);                      // prefetch the next step while this one computes
+        const long long p0 = g * 2;
+        float out[2];                                // after the reduce-scatter: output (lane & 15) of pixel i
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
+            if (has_aff && p0 + i < a.P) xv[i] = act4(xv[i], sc, sh, a.x.relu);
             float acc[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -72,22 +86,20 @@ __global__ void __launch_bounds__(256) conv_n16_kernel(const ConvArgs a) {
             }
             out[i] = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 16);
         }
-        // lane l now holds output (l & 15) of pixels 0..3 (each step keeps the half selected by the lane bit it crosses)
         const int o = lane & 15;
         if (CQ > 1) {
             if (lane < 16) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) part[warp][i][o] = out[i];
+                part[warp][0][o] = out[0];
+                part[warp][1][o] = out[1];
             }
-            __syncthreads();
+            pair_sync<CQ>(wp);
         }
         if (cq == 0 && lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 if (p0 + i >= a.P) break;
                 float v = out[i];
                 if (CQ > 1) {
-                    v = part[warp][i][o];
 #pragma unroll
                     for (int c = 1; c < CQ; ++c) v += part[warp + c][i][o];
                 }
@@ -102,12 +114,12 @@ __global__ void __launch_bounds__(256) conv_n16_kernel(const ConvArgs a) {
                 a.y[idx] = v;
             }
         }
-        if (CQ > 1) __syncthreads();                 // `part` is rewritten by the next iteration
+        if (CQ > 1) pair_sync<CQ>(wp);               // `part` is rewritten by the next step
     }
 }
 
-// ---- 16 -> C.  A warp covers 128 output channels of one pixel per step; CTA = 8 warps ----
-__global__ void __launch_bounds__(256) conv_k16_kernel(const ConvArgs a) {
+// ---- 16 -> C.  A warp covers 128 output channels of one pixel per step (software-pipelined); CTA = 8 warps ----
+__global__ void __launch_bounds__(256, 2) conv_k16_kernel(const ConvArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nq = a.Cout >> 7;                      // 128-channel slices per pixel
     const int slice = warp % nq;                     // host guarantees 8 % nq == 0
@@ -122,47 +134,46 @@ __global__ void __launch_bounds__(256) conv_k16_kernel(const ConvArgs a) {
     load_affine4(a.res.scale, a.res.shift, n0, rs, rt);
     const bool has_aff = a.x.scale != nullptr;
     const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
-    float4 xsc[4], xsh[4];
+    const long long pstride = (long long)gridDim.x * WPB;
+    struct Px { float4 x[4], r, o; };
+    auto load1 = [&](long long p, Px& d) {
+        d.r = make_float4(0.f, 0.f, 0.f, 0.f);
+        d.o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < a.P) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) load_affine4(a.x.scale, a.x.shift, q * 4, xsc[q], xsh[q]);
-    constexpr int PB = 2;                            // pixels per warp iteration
-    for (long long p0 = ((long long)blockIdx.x * WPB + wp) * PB; p0 < a.P; p0 += (long long)gridDim.x * WPB * PB) {
-        float4 xv[PB][4], rr[PB], oo[PB];
-#pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            const bool ok = p0 + i < a.P;
-            const long long p = ok ? p0 + i : p0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                xv[i][q] = ldg4(a.x.z + p * 16 + q * 4);         // warp-uniform address: one broadcast transaction
-                if (has_aff) xv[i][q] = act4(xv[i][q], xsc[q], xsh[q], a.x.relu);
-            }
-            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok && has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n0);
-            if (ok && a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n0);
+            for (int q = 0; q < 4; ++q) d.x[q] = ldg4(a.x.z + p * 16 + q * 4);       // warp-uniform address: one broadcast transaction
+            if (has_res) d.r = ldg4(a.res.z + p * a.Cout + n0);
+            if (a.accumulate) d.o = ld4(a.y + p * a.Cout + n0);
         }
+    };
+    long long p = (long long)blockIdx.x * WPB + wp;
+    Px nx;
+    load1(p, nx);
+    for (; p < a.P; p += pstride) {
+        Px cur = nx;
+        load1(p + pstride, nx);                      // prefetch the next pixel while this one computes
+        float4 v = bv;
 #pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            if (p0 + i >= a.P) break;
-            float4 v = bv;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x4 = xv[i][q];
-                const float4 w0 = wr[q * 4 + 0], w1 = wr[q * 4 + 1], w2 = wr[q * 4 + 2], w3 = wr[q * 4 + 3];
-                v.x += x4.x * w0.x + x4.y * w1.x + x4.z * w2.x + x4.w * w3.x;
-                v.y += x4.x * w0.y + x4.y * w1.y + x4.z * w2.y + x4.w * w3.y;
-                v.z += x4.x * w0.z + x4.y * w1.z + x4.z * w2.z + x4.w * w3.z;
-                v.w += x4.x * w0.w + x4.y * w1.w + x4.z * w2.w + x4.w * w3.w;
+        for (int q = 0; q < 4; ++q) {
+            float4 x4 = cur.x[q];
+            if (has_aff) {
+                float4 xsc, xsh;
+                load_affine4(a.x.scale, a.x.shift, q * 4, xsc, xsh);
+                x4 = act4(x4, xsc, xsh, a.x.relu);
             }
-            if (has_res) {
-                float4 q = rr[i];
-                if (res_aff) q = act4(q, rs, rt, a.res.relu);
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-            }
-            v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
-            st4(a.y + (p0 + i) * a.Cout + n0, v);
+            const float4 w0 = wr[q * 4 + 0], w1 = wr[q * 4 + 1], w2 = wr[q * 4 + 2], w3 = wr[q * 4 + 3];
+            v.x += x4.x * w0.x + x4.y * w1.x + x4.z * w2.x + x4.w * w3.x;
+            v.y += x4.x * w0.y + x4.y * w1.y + x4.z * w2.y + x4.w * w3.y;
+            v.z += x4.x * w0.z + x4.y * w1.z + x4.z * w2.z + x4.w * w3.z;
+            v.w += x4.x * w0.w + x4.y * w1.w + x4.z * w2.w + x4.w * w3.w;
         }
+        if (has_res) {
+            float4 q = cur.r;
+            if (res_aff) q = act4(q, rs, rt, a.res.relu);
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        v.x += cur.o.x; v.y += cur.o.y; v.z += cur.o.z; v.w += cur.o.w;
+        st4(a.y + p * a.Cout + n0, v);
     }
 }
 
@@ -174,14 +185,14 @@ int conv_skinny_try(const ConvArgs& a, cudaStream_t st) {
         off = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     if (off || a.ksize != 1 || a.stat_sum != nullptr) return 0;
-    const int grid = kNumSMs * 4;
     if (a.Cout == 16 && (a.Cin == 128 || a.Cin == 256)) {
-        if (a.Cin == 128) conv_n16_kernel<1><<<grid, 256, 0, st>>>(a);
-        else conv_n16_kernel<2><<<grid, 256, 0, st>>>(a);
+        const int grid = kNumSMs * 8;
+        if (a.Cin == 128) conv_n16_kernel<1><<<grid, 128, 0, st>>>(a);
+        else conv_n16_kernel<2><<<grid, 128, 0, st>>>(a);
         return 1;
     }
     if (a.Cin == 16 && (a.Cout == 128 || a.Cout == 256)) {
-        conv_k16_kernel<<<grid, 256, 0, st>>>(a);
+        conv_k16_kernel<<<kNumSMs * 4, 256, 0, st>>>(a);
         return 1;
     }
     return 0;

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
+#include "bn_fin.cuh"
 
 namespace hgk {
 
@@ -387,6 +388,16 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         if (ch + 1 < BN / CH) __syncthreads();       // staging tile is rewritten by the next chunk
     }
     if (tid == 0) HGK_STAMP(7);
+    // fused BatchNorm finaliser: the CTA that arrives last turns the complete sums into per-channel vectors
+    if (do_stats) {
+        if (!BWDSTATS && a.ffin.ticket != nullptr) {
+            if (last_cta_arrives(a.ffin.ticket, gridDim.x * gridDim.y))
+                bn_fwd_finalize_cta(a.ffin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
+        } else if (BWDSTATS && a.bfin.ticket != nullptr) {
+            if (last_cta_arrives(a.bfin.ticket, gridDim.x * gridDim.y))
+                bn_bwd_finalize_cta(a.bfin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1033,7 +1044,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
                         const float* res, const float* res_scale, const float* res_shift, int res_relu,
                         float* y, int accumulate, double* stat_sum, double* stat_sq,
                         const float* bz, const float* bscale, const float* bshift, const float* bmean,
-                        const float* binvstd, int brelu, void* stream) {
+                        const float* binvstd, int brelu, const BnFwdFin* ffin, const BnBwdFin* bfin, void* stream) {
     HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
     HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
     HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
@@ -1050,6 +1061,8 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     ta.c.y = y; ta.c.accumulate = accumulate; ta.c.stat_sum = stat_sum; ta.c.stat_sq = stat_sq;
     ta.c.P = (long long)N * H * W;
     ta.c.bz = bz; ta.c.bscale = bscale; ta.c.bshift = bshift; ta.c.bmean = bmean; ta.c.binvstd = binvstd; ta.c.brelu = brelu;
+    ta.c.ffin = ffin != nullptr ? *ffin : BnFwdFin{};
+    ta.c.bfin = bfin != nullptr ? *bfin : BnBwdFin{};
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1076,7 +1089,25 @@ extern "C" int hgk_conv_tc_nhwc(const float* x, const float* x_scale, const floa
                                 const float* res, const float* res_scale, const float* res_shift, int res_relu,
                                 float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream) {
     return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_lo, ksize, bias, Cout, res, res_scale, res_shift,
-                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
+                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                        stream);
+}
+
+extern "C" int hgk_conv_tc_bn_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                   int N, int H, int W, int Cin,
+                                   const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
+                                   const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                                   float* y, int accumulate, double* stat_sum, double* stat_sq,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* save_mean, float* save_invstd, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(stat_sum && stat_sq && gamma && beta && scale && shift && save_mean && save_invstd && ticket,
+                "hgk_conv_tc_bn_nhwc: null pointer");
+    HGK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "hgk_conv_tc_bn_nhwc: running stats must both be set");
+    BnFwdFin f{gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, ticket, eps, momentum};
+    return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_lo, ksize, bias, Cout, res, res_scale, res_shift,
+                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &f, nullptr,
+                        stream);
 }
 
 extern "C" int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int W, int Cin,
@@ -1087,7 +1118,22 @@ extern "C" int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int
                                               double* sum_g, double* sum_gx, void* stream) {
     HGK_REQUIRE(bz && bscale && bshift && bmean && binvstd && sum_g && sum_gx, "hgk_conv_tc_dgrad_bnstats_nhwc: null pointer");
     return conv_tc_impl(dz, nullptr, nullptr, 0, N, H, W, Cin, w_hi, w_lo, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
-                        dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, stream);
+                        dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, nullptr, nullptr, stream);
+}
+
+extern "C" int hgk_conv_tc_dgrad_bnfin_nhwc(const float* dz, int N, int H, int W, int Cin,
+                                            const float* w_hi, const float* w_lo, int ksize, int Cout,
+                                            const float* extra, float* dy, int accumulate,
+                                            const float* bz, const float* bscale, const float* bshift, int brelu,
+                                            const float* bmean, const float* binvstd,
+                                            double* sum_g, double* sum_gx,
+                                            const float* gamma, int training, float* dgamma, float* dbeta,
+                                            float* cA, float* cB, float* cC, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(bz && bscale && bshift && bmean && binvstd && sum_g && sum_gx && gamma && cA && cB && cC && ticket,
+                "hgk_conv_tc_dgrad_bnfin_nhwc: null pointer");
+    BnBwdFin f{gamma, bmean, binvstd, dgamma, dbeta, cA, cB, cC, ticket, training};
+    return conv_tc_impl(dz, nullptr, nullptr, 0, N, H, W, Cin, w_hi, w_lo, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
+                        dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, nullptr, &f, stream);
 }
 
 /* developer diagnostics: per-CTA globaltimer stamps of conv_tc_kernel ([512][16] int64), NULL disables */

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
+#include "bn_fin.cuh"
 
 namespace hgk {
 
@@ -378,6 +379,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
                 atomicAdd(a.stat_sq + ch * CH + tid, x2);
             }
             if (ch + 1 < BN / CH) __syncthreads();                       // `red` is rewritten by the next chunk
+        }
+    }
+    // fused BatchNorm finaliser: the CTA that arrives last turns the complete sums into per-channel vectors
+    if (do_stats) {
+        if (!BWDSTATS && a.ffin.ticket != nullptr) {
+            if (last_cta_arrives(a.ffin.ticket, gridDim.x)) bn_fwd_finalize_cta(a.ffin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
+        } else if (BWDSTATS && a.bfin.ticket != nullptr) {
+            if (last_cta_arrives(a.bfin.ticket, gridDim.x)) bn_bwd_finalize_cta(a.bfin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
         }
     }
 }

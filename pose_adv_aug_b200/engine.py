@@ -130,7 +130,7 @@ class ParamStore(object):
 class T(object):
     """A tensor node of the plan: NHWC buffer z [N,H,W,C] + optional on-load affine/ReLU."""
     __slots__ = ("z", "N", "H", "W", "C", "scale", "shift", "relu", "needs_grad", "grad", "contribs",
-                 "producer", "name", "bn", "n_cons", "bwd_stats_fused")
+                 "producer", "name", "bn", "n_cons", "bwd_stats_fused", "bwd_fin_fused")
 
     def __init__(self, z, N, H, W, C, scale=None, shift=None, relu=False, needs_grad=False, name=""):
         self.z, self.N, self.H, self.W, self.C = z, N, H, W, C
@@ -143,6 +143,7 @@ class T(object):
         self.bn = None            # BNRec whose (scale, shift) this tensor carries
         self.n_cons = 0           # number of ops that consume this tensor
         self.bwd_stats_fused = False   # the BN-backward reduction was produced by the consumer's data-gradient kernel
+        self.bwd_fin_fused = False     # ... and so were dgamma / dbeta / cA / cB / cC (last-CTA finaliser)
 
     def use(self):
         self.n_cons += 1
@@ -189,6 +190,11 @@ class Plan(object):
         # whole net); precise_grads -> 3xTF32 data gradients + fp32 SIMT weight gradients
         self.precise_grads = precise_grads
         self.fuse_bn_bwd = os.environ.get("HGK_FUSE_BN_BWD", "1") == "1"   # fold BN-backward reductions into single-consumer data-gradient epilogues
+        # BatchNorm finalisers (scale/shift/running stats; dgamma/dbeta/cA/cB/cC) run by the last CTA of the kernel that
+        # produced the sums instead of a C-length launch of their own
+        self.fuse_bn_fin = os.environ.get("HGK_FUSE_BN_FIN", "1") == "1"
+        self.tickets = torch.zeros(8192, device=device, dtype=torch.int32)   # last-CTA counters (re-armed by the kernels)
+        self.tickets_used = 0
         self.tc_entries = []       # (src param, mode, BN, hi offset, lo offset or -1)
         self.tc_used = 0
         self.tc_buf = None
@@ -241,6 +247,13 @@ class Plan(object):
             v = self.stat_b[self.stat_b_used:self.stat_b_used + C]
             self.stat_b_used += n
         return v
+
+    def ticket_alloc(self):
+        if self.tickets_used >= self.tickets.numel():
+            raise HGKError("plan ticket arena exhausted")
+        ptr = self.tickets.data_ptr() + 4 * self.tickets_used
+        self.tickets_used += 1
+        return ptr
 
     def launch(self, lst, fn_name, *args):
         fn = getattr(self.lib, fn_name)
@@ -572,6 +585,9 @@ class Plan(object):
 # argument positions written by each entry point (everything else is read-only); used by schedule_streams
 _WRITES = {
     "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20), "conv_tc_dgrad_bnstats_nhwc": (10, 18, 19),
+    "conv_tc_bn_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31),
+    "conv_tc_dgrad_bnfin_nhwc": (10, 18, 19, 22, 23, 24, 25, 26, 27),
+    "bn_bwd_reduce_fin": (9, 10, 13, 14, 15, 16, 17, 18),
     "conv_wgrad_nhwc": (11, 15), "conv_wgrad_tc_nhwc": (11, 12),
     "bn_finalize": (7, 8, 9, 10, 11, 12), "bn_eval_prepare": (5, 6, 7, 8),
     "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
@@ -725,11 +741,20 @@ class _StemOp(object):
 
 def _emit_bn_bwd(p, o, r, g):
     """dY (buffer g, gradient w.r.t. relu(bn(z))) -> dz in place."""
+    fin_args = [_ptr(r.gamma), int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB),
+                _ptr(r.cC)]
+    fin_done = o.bwd_fin_fused
     if not o.bwd_stats_fused:      # otherwise the consumer's data-gradient kernel already accumulated sum_g / sum_gx
-        p.launch(p.bwd, "bn_bwd_reduce", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean),
-                 _ptr(r.invstd), o.P, o.C, _ptr(r.sum_g), _ptr(r.sum_gx))
-    p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
-             int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
+        red_args = [_ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.invstd), o.P, o.C,
+                    _ptr(r.sum_g), _ptr(r.sum_gx)]
+        if p.fuse_bn_fin:
+            p.launch(p.bwd, "bn_bwd_reduce_fin", *(red_args + fin_args + [p.ticket_alloc()]))
+            fin_done = True
+        else:
+            p.launch(p.bwd, "bn_bwd_reduce", *red_args)
+    if not fin_done:
+        p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
+                 int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
     p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA),
              _ptr(r.cB), _ptr(r.cC), o.P, o.C)
 
@@ -758,11 +783,19 @@ class _ConvOp(object):
         self.bn = r = p.bn_rec(bn) if bn is not None else None
         stats = r is not None and r.training
         ra = res.act_args() if res is not None else [0, 0, 0, 0]
+        fin_fused = False
         if p.use_tc and p.lib.conv_tc_supported(Cin, Cout, k):
             # tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class accuracy)
             hi, lo = p.packed_weight_tc(w, 0, True)
-            p.launch(p.fwd, "conv_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, hi, lo, k, p.param_ptr(conv.bias), Cout]
-                                              + ra + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
+            base = x.act_args() + [x.N, x.H, x.W, Cin, hi, lo, k, p.param_ptr(conv.bias), Cout] + ra
+            if stats and p.fuse_bn_fin:
+                # the last CTA of the convolution finalises the BatchNorm (scale/shift, running statistics)
+                p.launch(p.fwd, "conv_tc_bn_nhwc", *(base + [_ptr(z), 0, _ptr(r.sum), _ptr(r.sq), _ptr(r.gamma), _ptr(r.beta),
+                                                             BN_EPS, BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale),
+                                                             _ptr(r.shift), _ptr(r.mean), _ptr(r.invstd), p.ticket_alloc()]))
+                fin_fused = True
+            else:
+                p.launch(p.fwd, "conv_tc_nhwc", *(base + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
         else:
             p.launch(p.fwd, "conv_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _PackRef(p.packed_weight(w, 0)), k, 0,
                                                            p.param_ptr(conv.bias), Cout] + ra +
@@ -770,7 +803,7 @@ class _ConvOp(object):
         if r is not None:
             self.out = T(z, x.N, x.H, x.W, Cout, r.scale, r.shift, relu, needs_grad=p.need_grad, name="conv")
             self.out.bn = r
-            if r.training:
+            if r.training and not fin_fused:
                 p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
                          BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
                          _ptr(r.invstd), Cout)
@@ -807,9 +840,16 @@ class _ConvOp(object):
                     # this launch produces the complete dL/d relu(bn(z)) of the previous layer: fuse that
                     # BatchNorm's backward reduction (sum g, sum g*xhat) into the epilogue
                     r = x.bn
-                    p.launch(p.bwd, "conv_tc_dgrad_bnstats_nhwc", _ptr(g), x.N, x.H, x.W, Cout, hi, lo, k, Cin,
-                             _ptr(extra), _ptr(gx), acc, _ptr(x.z), _ptr(x.scale), _ptr(x.shift), int(x.relu),
-                             _ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g), _ptr(r.sum_gx))
+                    args = [_ptr(g), x.N, x.H, x.W, Cout, hi, lo, k, Cin, _ptr(extra), _ptr(gx), acc, _ptr(x.z), _ptr(x.scale),
+                            _ptr(x.shift), int(x.relu), _ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g), _ptr(r.sum_gx)]
+                    if p.fuse_bn_fin:
+                        # ... and its finaliser (dgamma, dbeta, cA/cB/cC) runs in the last CTA
+                        p.launch(p.bwd, "conv_tc_dgrad_bnfin_nhwc", *(args + [
+                            _ptr(r.gamma), int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA),
+                            _ptr(r.cB), _ptr(r.cC), p.ticket_alloc()]))
+                        x.bwd_fin_fused = True
+                    else:
+                        p.launch(p.bwd, "conv_tc_dgrad_bnstats_nhwc", *args)
                     x.bwd_stats_fused = True
                 else:
                     p.launch(p.bwd, "conv_tc_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, hi, lo, k, 0, Cin,

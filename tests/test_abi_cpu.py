@@ -91,11 +91,17 @@ def test_plan_builds_and_covers_every_parameter():
         plan.output_nchw(o, no_grad=True)
     plan.finish()
     names = [r[2] for r in plan.fwd]
-    assert names.count("conv_tc_nhwc") + names.count("conv_nhwc") == 101 and names.count("stem_conv7_fwd") == 1
-    assert names.count("bn_finalize") == 96 and names.count("maxpool2_fwd") == 9 and names.count("add_fwd") == 8
+    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + names.count("conv_nhwc") == 101
+            and names.count("stem_conv7_fwd") == 1)
+    # 96 BatchNorms: 95 finalised by the last CTA of their tensor-core convolution, the stem's by its own launch
+    assert names.count("conv_tc_bn_nhwc") == 95 and names.count("bn_finalize") == 1
+    assert names.count("maxpool2_fwd") == 9 and names.count("add_fwd") == 8
     bnames = [r[2] for r in plan.bwd]
     assert bnames.count("conv_wgrad_tc_nhwc") + bnames.count("conv_wgrad_nhwc") == 101
     assert bnames.count("bn_bwd_apply") == 96 and "add_into" not in bnames     # all gradient fan-ins are aliased/fused
+    # every BN-backward finaliser rides on the kernel that produced its sums
+    assert bnames.count("conv_tc_dgrad_bnfin_nhwc") + bnames.count("bn_bwd_reduce_fin") == 96
+    assert "bn_bwd_finalize" not in bnames and "bn_bwd_reduce" not in bnames
     written = set()
     for fn, a, name in plan.bwd:
         written.update(x for x in a if isinstance(x, int))

@@ -474,6 +474,95 @@ def test_conv_tc_fwd_3xtf32(shape, variant):
     assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128, 1), (3, 5, 7, 32, 64, 3), (2, 8, 8, 128, 128, 3),
+                                   (5, 64, 64, 128, 256, 1), (3, 32, 48, 128, 128, 3), (6, 60, 60, 128, 128, 3)])
+def test_conv_tc_fused_bn_finalize(shape):
+    """conv + batch statistics + BatchNorm finaliser in ONE launch (last-CTA ticket): scale/shift/mean/invstd and the
+    running statistics must equal nn.BatchNorm2d's on the convolution output; the ticket re-arms itself."""
+    N, H, W, Ci, Co, k = shape
+    x = rnd("x", (N, Ci, H, W))
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    b = rnd("b", (Co,))
+    gamma, beta = rnd("gamma", (Co,), 0.5, 1.5), rnd("beta", (Co,), -0.3, 0.3)
+    rm0, rv0 = rnd("rm", (Co,), -0.2, 0.2), rnd("rv", (Co,), 0.5, 1.5)
+    ref = _conv_ref(x, w, b, k)
+    cnt = N * H * W
+    mean = ref.mean(dim=(0, 2, 3))
+    var = ref.var(dim=(0, 2, 3), unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    hi, lo = _pack_tc(w, 0, Co)
+    dx, db = nhwc(x), dev32(b)
+    dg, dbeta, drm, drv = dev32(gamma), dev32(beta), dev32(rm0), dev32(rv0)
+    y = torch.empty(N, H, W, Co, device=DEV)
+    sc, sh, sm, si = (torch.zeros(Co, device=DEV) for _ in range(4))
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    for rep in range(2):        # the second launch checks that the ticket was re-armed
+        ssum = torch.zeros(Co, device=DEV, dtype=torch.float64)
+        ssq = torch.zeros(Co, device=DEV, dtype=torch.float64)
+        call("conv_tc_bn_nhwc", ptr(dx), 0, 0, 0, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(db), Co, 0, 0, 0, 0, ptr(y), 0,
+             ptr(ssum), ptr(ssq), ptr(dg), ptr(dbeta), 1e-5, 0.1, ptr(drm), ptr(drv), ptr(sc), ptr(sh), ptr(sm), ptr(si),
+             ptr(ticket))
+        torch.cuda.synchronize()
+        assert int(ticket.item()) == 0
+        assert relerr(from_nhwc(y), ref) < 2e-5
+        assert relerr(sm.cpu(), mean) < 2e-5 and relerr(si.cpu(), invstd) < 2e-5
+        assert relerr(sc.cpu(), gamma * invstd) < 2e-5
+        assert relerr(sh.cpu(), beta - mean * gamma * invstd) < 5e-5
+    unb = var * cnt / (cnt - 1)
+    rm1 = 0.9 * (0.9 * rm0 + 0.1 * mean) + 0.1 * mean          # two momentum updates
+    rv1 = 0.9 * (0.9 * rv0 + 0.1 * unb) + 0.1 * unb
+    assert relerr(drm.cpu(), rm1) < 2e-5 and relerr(drv.cpu(), rv1) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (2, 8, 8, 128, 128, 3), (1, 64, 64, 128, 64, 1)])
+def test_bn_bwd_fused_finalizers(shape):
+    """dgrad + BN-backward sums + finaliser in one launch, and bn_bwd_reduce + finaliser in one launch, both against
+    the separate bn_bwd_reduce -> bn_bwd_finalize kernels."""
+    N, H, W, Ci, Co, k = shape
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    dz = rnd("dz", (N, Co, H, W))
+    bz = rnd("bz", (N, Ci, H, W))
+    gamma = rnd("gamma", (Ci,), 0.5, 1.5)
+    bsc, bsh = rnd("bsc", (Ci,), 0.5, 1.5), rnd("bsh", (Ci,), -0.3, 0.3)
+    bmu, biv = rnd("bmu", (Ci,), -0.2, 0.2), rnd("biv", (Ci,), 0.5, 2.0)
+    ddz, dbz = nhwc(dz), nhwc(bz)
+    dgam, dbsc, dbsh, dbmu, dbiv = dev32(gamma), dev32(bsc), dev32(bsh), dev32(bmu), dev32(biv)
+    hi, _ = _pack_tc(w, 1, Ci)
+    P = N * H * W
+
+    def fresh():
+        return dict(sg=torch.zeros(Ci, device=DEV, dtype=torch.float64), sgx=torch.zeros(Ci, device=DEV, dtype=torch.float64),
+                    dgamma=torch.full((Ci,), 0.25, device=DEV), dbeta=torch.full((Ci,), -0.5, device=DEV),
+                    cA=torch.zeros(Ci, device=DEV), cB=torch.zeros(Ci, device=DEV), cC=torch.zeros(Ci, device=DEV))
+    # reference chain: dgrad+bnstats -> bn_bwd_finalize
+    r = fresh()
+    gx_ref = torch.empty(N, H, W, Ci, device=DEV)
+    call("conv_tc_dgrad_bnstats_nhwc", ptr(ddz), N, H, W, Co, ptr(hi), 0, k, Ci, 0, ptr(gx_ref), 0, ptr(dbz), ptr(dbsc), ptr(dbsh), 1,
+         ptr(dbmu), ptr(dbiv), ptr(r["sg"]), ptr(r["sgx"]))
+    call("bn_bwd_finalize", ptr(r["sg"]), ptr(r["sgx"]), P, ptr(dgam), ptr(dbmu), ptr(dbiv), 1, ptr(r["dgamma"]), ptr(r["dbeta"]),
+         ptr(r["cA"]), ptr(r["cB"]), ptr(r["cC"]), Ci)
+    torch.cuda.synchronize()
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    # (a) fused in the data-gradient kernel
+    f = fresh()
+    gx = torch.empty(N, H, W, Ci, device=DEV)
+    call("conv_tc_dgrad_bnfin_nhwc", ptr(ddz), N, H, W, Co, ptr(hi), 0, k, Ci, 0, ptr(gx), 0, ptr(dbz), ptr(dbsc), ptr(dbsh), 1,
+         ptr(dbmu), ptr(dbiv), ptr(f["sg"]), ptr(f["sgx"]), ptr(dgam), 1, ptr(f["dgamma"]), ptr(f["dbeta"]), ptr(f["cA"]),
+         ptr(f["cB"]), ptr(f["cC"]), ptr(ticket))
+    torch.cuda.synchronize()
+    assert int(ticket.item()) == 0 and torch.equal(gx, gx_ref)
+    for key in ("dgamma", "dbeta", "cA", "cB", "cC"):
+        assert relerr(f[key], r[key]) < 1e-5, key
+    # (b) fused in the stand-alone reduction (gx_ref plays dY)
+    f2 = fresh()
+    call("bn_bwd_reduce_fin", ptr(gx_ref), ptr(dbz), ptr(dbsc), ptr(dbsh), 1, ptr(dbmu), ptr(dbiv), P, Ci, ptr(f2["sg"]),
+         ptr(f2["sgx"]), ptr(dgam), 1, ptr(f2["dgamma"]), ptr(f2["dbeta"]), ptr(f2["cA"]), ptr(f2["cB"]), ptr(f2["cC"]), ptr(ticket))
+    torch.cuda.synchronize()
+    assert int(ticket.item()) == 0
+    for key in ("dgamma", "dbeta", "cA", "cB", "cC"):
+        assert relerr(f2[key], r[key]) < 1e-5, key
+
+
 @pytest.mark.parametrize("shape", TC_SHAPES)
 def test_conv_tc_dgrad_1xtf32(shape):
     N, H, W, Ci, Co, k = shape
