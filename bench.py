@@ -219,7 +219,8 @@ def run_ours(args):
     x, t = build_inputs(args, rank)
     net = M.create_hg(args.stacks, 1, 16, args.chan)
     net.load_state_dict(sd)
-    tr = HourglassTrainer(net, args.batch, args.res, device=dev, use_graph=not args.no_graph, n_streams=args.streams)
+    tr = HourglassTrainer(net, args.batch, args.res, device=dev, use_graph=not args.no_graph, n_streams=args.streams,
+                          n_low=args.low_streams)
     xp, tp = x.pin_memory(), t.pin_memory()
     tr.x.copy_(xp)
     tr.t.copy_(tp)
@@ -285,7 +286,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(xp.numel() * 4 + tp.numel() * 4), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "api": "HourglassTrainer.step(images_pinned, heatmaps_pinned) -> loss.item()"},
             "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
-            "cuda_graph": not args.no_graph, "graph_streams": args.streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
+            "cuda_graph": not args.no_graph, "graph_streams": args.streams, "low_priority_streams": args.low_streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = cpu_sample(args, sd, x, t, budget_s=25.0, steps=2, warmup=0)
@@ -380,6 +381,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-path", type=int, default=None)
     ap.add_argument("--streams", type=int, default=6)
+    ap.add_argument("--low-streams", type=int, default=2, help="of --streams, low-priority streams reserved for weight gradients")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 2 if args.steps is None else args.steps

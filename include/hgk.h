@@ -92,6 +92,22 @@ int hgk_conv_tc_dgrad_bnfin_nhwc(const float* dz, int N, int H, int W, int Cin,
                                  double* sum_g, double* sum_gx,
                                  const float* gamma, int training, float* dgamma, float* dbeta,
                                  float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
+/* Data gradient of a convolution whose OUTPUT was followed by BatchNorm(+ReLU), with that BatchNorm's backward "apply"
+ * (hgk_bn_bwd_apply) evaluated on load by the image-tile kernel:  g = dL/d relu(bn(gz));
+ * dz = gcA*((g*[gz*gscale+gshift > 0] - gcC) - (gz - gmean)*gcB) is the convolution operand and is also written once to
+ * dz_out (for the weight-gradient kernel / the shortcut).  dy = [accumulate ? dy : 0] + conv^T(dz) + extra.
+ * bz != NULL additionally fuses the reduction + finaliser of the INPUT's BatchNorm exactly as
+ * hgk_conv_tc_dgrad_bnfin_nhwc does.  Shapes: hgk_conv_tc_bnapply_supported(N,H,W,Cin,Cout,ksize) (H, W multiples of 16). */
+int hgk_conv_tc_bnapply_supported(int N, int H, int W, int Cin, int Cout, int ksize);
+int hgk_conv_tc_dgrad_bnapply_nhwc(const float* g, const float* gz, const float* gscale, const float* gshift, int grelu,
+                                   const float* gmean, const float* gcA, const float* gcB, const float* gcC,
+                                   float* dz_out, int N, int H, int W, int Cin,
+                                   const float* w_hi, int ksize, int Cout,
+                                   const float* extra, float* dy, int accumulate,
+                                   const float* bz, const float* bscale, const float* bshift, int brelu,
+                                   const float* bmean, const float* binvstd, double* sum_g, double* sum_gx,
+                                   const float* gamma, int training, float* dgamma, float* dbeta,
+                                   float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
 /* table: n_entries x 8 int64 {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN};
  * mode 0 (forward operand): B[n][k;tap] = W[o=n][i=k][tap];  mode 1 (data-gradient operand):
  * B[n][k;tap] = W[o=k][i=n][taps-1-tap].  Destination: [n-tile][tap][k/32] blocks of [8][BN][4] floats,

@@ -22,6 +22,8 @@ SIGNATURES = {
                             P, P, F, F, P, P, P, P, P, P, P, P],
     "hgk_conv_tc_dgrad_bnfin_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P,
                                      P, I, P, P, P, P, P, P, P],
+    "hgk_conv_tc_dgrad_bnapply_nhwc": [P, P, P, P, I, P, P, P, P, P, I, I, I, I, P, I, I, P, P, I,
+                                       P, P, P, I, P, P, P, P, P, I, P, P, P, P, P, P, P],
     "hgk_bn_bwd_reduce_fin": [P, P, P, P, I, P, P, L, I, P, P, P, I, P, P, P, P, P, P, P],
     "hgk_pack_weights_tc": [P, P, P, I, P],
     "hgk_conv_wgrad_tc_nhwc": [P, P, P, I, I, I, I, I, P, I, I, P, P, P],
@@ -70,6 +72,8 @@ class _Lib(object):
         self.cdll.hgk_device_ok.restype = I
         self.cdll.hgk_conv_tc_supported.restype = I
         self.cdll.hgk_conv_tc_supported.argtypes = [I, I, I]
+        self.cdll.hgk_conv_tc_bnapply_supported.restype = I
+        self.cdll.hgk_conv_tc_bnapply_supported.argtypes = [I, I, I, I, I, I]
         self.cdll.hgk_conv_wgrad_tc_supported.restype = I
         self.cdll.hgk_conv_wgrad_tc_supported.argtypes = [I, I, I]
         for name, args in SIGNATURES.items():
@@ -80,6 +84,9 @@ class _Lib(object):
 
     def conv_tc_supported(self, cin, cout, k):
         return bool(self.cdll.hgk_conv_tc_supported(cin, cout, k))
+
+    def conv_tc_bnapply_supported(self, n, h, w, cin, cout, k):
+        return bool(self.cdll.hgk_conv_tc_bnapply_supported(n, h, w, cin, cout, k))
 
     def conv_wgrad_tc_supported(self, cin, cout, k):
         return bool(self.cdll.hgk_conv_wgrad_tc_supported(cin, cout, k))

@@ -30,6 +30,21 @@ struct BnBwdFin {
     int training;
 };
 
+// BatchNorm-backward "apply" of the convolution whose data gradient is being computed, evaluated ON LOAD by the
+// image-tile kernel: x.z holds dL/d relu(bn(z)) (= g); the operand is dz = cA*((g*[z*scale+shift > 0] - cC) -
+// (z - mean)*cB), which is also written once (tile-interior pixels) to `dz` for the weight-gradient kernel.
+struct BnApply {
+    const float* z;      // nullptr: disabled
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* cA;
+    const float* cB;
+    const float* cC;
+    float* dz;
+    int relu;
+};
+
 struct ConvArgs {
     Act x;
     int N, H, W, Cin;
@@ -53,6 +68,7 @@ struct ConvArgs {
     const float* binvstd;
     int brelu;
     BnFwdFin ffin;       // forward: (stat_sum, stat_sq) -> scale/shift/running stats
+    BnApply ap;          // image-tile data-gradient kernel only
     BnBwdFin bfin;       // BN-backward statistics mode: (stat_sum, stat_sq) = (sum g, sum g*xhat) -> dgamma/dbeta/cA/cB/cC
 };
 

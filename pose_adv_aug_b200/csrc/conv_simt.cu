@@ -401,7 +401,7 @@ extern "C" int hgk_conv_nhwc(const float* x, const float* x_scale, const float* 
     a.y = y; a.accumulate = accumulate; a.stat_sum = stat_sum; a.stat_sq = stat_sq;
     a.P = (long long)N * H * W;
     a.bz = nullptr; a.bscale = a.bshift = a.bmean = a.binvstd = nullptr; a.brelu = 0;
-    a.ffin = BnFwdFin{}; a.bfin = BnBwdFin{};
+    a.ffin = BnFwdFin{}; a.bfin = BnBwdFin{}; a.ap = BnApply{};
     cudaStream_t st = (cudaStream_t)stream;
     HGK_REQUIRE(path == 0 || path == 1, "hgk_conv_nhwc: this entry point is the fp32 SIMT kernel; use hgk_conv_tc_nhwc for tcgen05");
     long long mt = (a.P + CBM - 1) / CBM;

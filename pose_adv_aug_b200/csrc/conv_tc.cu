@@ -1044,7 +1044,8 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
                         const float* res, const float* res_scale, const float* res_shift, int res_relu,
                         float* y, int accumulate, double* stat_sum, double* stat_sq,
                         const float* bz, const float* bscale, const float* bshift, const float* bmean,
-                        const float* binvstd, int brelu, const BnFwdFin* ffin, const BnBwdFin* bfin, void* stream) {
+                        const float* binvstd, int brelu, const BnFwdFin* ffin, const BnBwdFin* bfin, void* stream,
+                        const BnApply* ap = nullptr) {
     HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
     HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
     HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
@@ -1063,6 +1064,10 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     ta.c.bz = bz; ta.c.bscale = bscale; ta.c.bshift = bshift; ta.c.bmean = bmean; ta.c.binvstd = binvstd; ta.c.brelu = brelu;
     ta.c.ffin = ffin != nullptr ? *ffin : BnFwdFin{};
     ta.c.bfin = bfin != nullptr ? *bfin : BnBwdFin{};
+    ta.c.ap = ap != nullptr ? *ap : BnApply{};
+    if (ap != nullptr)
+        HGK_REQUIRE(w_lo == nullptr && use_tile_kernel() && conv_tc2_eligible(ta), "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
+                    "image-tile kernel (see hgk_conv_tc_bnapply_supported)");
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1134,6 +1139,36 @@ extern "C" int hgk_conv_tc_dgrad_bnfin_nhwc(const float* dz, int N, int H, int W
     BnBwdFin f{gamma, bmean, binvstd, dgamma, dbeta, cA, cB, cC, ticket, training};
     return conv_tc_impl(dz, nullptr, nullptr, 0, N, H, W, Cin, w_hi, w_lo, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
                         dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, nullptr, &f, stream);
+}
+
+extern "C" int hgk_conv_tc_bnapply_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
+    if (!hgk_conv_tc_supported(Cin, Cout, ksize) || !use_tile_kernel() || N <= 0 || H <= 0 || W <= 0) return 0;
+    TcArgs ta;
+    ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
+    ta.c.P = (long long)N * H * W;
+    return conv_tc2_eligible(ta) ? 1 : 0;
+}
+
+extern "C" int hgk_conv_tc_dgrad_bnapply_nhwc(const float* g, const float* gz, const float* gscale, const float* gshift, int grelu,
+                                              const float* gmean, const float* gcA, const float* gcB, const float* gcC,
+                                              float* dz_out, int N, int H, int W, int Cin,
+                                              const float* w_hi, int ksize, int Cout,
+                                              const float* extra, float* dy, int accumulate,
+                                              const float* bz, const float* bscale, const float* bshift, int brelu,
+                                              const float* bmean, const float* binvstd, double* sum_g, double* sum_gx,
+                                              const float* gamma, int training, float* dgamma, float* dbeta,
+                                              float* cA, float* cB, float* cC, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(g && gz && gscale && gshift && gmean && gcA && gcB && gcC && dz_out, "hgk_conv_tc_dgrad_bnapply_nhwc: null pointer");
+    BnApply ap{gz, gscale, gshift, gmean, gcA, gcB, gcC, dz_out, grelu};
+    if (bz == nullptr)
+        return conv_tc_impl(g, nullptr, nullptr, 0, N, H, W, Cin, w_hi, nullptr, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
+                            dy, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                            stream, &ap);
+    HGK_REQUIRE(bscale && bshift && bmean && binvstd && sum_g && sum_gx && gamma && cA && cB && cC && ticket,
+                "hgk_conv_tc_dgrad_bnapply_nhwc: null pointer (fused reduction)");
+    BnBwdFin f{gamma, bmean, binvstd, dgamma, dbeta, cA, cB, cC, ticket, training};
+    return conv_tc_impl(g, nullptr, nullptr, 0, N, H, W, Cin, w_hi, nullptr, ksize, nullptr, Cout, extra, nullptr, nullptr, 0,
+                        dy, accumulate, sum_g, sum_gx, bz, bscale, bshift, bmean, binvstd, brelu, nullptr, &f, stream, &ap);
 }
 
 /* developer diagnostics: per-CTA globaltimer stamps of conv_tc_kernel ([512][16] int64), NULL disables */

@@ -67,8 +67,9 @@ struct T2Cfg {
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS>
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY>
 __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs args) {
+    static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
     using Cfg = T2Cfg<BN, SPLIT, KS>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
     constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
         const int quad = tid & 3;
         unsigned a_off[NJ], s_off[NJ];
         unsigned vmask = 0, smask = 0;          // pixel inside the image / item inside the tile
+        unsigned imask = 0;                     // BNAPPLY: pixel owned by this tile (its dz is written back)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int idx = tid + 256 * j;
@@ -136,22 +138,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
             s_off[j] = (unsigned)hp * 64u + (((unsigned)quad ^ (((unsigned)hp >> 1) & 3u)) << 4);
             if (in_img) vmask |= 1u << j;
             if (in_tile) smask |= 1u << j;
+            if (BNAPPLY && in_tile && hh >= PAD && hh < PAD + 16 && ww >= PAD && ww < PAD + 16) imask |= 1u << j;
         }
         const float* xz = a.x.z;
         const bool has_aff = a.x.scale != nullptr;
         const float x_clamp = a.x.relu ? 0.f : -INFINITY;
         float4 a_reg[2][NJ];
+        float4 z_reg[BNAPPLY ? 2 : 1][BNAPPLY ? NJ : 1];      // BNAPPLY: the pre-BN output z next to its gradient
+        const BnApply& ap = a.ap;
         auto load_a = [&](int set, int kc) {
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((vmask >> j) & 1u) v = ldg4(xz + (a_off[j] + (unsigned)kc * 16u));
                 a_reg[set][j] = v;
+                if (BNAPPLY) {
+                    float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((vmask >> j) & 1u) zz = ldg4(ap.z + (a_off[j] + (unsigned)kc * 16u));
+                    z_reg[BNAPPLY ? set : 0][BNAPPLY ? j : 0] = zz;
+                }
             }
         };
         auto store_a = [&](int s, int set, int kc) {
             float4 sc, sh;
             load_affine4(a.x.scale, a.x.shift, kc * 16 + quad * 4, sc, sh);
+            float4 bs, bt, bmu, bA, bB, bC;
+            if (BNAPPLY) {
+                const int c = kc * 16 + quad * 4;
+                bs = ldg4(ap.scale + c); bt = ldg4(ap.shift + c); bmu = ldg4(ap.mean + c);
+                bA = ldg4(ap.cA + c); bB = ldg4(ap.cB + c); bC = ldg4(ap.cC + c);
+            }
             uint8_t* base = sgen + s * A_STAGE;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
@@ -159,6 +175,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
                 float4 v = a_reg[set][j];
                 // zero padding is a zero of the ACTIVATED tensor: transform only pixels inside the image
                 if (has_aff && ((vmask >> j) & 1u)) v = actc4(v, sc, sh, x_clamp);
+                if (BNAPPLY && ((vmask >> j) & 1u)) {
+                    // dz = cA * ((g * relu-mask - cC) - (z - mean) * cB)   (bn_bwd_apply_kernel, bn.cu)
+                    const float4 z = z_reg[BNAPPLY ? set : 0][BNAPPLY ? j : 0];
+                    const float gx = (ap.relu && fmaf(z.x, bs.x, bt.x) <= 0.f) ? 0.f : v.x;
+                    const float gy = (ap.relu && fmaf(z.y, bs.y, bt.y) <= 0.f) ? 0.f : v.y;
+                    const float gz = (ap.relu && fmaf(z.z, bs.z, bt.z) <= 0.f) ? 0.f : v.z;
+                    const float gw = (ap.relu && fmaf(z.w, bs.w, bt.w) <= 0.f) ? 0.f : v.w;
+                    v.x = bA.x * ((gx - bC.x) - (z.x - bmu.x) * bB.x);
+                    v.y = bA.y * ((gy - bC.y) - (z.y - bmu.y) * bB.y);
+                    v.z = bA.z * ((gz - bC.z) - (z.z - bmu.z) * bB.z);
+                    v.w = bA.w * ((gw - bC.w) - (z.w - bmu.w) * bB.w);
+                    if ((imask >> j) & 1u) st4(ap.dz + (a_off[j] + (unsigned)kc * 16u), v);
+                }
                 const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
                 *reinterpret_cast<float4*>(base + s_off[j]) = hi;
                 if (SPLIT) {
@@ -391,12 +420,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
     }
 }
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS>
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false>
 static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
     constexpr int smem = T2Cfg<BN, SPLIT, KS>::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc (tile kernel): cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
@@ -404,12 +433,14 @@ static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
         configured = true;
     }
     const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 4));
-    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS><<<grid, T2_THREADS, smem, st>>>(ta);
+    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY><<<grid, T2_THREADS, smem, st>>>(ta);
     return HGK_OK;
 }
 
 template <int BN, int KS>
 static int launch_tc2_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream_t st) {
+    if (ta.c.ap.z != nullptr)        // data gradient with the BatchNorm-backward apply evaluated on load
+        return bwdstats ? launch_tc2_cfg<BN, false, KS, true, true>(ta, st) : launch_tc2_cfg<BN, false, KS, false, true>(ta, st);
     if (bwdstats) return launch_tc2_cfg<BN, false, KS, true>(ta, st);
     if (split) return launch_tc2_cfg<BN, true, KS, false>(ta, st);
     return launch_tc2_cfg<BN, false, KS, false>(ta, st);

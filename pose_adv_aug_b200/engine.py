@@ -130,7 +130,7 @@ class ParamStore(object):
 class T(object):
     """A tensor node of the plan: NHWC buffer z [N,H,W,C] + optional on-load affine/ReLU."""
     __slots__ = ("z", "N", "H", "W", "C", "scale", "shift", "relu", "needs_grad", "grad", "contribs",
-                 "producer", "name", "bn", "n_cons", "bwd_stats_fused", "bwd_fin_fused")
+                 "producer", "name", "bn", "n_cons", "n_done", "bwd_stats_fused", "bwd_fin_fused")
 
     def __init__(self, z, N, H, W, C, scale=None, shift=None, relu=False, needs_grad=False, name=""):
         self.z, self.N, self.H, self.W, self.C = z, N, H, W, C
@@ -142,6 +142,7 @@ class T(object):
         self.name = name
         self.bn = None            # BNRec whose (scale, shift) this tensor carries
         self.n_cons = 0           # number of ops that consume this tensor
+        self.n_done = 0           # ... of which have emitted their gradient contribution (backward plan construction)
         self.bwd_stats_fused = False   # the BN-backward reduction was produced by the consumer's data-gradient kernel
         self.bwd_fin_fused = False     # ... and so were dgamma / dbeta / cA / cB / cC (last-CTA finaliser)
 
@@ -193,6 +194,8 @@ class Plan(object):
         # BatchNorm finalisers (scale/shift/running stats; dgamma/dbeta/cA/cB/cC) run by the last CTA of the kernel that
         # produced the sums instead of a C-length launch of their own
         self.fuse_bn_fin = os.environ.get("HGK_FUSE_BN_FIN", "1") == "1"
+        # BatchNorm-backward apply evaluated on load by the image-tile data-gradient kernel (no bn_bwd_apply launch)
+        self.fuse_bn_apply = os.environ.get("HGK_FUSE_BN_APPLY", "1") == "1"
         self.tickets = torch.zeros(8192, device=device, dtype=torch.int32)   # last-CTA counters (re-armed by the kernels)
         self.tickets_used = 0
         self.tc_entries = []       # (src param, mode, BN, hi offset, lo offset or -1)
@@ -342,10 +345,12 @@ class Plan(object):
     def contribute(self, t, buf, donatable):
         if t is not None and t.needs_grad:
             t.contribs.append((buf, donatable))
+            t.n_done += 1
 
     def grad_target(self, t, allow_res=True):
         """(buffer, accumulate flag, residual buffer or None) for a kernel about to write d/d t."""
         res = None
+        t.n_done += 1
         if t.grad is None:
             for i, (b, don) in enumerate(t.contribs):
                 if don:
@@ -588,6 +593,7 @@ _WRITES = {
     "conv_tc_bn_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31),
     "conv_tc_dgrad_bnfin_nhwc": (10, 18, 19, 22, 23, 24, 25, 26, 27),
     "bn_bwd_reduce_fin": (9, 10, 13, 14, 15, 16, 17, 18),
+    "conv_tc_dgrad_bnapply_nhwc": (9, 18, 26, 27, 30, 31, 32, 33, 34, 35),
     "conv_wgrad_nhwc": (11, 15), "conv_wgrad_tc_nhwc": (11, 12),
     "bn_finalize": (7, 8, 9, 10, 11, 12), "bn_eval_prepare": (5, 6, 7, 8),
     "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
@@ -598,7 +604,8 @@ _WRITES = {
 }
 
 
-def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads")):
+def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads"),
+                     low_names=(), n_low=0):
     """Assign each launch of a static list to one of `n_streams` streams.
 
     Dependencies are derived from the launch arguments (device pointers; `_WRITES` says which positions
@@ -607,7 +614,11 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
     ordered against everything.  Returns (stream index per launch, for each launch the launches on OTHER
     streams it has to wait for).  The hourglass has coarse branch parallelism (skip residuals vs the down/up
     chain, weight- vs data-gradients): this lets the latency-bound 4x4 / 8x8 / 16x16 layers run under the
-    large 64x64 ones inside one CUDA graph."""
+    large 64x64 ones inside one CUDA graph.
+
+    `low_names` / `n_low`: launches with these entry-point names (the weight gradients: nothing on the critical path
+    waits for them) are confined to the LAST `n_low` streams, which the caller creates with a lower priority, so that
+    a data-gradient kernel whose CTAs are waiting for SMs is dispatched before the next weight-gradient CTA."""
     PTR_MIN = 1 << 32
     last_write = {}                    # ptr -> launch index of the last writer
     readers = {}                       # ptr -> launch indices that read it since that write
@@ -636,14 +647,19 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
             if barrier >= 0:
                 deps.add(barrier)
         deps.discard(i)
+        if n_low > 0:
+            pool = range(n_streams - n_low, n_streams) if name in low_names else range(0, n_streams - n_low)
+        else:
+            pool = range(n_streams)
         k = None
         for d in sorted(deps, reverse=True):       # continue on the stream of the most recent dependency
-            if tail[stream_of[d]] == d:
+            if tail[stream_of[d]] == d and stream_of[d] in pool:
                 k = stream_of[d]
                 break
         if k is None:
-            free = [q for q in lru if tail[q] < 0]
-            k = free[0] if free else lru[0]
+            cand = [q for q in lru if q in pool]
+            free = [q for q in cand if tail[q] < 0]
+            k = free[0] if free else cand[0]
         lru.remove(k)
         lru.append(k)
         best = {}
@@ -739,8 +755,9 @@ class _StemOp(object):
         p.dynamic("image", rec, 0)
 
 
-def _emit_bn_bwd(p, o, r, g):
-    """dY (buffer g, gradient w.r.t. relu(bn(z))) -> dz in place."""
+def _emit_bn_bwd(p, o, r, g, with_apply=True):
+    """dY (buffer g, gradient w.r.t. relu(bn(z))) -> dz in place (with_apply=False: only the reduction / finaliser; the
+    caller's data-gradient kernel evaluates the apply on load)."""
     fin_args = [_ptr(r.gamma), int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB),
                 _ptr(r.cC)]
     fin_done = o.bwd_fin_fused
@@ -755,8 +772,9 @@ def _emit_bn_bwd(p, o, r, g):
     if not fin_done:
         p.launch(p.bwd, "bn_bwd_finalize", _ptr(r.sum_g), _ptr(r.sum_gx), o.P, _ptr(r.gamma), _ptr(r.mean), _ptr(r.invstd),
                  int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C)
-    p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA),
-             _ptr(r.cB), _ptr(r.cC), o.P, o.C)
+    if with_apply:
+        p.launch(p.bwd, "bn_bwd_apply", _ptr(g), _ptr(o.z), _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA),
+                 _ptr(r.cB), _ptr(r.cC), o.P, o.C)
 
 
 class _ConvOp(object):
@@ -816,37 +834,59 @@ class _ConvOp(object):
         g = p.finalize_grad(o)
         if g is None:
             return
-        if self.bn is not None:
-            _emit_bn_bwd(p, o, self.bn, g)
         w = self.conv.weight
         k, Cin, Cout = self.k, self.Cin, self.Cout
-        if p.use_tc and not p.precise_grads and p.lib.conv_wgrad_tc_supported(Cin, Cout, k):
-            # tensor cores; 1x1: tap-major == OIHW, accumulate straight into .grad; 3x3: via the tap-major scratch
-            dst = p.param_grad_ptr(w) if k == 1 else p.wgrad_scratch(w)
-            p.launch(p.bwd, "conv_wgrad_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k, dst,
-                                                                    p.param_grad_ptr(self.conv.bias)]))
-        else:
-            # fp32 SIMT kernel, weight / bias gradient straight into the OIHW .grad views
-            p.launch(p.bwd, "conv_wgrad_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(g), Cout, k,
-                                                                 p.param_grad_ptr(w), Cin * k * k, k * k, 1,
-                                                                 p.param_grad_ptr(self.conv.bias)]))
+        dgrad_tc = x.needs_grad and p.use_tc and p.lib.conv_tc_supported(Cout, Cin, k)
+        # BatchNorm-backward apply on load: the data-gradient kernel reads (g, z), forms dz on the fly and writes it once
+        # to `dzb` for the weight gradient and the shortcut -- no bn_bwd_apply pass over the tensor
+        ap = (self.bn is not None and dgrad_tc and p.fuse_bn_apply and not p.precise_grads
+              and p.lib.conv_tc_bnapply_supported(x.N, x.H, x.W, Cout, Cin, k))
+        if self.bn is not None:
+            _emit_bn_bwd(p, o, self.bn, g, with_apply=not ap)
+        dzb = p.buf(o.N, o.H, o.W, o.C) if ap else g
+
+        def emit_wgrad():
+            if p.use_tc and not p.precise_grads and p.lib.conv_wgrad_tc_supported(Cin, Cout, k):
+                # tensor cores; 1x1: tap-major == OIHW, accumulate straight into .grad; 3x3: via the tap-major scratch
+                dst = p.param_grad_ptr(w) if k == 1 else p.wgrad_scratch(w)
+                p.launch(p.bwd, "conv_wgrad_tc_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(dzb), Cout, k, dst,
+                                                                        p.param_grad_ptr(self.conv.bias)]))
+            else:
+                # fp32 SIMT kernel, weight / bias gradient straight into the OIHW .grad views
+                p.launch(p.bwd, "conv_wgrad_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _ptr(dzb), Cout, k,
+                                                                     p.param_grad_ptr(w), Cin * k * k, k * k, 1,
+                                                                     p.param_grad_ptr(self.conv.bias)]))
+        if not ap:
+            emit_wgrad()
         # data gradient: same kernel on dz with the [tap][Cout][Cin] weights, taps flipped
         if x.needs_grad:
             gx, acc, extra = p.grad_target(x)
-            if p.use_tc and p.lib.conv_tc_supported(Cout, Cin, k):
+            if dgrad_tc:
                 hi, lo = p.packed_weight_tc(w, 1, p.precise_grads)   # plain TF32 is enough for gradients
-                if (x.bn is not None and x.n_cons == 1 and acc == 0 and not x.contribs and p.fuse_bn_bwd
-                        and not p.precise_grads):
-                    # this launch produces the complete dL/d relu(bn(z)) of the previous layer: fuse that
-                    # BatchNorm's backward reduction (sum g, sum g*xhat) into the epilogue
-                    r = x.bn
-                    args = [_ptr(g), x.N, x.H, x.W, Cout, hi, lo, k, Cin, _ptr(extra), _ptr(gx), acc, _ptr(x.z), _ptr(x.scale),
-                            _ptr(x.shift), int(x.relu), _ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g), _ptr(r.sum_gx)]
+                fuse_red = (x.bn is not None and x.n_done == x.n_cons and not x.contribs and p.fuse_bn_bwd
+                            and not p.precise_grads)
+                # fuse_red: every consumer of x has contributed and this launch folds the rest in (accumulate / extra): it
+                # produces the COMPLETE dL/d relu(bn(z)) of the previous layer, so that BatchNorm's backward
+                # reduction (sum g, sum g*xhat) is fused into the epilogue
+                r = x.bn
+                red = ([_ptr(x.z), _ptr(x.scale), _ptr(x.shift), int(x.relu), _ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g),
+                        _ptr(r.sum_gx)] if fuse_red else None)
+                fin = ([_ptr(r.gamma), int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA),
+                        _ptr(r.cB), _ptr(r.cC)] if fuse_red else None)
+                if ap:
+                    ro = self.bn
+                    head = [_ptr(g), _ptr(o.z), _ptr(ro.scale), _ptr(ro.shift), int(o.relu), _ptr(ro.mean), _ptr(ro.cA),
+                            _ptr(ro.cB), _ptr(ro.cC), _ptr(dzb), x.N, x.H, x.W, Cout, hi, k, Cin, _ptr(extra), _ptr(gx), acc]
+                    if fuse_red:
+                        p.launch(p.bwd, "conv_tc_dgrad_bnapply_nhwc", *(head + red + fin + [p.ticket_alloc()]))
+                        x.bwd_stats_fused = x.bwd_fin_fused = True
+                    else:
+                        p.launch(p.bwd, "conv_tc_dgrad_bnapply_nhwc", *(head + [0] * 16))
+                elif fuse_red:
+                    args = [_ptr(g), x.N, x.H, x.W, Cout, hi, lo, k, Cin, _ptr(extra), _ptr(gx), acc] + red
                     if p.fuse_bn_fin:
                         # ... and its finaliser (dgamma, dbeta, cA/cB/cC) runs in the last CTA
-                        p.launch(p.bwd, "conv_tc_dgrad_bnfin_nhwc", *(args + [
-                            _ptr(r.gamma), int(r.training), p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA),
-                            _ptr(r.cB), _ptr(r.cC), p.ticket_alloc()]))
+                        p.launch(p.bwd, "conv_tc_dgrad_bnfin_nhwc", *(args + fin + [p.ticket_alloc()]))
                         x.bwd_fin_fused = True
                     else:
                         p.launch(p.bwd, "conv_tc_dgrad_bnstats_nhwc", *args)
@@ -858,9 +898,11 @@ class _ConvOp(object):
                 wref = p.param_ptr(w) if k == 1 else _PackRef(p.packed_weight(w, 1))
                 p.launch(p.bwd, "conv_nhwc", _ptr(g), 0, 0, 0, x.N, x.H, x.W, Cout, wref, k, 1, 0, Cin,
                          _ptr(extra), 0, 0, 0, _ptr(gx), acc, 0, 0, 0)
+        if ap:
+            emit_wgrad()          # reads the dz written by the data-gradient kernel
         # shortcut: d/d res = dz (donated: this op never touches the buffer again)
         if self.res is not None:
-            p.contribute(self.res, g, True)
+            p.contribute(self.res, dzb, True)
 
 
 class _PoolOp(object):

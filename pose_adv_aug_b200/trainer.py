@@ -13,7 +13,7 @@ from . import dist as hdist
 
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None, n_streams=6):
+                 distributed=None, n_streams=6, n_low=2):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
@@ -44,6 +44,7 @@ class HourglassTrainer(object):
         self.graph_update = None
         self._sched = None
         self.n_streams = n_streams
+        self.n_low = n_low          # of those, low-priority streams reserved for the weight-gradient kernels
         self.use_graph = use_graph
         self.steps = 0
 
@@ -88,10 +89,14 @@ class HourglassTrainer(object):
         if plan.tc_launch is not None:
             launches.append(plan.tc_launch)
         launches += plan.fwd + plan.bwd
+        n_low = min(self.n_low, n_streams - 1)
         if self._sched is None:
-            self._sched = schedule_streams(launches, n_streams)
+            self._sched = schedule_streams(launches, n_streams, n_low=n_low,
+                                           low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad"))
         stream_of, cross = self._sched
-        side = [torch.cuda.Stream(self.device) for _ in range(n_streams - 1)]
+        # with a low-priority pool the other side streams are high priority (-1); the capture stream keeps priority 0
+        side = [torch.cuda.Stream(self.device, priority=(0 if (n_low and i >= n_streams - 1 - n_low) else (-1 if n_low else 0)))
+                for i in range(n_streams - 1)]
         streams = [main] + side
         fork = torch.cuda.Event()
         fork.record(main)

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from hgk_testlib import (DEV, call, ptr, rnd, dev32, nhwc, from_nhwc, relerr, affine_act, pack_w)
+from hgk_testlib import (DEV, call, ptr, rnd, dev32, nhwc, from_nhwc, relerr, affine_act, pack_w, lib)
 
 pytestmark = pytest.mark.gpu
 
@@ -561,6 +561,57 @@ def test_bn_bwd_fused_finalizers(shape):
     assert int(ticket.item()) == 0
     for key in ("dgamma", "dbeta", "cA", "cB", "cC"):
         assert relerr(f2[key], r[key]) < 1e-5, key
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (1, 64, 64, 128, 128, 3), (2, 32, 48, 64, 128, 1),
+                                   (1, 16, 32, 256, 256, 1), (1, 128, 128, 64, 64, 3)])
+@pytest.mark.parametrize("with_red", [0, 1])
+def test_conv_tc_dgrad_bnapply(shape, with_red):
+    """BatchNorm-backward apply evaluated on load by the image-tile data-gradient kernel == bn_bwd_apply followed by the
+    plain data-gradient kernel; the dz side output equals bn_bwd_apply's result exactly."""
+    N, H, W, Ci, Co, k = shape           # conv Ci -> Co; g, gz live on the Co side
+    assert lib().conv_tc_bnapply_supported(N, H, W, Co, Ci, k)
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    g, gz = nhwc(rnd("g", (N, Co, H, W))), nhwc(rnd("gz", (N, Co, H, W)))
+    v = {n: dev32(rnd(n, (Co,), lo, hi)) for n, lo, hi in (("sc", 0.5, 1.5), ("sh", -0.3, 0.3), ("mu", -0.2, 0.2),
+                                                           ("cA", 0.5, 1.5), ("cB", -0.2, 0.2), ("cC", -0.1, 0.1))}
+    hi, _ = _pack_tc(w, 1, Ci)
+    extra = nhwc(rnd("extra", (N, Ci, H, W)))
+    P = N * H * W
+    # reference chain
+    dz_ref = g.clone()
+    call("bn_bwd_apply", ptr(dz_ref), ptr(gz), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["cA"]), ptr(v["cB"]), ptr(v["cC"]), P, Co)
+    gx_ref = torch.empty(N, H, W, Ci, device=DEV)
+    bz = nhwc(rnd("bz", (N, Ci, H, W)))
+    b = {n: dev32(rnd(n, (Ci,), lo, hi)) for n, lo, hi in (("bsc", 0.5, 1.5), ("bsh", -0.3, 0.3), ("bmu", -0.2, 0.2),
+                                                           ("biv", 0.5, 2.0), ("gamma", 0.5, 1.5))}
+
+    def fresh():
+        return dict(sg=torch.zeros(Ci, device=DEV, dtype=torch.float64), sgx=torch.zeros(Ci, device=DEV, dtype=torch.float64),
+                    dgamma=torch.zeros(Ci, device=DEV), dbeta=torch.zeros(Ci, device=DEV),
+                    cA=torch.zeros(Ci, device=DEV), cB=torch.zeros(Ci, device=DEV), cC=torch.zeros(Ci, device=DEV))
+    r, f = fresh(), fresh()
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    if with_red:
+        call("conv_tc_dgrad_bnfin_nhwc", ptr(dz_ref), N, H, W, Co, ptr(hi), 0, k, Ci, ptr(extra), ptr(gx_ref), 0, ptr(bz), ptr(b["bsc"]),
+             ptr(b["bsh"]), 1, ptr(b["bmu"]), ptr(b["biv"]), ptr(r["sg"]), ptr(r["sgx"]), ptr(b["gamma"]), 1, ptr(r["dgamma"]),
+             ptr(r["dbeta"]), ptr(r["cA"]), ptr(r["cB"]), ptr(r["cC"]), ptr(ticket))
+    else:
+        call("conv_tc_nhwc", ptr(dz_ref), 0, 0, 0, N, H, W, Co, ptr(hi), 0, k, 0, Ci, ptr(extra), 0, 0, 0, ptr(gx_ref), 0, 0, 0)
+    # fused
+    dz = torch.full((N, H, W, Co), 7.0, device=DEV)
+    gx = torch.empty(N, H, W, Ci, device=DEV)
+    red = ([ptr(bz), ptr(b["bsc"]), ptr(b["bsh"]), 1, ptr(b["bmu"]), ptr(b["biv"]), ptr(f["sg"]), ptr(f["sgx"]), ptr(b["gamma"]), 1,
+            ptr(f["dgamma"]), ptr(f["dbeta"]), ptr(f["cA"]), ptr(f["cB"]), ptr(f["cC"]), ptr(ticket)] if with_red else [0] * 16)
+    call("conv_tc_dgrad_bnapply_nhwc", ptr(g), ptr(gz), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["cA"]), ptr(v["cB"]),
+         ptr(v["cC"]), ptr(dz), N, H, W, Co, ptr(hi), k, Ci, ptr(extra), ptr(gx), 0, *red)
+    torch.cuda.synchronize()
+    assert torch.equal(dz, dz_ref)               # same fp32 expression, every pixel written exactly once
+    assert torch.equal(gx, gx_ref)               # same operand values -> bit-identical accumulation
+    if with_red:
+        assert int(ticket.item()) == 0
+        for key in ("dgamma", "dbeta", "cA", "cB", "cC"):
+            assert relerr(f[key], r[key]) < 1e-5, key
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
