@@ -329,7 +329,7 @@ def dominant_kernel_roofline(tr, pk, torch):
         a = rec[1]
         if rec[2] == "conv_nhwc":
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[9], a[12]
-        elif rec[2] == "conv_tc_nhwc":
+        elif rec[2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc"):
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[10], a[12]
         else:
             continue
@@ -354,12 +354,18 @@ def dominant_kernel_roofline(tr, pk, torch):
     ms = e0.elapsed_time(e1) / (reps * len(recs))
     a = recs[0][1]
     N, H, W, Cin, Cout = a[4], a[5], a[6], a[7], a[12]
-    tc = recs[0][2] == "conv_tc_nhwc"
+    tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc")
     achieved = top / (ms / 1e3) / 1e12
+    tile = tc and H % 16 == 0 and W % 16 == 0
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the committed ncu --set full
+            # capture profiles/r1f_kernels_ncu.txt (24x64x64, 128->128: 51.6 MB read + 7.1 MB written back before the
+            # kernel ended; the 50 MB output largely stays dirty in the 126 MB L2)
+            "traffic": 58.6e6 if (tile and (N, H, W, Cin, Cout) == (24, 64, 64, 128, 128)) else None,
             "kernel": "%s 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this FLOP class/step)" %
-                      ("conv_tc_kernel (tcgen05, 3xTF32)" if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
+                      (("conv_tc2_kernel (tcgen05 image-tile kernel, 3xTF32)" if tile else "conv_tc_kernel (tcgen05, 3xTF32)")
+                       if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
             "ms_per_launch": ms, "flop_per_launch": top, "algorithmic_bytes_per_launch": 4.0 * N * H * W * (Cin + Cout),
             "mma_flop_per_launch": top * (3 if tc else 1),
             "frac_of_3xtf32_ceiling": achieved / (pk["bf16_tflops"] / 6.0) if tc else None,

@@ -51,24 +51,29 @@ struct T2Cfg {
     static constexpr int A_STAGE = (SPLIT ? 2 : 1) * A_HALF;
     static constexpr int B_HALF = BN * BK * 4;
     static constexpr int B_STAGE = (SPLIT ? 2 : 1) * B_HALF;
-    static constexpr int NSA = KS == 3 ? 2 : 3;                            // activation stages (one per chunk)
-    static constexpr int NSB = KS == 3 ? 8 : 3;                            // weight stages (one per chunk x tap)
-    static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
-    // accumulators per 128-pixel half, see conv_tc.cu (fp32 accumulator truncation of the tensor core)
-    static constexpr int NMAIN = (SPLIT && BN <= 64) ? 2 : 1;
-    static constexpr int NACC = !SPLIT ? 1 : (BN >= 256 ? 1 : NMAIN + 1);
+    // accumulators per 128-pixel half, see conv_tc.cu (fp32 accumulator truncation of the tensor core): 3x3 chains
+    // (K = 9 Cin) split into hi*hi / cross-term accumulators; a 1x1 chain is at most 3*256/8 = 96 MMAs long -- the
+    // same length conv_tc.cu accepts for its single-accumulator BN = 256 case
+    static constexpr int NMAIN = (SPLIT && KS == 3 && BN <= 64) ? 2 : 1;
+    static constexpr int NACC = (!SPLIT || KS == 1 || BN >= 256) ? 1 : NMAIN + 1;
     static constexpr int SUBCOLS = NACC * BN;
     static constexpr int TMEM_COLS = (2 * SUBCOLS <= 128) ? 128 : (2 * SUBCOLS <= 256) ? 256 : 512;
+    // two CTAs per SM wherever TMEM (<= 256 columns each) allows it: the prologue / epilogue of one CTA then overlaps
+    // the main loop of the other (every phase of this kernel is a serial latency chain inside one CTA)
+    static constexpr bool OCC2 = TMEM_COLS <= 256;
+    static constexpr int NSA = KS == 3 ? 2 : (OCC2 && SPLIT ? 2 : 3);      // activation stages (one per chunk)
+    static constexpr int NSB = KS == 3 ? (OCC2 ? 4 : 8) : NSA;             // weight stages (one per chunk x tap)
+    static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
     static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
     static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
     static constexpr int SMEM = (PIPE > STG_BYTES ? PIPE : STG_BYTES) + 1024;
     static_assert(2 * SUBCOLS <= 512, "TMEM capacity");
     static_assert(A_HALF % 1024 == 0 && B_HALF % 1024 == 0, "stage alignment (swizzle atoms)");
-    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert(SMEM <= (OCC2 ? 113 : 227) * 1024, "shared memory");
 };
 
 template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY>
-__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs args) {
+__global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 1)) conv_tc2_kernel(const TcArgs args) {
     static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
     using Cfg = T2Cfg<BN, SPLIT, KS>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
@@ -143,8 +148,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
         const float* xz = a.x.z;
         const bool has_aff = a.x.scale != nullptr;
         const float x_clamp = a.x.relu ? 0.f : -INFINITY;
-        float4 a_reg[2][NJ];
-        float4 z_reg[BNAPPLY ? 2 : 1][BNAPPLY ? NJ : 1];      // BNAPPLY: the pre-BN output z next to its gradient
+        // register prefetch depth: two chunks when the CTA has the SM to itself, one when a second CTA covers the latency
+        constexpr int NSET = Cfg::OCC2 ? 1 : 2;
+        float4 a_reg[NSET][NJ];
+        float4 z_reg[BNAPPLY ? NSET : 1][BNAPPLY ? NJ : 1];   // BNAPPLY: the pre-BN output z next to its gradient
         const BnApply& ap = a.ap;
         auto load_a = [&](int set, int kc) {
 #pragma unroll
@@ -197,15 +204,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
             }
         };
         load_a(0, 0);
-        if (KC > 1) load_a(1, 1);
+        if (NSET > 1 && KC > 1) load_a(NSET - 1, 1);
         int sa = 0;
         unsigned ea_par = 1;                 // parity of the previous use of the stage (toggles when sa wraps)
         for (int kc = 0; kc < KC; ++kc) {
             if (kc >= NSA) mbar_wait(bar_ea + 8 * sa, ea_par);            // stage drained by the tensor core
-            if (kc & 1) store_a(sa, 1, kc); else store_a(sa, 0, kc);
+            if (NSET > 1 && (kc & 1)) store_a(sa, NSET - 1, kc); else store_a(sa, 0, kc);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
             mbar_arrive(bar_fa + 8 * sa);
-            if (kc + 2 < KC) { if (kc & 1) load_a(1, kc + 2); else load_a(0, kc + 2); }
+            if (kc + NSET < KC) { if (NSET > 1 && (kc & 1)) load_a(NSET - 1, kc + NSET); else load_a(0, kc + NSET); }
             if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
         }
         mbar_wait(bar_done, 0);              // every MMA retired: accumulators complete, shared memory reusable
@@ -334,13 +341,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
             if (ch == BN / CH - 1 && sub == 1 && warp == 0)
                 asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
             float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-            // rows are processed 4 at a time with all global loads (shortcut / previous output / BN input) issued first
+            // rows are processed RB at a time with all global loads (shortcut / previous output / BN input) issued first
+            constexpr int RB = Cfg::OCC2 ? 2 : 4;
 #pragma unroll 1
-            for (int g = 0; epi && g < ROWS; g += 4) {
-                float4 rr[4], oo[4], zz[4];
-                long long pp[4];
+            for (int g = 0; epi && g < ROWS; g += RB) {
+                float4 rr[RB], oo[RB], zz[RB];
+                long long pp[RB];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RB; ++i) {
                     const int r = r0 + (g + i) * RL;
                     pp[i] = (pix0 + (long long)(r >> 3) * a.W + (sub * 8 + (r & 7))) * a.Cout + n;
                     rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const TcArgs ar
                     if (BWDSTATS) zz[i] = ldg4(a.bz + pp[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RB; ++i) {
                     const int r = r0 + (g + i) * RL;
                     float4 v = ld4(stg + r * SROW + cg * 4);
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;

@@ -13,6 +13,7 @@ def run(N,H,W,Ci,Co,k,split):
     hi, lo = dst[:w.numel()], dst[w.numel():]
     for rep in range(3):
         buf.zero_()
+        flush = torch.empty(64 << 20, device=DEV).fill_(1.0); del flush      # 256 MB write: evicts the weights from L2
         L.cdll.hgk_debug_set_timeline(buf.data_ptr() if rep==2 else 0)
         torch.cuda.synchronize()
         e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
@@ -24,9 +25,17 @@ def run(N,H,W,Ci,Co,k,split):
     t0 = b[:,0][b[:,0]>0].min()
     print('conv %dx%d %d->%d k%d split=%d: %.1f us total' % (H,W,Ci,Co,k,split, e0.elapsed_time(e1)*1e3))
     names=['start','alloc+sync','loads issued','stage0 stored','producer loop end','mma done','epi1 done','epi2 done','issuer fullA0','issuer fullB0']
-    for cta in (0, 1, 147, 148, 300):
+    for cta in ((0, 1, 2) if N*H*W <= 4096 else (0, 1, 147, 148, 300)):
         r = b[cta]
         print('  cta %3d start@%7.1fus ' % (cta, (r[0]-t0)/1e3) + ' '.join('%s=%.1f' % (names[i].split()[0], (r[i]-r[0])/1e3) for i in (1,2,3,8,9,4,5,6,7)))
-run(24,64,64,128,256,1,0)
-run(24,64,64,256,128,1,1)
-run(24,64,64,128,128,3,1)
+import os
+if os.environ.get("TL_SMALL"):
+    # cold weights: flush L2 between repetitions by touching a large buffer
+    run(24,8,8,128,128,3,1)
+    run(24,4,4,128,128,3,1)
+    run(24,8,8,256,128,1,1)
+    run(24,4,4,128,256,1,1)
+else:
+    run(24,64,64,128,256,1,0)
+    run(24,64,64,256,128,1,1)
+    run(24,64,64,128,128,3,1)

@@ -57,9 +57,15 @@ rows = []
 for i, (fn, a, name) in enumerate(recs):
     ms = evs[i].elapsed_time(evs[i + 1])
     key = name
-    if name in ("conv_nhwc", "conv_tc_nhwc"):
+    if name in ("conv_tc_dgrad_bnfin_nhwc", "conv_tc_dgrad_bnstats_nhwc"):
+        key = "%s k%d" % (name, a[7])
+        desc = "%dx%d %d->%d" % (a[2], a[3], a[4], a[8])
+    elif name == "conv_tc_dgrad_bnapply_nhwc":
+        key = "%s k%d" % (name, a[15])
+        desc = "%dx%d %d->%d%s" % (a[11], a[12], a[13], a[16], " +red" if a[20] else "")
+    elif name in ("conv_nhwc", "conv_tc_nhwc", "conv_tc_bn_nhwc"):
         N, H, W, Cin = a[4:8]
-        if name == "conv_tc_nhwc":
+        if name != "conv_nhwc":
             k, Cout, split = a[10], a[12], a[9] != 0
             key = "%s k%d %s" % (name, k, "3xtf32" if split else "tf32")
         else:
