@@ -339,6 +339,11 @@ def dominant_kernel_roofline(tr, pk, torch):
         return None
     top = max(c[0] for c in cand)
     recs = [r for f, r in cand if f == top]
+    # several layer shapes can share the top FLOP count (64->64 @128x128 and 128->128 @64x64): keep the most frequent one
+    import collections
+    shape_of = lambda r: tuple(r[1][4:8])
+    common = collections.Counter(shape_of(r) for r in recs).most_common(1)[0][0]
+    recs = [r for r in recs if shape_of(r) == common]
     stream = torch.cuda.current_stream().cuda_stream
     for r in recs:
         r[0](*r[1], stream)

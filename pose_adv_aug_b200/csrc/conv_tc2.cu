@@ -36,9 +36,12 @@ __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t saddr, uint32_t sbo) 
 
 constexpr int T2_THREADS = 320;      // 8 producer/epilogue warps + MMA warp + weight-copy warp
 
-template <int BN, bool SPLIT, int KS>
+// NSUB = 128-pixel halves per tile: 2 (16x16 tiles, each weight stage feeds two MMAs per k-step) for the large
+// layers; 1 (16 rows x 8 columns) when the 16x16 grid would leave SMs idle (16x16 and 32x32 layers): twice the
+// CTAs, half the serial work per CTA, half the TMEM (so two CTAs fit on an SM)
+template <int BN, bool SPLIT, int KS, int NSUB = 2>
 struct T2Cfg {
-    static constexpr int TH = 16, TW = 16;
+    static constexpr int TH = 16, TW = 8 * NSUB;
     static constexpr int PAD = KS / 2;
     static constexpr int HH = TH + 2 * PAD, HWD = TW + 2 * PAD;           // halo tile
     static constexpr int NPIX = HH * HWD;
@@ -57,25 +60,25 @@ struct T2Cfg {
     static constexpr int NMAIN = (SPLIT && KS == 3 && BN <= 64) ? 2 : 1;
     static constexpr int NACC = (!SPLIT || KS == 1 || BN >= 256) ? 1 : NMAIN + 1;
     static constexpr int SUBCOLS = NACC * BN;
-    static constexpr int TMEM_COLS = (2 * SUBCOLS <= 128) ? 128 : (2 * SUBCOLS <= 256) ? 256 : 512;
+    static constexpr int TMEM_COLS = (NSUB * SUBCOLS <= 64) ? 64 : (NSUB * SUBCOLS <= 128) ? 128 : (NSUB * SUBCOLS <= 256) ? 256 : 512;
     // two CTAs per SM wherever TMEM (<= 256 columns each) allows it: the prologue / epilogue of one CTA then overlaps
     // the main loop of the other (every phase of this kernel is a serial latency chain inside one CTA)
     static constexpr bool OCC2 = TMEM_COLS <= 256;
     static constexpr int NSA = KS == 3 ? 2 : (OCC2 && SPLIT ? 2 : 3);      // activation stages (one per chunk)
-    static constexpr int NSB = KS == 3 ? (OCC2 ? 4 : 8) : NSA;             // weight stages (one per chunk x tap)
+    static constexpr int NSB = KS == 3 ? (OCC2 ? (SPLIT ? 3 : 4) : 8) : NSA;   // weight stages (one per chunk x tap)
     static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
     static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
     static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
     static constexpr int SMEM = (PIPE > STG_BYTES ? PIPE : STG_BYTES) + 1024;
-    static_assert(2 * SUBCOLS <= 512, "TMEM capacity");
+    static_assert(NSUB * SUBCOLS <= 512, "TMEM capacity");
     static_assert(A_HALF % 1024 == 0 && B_HALF % 1024 == 0, "stage alignment (swizzle atoms)");
     static_assert(SMEM <= (OCC2 ? 113 : 227) * 1024, "shared memory");
 };
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY>
-__global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 1)) conv_tc2_kernel(const TcArgs args) {
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB>
+__global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 ? 2 : 1)) conv_tc2_kernel(const TcArgs args) {
     static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
-    using Cfg = T2Cfg<BN, SPLIT, KS>;
+    using Cfg = T2Cfg<BN, SPLIT, KS, NSUB>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
     constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
     constexpr uint32_t SBO_A = Cfg::SBO_A, LBO_B = BN * 16, SBO_B = 128;
@@ -91,10 +94,10 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles_w = a.W >> 4, tiles_hw = (a.H >> 4) * tiles_w;
+    const int tiles_w = a.W / Cfg::TW, tiles_hw = (a.H >> 4) * tiles_w;
     const int n_img = blockIdx.x / tiles_hw;
     const int trem = blockIdx.x - n_img * tiles_hw;
-    const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) << 4;
+    const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) * Cfg::TW;
     const int KC = a.Cin >> 4;
     const uint32_t bar_fa = smem_u32(&bars[0]), bar_ea = smem_u32(&bars[NSA]);
     const uint32_t bar_fb = smem_u32(&bars[2 * NSA]), bar_eb = smem_u32(&bars[2 * NSA + NSB]);
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
             s_off[j] = (unsigned)hp * 64u + (((unsigned)quad ^ (((unsigned)hp >> 1) & 3u)) << 4);
             if (in_img) vmask |= 1u << j;
             if (in_tile) smask |= 1u << j;
-            if (BNAPPLY && in_tile && hh >= PAD && hh < PAD + 16 && ww >= PAD && ww < PAD + 16) imask |= 1u << j;
+            if (BNAPPLY && in_tile && hh >= PAD && hh < PAD + 16 && ww >= PAD && ww < PAD + Cfg::TW) imask |= 1u << j;
         }
         const float* xz = a.x.z;
         const bool has_aff = a.x.scale != nullptr;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
                     const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
                     const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
+                    for (int sub = 0; sub < NSUB; ++sub) {
                         const uint32_t t_sub = tmem + sub * SUBCOLS;
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
         if (BWDSTATS) { bsc = ldg4(a.bscale + n); bsh = ldg4(a.bshift + n); bmu = ldg4(a.bmean + n); biv = ldg4(a.binvstd + n); }
         double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
 #pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
+        for (int sub = 0; sub < NSUB; ++sub) {
             if (warp < 8) {
                 const int lq = warp & 3;
                 const int row = lq * 32 + lane;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (ch == BN / CH - 1 && sub == 1 && warp == 0)
+            if (ch == BN / CH - 1 && sub == NSUB - 1 && warp == 0)
                 asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
             float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
             // rows are processed RB at a time with all global loads (shortcut / previous output / BN input) issued first
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
                     for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
                 }
             }
-            if (!(ch == BN / CH - 1 && sub == 1)) __syncthreads();       // staging tile is rewritten by the next half / chunk
+            if (!(ch == BN / CH - 1 && sub == NSUB - 1)) __syncthreads();   // staging tile is rewritten by the next half / chunk
         }
         if (do_stats) {
             if (epi) {
@@ -428,21 +431,29 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS>::OCC2 ? 2 : 
     }
 }
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false>
-static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB>
+static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
-    constexpr int smem = T2Cfg<BN, SPLIT, KS>::SMEM;
+    constexpr int smem = T2Cfg<BN, SPLIT, KS, NSUB>::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc (tile kernel): cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
         }
         configured = true;
     }
-    const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 4));
-    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY><<<grid, T2_THREADS, smem, st>>>(ta);
+    const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W / (8 * NSUB)));
+    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB><<<grid, T2_THREADS, smem, st>>>(ta);
     return HGK_OK;
+}
+
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false>
+static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
+    // 16x16 tiles when they fill the machine, 16x8 tiles (twice the CTAs) for the 16x16 / 32x32 layers
+    const long long tiles16 = (long long)ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 4);
+    if (tiles16 < kNumSMs) return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 1>(ta, st);
+    return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 2>(ta, st);
 }
 
 template <int BN, int KS>

@@ -417,6 +417,11 @@ TC_SHAPES = [
     (1, 16, 32, 64, 64, 1),
     (2, 16, 16, 256, 256, 1),
     (1, 48, 16, 128, 64, 1),
+    # >= 148 tiles of 16x16: the two-halves-per-tile configuration (fewer tiles take the 16x8 configuration)
+    (10, 64, 64, 128, 128, 3),
+    (10, 64, 64, 128, 256, 1),
+    (10, 64, 64, 64, 64, 3),
+    (10, 64, 64, 256, 128, 1),
     # the same layer classes just off the 16-pixel grid: conv_tc_kernel, two-CTAs-per-SM configuration
     (6, 60, 60, 128, 128, 3),
     (8, 60, 60, 64, 128, 1),
@@ -475,7 +480,8 @@ def test_conv_tc_fwd_3xtf32(shape, variant):
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128, 1), (3, 5, 7, 32, 64, 3), (2, 8, 8, 128, 128, 3),
-                                   (5, 64, 64, 128, 256, 1), (3, 32, 48, 128, 128, 3), (6, 60, 60, 128, 128, 3)])
+                                   (5, 64, 64, 128, 256, 1), (3, 32, 48, 128, 128, 3), (6, 60, 60, 128, 128, 3),
+                                   (10, 64, 64, 128, 128, 3)])
 def test_conv_tc_fused_bn_finalize(shape):
     """conv + batch statistics + BatchNorm finaliser in ONE launch (last-CTA ticket): scale/shift/mean/invstd and the
     running statistics must equal nn.BatchNorm2d's on the convolution output; the ticket re-arms itself."""
@@ -564,7 +570,8 @@ def test_bn_bwd_fused_finalizers(shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (1, 64, 64, 128, 128, 3), (2, 32, 48, 64, 128, 1),
-                                   (1, 16, 32, 256, 256, 1), (1, 128, 128, 64, 64, 3)])
+                                   (1, 16, 32, 256, 256, 1), (1, 128, 128, 64, 64, 3), (10, 64, 64, 128, 128, 3),
+                                   (10, 64, 64, 256, 128, 1)])
 @pytest.mark.parametrize("with_red", [0, 1])
 def test_conv_tc_dgrad_bnapply(shape, with_red):
     """BatchNorm-backward apply evaluated on load by the image-tile data-gradient kernel == bn_bwd_apply followed by the
