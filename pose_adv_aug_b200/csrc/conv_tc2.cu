@@ -21,6 +21,7 @@
 //   * roles: warps 0-7 load/transform/store the halo tiles (two chunks of register prefetch), warp 8 issues
 //     tcgen05.mma.kind::tf32 into TMEM and commits stages back, warp 9 streams the weights; all 8 producer
 //     warps then run the epilogue (tcgen05.ld -> smem tile -> coalesced stores + fp64 channel statistics).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
@@ -450,9 +451,16 @@ static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
 
 template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false>
 static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
-    // 16x16 tiles when they fill the machine, 16x8 tiles (twice the CTAs) for the 16x16 / 32x32 layers
+    // 16x8 tiles (twice the CTAs, two per SM: prologue / epilogue of one overlaps the main loop of the other) up to the
+    // 64x64 layers; 16x16 tiles (half the weight stream per pixel) for the 128x128 layers.  Measured on the config-2
+    // step: switch-over at 148 tiles 12.44 ms, at 400 tiles 12.28 ms, always 16x8 12.31 ms.
     const long long tiles16 = (long long)ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 4);
-    if (tiles16 < kNumSMs) return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 1>(ta, st);
+    static long long below = -1;          // HGK_TC2_SUB1_BELOW overrides the switch-over point (tuning knob)
+    if (below < 0) {
+        const char* e = getenv("HGK_TC2_SUB1_BELOW");
+        below = e != nullptr ? atoll(e) : 400;
+    }
+    if (tiles16 < below) return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 1>(ta, st);
     return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 2>(ta, st);
 }
 
