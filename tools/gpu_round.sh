@@ -16,8 +16,8 @@ head -45 $OUT/${TAG}_time_plan.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv \
    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 python tools/agg_launches.py $OUT/${TAG}_launches.csv 24 > $OUT/${TAG}_launches_summary.txt 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 150 -c 6 \
-   -o $OUT/${TAG}_conv_tc -f python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 100 -c 4 \
-   -o $OUT/${TAG}_wgrad_tc -f python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline >> $OUT/${TAG}_ncu_full.log 2>&1
+# ncu --set full of the big-layer kernels in isolation (cold inputs: rotating buffers > L2), third repetition
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2_kernel|wgrad2_tc_kernel" -s 18 -c 9 \
+   -o $OUT/${TAG}_kernels -f python tools/prof_kernels.py 3 > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 300 python tools/graph_timeline.py --out $OUT/${TAG}_graph_timeline.json > $OUT/${TAG}_graph_timeline.txt 2>&1
 ls -la $OUT
