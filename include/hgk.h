@@ -222,6 +222,42 @@ int hgk_rmsprop_flat(float* p, const float* g, float* v, long long n, float lr, 
 /* y[i] = (float)x[i]  (double loss accumulators -> fp32 scalars) */
 int hgk_f64_to_f32(const double* x, float* y, int n, float mul, void* stream);
 
+/* ==== callers either side of the training path (row a8) ==== */
+
+/* ---- pylib/Evaluation.py: get_preds (:6-23) and final_preds (:169-193) ----
+ * scores: NCHW [N,J,H,W].  preds [N,J,2] = 1-based (x, y) of the first maximum of every map, (0,0) where max <= 0
+ * (row = floor(idx / H) + 1 exactly as the reference, which divides by size(2)).  mode 1 adds final_preds' quarter-
+ * pixel shift (needs 1 < x < res0, 1 < y < res1), + 0.5, and -- when tinv != NULL -- the inverse crop transform:
+ * tinv[n] is the row-major 2x3 fp64 top of inv(GetTransform(center, scale, rot, res0, 200)) computed by the host
+ * exactly as the reference does; result = trunc(tinv * (x-1, y-1, 1)) + 1.  maxval [N,J] optional.                  */
+int hgk_heatmap_peaks(const float* scores, int N, int J, int H, int W, int mode, int res0, int res1,
+                      const double* tinv, float* preds, float* maxval, void* stream);
+/* ---- calc_dists (:25-39) + dist_acc (:41-54) + the averaging loop of accuracy / accuracy_origin_res (:56-104) ----
+ * dists [J,N]: |preds - target|_2 / normalize[n] where both target coordinates > boundary, else -1;
+ * acc [n_idx+1] (optional): acc[k+1] = share of valid dists[idxs[k]] <= thr (-1 if none valid), acc[0] = their mean. */
+int hgk_pck_accuracy(const float* preds, const float* target, const float* normalize, int N, int J,
+                     float boundary, float thr, const int* idxs, int n_idx, float* dists, float* acc, void* stream);
+/* dist_acc (:41-54) of a flat vector: out[0] = share of entries != -1 that are <= thr (-1 if none) */
+int hgk_dist_acc(const float* dists, int n, float thr, float* out, void* stream);
+/* per_person_pckh (:106-167): acc_vec[n] over the joints idxs; gt_preds = get_preds of the ground-truth heat-maps */
+int hgk_per_person_pckh(const float* dists, const float* gt_preds, int N, int J, const int* idxs, int n_idx,
+                        float thr, float* acc_vec, void* stream);
+/* ---- flip test (stack-hg.py:225-232; pylib/HumanAug.py:179-210) ----
+ * f(b)[n,c,h,w] = b[n, perm[c], h, flip_w ? W-1-w : w], perm = the n_pairs (i1,i2) channel swaps of the HOST array
+ * `pairs` applied in order;  out = a ? (a + f(b)) / 2 : f(b).  NCHW, W % 4 == 0, C <= 32, out != b.                 */
+int hgk_flip_merge_nchw(const float* a, const float* b_flipped, int N, int C, int H, int W, const int* pairs,
+                        int n_pairs, int flip_w, float* out, void* stream);
+/* ---- agent sampling (joint-train-pose-s-r-agent.py:252-271,344-363) ----
+ * probs [N,K] = softmax(logits); index[n] = np.random.choice(K, 1, p=probs[n]) for the uniform u[n] in [0,1)
+ * (first k whose normalised fp64 running sum exceeds u).  probs or index may be NULL.                                */
+int hgk_softmax_sample(const float* logits, int N, int K, const double* u, float* probs, long long* index,
+                       void* stream);
+/* ---- ASN dropout (models/asn_stacked_hg.py:79-100): y = T(x) * nearest_upsample(mask [N,MH,MW]) ; x, y NHWC ---- */
+int hgk_mask_mul_fwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, const float* mask,
+                     int N, int H, int W, int C, int MH, int MW, float* y, void* stream);
+int hgk_mask_mul_bwd(const float* g, const float* mask, int N, int H, int W, int C, int MH, int MW, float* gx,
+                     int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -201,6 +201,57 @@ def hg_stem(sd, x, st):
     return x
 
 
+def dropout(x, masks):
+    """_Hourglass._dropout, :79-100: x * nearest-upsampled [N,1,4,4] masks."""
+    scale = x.size(2) // 4
+    if scale != 1:
+        masks = masks.repeat_interleave(scale, dim=2).repeat_interleave(scale, dim=3)
+    return x * masks.to(x.dtype).expand(x.size())
+
+
+def sample_mask(pred_masks, dropout_num=2):
+    """_Hourglass._sample_mask, :102-136: softmax over the 16 cells, np.random.choice(16, 2, replace=False) per sample
+    from the GLOBAL numpy RandomState (seed it before calling), chosen cells zeroed in an all-ones mask."""
+    import numpy as np
+    n, _, h, w = pred_masks.shape
+    masks = torch.ones(pred_masks.size(), dtype=pred_masks.dtype)
+    probs = F.softmax(pred_masks.view(n, -1).float(), dim=1).detach().cpu().numpy()
+    indexes = torch.zeros(n, dropout_num).long()
+    for i in range(n):
+        idx = np.random.choice(h * w, dropout_num, p=probs[i], replace=False)
+        for j in range(len(idx)):
+            masks[i, 0, int(idx[j]) // w, int(idx[j]) % w] = 0
+            indexes[i, j] = int(idx[j])
+    return masks, indexes
+
+
+def hg_forward_dropout(sd, x, num_stacks, asn_sd, num_modules=1, training=True, asn_training=False, is_half_hg=False):
+    """_Hourglass_Wrapper.forward in is_dropout mode, :308-322,340: half -> pred_mask; whole ->
+    (outs, pred_mask, indexes, masks) with the masks of stack 0 re-applied in every later stack."""
+    st = BNState(training)
+    x = hg_stem(sd, x, st)
+    outs, masks, pred, indexes = [], None, None, None
+    for i in range(num_stacks):
+        p = "hg.%d" % i
+        neck, s1, s2, s3, s4 = hourglass_down(sd, p, x, st, num_modules)
+        if i == 0:
+            feats = {"neck": neck.detach(), "skip1": s1.detach(), "skip2": s2.detach(),
+                     "skip3": s3.detach(), "skip4": s4.detach()}
+            pred = asn_forward(asn_sd, feats, training=asn_training)[0]
+            if is_half_hg:
+                return pred, st
+            masks, indexes = sample_mask(pred)
+        neck, s1, s2, s3, s4 = (dropout(t, masks) for t in (neck, s1, s2, s3, s4))
+        y = hourglass_up(sd, p, neck, s1, s2, s3, s4, st, num_modules)
+        y = stack(sd, "post_res.%d" % i, y, st, num_modules)
+        y = F.relu(batchnorm(sd, "linear.%d.1" % i, conv(sd, "linear.%d.0" % i, y, 1), st))
+        o = conv(sd, "out_conv.%d" % i, y, 1)
+        outs.append(o)
+        if i < num_stacks - 1:
+            x = x + conv(sd, "forth_conv.%d" % i, y, 1) + conv(sd, "in_conv.%d" % i, o, 1)
+    return (outs, pred, indexes, masks), st
+
+
 def hg_forward(sd, x, num_stacks, num_modules=1, training=True, asn_sd=None, is_half_hg=False):
     """_Hourglass_Wrapper.forward, models/asn_stacked_hg.py:282-342.
 

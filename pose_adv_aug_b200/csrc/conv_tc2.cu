@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) HGK_STAMP(0);          // developer timeline (tools/dbg_timeline2.py); a predicated-off store otherwise
     const int tiles_w = a.W / Cfg::TW, tiles_hw = (a.H >> 4) * tiles_w;
     const int n_img = blockIdx.x / tiles_hw;
     const int trem = blockIdx.x - n_img * tiles_hw;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (tid == 0) HGK_STAMP(1);
 
     if (warp < 8) {
         // ===== producers: halo tile of one 16-channel chunk -> registers -> BN+ReLU, hi/lo -> shared memory =====
@@ -209,17 +211,23 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         };
         load_a(0, 0);
         if (NSET > 1 && KC > 1) load_a(NSET - 1, 1);
+        if (tid == 0) HGK_STAMP(2);
         int sa = 0;
         unsigned ea_par = 1;                 // parity of the previous use of the stage (toggles when sa wraps)
         for (int kc = 0; kc < KC; ++kc) {
             if (kc >= NSA) mbar_wait(bar_ea + 8 * sa, ea_par);            // stage drained by the tensor core
+            if (tid == 0) HGK_TRACE(0, kc);
             if (NSET > 1 && (kc & 1)) store_a(sa, NSET - 1, kc); else store_a(sa, 0, kc);
+            if (tid == 0) HGK_TRACE(6, kc);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
             mbar_arrive(bar_fa + 8 * sa);
+            if (tid == 0) { HGK_TRACE(1, kc); if (kc == 0) HGK_STAMP(3); }
             if (kc + NSET < KC) { if (NSET > 1 && (kc & 1)) load_a(NSET - 1, kc + NSET); else load_a(0, kc + NSET); }
             if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
         }
+        if (tid == 0) HGK_STAMP(4);
         mbar_wait(bar_done, 0);              // every MMA retired: accumulators complete, shared memory reusable
+        if (tid == 0) HGK_STAMP(5);
     } else if (warp == 8) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -227,10 +235,14 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             unsigned fa_par = 0, fb_par = 0;
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar_fa + 8 * sa, fa_par);
+                if (kc == 0) HGK_STAMP(8);
+                HGK_TRACE(2, kc);
                 const uint32_t a_stage = sbase + sa * A_STAGE;
 #pragma unroll 1
                 for (int tap = 0; tap < TAPS; ++tap, ++it) {
                     mbar_wait(bar_fb + 8 * sb, fb_par);
+                    if (it == 0) HGK_STAMP(9);
+                    if (tap == 0) HGK_TRACE(3, kc);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
                     const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
@@ -264,6 +276,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                     if (++sb == NSB) { sb = 0; fb_par ^= 1u; }
                 }
                 umma_commit(bar_ea + 8 * sa);                              // activation stage free
+                HGK_TRACE(4, kc);
                 if (++sa == NSA) { sa = 0; fa_par ^= 1u; }
             }
             umma_commit(bar_done);
@@ -277,6 +290,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             for (int kc = 0; kc < KC; ++kc) {
                 for (int tap = 0; tap < TAPS; ++tap, ++it) {
                     if (it >= NSB) mbar_wait(bar_eb + 8 * sb, eb_par);
+                    if (tap == 0) HGK_TRACE(5, kc);
                     const size_t off = ((size_t)tap * KC32 + (kc >> 1)) * (size_t)(BN * 32) + (size_t)(kc & 1) * (BN * 16);
                     const uint32_t bb = bar_fb + 8 * sb;
                     const uint32_t dst = sbase + B_OFF + sb * B_STAGE;
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             if (ch + 1 < BN / CH) __syncthreads();                       // `red` is rewritten by the next chunk
         }
     }
+    if (tid == 0) HGK_STAMP(6);
     // fused BatchNorm finaliser: the CTA that arrives last turns the complete sums into per-channel vectors
     if (do_stats) {
         if (!BWDSTATS && a.ffin.ticket != nullptr) {

@@ -21,7 +21,13 @@ __device__ __forceinline__ long long gtimer() {
 }
 #define HGK_STAMP(slot)                                                                   \
     do {                                                                                  \
-        if (args.dbg != nullptr && blockIdx.x < 512) args.dbg[blockIdx.x * 16 + (slot)] = gtimer(); \
+        if (args.dbg != nullptr && blockIdx.x < 256) args.dbg[blockIdx.x * 16 + (slot)] = gtimer(); \
+    } while (0)
+
+// per-chunk trace of CTA 0 (SM cycle counter): row 256 + kind, column = chunk index (< 16)
+#define HGK_TRACE(kind, col)                                                                      \
+    do {                                                                                          \
+        if (args.dbg != nullptr && blockIdx.x == 0 && (col) < 16) args.dbg[(256 + (kind)) * 16 + (col)] = clock64(); \
     } while (0)
 
 constexpr int TBM = 128, TNT = 256;

@@ -436,6 +436,38 @@ class Plan(object):
         self.tape.append(op)
         return op.out
 
+    def materialize(self, x):
+        """relu(bn(z)) written out as a plain NHWC tensor (AvgPool2d(1): the 1x1 window of the pooling kernel)."""
+        return self.avgpool(x, 1) if x.scale is not None else x
+
+    def input_plain(self, N, H, W, C, key):
+        """A no-gradient NHWC input read in place through a per-call pointer (e.g. the [N,1,4,4] dropout masks, whose
+        NCHW and NHWC layouts coincide because C == 1)."""
+        t = T(None, N, H, W, C, name=key)
+        self.inputs.append((key, t))
+        return t
+
+    def dropout(self, x, mask):
+        """x * nearest_upsample(mask) (models/asn_stacked_hg.py:79-100); mask: [N,MH,MW,1] plan tensor, no gradient."""
+        op = _DropoutOp(self, x, mask)
+        self.tape.append(op)
+        return op.out
+
+    def sample_mask(self, pred):
+        """Host sampling of the dropout cells (models/asn_stacked_hg.py:102-136) between two launches of the forward
+        list: returns the [N,MH,MW,1] mask tensor (no gradient); the chosen indexes are left in `plan.mask_indexes`."""
+        op = _SampleMaskOp(self, pred)
+        self.tape.append(op)
+        return op.out
+
+    def output_plain(self, x):
+        """A plain plan tensor whose NHWC buffer IS the NCHW result (C == 1 or H == W == 1), e.g. the ASN dropout head's
+        [N,1,4,4] mask logits."""
+        op = _OutputOp(self, x, len(self.outputs), rows=True)
+        self.tape.append(op)
+        self.outputs.append(op)
+        return op
+
     def detach(self, x):
         """Same values, no gradient flow (x.detach(), models/asn_stacked_hg.py:161)."""
         x.use()      # a detached reader still means "more than one consumer" for fusion decisions
@@ -983,15 +1015,15 @@ class _LinearOp(object):
     def __init__(self, plan, x, fc):
         self.plan, self.x, self.fc = plan, x, fc
         x.use()
-        if x.H != 1 or x.W != 1 or x.scale is not None:
-            raise ValueError("linear expects a plain [N,1,1,C] tensor")
-        Nout, K = fc.weight.shape
+        if x.scale is not None:
+            raise ValueError("linear expects a plain (materialised) tensor")
+        Nout, K = fc.weight.shape[0], fc.weight[0].numel()      # nn.Linear [Nout,K] or a 1x1 nn.Conv2d [Nout,K,1,1]
         if K != x.C:
             raise ValueError("linear expects %d features, got %d" % (K, x.C))
-        z = plan.buf(x.N, 1, 1, Nout)
-        plan.launch(plan.fwd, "linear_fwd", _ptr(x.z), plan.param_ptr(fc.weight), plan.param_ptr(fc.bias), x.N, K, Nout,
+        z = plan.buf(x.N, x.H, x.W, Nout)
+        plan.launch(plan.fwd, "linear_fwd", _ptr(x.z), plan.param_ptr(fc.weight), plan.param_ptr(fc.bias), x.P, K, Nout,
                     _ptr(z))
-        self.out = T(z, x.N, 1, 1, Nout, needs_grad=plan.need_grad, name="linear")
+        self.out = T(z, x.N, x.H, x.W, Nout, needs_grad=plan.need_grad, name="linear")
         self.out.producer = self
 
     def emit_bwd(self):
@@ -999,14 +1031,88 @@ class _LinearOp(object):
         g = p.finalize_grad(self.out)
         if g is None:
             return
-        Nout, K = fc.weight.shape
+        Nout, K = fc.weight.shape[0], fc.weight[0].numel()
         gx = 0
         if x.needs_grad:
-            tmp = p.buf(x.N, 1, 1, K)
+            tmp = p.buf(x.N, x.H, x.W, K)
             gx = _ptr(tmp)
             p.contribute(x, tmp, True)
-        p.launch(p.bwd, "linear_bwd", _ptr(x.z), p.param_ptr(fc.weight), _ptr(g), x.N, K, Nout, gx,
+        p.launch(p.bwd, "linear_bwd", _ptr(x.z), p.param_ptr(fc.weight), _ptr(g), x.P, K, Nout, gx,
                  p.param_grad_ptr(fc.weight), p.param_grad_ptr(fc.bias))
+
+
+class _DropoutOp(object):
+    """`_Hourglass._dropout` (models/asn_stacked_hg.py:79-100): multiply the activated tensor by the nearest-upsampled
+    [N,1,4,4] mask.  The product is materialised (its consumers read a plain tensor)."""
+
+    def __init__(self, plan, x, mask):
+        self.plan, self.x, self.mask = plan, x, mask
+        x.use()
+        if mask.C != 1 or mask.N != x.N or x.H % mask.H or x.W % mask.W or x.H // mask.H != x.W // mask.W:
+            raise ValueError("dropout: mask [%d,%d,%d,%d] does not tile the %dx%d feature map"
+                             % (mask.N, mask.H, mask.W, mask.C, x.H, x.W))
+        z = plan.buf(x.N, x.H, x.W, x.C)
+        rec = plan.launch(plan.fwd, "mask_mul_fwd", *(x.act_args() + [_ptr(mask.z), x.N, x.H, x.W, x.C, mask.H, mask.W, _ptr(z)]))
+        if mask.z is None:
+            plan.dynamic(mask.name, rec, 4)
+        self.out = T(z, x.N, x.H, x.W, x.C, needs_grad=x.needs_grad, name="dropout")
+        self.out.producer = self
+
+    def emit_bwd(self):
+        p, x, m = self.plan, self.x, self.mask
+        g = p.finalize_grad(self.out)
+        if g is None or not x.needs_grad:
+            return
+        gx, acc, _ = p.grad_target(x, allow_res=False)
+        rec = p.launch(p.bwd, "mask_mul_bwd", _ptr(g), _ptr(m.z), x.N, x.H, x.W, x.C, m.H, m.W, _ptr(gx), acc)
+        if m.z is None:
+            p.dynamic(m.name, rec, 1)
+
+
+class _SampleMaskOp(object):
+    """`_Hourglass._sample_mask` (models/asn_stacked_hg.py:102-136): softmax over the MH*MW mask logits of every sample,
+    then `np.random.choice(MH*MW, 2, p=probs[i], replace=False)` on the HOST, exactly as the reference (same numpy
+    RandomState stream); the two chosen cells are zeroed in an all-ones mask.  Runs between two kernel launches of the
+    forward list (one stream synchronisation, as the reference's `.cpu()`); the softmax itself is a libhgk kernel."""
+
+    DROPOUT_NUM = 2
+
+    def __init__(self, plan, pred):
+        import numpy as np
+        self.plan, self.pred = plan, pred
+        pred.use()
+        if pred.C != 1 or pred.scale is not None or pred.H != pred.W:
+            raise ValueError("sample_mask expects plain [N,H,W,1] mask logits with H == W")
+        N, K = pred.N, pred.H * pred.W
+        dev = plan.device
+        self.probs = torch.empty(N, K, device=dev, dtype=torch.float32)
+        self.mask = plan.buf(N, pred.H, pred.W, 1)
+        self.host_probs = torch.empty(N, K, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.empty(N, K)
+        self.host_mask = torch.empty(N, pred.H, pred.W, 1, dtype=torch.float32)
+        if dev.type == "cuda":
+            self.host_mask = self.host_mask.pin_memory()
+        plan.mask_indexes = torch.zeros(N, self.DROPOUT_NUM, dtype=torch.long)
+        plan.launch(plan.fwd, "softmax_sample", _ptr(pred.z), N, K, 0, _ptr(self.probs), 0)
+        lib = plan.lib
+
+        def host_sample(stream):
+            self.host_probs.copy_(self.probs, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            probs = self.host_probs.numpy()
+            self.host_mask.fill_(1.0)
+            hm = self.host_mask.view(N, K)
+            for i in range(N):
+                idx = np.random.choice(K, self.DROPOUT_NUM, p=probs[i], replace=False)      # ref:122
+                for j in range(len(idx)):
+                    hm[i, int(idx[j])] = 0.0                                                 # ref:124-128
+                    plan.mask_indexes[i, j] = int(idx[j])                                    # ref:131
+            self.mask.copy_(self.host_mask, non_blocking=True)
+            return 0
+        plan.fwd.append([host_sample, [], "host_sample_mask"])
+        self.out = T(self.mask, N, pred.H, pred.W, 1, name="dropout_mask")
+
+    def emit_bwd(self):
+        pass
 
 
 class _MSEOp(object):
@@ -1032,10 +1138,10 @@ class _OutputOp(object):
             x.use()
         p = plan
         if rows:
-            if x.H != 1 or x.W != 1 or x.scale is not None:
-                raise ValueError("row output expects a plain [N,1,1,C] tensor")
-            self.result = x.z.view(x.N, x.C)
-            self.gsrc = torch.zeros(x.N, x.C, device=p.device, dtype=torch.float32) if (p.need_grad and not no_grad) else None
+            if x.scale is not None or not ((x.H == 1 and x.W == 1) or x.C == 1):
+                raise ValueError("row output expects a plain [N,1,1,C] or [N,H,W,1] tensor")
+            self.result = x.z.view(x.N, x.C) if (x.H == 1 and x.W == 1) else x.z.view(x.N, 1, x.H, x.W)
+            self.gsrc = torch.zeros_like(self.result) if (p.need_grad and not no_grad) else None
         else:
             self.result = torch.empty(x.N, x.C, x.H, x.W, device=p.device, dtype=torch.float32)
             p.bytes_alloc += self.result.numel() * 4
@@ -1048,7 +1154,7 @@ class _OutputOp(object):
             return
         g = p.buf(x.N, x.H, x.W, x.C)
         if self.rows:
-            rec = p.launch(p.bwd, "add_into", 0, _ptr(g), x.N * x.C, 0)
+            rec = p.launch(p.bwd, "add_into", 0, _ptr(g), x.P * x.C, 0)
         else:
             rec = p.launch(p.bwd, "nchw_to_nhwc", 0, x.N, x.C, x.H, x.W, _ptr(g))
         p.dynamic("gout%d" % self.index, rec, 0)

@@ -234,43 +234,60 @@ class _Hourglass(nn.Module):
         x = plan.add(_build_stack(self.up1, plan, x), s1, upsample_a=True)
         return x
 
-    def _build(self, plan, x, asn=None, is_half_hg=False):
-        """Returns (y or None, agent outputs or None)."""
+    def _build(self, plan, x, asn=None, is_half_hg=False, is_dropout=False, mask=None):
+        """Returns (y or None, agent outputs or None, dropout mask tensor or None)."""
         neck, s1, s2, s3, s4 = self._build_down(plan, x)
         agent = None
         if asn is not None:
+            assert mask is None                                                      # ref:160
             feats = {'neck': plan.detach(neck), 'skip1': plan.detach(s1), 'skip2': plan.detach(s2),
                      'skip3': plan.detach(s3), 'skip4': plan.detach(s4)}           # ref:161-162
             mode = plan.training
             plan.training = asn.training
-            agent = asn._build(plan, feats)
+            agent = asn._build(plan, feats, is_dropout=is_dropout)
             plan.training = mode
             if is_half_hg:
-                return None, agent                                                   # ref:169-171
-        return self._build_up(plan, neck, s1, s2, s3, s4), agent
+                return None, agent, None                                             # ref:169-171,174-176
+            if is_dropout:
+                mask = plan.sample_mask(agent[0])                                    # ref:178
+        if mask is not None:                                                         # ref:179-190
+            neck = plan.dropout(neck, mask)
+            s1, s2, s3, s4 = (plan.dropout(t, mask) for t in (s1, s2, s3, s4))
+        return self._build_up(plan, neck, s1, s2, s3, s4), agent, mask
 
     def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False, dropout_masks=None):
-        if is_dropout or dropout_masks is not None:
-            raise NotImplementedError("ASN dropout mode (ref:172-190) is not invoked by any reference script "
-                                      "and is not built yet")
-        if asn is not None and not is_aug:
-            raise AssertionError("is_aug != is_dropout (ref:165)")
+        if asn is not None:
+            assert dropout_masks is None                                             # ref:160
+            assert is_aug != is_dropout                                              # ref:165
+        inputs = [x] if dropout_masks is None else [x, dropout_masks]
 
         def build(plan):
             t = plan.input_nchw(*x.shape, needs_grad=x.requires_grad)
-            y, agent = self._build(plan, t, asn, is_half_hg)
+            mask = None
+            if dropout_masks is not None:
+                if dropout_masks.dim() != 4 or dropout_masks.shape[1] != 1:
+                    raise ValueError("dropout_masks must be [N,1,h,w] (ref:81)")
+                mask = plan.input_plain(dropout_masks.shape[0], dropout_masks.shape[2], dropout_masks.shape[3], 1, "dropout_masks")
+            y, agent, m = self._build(plan, t, asn, is_half_hg, is_dropout, mask)
             if y is not None:
                 plan.output_nchw(y)
             if agent is not None:
-                plan.output_rows(agent[0])
-                plan.output_rows(agent[1])
+                for a in agent:
+                    (plan.output_plain if is_dropout else plan.output_rows)(a)
+            return m
         extra = (asn,) if asn is not None else ()
-        outs = _run(self, extra, ("hourglass", asn is not None, is_half_hg), [x], build)[1]
+        key = ("hourglass", asn is not None, is_half_hg, is_dropout, dropout_masks is not None)
+        plan, outs = _run(self, extra, key, inputs, build)
         if asn is None:
             return outs[0]
+        if is_aug:
+            if is_half_hg:
+                return outs[0], outs[1]
+            return outs[0], outs[1], outs[2]                                         # ref:208
         if is_half_hg:
-            return outs[0], outs[1]
-        return outs[0], outs[1], outs[2]                                             # ref:208
+            return outs[0]                                                           # ref:176
+        m = plan.structure
+        return outs[0], outs[1], plan.mask_indexes.clone(), m.z.view(m.N, 1, m.H, m.W).clone()   # ref:210
 
 
 class _Hourglass_Wrapper(nn.Module):
@@ -314,21 +331,21 @@ class _Hourglass_Wrapper(nn.Module):
         adapter = nn.Conv2d(in_num, out_num, kernel_size=1, stride=1, bias=True)
         return _Residual(in_num, out_num, adapter)
 
-    def _build(self, plan, img, asn=None, is_half_hg=False):
+    def _build(self, plan, img, asn=None, is_half_hg=False, is_dropout=False):
         """ref:282-342.  Returns (list of per-stack heat-map tensors, agent outputs or None)."""
         x = plan.stem(img, self.conv1, self.bn1)                        # ref:283-285
         x = self.residual1._build(plan, x)
         x = plan.maxpool(x)
         x = self.residual2._build(plan, x)
         x = self.residual3._build(plan, x)
-        outs, agent = [], None
+        outs, agent, mask = [], None, None
         for i in range(self.num_stacks):
             if i == 0 and asn is not None:
-                y, agent = self.hg[i]._build(plan, x, asn, is_half_hg)
+                y, agent, mask = self.hg[i]._build(plan, x, asn, is_half_hg, is_dropout)
                 if is_half_hg:
-                    return outs, agent                                  # ref:302-304
+                    return outs, agent                                  # ref:302-304,311-313
             else:
-                y, _ = self.hg[i]._build(plan, x)
+                y, _, _ = self.hg[i]._build(plan, x, mask=mask)         # ref:320-322: later stacks reuse the masks
             y = _build_stack(self.post_res[i], plan, y)                 # ref:327
             y = plan.conv(y, self.linear[i][0], bn=self.linear[i][1])   # ref:328
             o = plan.conv(y, self.out_conv[i])                          # ref:329
@@ -339,32 +356,33 @@ class _Hourglass_Wrapper(nn.Module):
         return outs, agent
 
     def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False):
-        if is_dropout:
-            raise NotImplementedError("ASN dropout mode (ref:308-316) is not invoked by any reference script "
-                                      "and is not built yet")
-        if asn is not None and not is_aug:
-            raise AssertionError("is_aug != is_dropout (ref:297)")
+        if asn is not None:
+            assert is_aug != is_dropout                                 # ref:297
         _check_input(x)
         if x.shape[1] != 3 or x.shape[2] % 64 or x.shape[3] % 64:
             raise ValueError("expected [N,3,H,W] images with H, W multiples of 64 (got %s)" % (tuple(x.shape),))
 
         def build(plan):
             img = plan.input_image(x.shape[0], x.shape[2], x.shape[3])
-            outs, agent = self._build(plan, img, asn, is_half_hg)
+            outs, agent = self._build(plan, img, asn, is_half_hg, is_dropout and asn is not None)
             for o in outs:
                 plan.output_nchw(o)
             if agent is not None:
-                plan.output_rows(agent[0])
-                plan.output_rows(agent[1])
+                for a in agent:
+                    (plan.output_plain if is_dropout else plan.output_rows)(a)
             return len(outs)
         extra = (asn,) if asn is not None else ()
-        plan, outs = _run(self, extra, ("wrapper", asn is not None, is_half_hg), [x], build)
+        plan, outs = _run(self, extra, ("wrapper", asn is not None, is_half_hg, is_dropout), [x], build)
         n = plan.structure
         if asn is None:
             return outs[:n]                                             # ref:342
+        if is_aug:
+            if is_half_hg:
+                return outs[n], outs[n + 1]                             # ref:304
+            return outs[:n], outs[n], outs[n + 1]                       # ref:338
         if is_half_hg:
-            return outs[n], outs[n + 1]                                 # ref:304
-        return outs[:n], outs[n], outs[n + 1]                           # ref:338
+            return outs[n]                                              # ref:313
+        return outs[:n], outs[n], plan.mask_indexes.clone()             # ref:340
 
 
 def create_hg(num_stacks, num_modules, num_classes, chan):
@@ -408,10 +426,10 @@ class ASN(nn.Module):
     def _stack_residual(self):
         return nn.Sequential(*[_Residual(self.chan_out, self.chan_out) for _ in range(self.num_modules)])
 
-    def _build(self, plan, f):
-        """ref:401-436 (is_aug).  f: dict of plan tensors."""
-        if not hasattr(self, "fc_scale"):
-            raise NotImplementedError("ASN dropout head (ref:437-439) is not built yet")
+    def _build(self, plan, f, is_dropout=False):
+        """ref:401-439.  f: dict of plan tensors.  Returns (scale, rotation) logits or (mask logits,)."""
+        if is_dropout != hasattr(self, "out_conv"):
+            raise ValueError("this ASN was created with is_%s=True (ref:351,400-405)" % ("dropout" if hasattr(self, "out_conv") else "aug"))
         skip1 = self.residual_skip1._build(plan, f['skip1'])
         skip2 = self.residual_skip2._build(plan, f['skip2'])
         skip3 = self.residual_skip3._build(plan, f['skip3'])
@@ -422,24 +440,26 @@ class ASN(nn.Module):
         x = self.merge3._build(plan, plan.add(plan.maxpool(x), skip4))
         x = self.merge4._build(plan, plan.add(plan.maxpool(x), neck))
         x = _build_stack(self.deep_merge, plan, x)
+        if is_dropout:
+            # ref:437-439: out_conv = Conv2d(chan_out, 1, 1x1): one dot product per cell of the 4x4 map
+            return (plan.linear(plan.materialize(x), self.out_conv),)
         x = plan.avgpool(x, 4)                                          # ref:431
         if x.H != 1 or x.W != 1:
             raise ValueError("ASN head needs a 4x4 neck (256x256 input); got %dx%d after AvgPool2d(4)" % (x.H, x.W))
         return plan.linear(x, self.fc_scale), plan.linear(x, self.fc_rotation)   # ref:434-435
 
     def forward(self, x, is_aug=False, is_dropout=False):
-        if is_dropout or not is_aug:
-            raise NotImplementedError("ASN dropout mode (ref:437-439) is not built yet")
+        if is_aug == is_dropout:
+            return None                                                 # ref:430-439: neither branch returns
         keys = ['neck', 'skip1', 'skip2', 'skip3', 'skip4']
         tensors = [x[k] for k in keys]
 
         def build(plan):
             f = dict((k, plan.input_nchw(*t.shape, needs_grad=t.requires_grad)) for k, t in zip(keys, tensors))
-            s, r = self._build(plan, f)
-            plan.output_rows(s)
-            plan.output_rows(r)
-        outs = _run(self, (), "asn", tensors, build)[1]
-        return outs[0], outs[1]
+            for o in self._build(plan, f, is_dropout=is_dropout):
+                (plan.output_plain if is_dropout else plan.output_rows)(o)
+        outs = _run(self, (), ("asn", is_dropout), tensors, build)[1]
+        return outs[0] if is_dropout else (outs[0], outs[1])
 
 
 def create_asn(chan_in, chan_out, scale_num=None, rotation_num=None, is_aug=False, is_dropout=False):

@@ -315,7 +315,9 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
                 d = (pa - pb).abs()
                 assert float(d.max()) < 2e-2, k
                 if k.startswith("out_conv.1") and k.endswith("weight"):
-                    assert float((d > 1e-5).float().mean()) < 0.02, k
+                    # (1e-4 = 4 % of one RMSprop step: observed differences are 3e-6 .. 1e-5 depending on the
+                    # atomics order of the run, so a 1e-5 gate was flaky)
+                    assert float((d > 1e-4).float().mean()) < 0.02, k
         hm = tr.heatmaps()
         assert len(hm) == S and tuple(hm[0].shape) == (N, K, R // 4, R // 4)
     # oracle: same three steps on CPU fp32.  Step 0 (before any update) must agree tightly; after that every
@@ -370,3 +372,90 @@ def test_cpu_input_fails_loudly():
     net = M.create_hg(1, 1, 16, 32)
     with pytest.raises(HGKError):
         net(torch.rand(1, 3, 64, 64))
+
+
+def test_asn_dropout_mode_vs_reference_golden():
+    """ASN dropout mode (ref models/asn_stacked_hg.py:79-136,172-190,308-322,340): half-hg mask logits,
+    whole two-stack net with np.random-sampled masks (same numpy seed as the reference run -> same cells), loss,
+    gradients, the agent-side gradient, and the `dropout_masks=` path of _Hourglass.forward against the oracle."""
+    M = _mods()
+    g = np.load(os.path.join(GOLD, "dropout_s2_c32_n2_r256_f32.npz"))
+    S, C, N, R = 2, 32, 2, 256
+    sd = synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=21)
+    asd = synth.make_state_dict(O.asn_schema(C, C, is_dropout=True), seed=22)
+    net = _load(M.create_hg(S, 1, 16, C), sd).to(DEV)
+    asn = _load(M.create_asn(C, C, is_dropout=True), asd).to(DEV)
+    x = synth.make_images(N, R, seed=23).to(DEV)
+    t = synth.make_heatmaps(N, R, 16, seed=24).to(DEV)
+    net.train()
+    asn.eval()
+    pm = net(x, asn, is_half_hg=True, is_dropout=True)
+    assert tuple(pm.shape) == (N, 1, 4, 4)
+    assert relerr(pm, torch.from_numpy(g["half_pred_mask"])) < 1e-3
+    _load(net, sd)
+    np.random.seed(4321)
+    outs, pm2, indexes = net(x, asn, is_dropout=True)
+    assert isinstance(outs, list) and len(outs) == S and tuple(pm2.shape) == (N, 1, 4, 4)
+    assert indexes.dtype == torch.long and np.array_equal(indexes.cpu().numpy(), g["indexes"])
+    loss = 0
+    for o in outs:
+        tmp = (o - t) ** 2
+        loss = loss + tmp.sum() / tmp.numel()
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * float(g["loss"])
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(g["out%d_sub" % i])
+        assert relerr(o[:, :, ::3, ::3], ref) < 1e-3
+    for p in net.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k, tol in (("out_conv.1.weight", 1e-3), ("hg.1.skip2.0.conv1.weight", 3e-2), ("hg.0.skip1.0.conv3.weight", 3e-2),
+                   ("hg.0.neck.0.conv2.weight", 3e-2), ("residual1.conv1.weight", 5e-2)):
+        assert relerr(params[k].grad, torch.from_numpy(g["grad:" + k])) < tol, k
+    # agent side: hg.eval(), asn.train(), gradient of sum(pred_mask * w) reaches the ASN only
+    _load(net, sd)
+    net.eval()
+    asn.train()
+    pm3 = net(x, asn, is_half_hg=True, is_dropout=True)
+    assert relerr(pm3, torch.from_numpy(g["half_pred_mask_asntrain"])) < 1e-3
+    w = synth.make_tensor("mask_w", tuple(pm3.shape), seed=25).to(DEV)
+    for p in list(asn.parameters()) + list(net.parameters()):
+        if p.grad is not None:
+            p.grad.zero_()
+    (pm3 * w).sum().backward()
+    assert relerr(asn.out_conv.weight.grad, torch.from_numpy(g["grad:asn.out_conv.weight"])) < 1e-3
+    assert relerr(asn.merge4.conv3.weight.grad, torch.from_numpy(g["grad:asn.merge4.conv3.weight"])) < 2e-2
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in net.parameters() if p.grad is not None)
+    # _Hourglass.forward(x, dropout_masks=...) (ref:184-190) and _Hourglass whole dropout mode (ref:210) vs the oracle
+    hg = net.hg[0]
+    hg.train()
+    feat = synth.make_tensor("hg_feat", (N, C, 64, 64), seed=26, lo=0.0, hi=1.0)
+    masks = torch.ones(N, 1, 4, 4)
+    masks[0, 0, 1, 2] = 0
+    masks[0, 0, 3, 3] = 0
+    masks[1, 0, 0, 0] = 0
+    y = hg(feat.to(DEV), dropout_masks=masks.to(DEV))
+    sd0 = OrderedDict((k[len("hg.0."):], v.double()) for k, v in sd.items() if k.startswith("hg.0."))
+    st = O.BNState(True)
+    neck, s1, s2, s3, s4 = O.hourglass_down(sd0, "", feat.double(), st, 1) if False else (None,) * 5
+    sdp = OrderedDict(("h." + k, v) for k, v in sd0.items())
+    neck, s1, s2, s3, s4 = O.hourglass_down(sdp, "h", feat.double(), st, 1)
+    neck, s1, s2, s3, s4 = (O.dropout(v, masks.double()) for v in (neck, s1, s2, s3, s4))
+    yref = O.hourglass_up(sdp, "h", neck, s1, s2, s3, s4, st, 1)
+    assert relerr(y, yref) < 1e-3
+    asn.eval()
+    np.random.seed(7)
+    y2, pmh, idxh, dm = hg(feat.to(DEV), asn, is_dropout=True)
+    assert tuple(dm.shape) == (N, 1, 4, 4) and float(dm.sum()) == N * 14 and tuple(idxh.shape) == (N, 2)
+    for i in range(N):
+        for j in range(2):
+            assert float(dm[i, 0, int(idxh[i, j]) // 4, int(idxh[i, j]) % 4]) == 0.0
+    # standalone ASN dropout head on an NCHW feature dict (ref:401,437-439)
+    feats = {"neck": torch.rand(N, C, 4, 4, device=DEV), "skip1": torch.rand(N, C, 64, 64, device=DEV),
+             "skip2": torch.rand(N, C, 32, 32, device=DEV), "skip3": torch.rand(N, C, 16, 16, device=DEV),
+             "skip4": torch.rand(N, C, 8, 8, device=DEV)}
+    m1 = asn(feats, is_dropout=True)
+    mref, _ = O.asn_forward(OrderedDict((k, v.cpu().double()) for k, v in asn.state_dict().items()),
+                            dict((k, v.cpu().double()) for k, v in feats.items()), training=False)
+    assert relerr(m1, mref) < 1e-3

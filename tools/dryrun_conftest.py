@@ -27,7 +27,7 @@ def pytest_configure(config):
         setattr(lib, name[4:], make(fn))
     lib.cdll.hgk_device_ok = lambda: 1
     torch.cuda.synchronize = lambda *a, **k: None
-    torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
+    torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.cuda.current_device = lambda: 0
     import pose_adv_aug_b200.models.asn_stacked_hg as M
@@ -36,6 +36,19 @@ def pytest_configure(config):
         if x.dim() != 4:
             raise ValueError("dims")
     M._check_input = chk
+    import pose_adv_aug_b200.pylib.Evaluation as EV
+    import pose_adv_aug_b200.pylib.HumanAug as HA
+    import pose_adv_aug_b200.agent as AG
+    EV._cuda_f32 = lambda t, what: t.contiguous().float()
+    HA._check = lambda t, what: t.contiguous().float()
+    type(torch.empty(0)).is_cuda = property(lambda self: True) if False else type(torch.empty(0)).is_cuda
+    _orig_ss = AG.softmax_sample
+
+    def _ss(logits, u):
+        class _Fake(torch.Tensor):
+            is_cuda = True
+        return _orig_ss(logits.as_subclass(_Fake), u)
+    AG.softmax_sample = _ss
     import pose_adv_aug_b200.trainer as TR
     orig = TR.HourglassTrainer.__init__
 
