@@ -89,16 +89,18 @@ class ClockSampler(threading.Thread):
 
 
 def build_inputs(args, rank):
-    from oracle import synth
+    from pose_adv_aug_b200 import synth
     x = synth.make_images(args.batch, args.res, seed=100 + rank)
     t = synth.make_heatmaps(args.batch, args.res, 16, seed=200 + rank)
     return x, t
 
 
 def make_weights(args):
-    from oracle import synth
-    from oracle import hg_oracle as O
-    return synth.make_state_dict(O.hg_schema(args.stacks, 1, 16, args.chan), seed=1, perturb_bn=False)
+    """Seeded reference-initialiser-shaped weights, keyed by the drop-in module's own state_dict schema (== the
+    reference's, tests/test_abi_cpu.py); both arms load the same dict.  Nothing under oracle/ is touched here."""
+    from pose_adv_aug_b200 import synth
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    return synth.make_state_dict(synth.schema_of(M.create_hg(args.stacks, 1, 16, args.chan)), seed=1, perturb_bn=False)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -288,6 +290,8 @@ def run_ours(args):
             "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
             "cuda_graph": not args.no_graph, "graph_streams": args.streams, "low_priority_streams": args.low_streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
     if world == 1 and not args.no_cpu_baseline:
+        # ---- cpu_baseline leg (the only place this arm executes anything under oracle/): the reference's CPU step on
+        #      the host cores, timed on a bounded sample, and -- as the checker -- its heat-maps against ours ----
         try:
             r = cpu_sample(args, sd, x, t, budget_s=25.0, steps=2, warmup=0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -360,12 +360,12 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
                     }
                 }
             }
-            if (do_stats) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
-            }
         }
         if (do_stats) {
+            // fp32 partial sums over this thread's ROWS (<= 16) values, fp64 from here on (one conversion per chunk:
+            // the F2F.F64 / DADD pair per 4 rows was ~40 % of the row loop, profiles/r2_tile_kernel_timeline.md)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
             if (epi) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

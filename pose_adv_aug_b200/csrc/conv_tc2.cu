@@ -65,7 +65,14 @@ struct T2Cfg {
     // two CTAs per SM wherever TMEM (<= 256 columns each) allows it: the prologue / epilogue of one CTA then overlaps
     // the main loop of the other (every phase of this kernel is a serial latency chain inside one CTA)
     static constexpr bool OCC2 = TMEM_COLS <= 256;
-    static constexpr int NSA = KS == 3 ? 2 : (OCC2 && SPLIT ? 2 : 3);      // activation stages (one per chunk)
+    // PAIR: the producers fill TWO 16-channel stages per round (one proxy fence, twice the independent work per
+    // thread): for the plain-TF32 1x1 kernels (data gradients) the producers' serial chain per chunk (~1300 cycles:
+    // transform ~600 + fence / arrive ~300-1000) is what bounds the main loop, not the tensor pipe (184-366 cycles per
+    // chunk) -- profiles/r2_tile_kernel_timeline.md.  Needs an even number (>= 4) of activation stages.  The kernel
+    // switches it off for the BNAPPLY instantiations (measured slower there: 113 -> 119 us on the 64x64 256->128 data
+    // gradient; the doubled register sets spill inside the producer loop).
+    static constexpr bool PAIR = KS == 1 && NSUB == 1 && !SPLIT;
+    static constexpr int NSA = KS == 3 ? 2 : (PAIR ? 4 : (OCC2 && SPLIT ? 2 : 3));      // activation stages (one per chunk)
     static constexpr int NSB = KS == 3 ? (OCC2 ? (SPLIT ? 3 : 4) : 8) : NSA;   // weight stages (one per chunk x tap)
     static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
     static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
@@ -155,7 +162,8 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         const bool has_aff = a.x.scale != nullptr;
         const float x_clamp = a.x.relu ? 0.f : -INFINITY;
         // register prefetch depth: two chunks when the CTA has the SM to itself, one when a second CTA covers the latency
-        constexpr int NSET = Cfg::OCC2 ? 1 : 2;
+        constexpr bool PAIR = Cfg::PAIR && !BNAPPLY;
+        constexpr int NSET = (PAIR || !Cfg::OCC2) ? 2 : 1;
         float4 a_reg[NSET][NJ];
         float4 z_reg[BNAPPLY ? NSET : 1][BNAPPLY ? NJ : 1];   // BNAPPLY: the pre-BN output z next to its gradient
         const BnApply& ap = a.ap;
@@ -214,16 +222,37 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         if (tid == 0) HGK_STAMP(2);
         int sa = 0;
         unsigned ea_par = 1;                 // parity of the previous use of the stage (toggles when sa wraps)
-        for (int kc = 0; kc < KC; ++kc) {
-            if (kc >= NSA) mbar_wait(bar_ea + 8 * sa, ea_par);            // stage drained by the tensor core
-            if (tid == 0) HGK_TRACE(0, kc);
-            if (NSET > 1 && (kc & 1)) store_a(sa, NSET - 1, kc); else store_a(sa, 0, kc);
-            if (tid == 0) HGK_TRACE(6, kc);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-            mbar_arrive(bar_fa + 8 * sa);
-            if (tid == 0) { HGK_TRACE(1, kc); if (kc == 0) HGK_STAMP(3); }
-            if (kc + NSET < KC) { if (NSET > 1 && (kc & 1)) load_a(NSET - 1, kc + NSET); else load_a(0, kc + NSET); }
-            if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
+        if (PAIR) {
+            // two chunks per round (KC is even: Cin % 32 == 0); stages sa, sa+1 wrap together (NSA even)
+            for (int kc = 0; kc < KC; kc += 2) {
+                if (kc >= NSA) {
+                    mbar_wait(bar_ea + 8 * sa, ea_par);
+                    mbar_wait(bar_ea + 8 * (sa + 1), ea_par);
+                }
+                if (tid == 0) HGK_TRACE(0, kc);
+                store_a(sa, 0, kc);
+                store_a(sa + 1, NSET - 1, kc + 1);
+                if (tid == 0) HGK_TRACE(6, kc);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(bar_fa + 8 * sa);
+                mbar_arrive(bar_fa + 8 * (sa + 1));
+                if (tid == 0) { HGK_TRACE(1, kc); if (kc == 0) HGK_STAMP(3); }
+                if (kc + 2 < KC) { load_a(0, kc + 2); load_a(NSET - 1, kc + 3); }
+                sa += 2;
+                if (sa == NSA) { sa = 0; ea_par ^= 1u; }
+            }
+        } else {
+            for (int kc = 0; kc < KC; ++kc) {
+                if (kc >= NSA) mbar_wait(bar_ea + 8 * sa, ea_par);            // stage drained by the tensor core
+                if (tid == 0) HGK_TRACE(0, kc);
+                if (NSET > 1 && (kc & 1)) store_a(sa, NSET - 1, kc); else store_a(sa, 0, kc);
+                if (tid == 0) HGK_TRACE(6, kc);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(bar_fa + 8 * sa);
+                if (tid == 0) { HGK_TRACE(1, kc); if (kc == 0) HGK_STAMP(3); }
+                if (kc + NSET < KC) { if (NSET > 1 && (kc & 1)) load_a(NSET - 1, kc + NSET); else load_a(0, kc + NSET); }
+                if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
+            }
         }
         if (tid == 0) HGK_STAMP(4);
         mbar_wait(bar_done, 0);              // every MMA retired: accumulators complete, shared memory reusable
@@ -317,7 +346,9 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     const int cg = (epi ? tid : 0) % CG, r0 = (epi ? tid : 0) / CG;
     const bool do_stats = a.stat_sum != nullptr;
     const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
-    const long long pix0 = ((long long)n_img * a.H + th0) * a.W + tw0;
+    // element offsets fit 32 bits (conv_tc2_eligible: P * max(Cin, Cout) < 2^32)
+    const unsigned pix0 = (unsigned)((n_img * a.H + th0) * a.W + tw0);
+    const unsigned uW = (unsigned)a.W, uCout = (unsigned)a.Cout;
 #pragma unroll 1
     for (int ch = 0; ch < BN / CH; ++ch) {
         const int n = ch * CH + cg * 4;
@@ -330,6 +361,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
 #pragma unroll 1
         for (int sub = 0; sub < NSUB; ++sub) {
+            if (tid == 0) HGK_TRACE(8, ch * NSUB + sub);
             if (warp < 8) {
                 const int lq = warp & 3;
                 const int row = lq * 32 + lane;
@@ -358,17 +390,18 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             __syncthreads();
             if (ch == BN / CH - 1 && sub == NSUB - 1 && warp == 0)
                 asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+            if (tid == 0) HGK_TRACE(9, ch * NSUB + sub);
             float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
             // rows are processed RB at a time with all global loads (shortcut / previous output / BN input) issued first
             constexpr int RB = Cfg::OCC2 ? 2 : 4;
 #pragma unroll 1
             for (int g = 0; epi && g < ROWS; g += RB) {
                 float4 rr[RB], oo[RB], zz[RB];
-                long long pp[RB];
+                unsigned pp[RB];
 #pragma unroll
                 for (int i = 0; i < RB; ++i) {
                     const int r = r0 + (g + i) * RL;
-                    pp[i] = (pix0 + (long long)(r >> 3) * a.W + (sub * 8 + (r & 7))) * a.Cout + n;
+                    pp[i] = (pix0 + (unsigned)(r >> 3) * uW + (unsigned)(sub * 8 + (r & 7))) * uCout + (unsigned)n;
                     rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     zz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -407,11 +440,12 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                         }
                     }
                 }
-                if (do_stats) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
-                }
             }
+            if (do_stats) {      // fp32 partial sums over this thread's ROWS (16 / 8) values, fp64 from here on
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
+            }
+            if (tid == 0) HGK_TRACE(10, ch * NSUB + sub);
             if (!(ch == BN / CH - 1 && sub == NSUB - 1)) __syncthreads();   // staging tile is rewritten by the next half / chunk
         }
         if (do_stats) {
@@ -434,6 +468,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                 atomicAdd(a.stat_sq + ch * CH + tid, x2);
             }
             if (ch + 1 < BN / CH) __syncthreads();                       // `red` is rewritten by the next chunk
+            if (tid == 0) HGK_TRACE(11, ch);
         }
     }
     if (tid == 0) HGK_STAMP(6);

@@ -118,3 +118,20 @@ def test_plan_builds_and_covers_every_parameter():
             direct += 1
     # 3x3 conv weights are reached through the tap-major scratch + unpack table, everything else directly
     assert direct + len(plan.wg_entries) == len(st.params)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package (nor the GPU arm of bench.py before its
+    cpu_baseline leg) may import it."""
+    pkg = os.path.join(ROOT, "pose_adv_aug_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    ours = bench[bench.index("def run_ours"):bench.index("def parity_vs_cpu")]
+    assert "oracle" not in ours.split("cpu_baseline leg")[0]

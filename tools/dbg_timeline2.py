@@ -33,7 +33,7 @@ def run(N, H, W, Ci, Co, k, split, stats):
              0, 0, 0, 0, ptr(y), 0, ptr(s1) if stats else 0, ptr(s2) if stats else 0)
         e1.record(); torch.cuda.synchronize()
     L.cdll.hgk_debug_set_timeline(0)
-    b = buf.cpu().double()
+    b = buf.cpu().double()[:256]
     live = b[:, 0] > 0
     t0 = b[live, 0].min()
     print('conv %dx%d %d->%d k%d split=%d stats=%d: %.1f us total, %d CTAs stamped' %
@@ -55,6 +55,11 @@ def run(N, H, W, Ci, Co, k, split, stats):
     print('  CTA 0 per-chunk trace (SM cycles from the first event; chunk = 16 input channels):')
     for k in (0, 6, 1, 5, 2, 3, 4):
         print('   %-10s ' % kinds[k] + ' '.join('%6d' % int(tr[k, c] - base) if tr[k, c] > 0 else '     -' for c in range(min(KC, 16))))
+    te = buf.cpu()[264:268].double()
+    ek = ['E start', 'E tmem->stg', 'E rows done', 'E stats done']
+    print('  CTA 0 epilogue trace (SM cycles from the first event; column = Cout chunk of 128 x pixel half):')
+    for k in range(4):
+        print('   %-12s ' % ek[k] + ' '.join('%6d' % int(te[k, c] - base) if te[k, c] > 0 else '     -' for c in range(4)))
     for cta in (0, 1, 200):
         if cta < r.shape[0]:
             q = r[cta]

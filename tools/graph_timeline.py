@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
-from oracle import hg_oracle as O, synth
+from pose_adv_aug_b200 import synth
 from pose_adv_aug_b200.models import asn_stacked_hg as M
 from pose_adv_aug_b200 import HourglassTrainer
 
@@ -17,7 +17,7 @@ ap.add_argument("--out", default="gpurun_out/graph_timeline.json")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 net = M.create_hg(2, 1, 16, 256)
-net.load_state_dict(synth.make_state_dict(O.hg_schema(2, 1, 16, 256), seed=1, perturb_bn=False))
+net.load_state_dict(synth.make_state_dict(synth.schema_of(net), seed=1, perturb_bn=False))
 tr = HourglassTrainer(net, 24, 256, device=dev, use_graph=True, n_streams=args.streams, n_low=args.low_streams)
 tr.x.copy_(synth.make_images(24, 256, seed=100)); tr.t.copy_(synth.make_heatmaps(24, 256, 16, seed=200))
 for _ in range(4):

@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import hg_oracle as O, synth                      # noqa: E402
+from pose_adv_aug_b200 import synth                           # noqa: E402
 from pose_adv_aug_b200.models import asn_stacked_hg as M      # noqa: E402
 from pose_adv_aug_b200 import HourglassTrainer                # noqa: E402
 
@@ -25,7 +25,7 @@ args = ap.parse_args()
 M.CONV_PATH = args.conv_path
 dev = torch.device("cuda", 0)
 net = M.create_hg(args.stacks, 1, 16, args.chan)
-net.load_state_dict(synth.make_state_dict(O.hg_schema(args.stacks, 1, 16, args.chan), seed=1, perturb_bn=False))
+net.load_state_dict(synth.make_state_dict(synth.schema_of(net), seed=1, perturb_bn=False))
 tr = HourglassTrainer(net, args.batch, args.res, device=dev, use_graph=False)
 tr.x.copy_(synth.make_images(args.batch, args.res, seed=100))
 tr.t.copy_(synth.make_heatmaps(args.batch, args.res, 16, seed=200))
