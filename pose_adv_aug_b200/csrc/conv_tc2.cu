@@ -130,11 +130,17 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_slot;
-    if (tid == 0) HGK_STAMP(1);
+    // The CTA-wide rendezvous that publishes the barriers and the TMEM base is a NAMED barrier executed inside each role
+    // branch (bar.sync 1, 320): the producers issue their first global loads BEFORE it, so the ~0.6 us of barrier
+    // initialisation / TMEM allocation overlaps the first memory round trip (profiles/r2_tile_kernel_timeline.md).
+#define T2_RENDEZVOUS()                                                           \
+    do {                                                                          \
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");          \
+        asm volatile("bar.sync 1, 320;" ::: "memory");                            \
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");           \
+    } while (0)
+    static_assert(T2_THREADS == 320, "T2_RENDEZVOUS counts 320 threads");
+    uint32_t tmem = 0;
 
     if (warp < 8) {
         // ===== producers: halo tile of one 16-channel chunk -> registers -> BN+ReLU, hi/lo -> shared memory =====
@@ -220,6 +226,8 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         load_a(0, 0);
         if (NSET > 1 && KC > 1) load_a(NSET - 1, 1);
         if (tid == 0) HGK_STAMP(2);
+        T2_RENDEZVOUS();
+        if (tid == 0) HGK_STAMP(1);
         int sa = 0;
         unsigned ea_par = 1;                 // parity of the previous use of the stage (toggles when sa wraps)
         if (PAIR) {
@@ -259,6 +267,8 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         if (tid == 0) HGK_STAMP(5);
     } else if (warp == 8) {
         // ===== MMA issuer =====
+        T2_RENDEZVOUS();
+        tmem = tmem_slot;
         if (lane == 0) {
             int sa = 0, sb = 0, it = 0;
             unsigned fa_par = 0, fb_par = 0;
@@ -312,6 +322,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         }
     } else {
         // ===== weight stream: one cp.async.bulk per (chunk, tap) stage; packed blocks are [tap][Cin/32][8 quads][BN][4] =====
+        T2_RENDEZVOUS();
         if (lane == 0) {
             const int KC32 = a.Cin >> 5;
             int sb = 0, it = 0;
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
+    tmem = tmem_slot;
 
     // ---- epilogue: per column chunk of CH and per 128-pixel half: TMEM -> registers -> staging tile -> coalesced
     //      bias / shortcut / accumulate / store + BN statistics (row r of half `sub` = pixel (th0 + r/8, tw0 + 8 sub + r%8)) ----
