@@ -232,6 +232,12 @@ int hgk_f64_to_f32(const double* x, float* y, int n, float mul, void* stream);
  * exactly as the reference does; result = trunc(tinv * (x-1, y-1, 1)) + 1.  maxval [N,J] optional.                  */
 int hgk_heatmap_peaks(const float* scores, int N, int J, int H, int W, int mode, int res0, int res1,
                       const double* tinv, float* preds, float* maxval, void* stream);
+/* mode 2 of hgk_heatmap_peaks = HumanPts.heatmap2pts (pylib/HumanPts.py:118-137): (idx % W, floor(idx / W) + 0.5), masked.
+ * ---- HumanPts.pts2heatmap + draw_gaussian (pylib/HumanPts.py:36-48,82-116): ground-truth heat-map rendering ----
+ * pts [M,2] (x, y); heatmap [M,H,W] = zeros + the size x size blob g (host-computed as the reference does) pasted at
+ * (int(x - size/2), int(y - size/2)), clipped; points outside (0,W] x (0,H] give a zero map and a zero valid_pts row. */
+int hgk_pts2heatmap(const float* pts, int M, int H, int W, const float* g, int size, float* heatmap, float* valid_pts,
+                    void* stream);
 /* ---- calc_dists (:25-39) + dist_acc (:41-54) + the averaging loop of accuracy / accuracy_origin_res (:56-104) ----
  * dists [J,N]: |preds - target|_2 / normalize[n] where both target coordinates > boundary, else -1;
  * acc [n_idx+1] (optional): acc[k+1] = share of valid dists[idxs[k]] <= thr (-1 if none valid), acc[0] = their mean. */

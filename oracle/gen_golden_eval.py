@@ -51,6 +51,23 @@ def eval_inputs(n=6, seed=40):
     return out.contiguous(), tgt.contiguous(), center, scale, rot, grnd_pts, normalizer
 
 
+def pts_inputs(n=5, j=16, seed=60):
+    """Joint coordinates as the datasets hand them to pts2heatmap (1-based crop coordinates after TransformPts, floats):
+    interior points, points within 3 px of every border (clipped blobs), exactly on the accept/reject limits, outside."""
+    r = np.random.Generator(np.random.PCG64(seed))
+    p = r.integers(-6, 72, size=(n, j, 2)).astype(np.float64)
+    p[0, 0] = [1, 1]
+    p[0, 1] = [64, 64]
+    p[0, 2] = [0, 10]
+    p[0, 3] = [10, 65]
+    p[0, 4] = [64, 1]
+    p[0, 5] = [2.6, 61.4]                                        # non-integer: int() truncation of pt -+ tmp_size
+    p[0, 6] = [33.5, 0.5]
+    p[1, 0] = [3, 3]
+    p[1, 1] = [62, 2]
+    return p
+
+
 def run_dropout_case(ref):
     """ASN dropout mode (models/asn_stacked_hg.py:79-136,172-190,308-322,340), never invoked by the shipped scripts:
     half-hg mask logits, then the whole two-stack net with np.random-sampled masks, loss and a few gradients."""
@@ -157,6 +174,22 @@ def main():
     g["agent_probs_s"], g["agent_probs_r"] = ps, pr
     g["agent_idx_s"], g["agent_idx_r"] = np.asarray(si, dtype=np.int64), np.asarray(ri, dtype=np.int64)
     np.savez_compressed(os.path.join(GOLD, "eval_n6_f32.npz"), **g)
+    hp = make_ref.load(with_eval=True, with_pts=True)[3]
+    pp = pts_inputs()
+    hms, vps = [], []
+    for n in range(pp.shape[0]):
+        hm, vp = hp.pts2heatmap(pp[n].copy(), [64, 64], sigma=1)
+        hms.append(hm)
+        vps.append(vp)
+    hm = torch.from_numpy(np.stack(hms)).float()               # as the datasets do (data/mpii_for_mpii.py:151-153)
+    gp = {"pts": pp, "valid_pts": np.stack(vps).astype(np.float32), "heatmap_sum": hm.double().sum(dim=(2, 3)).numpy(),
+          "heatmap_rows": hm[:, :, ::9].numpy().copy()}
+    # (HumanPts.heatmap2pts cannot be executed: `max.gt(0).repeat(1, 1, 2)` at :133 assumes a kept dimension that
+    #  torch.max(dim) has not returned since torch 0.2 -- it is dead code in the reference, only called from
+    #  commented-out lines; oracle/eval_oracle.py restates its evident intent, parity unpinned for that one function)
+    hm2, vp2 = hp.pts2heatmap(pp[0].copy(), [64, 64], sigma=2)
+    gp["heatmap_sigma2_sum"] = hm2.sum(axis=(1, 2))
+    np.savez_compressed(os.path.join(GOLD, "humanpts_f32.npz"), **gp)
     d = run_dropout_case(ref)
     np.savez_compressed(os.path.join(GOLD, "dropout_s2_c32_n2_r256_f32.npz"), **d)
     print("dropout golden: loss", float(d["loss"]), "indexes", d["indexes"].tolist())

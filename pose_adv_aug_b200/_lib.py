@@ -52,6 +52,7 @@ SIGNATURES = {
     "hgk_rmsprop_flat": [P, P, P, L, F, F, F, F, P],
     "hgk_f64_to_f32": [P, P, I, F, P],
     "hgk_heatmap_peaks": [P, I, I, I, I, I, I, I, P, P, P, P],
+    "hgk_pts2heatmap": [P, I, I, I, P, I, P, P, P],
     "hgk_pck_accuracy": [P, P, P, I, I, F, F, P, I, P, P, P],
     "hgk_dist_acc": [P, I, F, P, P],
     "hgk_per_person_pckh": [P, P, I, I, P, I, F, P, P],

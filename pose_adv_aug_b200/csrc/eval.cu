@@ -49,6 +49,11 @@ __global__ void __launch_bounds__(128) heatmap_peaks_kernel(const float* __restr
     float y = floorf((float)bidx / (float)H) + 1.f;
     if (!(best > 0.f)) { x = 0.f; y = 0.f; }             // pred_mask = maxval.gt(0)
     if (maxval != nullptr) maxval[nj] = best;
+    if (mode == 2) {                                     // HumanPts.heatmap2pts (pylib/HumanPts.py:118-137): 0-based x, row + 0.5
+        x = (float)(bidx % W);
+        y = floorf((float)bidx / (float)W) + 0.5f;
+        if (!(best > 0.f)) { x = 0.f; y = 0.f; }
+    }
     if (mode == 1) {
         const int px = (int)floorf(x), py = (int)floorf(y);
         if (px > 1 && px < res0 && py > 1 && py < res1) {
@@ -273,6 +278,37 @@ __global__ void __launch_bounds__(256) mask_mul_bwd_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// HumanPts.pts2heatmap + draw_gaussian (pylib/HumanPts.py:36-48,82-116): one map per point, zeros plus the size x size
+// blob g (computed on the host exactly as the reference: exp(-((x-x0)^2+(y-y0)^2)/tmp_size^2), tmp_size = ceil(3 sigma),
+// size = 2 tmp_size + 1) pasted with its upper-left corner at (int(px - tmp_size), int(py - tmp_size)), clipped to the
+// map.  Points with x <= 0, y <= 0, x > W or y > H leave an all-zero map and a zero row in valid_pts.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pts2heatmap_kernel(const float* __restrict__ pts, int H, int W, const float* __restrict__ g,
+                                                          int size, float* __restrict__ heatmap, float* __restrict__ valid_pts) {
+    const int m = blockIdx.x;
+    const float px = pts[(size_t)m * 2], py = pts[(size_t)m * 2 + 1];
+    const bool valid = !(px <= 0.f || py <= 0.f || px > (float)W || py > (float)H);
+    const int tmp = size >> 1;
+    const int ulx = (int)(px - (float)tmp), uly = (int)(py - (float)tmp);      // int() truncates towards zero
+    const int brx = (int)(px + (float)tmp), bry = (int)(py + (float)tmp);
+    const bool draw = valid && !(ulx >= W || uly >= H || brx < 0 || bry < 0);
+    // image range [x0,x1) x [y0,y1), blob offset (gx0, gy0)
+    const int x0 = max(0, ulx), x1 = min(brx + 1, W), y0 = max(0, uly), y1 = min(bry + 1, H);
+    const int gx0 = max(0, -ulx), gy0 = max(0, -uly);
+    float* out = heatmap + (size_t)m * H * W;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        float v = 0.f;
+        if (draw && x >= x0 && x < x1 && y >= y0 && y < y1) v = __ldg(g + (gy0 + y - y0) * size + (gx0 + x - x0));
+        out[i] = v;
+    }
+    if (threadIdx.x == 0 && valid_pts != nullptr) {
+        valid_pts[(size_t)m * 2] = valid ? px : 0.f;
+        valid_pts[(size_t)m * 2 + 1] = valid ? py : 0.f;
+    }
+}
+
 static int stream_grid(long long n4) {
     long long b = (n4 + 255) / 256;
     const long long cap = (long long)kNumSMs * 8;
@@ -289,13 +325,24 @@ int hgk_heatmap_peaks(const float* scores, int N, int J, int H, int W, int mode,
                       float* preds, float* maxval, void* stream) {
     HGK_REQUIRE(scores != nullptr && preds != nullptr, "hgk_heatmap_peaks: null pointer");
     HGK_REQUIRE(N >= 0 && J >= 1 && H >= 1 && W >= 1 && (long long)H * W < (1LL << 30), "hgk_heatmap_peaks: bad shape");
-    HGK_REQUIRE(mode == 0 || mode == 1, "hgk_heatmap_peaks: mode must be 0 (get_preds) or 1 (final_preds)");
-    HGK_REQUIRE(mode == 0 || (res0 >= 1 && res0 <= W && res1 >= 1 && res1 <= H),
+    HGK_REQUIRE(mode >= 0 && mode <= 2, "hgk_heatmap_peaks: mode must be 0 (get_preds), 1 (final_preds) or 2 (heatmap2pts)");
+    HGK_REQUIRE(mode != 1 || (res0 >= 1 && res0 <= W && res1 >= 1 && res1 <= H),
                 "hgk_heatmap_peaks: res (%d,%d) must lie inside the %dx%d heat-map", res0, res1, W, H);
     if ((long long)N * J == 0) return HGK_OK;
     HGK_REQUIRE((long long)N * J < (1LL << 31), "hgk_heatmap_peaks: too many maps");
     heatmap_peaks_kernel<<<(unsigned)(N * J), 128, 0, (cudaStream_t)stream>>>(scores, H, W, mode, res0, res1, tinv, J, preds, maxval);
     HGK_CHECK_LAUNCH("hgk_heatmap_peaks");
+    return HGK_OK;
+}
+
+int hgk_pts2heatmap(const float* pts, int M, int H, int W, const float* g, int size, float* heatmap, float* valid_pts,
+                    void* stream) {
+    HGK_REQUIRE(pts != nullptr && g != nullptr && heatmap != nullptr, "hgk_pts2heatmap: null pointer");
+    HGK_REQUIRE(M >= 0 && H >= 1 && W >= 1 && (long long)H * W < (1LL << 30), "hgk_pts2heatmap: bad shape");
+    HGK_REQUIRE(size >= 1 && (size & 1), "hgk_pts2heatmap: the blob size must be odd (2 ceil(3 sigma) + 1), got %d", size);
+    if (M == 0) return HGK_OK;
+    pts2heatmap_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(pts, H, W, g, size, heatmap, valid_pts);
+    HGK_CHECK_LAUNCH("hgk_pts2heatmap");
     return HGK_OK;
 }
 

@@ -164,3 +164,39 @@ def test_mask_mul_kernels():
     y4 = torch.empty_like(x4)
     call("mask_mul_fwd", ptr(x4), 0, 0, 0, ptr(mask), N, 4, 4, C, 4, 4, ptr(y4))
     assert torch.equal(y4, x4 * mask.unsqueeze(3))
+
+
+def test_pts2heatmap_and_heatmap2pts():
+    """GPU ground-truth rendering (pylib/HumanPts.py:36-48,82-116) bit-exact vs the oracle and the reference golden,
+    incl. clipped blobs at every border, the accept/reject limits, non-integer points and sigma=2; heatmap2pts vs the
+    oracle restatement and as the inverse of the rendering for interior points."""
+    from pose_adv_aug_b200.pylib import HumanPts as HP
+    g = np.load(os.path.join(ROOT, "tests", "golden", "humanpts_f32.npz"))
+    pts = g["pts"]
+    hm, vp = HP.pts2heatmap(torch.from_numpy(pts).to(DEV), [64, 64], sigma=1)
+    assert tuple(hm.shape) == (5, 16, 64, 64) and hm.is_cuda
+    assert np.array_equal(vp.cpu().numpy(), g["valid_pts"])
+    assert np.array_equal(hm.cpu().numpy()[:, :, ::9], g["heatmap_rows"])
+    for n in range(pts.shape[0]):
+        ref, _ = E.pts2heatmap(pts[n].copy(), [64, 64], sigma=1)
+        assert np.array_equal(hm[n].cpu().numpy(), torch.from_numpy(ref).float().numpy())
+    h1, v1 = HP.pts2heatmap(torch.from_numpy(pts[0]).to(DEV), [64, 64], sigma=2)       # [J,2] form, 13x13 blob
+    ref2, _ = E.pts2heatmap(pts[0].copy(), [64, 64], sigma=2)
+    assert np.array_equal(h1.cpu().numpy(), torch.from_numpy(ref2).float().numpy())
+    hr, _ = HP.pts2heatmap(torch.from_numpy(pts[:2]).to(DEV), [48, 80], sigma=1)        # H != W
+    for n in range(2):
+        ref, _ = E.pts2heatmap(pts[n].copy(), [48, 80], sigma=1)
+        assert np.array_equal(hr[n].cpu().numpy(), torch.from_numpy(ref).float().numpy())
+    # heatmap2pts
+    p2 = HP.heatmap2pts(hm)
+    assert np.array_equal(p2.cpu().numpy(), E.heatmap2pts(hm.cpu().numpy()))
+    interior = (pts[..., 0] >= 4) & (pts[..., 0] <= 60) & (pts[..., 1] >= 4) & (pts[..., 1] <= 60)
+    q = p2.cpu().numpy()
+    assert np.array_equal(q[interior][:, 0], pts[interior][:, 0]) and np.array_equal(q[interior][:, 1], pts[interior][:, 1] + 0.5)
+    out = eval_inputs()[0]
+    assert np.array_equal(HP.heatmap2pts(out.to(DEV)).cpu().numpy(), E.heatmap2pts(out.numpy()))
+    # a full config-2 batch of targets: every map sums to the blob mass or to 0
+    big = torch.randint(4, 60, (24, 16, 2), device=DEV).float()
+    hb, _ = HP.pts2heatmap(big, [64, 64])
+    mass = float(HP.gaussian_blob(1).double().sum())
+    assert torch.allclose(hb.double().sum(dim=(2, 3)), torch.full((24, 16), mass, dtype=torch.float64, device=DEV), rtol=1e-6)

@@ -90,3 +90,18 @@ def test_dropout_mode_oracle_vs_reference_golden():
     for i, o in enumerate(outs):
         ref = g["out%d_sub" % i]
         assert np.abs(o.numpy()[:, :, ::3, ::3] - ref).max() < 1e-3 * np.abs(ref).max()
+
+
+def test_pts2heatmap_oracle_vs_reference_golden():
+    """oracle pts2heatmap / draw_gaussian (pylib/HumanPts.py:36-48,82-116) vs the reference's own output."""
+    import torch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "humanpts_f32.npz"))
+    pts = g["pts"]
+    for n in range(pts.shape[0]):
+        hm, vp = E.pts2heatmap(pts[n].copy(), [64, 64], sigma=1)
+        hm32 = torch.from_numpy(hm).float().numpy()
+        assert np.array_equal(vp.astype(np.float32), g["valid_pts"][n])
+        assert np.array_equal(hm32[:, ::9], g["heatmap_rows"][n])
+        np.testing.assert_allclose(hm32.astype(np.float64).sum(axis=(1, 2)), g["heatmap_sum"][n], rtol=1e-12)
+    hm2, _ = E.pts2heatmap(pts[0].copy(), [64, 64], sigma=2)
+    np.testing.assert_allclose(hm2.sum(axis=(1, 2)), g["heatmap_sigma2_sum"], rtol=1e-12)
