@@ -459,3 +459,34 @@ def test_asn_dropout_mode_vs_reference_golden():
     mref, _ = O.asn_forward(OrderedDict((k, v.cpu().double()) for k, v in asn.state_dict().items()),
                             dict((k, v.cpu().double()) for k, v in feats.items()), training=False)
     assert relerr(m1, mref) < 1e-3
+
+
+def test_config5_eight_stack_forward_vs_oracle():
+    """BASELINE.json configs[4] (8-stack hourglass, C=256, 256x256) at a batch the CPU oracle finishes in seconds:
+    every one of the 8 heat-map outputs within 1e-3 of the fp32 oracle, loss within 1e-3; and one full-size (bs 16)
+    train step runs with a finite loss equal to the sum of its per-stack MSEs (size-independent property)."""
+    M = _mods()
+    S, C, N, R = 8, 256, 2, 256
+    sd = synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=51, perturb_bn=False)
+    net = _load(M.create_hg(S, 1, 16, C), sd).to(DEV)
+    net.train()
+    x = synth.make_images(N, R, seed=52)
+    t = synth.make_heatmaps(N, R, 16, seed=53)
+    with torch.no_grad():
+        outs = net(x.to(DEV))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref, _ = O.hg_forward(OrderedDict((k, v.clone()) for k, v in sd.items()), x, S, 1, training=True)
+    assert len(outs) == S
+    for i, (a, b) in enumerate(zip(outs, ref)):
+        assert relerr(a, b) < 1e-3, "stack %d" % i
+    la, lb = float(O.mse_loss(outs, t.to(DEV))), float(O.mse_loss(ref, t))
+    assert abs(la - lb) < 1e-3 * abs(lb)
+    from pose_adv_aug_b200 import HourglassTrainer
+    _load(net, sd)
+    tr = HourglassTrainer(net, 16, R, use_graph=False)
+    x16, t16 = synth.make_images(16, R, seed=54), synth.make_heatmaps(16, R, 16, seed=55)
+    loss = float(tr.step(x16.pin_memory(), t16.pin_memory()))
+    hm = tr.heatmaps()
+    per_stack = sum(float(((h - t16.to(DEV)) ** 2).mean()) for h in hm)
+    assert np.isfinite(loss) and abs(loss - per_stack) < 1e-4 * per_stack
