@@ -490,3 +490,32 @@ def test_config5_eight_stack_forward_vs_oracle():
     hm = tr.heatmaps()
     per_stack = sum(float(((h - t16.to(DEV)) ** 2).mean()) for h in hm)
     assert np.isfinite(loss) and abs(loss - per_stack) < 1e-4 * per_stack
+
+
+def test_prefetched_step_equals_serial_step():
+    """HourglassTrainer.prefetch()/step_prefetched() (upload of the next batch on a copy stream under the current
+    step) computes exactly what step(images, heatmaps) does on the same batch sequence."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer, HGKError
+    S, C, N, R = 1, 32, 2, 64
+    sd = synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=61)
+    batches = [(synth.make_images(N, R, seed=70 + i).pin_memory(), synth.make_heatmaps(N, R, 16, seed=80 + i).pin_memory())
+               for i in range(4)]
+    ta = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, use_graph=True, n_streams=1)
+    tb = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, use_graph=True, n_streams=1)
+    la = [float(ta.step(x, t)) for x, t in batches]
+    with pytest.raises(HGKError):
+        tb.step_prefetched()
+    tb.prefetch(*batches[0])
+    lb = []
+    for i in range(4):
+        loss = tb.step_prefetched()
+        if i + 1 < 4:
+            tb.prefetch(*batches[i + 1])
+        lb.append(float(loss))
+    # (same kernels, same order; fp64 atomics may differ in the last bit between two runs, and every batch is different
+    #  data, so a batch consumed out of order would show up at the 1e-1 level)
+    for i, (a, b) in enumerate(zip(la, lb)):
+        # the tiny 1x1-neck net amplifies last-bit differences after the first updates (see the trainer test above)
+        assert abs(a - b) < (1e-5 if i < 2 else 2e-2) * abs(a), (la, lb)
+    assert len(set(round(v, 6) for v in la)) == 4
