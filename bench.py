@@ -272,6 +272,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier()
     e2e_s = time.time() - t0
+    if os.environ.get("HGK_BENCH_E2E_REPEAT"):        # developer: repeatability of the two input paths
+        for rep in range(3):
+            torch.cuda.synchronize(); ta = time.time()
+            tr.prefetch(xp, tp)
+            for i in range(e2e_steps):
+                loss_dev = tr.step_prefetched()
+                if i + 1 < e2e_steps:
+                    tr.prefetch(xp, tp)
+                last = float(loss_dev.item())
+            torch.cuda.synchronize(); tb = time.time()
+            for _ in range(e2e_steps):
+                last = float(tr.step(xp, tp).item())
+            torch.cuda.synchronize(); tc = time.time()
+            sys.stderr.write("e2e repeat %d: prefetched %.3f ms/step, serial %.3f ms/step\n" %
+                             (rep, (tb - ta) / e2e_steps * 1e3, (tc - tb) / e2e_steps * 1e3))
     # the same without lookahead: copies, then the step, then the loss read, all serial
     barrier()
     torch.cuda.synchronize()

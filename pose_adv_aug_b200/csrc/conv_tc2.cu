@@ -22,6 +22,7 @@
 //     tcgen05.mma.kind::tf32 into TMEM and commits stages back, warp 9 streams the weights; all 8 producer
 //     warps then run the epilogue (tcgen05.ld -> smem tile -> coalesced stores + fp64 channel statistics).
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
@@ -406,53 +407,62 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
             // rows are processed RB at a time with all global loads (shortcut / previous output / BN input) issued first
             constexpr int RB = Cfg::OCC2 ? 2 : 4;
+            // PLAIN (no shortcut, no accumulation -- conv1 / conv2 of every residual block): the row loop is issue-bound
+            // (~40 instructions per row), so the unused shortcut / accumulate registers and adds are compiled out
+            auto row_loop = [&](auto plain_tag) {
+                constexpr bool PLAIN = decltype(plain_tag)::value;
 #pragma unroll 1
-            for (int g = 0; epi && g < ROWS; g += RB) {
-                float4 rr[RB], oo[RB], zz[RB];
-                unsigned pp[RB];
+                for (int g = 0; epi && g < ROWS; g += RB) {
+                    float4 rr[RB], oo[RB], zz[RB];
+                    unsigned pp[RB];
 #pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                    const int r = r0 + (g + i) * RL;
-                    pp[i] = (pix0 + (unsigned)(r >> 3) * uW + (unsigned)(sub * 8 + (r & 7))) * uCout + (unsigned)n;
-                    rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    zz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_res) rr[i] = ldg4(a.res.z + pp[i]);
-                    if (a.accumulate) oo[i] = ld4(a.y + pp[i]);
-                    if (BWDSTATS) zz[i] = ldg4(a.bz + pp[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                    const int r = r0 + (g + i) * RL;
-                    float4 v = ld4(stg + r * SROW + cg * 4);
-                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                    if (has_res) {
-                        float4 q = rr[i];
-                        if (res_aff) q = act4(q, rs, rt, a.res.relu);
-                        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    for (int i = 0; i < RB; ++i) {
+                        const int r = r0 + (g + i) * RL;
+                        pp[i] = (pix0 + (unsigned)(r >> 3) * uW + (unsigned)(sub * 8 + (r & 7))) * uCout + (unsigned)n;
+                        if (!PLAIN) {
+                            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (has_res) rr[i] = ldg4(a.res.z + pp[i]);
+                            if (a.accumulate) oo[i] = ld4(a.y + pp[i]);
+                        }
+                        if (BWDSTATS) zz[i] = ldg4(a.bz + pp[i]);
                     }
-                    v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
-                    st4(a.y + pp[i], v);
-                    if (do_stats) {
-                        if (BWDSTATS) {
-                            const float4 z = zz[i];
-                            const float gx = (a.brelu && fmaf(z.x, bsc.x, bsh.x) <= 0.f) ? 0.f : v.x;
-                            const float gy = (a.brelu && fmaf(z.y, bsc.y, bsh.y) <= 0.f) ? 0.f : v.y;
-                            const float gz = (a.brelu && fmaf(z.z, bsc.z, bsh.z) <= 0.f) ? 0.f : v.z;
-                            const float gw = (a.brelu && fmaf(z.w, bsc.w, bsh.w) <= 0.f) ? 0.f : v.w;
-                            s1[0] += gx; s2[0] = fmaf(gx, (z.x - bmu.x) * biv.x, s2[0]);
-                            s1[1] += gy; s2[1] = fmaf(gy, (z.y - bmu.y) * biv.y, s2[1]);
-                            s1[2] += gz; s2[2] = fmaf(gz, (z.z - bmu.z) * biv.z, s2[2]);
-                            s1[3] += gw; s2[3] = fmaf(gw, (z.w - bmu.w) * biv.w, s2[3]);
-                        } else {
-                            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-                            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-                            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-                            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) {
+                        const int r = r0 + (g + i) * RL;
+                        float4 v = ld4(stg + r * SROW + cg * 4);
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        if (!PLAIN) {
+                            if (has_res) {
+                                float4 q = rr[i];
+                                if (res_aff) q = act4(q, rs, rt, a.res.relu);
+                                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                            }
+                            v.x += oo[i].x; v.y += oo[i].y; v.z += oo[i].z; v.w += oo[i].w;
+                        }
+                        st4(a.y + pp[i], v);
+                        if (do_stats) {
+                            if (BWDSTATS) {
+                                const float4 z = zz[i];
+                                const float gx = (a.brelu && fmaf(z.x, bsc.x, bsh.x) <= 0.f) ? 0.f : v.x;
+                                const float gy = (a.brelu && fmaf(z.y, bsc.y, bsh.y) <= 0.f) ? 0.f : v.y;
+                                const float gz = (a.brelu && fmaf(z.z, bsc.z, bsh.z) <= 0.f) ? 0.f : v.z;
+                                const float gw = (a.brelu && fmaf(z.w, bsc.w, bsh.w) <= 0.f) ? 0.f : v.w;
+                                s1[0] += gx; s2[0] = fmaf(gx, (z.x - bmu.x) * biv.x, s2[0]);
+                                s1[1] += gy; s2[1] = fmaf(gy, (z.y - bmu.y) * biv.y, s2[1]);
+                                s1[2] += gz; s2[2] = fmaf(gz, (z.z - bmu.z) * biv.z, s2[2]);
+                                s1[3] += gw; s2[3] = fmaf(gw, (z.w - bmu.w) * biv.w, s2[3]);
+                            } else {
+                                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                            }
                         }
                     }
                 }
-            }
+            };
+            if (!has_res && !a.accumulate) row_loop(std::true_type{}); else row_loop(std::false_type{});
             if (do_stats) {      // fp32 partial sums over this thread's ROWS (16 / 8) values, fp64 from here on
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }

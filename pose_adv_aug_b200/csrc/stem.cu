@@ -2,6 +2,7 @@
 // _Hourglass_Wrapper (reference models/asn_stacked_hg.py:223,283): direct convolution that reads
 // the NCHW image the reference API is fed with and writes the NHWC pre-BN tensor + the batch
 // statistics of bn1 (:224).  Cin = 3 makes this an FFMA kernel (K = 147), 2 % of the step FLOPs.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace hgk {
@@ -174,6 +175,97 @@ __global__ void __launch_bounds__(256) stem_conv7_wgrad_kernel(const float* __re
     if (dbias != nullptr && tid < ST_CO) atomicAdd(dbias + tid, bsum);
 }
 
+// Second-generation weight gradient.  The first kernel above issues 11 shared-memory loads per 40 FFMA (one scalar
+// patch load per tap): LSU-bound at ~14 TFLOP/s, and it is the LAST kernel of the backward pass, alone on the GPU for
+// 0.45-0.53 ms.  Here a thread owns 4 couts x the 7 kw taps of ONE (channel, kh) patch row (21 rows -> 21 groups of 16
+// threads) and walks the tile in PAIRS of horizontally adjacent output pixels: their two 7-tap windows are the 9
+// consecutive floats prow[4p .. 4p+8] (stride 2), i.e. two LDS.128 + one LDS.32 feed 56 FFMA (with the two dz float4
+// loads: 11 FFMA per load).  Patch rows are padded to 40 floats so that every window start is 16-byte aligned.
+constexpr int ST_PWP = 40;
+constexpr int ST_WG2_THREADS = 352;       // 21 x 16 workers + 16 idle lanes of the 11th warp
+
+__global__ void __launch_bounds__(ST_WG2_THREADS, 2) stem_conv7_wgrad2_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                                             const float* __restrict__ dz, float* dw, float* dbias,
+                                                                             int tiles_x, int tiles_y) {
+    __shared__ __align__(16) float dzs[ST_TH * ST_TW * ST_CO];     // [pixel][co]
+    __shared__ __align__(16) float patch[3 * ST_PH * ST_PWP];      // [c][py][px], rows padded to 40
+    const int tid = threadIdx.x;
+    const int OH = H / 2, OW = W / 2;
+    const int tx = tid & 15, ty = tid >> 4;
+    const bool worker = ty < 21;
+    const int c = worker ? ty / 7 : 0, kh = worker ? ty - (ty / 7) * 7 : 0;
+    float acc[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    const int total = tiles_x * tiles_y * N;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n = t / (tiles_x * tiles_y);
+        const int r = t - n * (tiles_x * tiles_y);
+        const int tyi = r / tiles_x, txi = r - tyi * tiles_x;
+        const int oy0 = tyi * ST_TH, ox0 = txi * ST_TW;
+        const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+        __syncthreads();                                     // previous tile fully consumed
+        for (int i = tid; i < 3 * ST_PH * ST_PWP; i += ST_WG2_THREADS) {
+            const int cc = i / (ST_PH * ST_PWP);
+            const int rr = i - cc * (ST_PH * ST_PWP);
+            const int py = rr / ST_PWP, px = rr - py * ST_PWP;
+            const int iy = iy0 + py, ix = ix0 + px;
+            float v = 0.f;
+            if (px < ST_PW && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+                v = __ldg(img + ((size_t)(n * 3 + cc) * H + iy) * W + ix);
+            patch[i] = v;
+        }
+        for (int i = tid; i < ST_TH * ST_TW * (ST_CO / 4); i += ST_WG2_THREADS) {
+            const int q = i >> 4, cv = i & 15;
+            const int gy = oy0 + q / ST_TW, gx = ox0 + (q % ST_TW);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy < OH && gx < OW) v = ldg4(dz + (((size_t)n * OH + gy) * OW + gx) * ST_CO + cv * 4);
+            st4(dzs + q * ST_CO + cv * 4, v);
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 1
+            for (int oy = 0; oy < ST_TH; ++oy) {
+                const float* prow = patch + (c * ST_PH + 2 * oy + kh) * ST_PWP;
+                const float* arow = dzs + (oy * ST_TW) * ST_CO + tx * 4;
+#pragma unroll 2
+                for (int p = 0; p < ST_TW / 2; ++p) {
+                    const float4 a0 = ld4(arow + (2 * p) * ST_CO);
+                    const float4 a1 = ld4(arow + (2 * p + 1) * ST_CO);
+                    const float4 b0 = ld4(prow + 4 * p), b1 = ld4(prow + 4 * p + 4);
+                    const float b8 = prow[4 * p + 8];
+                    const float b[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b8};
+#pragma unroll
+                    for (int kw = 0; kw < 7; ++kw) {
+                        acc[0][kw] = fmaf(a0.x, b[kw], acc[0][kw]);
+                        acc[1][kw] = fmaf(a0.y, b[kw], acc[1][kw]);
+                        acc[2][kw] = fmaf(a0.z, b[kw], acc[2][kw]);
+                        acc[3][kw] = fmaf(a0.w, b[kw], acc[3][kw]);
+                        acc[0][kw] = fmaf(a1.x, b[kw + 2], acc[0][kw]);
+                        acc[1][kw] = fmaf(a1.y, b[kw + 2], acc[1][kw]);
+                        acc[2][kw] = fmaf(a1.z, b[kw + 2], acc[2][kw]);
+                        acc[3][kw] = fmaf(a1.w, b[kw + 2], acc[3][kw]);
+                    }
+                }
+            }
+        }
+        if (dbias != nullptr && tid < ST_CO) {
+            for (int q = 0; q < ST_TH * ST_TW; ++q) bsum += dzs[q * ST_CO + tid];
+        }
+    }
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw)
+                atomicAdd(dw + (size_t)(tx * 4 + i) * ST_K + (c * 7 + kh) * 7 + kw, acc[i][kw]);
+    }
+    if (dbias != nullptr && tid < ST_CO) atomicAdd(dbias + tid, bsum);
+}
+
 }  // namespace hgk
 
 using namespace hgk;
@@ -199,7 +291,15 @@ extern "C" int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const
     int tiles_x = (W / 2 + ST_TW - 1) / ST_TW, tiles_y = (H / 2 + ST_TH - 1) / ST_TH;
     long long total = (long long)tiles_x * tiles_y * N;
     int grid = (int)(total < 2 * kNumSMs ? total : 2 * kNumSMs);
-    stem_conv7_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, dz, dw, dbias, tiles_x, tiles_y);
+    static int gen = -1;                  // HGK_STEM_WGRAD=1 selects the first-generation kernel (A/B measurements)
+    if (gen < 0) {
+        const char* e = getenv("HGK_STEM_WGRAD");
+        gen = (e != nullptr && e[0] == '1') ? 1 : 2;
+    }
+    if (gen == 1)
+        stem_conv7_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, dz, dw, dbias, tiles_x, tiles_y);
+    else
+        stem_conv7_wgrad2_kernel<<<grid, ST_WG2_THREADS, 0, (cudaStream_t)stream>>>(img, N, H, W, dz, dw, dbias, tiles_x, tiles_y);
     HGK_CHECK_LAUNCH("hgk_stem_conv7_wgrad");
     return HGK_OK;
 }

@@ -501,8 +501,10 @@ def test_prefetched_step_equals_serial_step():
     sd = synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=61)
     batches = [(synth.make_images(N, R, seed=70 + i).pin_memory(), synth.make_heatmaps(N, R, 16, seed=80 + i).pin_memory())
                for i in range(4)]
-    ta = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, use_graph=True, n_streams=1)
-    tb = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, use_graph=True, n_streams=1)
+    # lr = 0: the loss of step i depends on batch i only (train-mode BN uses batch statistics), so the comparison is not
+    # blurred by the chaotic amplification of last-bit gradient differences that weight updates cause on this tiny net
+    ta = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, lr=0.0, use_graph=True, n_streams=1)
+    tb = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, lr=0.0, use_graph=True, n_streams=1)
     la = [float(ta.step(x, t)) for x, t in batches]
     with pytest.raises(HGKError):
         tb.step_prefetched()
@@ -515,7 +517,6 @@ def test_prefetched_step_equals_serial_step():
         lb.append(float(loss))
     # (same kernels, same order; fp64 atomics may differ in the last bit between two runs, and every batch is different
     #  data, so a batch consumed out of order would show up at the 1e-1 level)
-    for i, (a, b) in enumerate(zip(la, lb)):
-        # the tiny 1x1-neck net amplifies last-bit differences after the first updates (see the trainer test above)
-        assert abs(a - b) < (1e-5 if i < 2 else 2e-2) * abs(a), (la, lb)
+    for a, b in zip(la, lb):
+        assert abs(a - b) < 1e-5 * abs(a), (la, lb)
     assert len(set(round(v, 6) for v in la)) == 4
