@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         unsigned em_par = 1;               // parity of the previous use of the stage (toggles when s wraps)
         for (int it = 0; it < T; ++it) {
             if (it >= NST) mbar_wait(bar_em + 8 * s, em_par);          // stage s drained by the tensor core
+            if (tid == 0) HGK_TRACE(0, it);
             if (tid == 0) {
                 const uint32_t bb = bar_fb + 8 * s;
                 const uint32_t dst = sbase + s * STAGE + (SPLIT ? 2 : 1) * A_BYTES;
@@ -203,8 +204,10 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
             wsrc_hi += wblk;
             if (SPLIT) wsrc_lo += wblk;
             if (it & 1) store_a(s, 1); else store_a(s, 0);
+            if (tid == 0) HGK_TRACE(6, it);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
             mbar_arrive(bar_fa + 8 * s);
+            if (tid == 0) HGK_TRACE(1, it);
             if (tid == 0 && it == 0) HGK_STAMP(3);
             if (it + 2 < T) { if (it & 1) load_a(1); else load_a(0); }
             if (++s == NST) { s = 0; em_par ^= 1u; }
@@ -219,8 +222,10 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
             const int s = it % NST, u = it / NST;
             mbar_wait(bar_fa + 8 * s, u & 1);
             if (it == 0) HGK_STAMP(8);
+            HGK_TRACE(2, it);
             mbar_wait(bar_fb + 8 * s, u & 1);
             if (it == 0) HGK_STAMP(9);
+            HGK_TRACE(3, it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = sbase + s * STAGE;
             const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_BYTES;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
                 }
             }
             umma_commit(bar_em + 8 * s);
+            HGK_TRACE(4, it);
         }
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

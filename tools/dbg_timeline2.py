@@ -66,6 +66,37 @@ def run(N, H, W, Ci, Co, k, split, stats):
             print('  cta %3d start@%7.1f ' % (cta, float((q[0] - t0) / 1e3)) + ' '.join('%s=%.1f' % (NAMES[i], float((q[i] - q[0]) / 1e3)) for i in order))
 
 
+if os.environ.get("TL_SMALL"):
+    # the 8x8 / 4x4 rungs (conv_tc_kernel, 128 linear pixels per CTA): trace columns are pipeline iterations (32 channels x tap)
+    def run_small(N, H, W, Ci, Co, k):
+        global buf
+        x = torch.randn(N, H, W, Ci, device=DEV); y = torch.empty(N, H, W, Co, device=DEV)
+        sc = torch.rand(Ci, device=DEV) + 0.5; sh = torch.randn(Ci, device=DEV) * 0.1
+        w = torch.randn(Co, Ci, k, k, dtype=torch.float64) * 0.1
+        src = dev32(w.reshape(-1)); dst = torch.zeros(2 * w.numel(), device=DEV)
+        table = torch.tensor([[0, 0, w.numel(), Co, Ci, k * k, 0, Co]], dtype=torch.long, device=DEV)
+        call("pack_weights_tc", ptr(src), ptr(dst), ptr(table), 1)
+        hi, lo = dst[:w.numel()], dst[w.numel():]
+        s1 = torch.zeros(Co, dtype=torch.float64, device=DEV); s2 = torch.zeros(Co, dtype=torch.float64, device=DEV)
+        for rep in range(3):
+            buf.zero_()
+            L.cdll.hgk_debug_set_timeline(buf.data_ptr() if rep == 2 else 0)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call("conv_tc_nhwc", ptr(x), ptr(sc), ptr(sh), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, 0, Co, 0, 0, 0, 0, ptr(y), 0, ptr(s1), ptr(s2))
+            e1.record(); torch.cuda.synchronize()
+        L.cdll.hgk_debug_set_timeline(0)
+        tr = buf.cpu()[256:263].double()
+        base = tr[tr > 0].min()
+        kinds = ['P pass em', 'P arrived', 'M got fa', 'M got fb', 'M issued', '-', 'P stored']
+        print('conv_tc_kernel %dx%d %d->%d k%d (warm L2): %.1f us; CTA 0 per-iteration trace (SM cycles):' % (H, W, Ci, Co, k, e0.elapsed_time(e1) * 1e3))
+        for kk in (0, 6, 1, 2, 3, 4):
+            print('   %-10s ' % kinds[kk] + ' '.join('%6d' % int(tr[kk, c] - base) if tr[kk, c] > 0 else '     -' for c in range(16)))
+    run_small(24, 4, 4, 128, 128, 3)
+    run_small(24, 8, 8, 128, 128, 3)
+    run_small(24, 4, 4, 256, 128, 1)
+    sys.exit(0)
 run(24, 64, 64, 128, 256, 1, 1, 1)
 run(24, 64, 64, 256, 128, 1, 1, 1)
 run(24, 64, 64, 128, 128, 3, 1, 1)
