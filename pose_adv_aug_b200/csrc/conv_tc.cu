@@ -1003,7 +1003,12 @@ template <int BN, bool SPLIT, bool BWDSTATS = false>
 static int launch_tc(const TcArgs& ta, cudaStream_t st) {
     // at most one CTA per SM anyway -> the large-stage single-CTA configuration
     const long long ctas = ((ta.c.P + TBM - 1) / TBM) * (ta.c.Cout / BN);
-    if (ctas <= kNumSMs) return launch_tc_cfg<BN, SPLIT, BWDSTATS, true>(ta, st);
+    static int big_off = -1;              // HGK_TC_BIG_OFF=1: always the two-CTAs-per-SM configuration (tuning knob)
+    if (big_off < 0) {
+        const char* e = getenv("HGK_TC_BIG_OFF");
+        big_off = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (ctas <= kNumSMs && !big_off) return launch_tc_cfg<BN, SPLIT, BWDSTATS, true>(ta, st);
     return launch_tc_cfg<BN, SPLIT, BWDSTATS, false>(ta, st);
 }
 

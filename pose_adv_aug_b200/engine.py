@@ -221,6 +221,8 @@ class Plan(object):
         self.fwd_count = 0
         self.bytes_alloc = 0
         self.finished = False
+        self.low_recs = set()      # id() of forward launches built inside a low_scope() (off the critical path)
+        self.after = {}            # id(launch) -> id(earlier launch) it must additionally wait for (scheduling-only edge)
 
     # ---- allocation helpers ----
     def buf(self, *shape):
@@ -257,6 +259,40 @@ class Plan(object):
         ptr = self.tickets.data_ptr() + 4 * self.tickets_used
         self.tickets_used += 1
         return ptr
+
+    def defer_scope(self, anchor_rec):
+        """Context manager: the forward launches appended inside are low priority AND may not start before `anchor_rec`
+        (an earlier launch) has finished -- a scheduling-only edge with which the big skip-branch kernels are held back
+        until the down/up chain reaches its small rungs, so that they run UNDER that latency chain instead of before it."""
+        plan = self
+
+        class _Scope(object):
+            def __enter__(self_):
+                self_.start = len(plan.fwd)
+
+            def __exit__(self_, *exc):
+                for rec in plan.fwd[self_.start:]:
+                    plan.low_recs.add(id(rec))
+                    if anchor_rec is not None:
+                        plan.after[id(rec)] = id(anchor_rec)
+                return False
+        return _Scope()
+
+    def low_scope(self):
+        """Context manager: forward launches appended inside are marked as off the critical path (the hourglass skip
+        branches: ready early, needed late).  The multi-stream scheduler confines them to the low-priority streams so
+        that they fill the SMs the 16x16 / 8x8 / 4x4 rungs of the down/up chain leave idle instead of racing ahead."""
+        plan = self
+
+        class _Scope(object):
+            def __enter__(self_):
+                self_.start = len(plan.fwd)
+
+            def __exit__(self_, *exc):
+                for rec in plan.fwd[self_.start:]:
+                    plan.low_recs.add(id(rec))
+                return False
+        return _Scope()
 
     def launch(self, lst, fn_name, *args):
         fn = getattr(self.lib, fn_name)
@@ -637,7 +673,7 @@ _WRITES = {
 
 
 def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads"),
-                     low_names=(), n_low=0):
+                     low_names=(), n_low=0, low_ids=(), after=None):
     """Assign each launch of a static list to one of `n_streams` streams.
 
     Dependencies are derived from the launch arguments (device pointers; `_WRITES` says which positions
@@ -659,7 +695,9 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
     barrier = -1
     lru = list(range(n_streams))
     waited = [[-1] * n_streams for _ in range(n_streams)]   # waited[k][kd]: newest launch of stream kd that k already waits for
+    index_of = {}
     for i, (fn, args, name) in enumerate(launches):
+        index_of[id(launches[i])] = i
         wpos = _WRITES.get(name)
         rd, wr = [], []
         for j, a in enumerate(args):
@@ -678,9 +716,14 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
                 deps.update(readers.get(p, ()))
             if barrier >= 0:
                 deps.add(barrier)
+            if after:
+                anchor = index_of.get(after.get(id(launches[i])))
+                if anchor is not None and anchor < i:
+                    deps.add(anchor)
         deps.discard(i)
         if n_low > 0:
-            pool = range(n_streams - n_low, n_streams) if name in low_names else range(0, n_streams - n_low)
+            is_low = name in low_names or id(launches[i]) in low_ids
+            pool = range(n_streams - n_low, n_streams) if is_low else range(0, n_streams - n_low)
         else:
             pool = range(n_streams)
         k = None

@@ -13,7 +13,7 @@ from . import dist as hdist
 
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None, n_streams=6, n_low=2):
+                 distributed=None, n_streams=8, n_low=3):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
@@ -91,7 +91,11 @@ class HourglassTrainer(object):
         launches += plan.fwd + plan.bwd
         n_low = min(self.n_low, n_streams - 1)
         if self._sched is None:
-            self._sched = schedule_streams(launches, n_streams, n_low=n_low,
+            import os
+            low_on = os.environ.get("HGK_LOW_SKIPS", "0") == "1" or M.DEFER_SKIPS
+            low_ids = plan.low_recs if low_on else ()
+            self._sched = schedule_streams(launches, n_streams, n_low=n_low, low_ids=low_ids,
+                                           after=plan.after if M.DEFER_SKIPS else None,
                                            low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad"))
         stream_of, cross = self._sched
         # with a low-priority pool the other side streams are high priority (-1); the capture stream keeps priority 0

@@ -85,3 +85,34 @@ def test_write_table_covers_plan_entry_points():
     names = set(r[2] for r in L)
     for n in names:
         assert n in _WRITES or n in ("pack_weights", "pack_weights_tc", "unpack_add_grads"), n
+
+
+def test_deferred_skip_branches_are_low_priority_and_held_back():
+    """The hourglass skip branches are built after the down chain, confined to the low-priority streams and ordered
+    (by a scheduling-only edge) after the launch that ends the 32x32 rung -- and the data dependencies still hold."""
+    assert M.DEFER_SKIPS
+    plan, keep, L = _plan()
+    assert plan.low_recs and plan.after
+    ns, n_low = 8, 3
+    so, cross = schedule_streams(L, ns, n_low=n_low, low_ids=plan.low_recs, after=plan.after,
+                                 low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad"))
+    index = dict((id(r), i) for i, r in enumerate(L))
+    vc, tail = [], [-1] * ns
+    for i in range(len(L)):
+        k = so[i]
+        c = list(vc[tail[k]]) if tail[k] >= 0 else [-1] * ns
+        for d in cross[i]:
+            c = [max(x, y) for x, y in zip(c, vc[d])]
+        c[k] = i
+        vc.append(c)
+        tail[k] = i
+    n_edges = 0
+    for i, r in enumerate(L):
+        if id(r) in plan.low_recs:
+            assert so[i] >= ns - n_low, "skip-branch launch %d (%s) on a normal-priority stream" % (i, r[2])
+        a = plan.after.get(id(r))
+        if a is not None:
+            d = index[a]
+            assert d < i and vc[i][so[d]] >= d, "launch %d is not held back behind its anchor %d" % (i, d)
+            n_edges += 1
+    assert n_edges >= 2 * 3 * 3          # two hourglasses x (skip1, skip2, skip3) x three convolutions
