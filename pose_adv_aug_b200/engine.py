@@ -672,6 +672,11 @@ _WRITES = {
 }
 
 
+# entry points that read neither packed-weight arena: they need not wait for the weight repack at the head of the step
+# (the stem convolution reads the raw OIHW weights, the target transpose no weights at all)
+_NO_PACK_DEP = ("stem_conv7_fwd", "nchw_to_nhwc")
+
+
 def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads"),
                      low_names=(), n_low=0, low_ids=(), after=None):
     """Assign each launch of a static list to one of `n_streams` streams.
@@ -714,7 +719,7 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
                 if p in last_write:
                     deps.add(last_write[p])
                 deps.update(readers.get(p, ()))
-            if barrier >= 0:
+            if barrier >= 0 and not (name in _NO_PACK_DEP and launches[barrier][2] in ("pack_weights", "pack_weights_tc")):
                 deps.add(barrier)
             if after:
                 anchor = index_of.get(after.get(id(launches[i])))
