@@ -407,9 +407,9 @@ def dominant_kernel_roofline(tr, pk, torch):
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the committed ncu --set full
-            # capture profiles/r1z_kernels_ncu.txt (24x64x64, 128->128: 51.5 MB read + 8.2 MB written back before the
+            # capture profiles/r2z_kernels_ncu.txt (24x64x64, 128->128: 51.6 MB read + 7.3 MB written back before the
             # kernel ended; the 50 MB output largely stays dirty in the 126 MB L2)
-            "traffic": 59.8e6 if (tile and (N, H, W, Cin, Cout) == (24, 64, 64, 128, 128)) else None,
+            "traffic": 58.8e6 if (tile and (N, H, W, Cin, Cout) == (24, 64, 64, 128, 128)) else None,
             "kernel": "%s 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this FLOP class/step)" %
                       (("conv_tc2_kernel (tcgen05 image-tile kernel, 3xTF32)" if tile else "conv_tc_kernel (tcgen05, 3xTF32)")
                        if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
