@@ -118,3 +118,46 @@ def test_deferred_skip_branches_are_low_priority_and_held_back():
             assert d < i and vc[i][so[d]] >= d, "launch %d is not held back behind its anchor %d" % (i, d)
             n_edges += 1
     assert n_edges >= 2 * 3 * 3          # two hourglasses x (skip1, skip2, skip3) x three convolutions
+
+
+def test_plan_structure_of_agent_and_dropout_modes_on_cpu():
+    """Host logic only (no launches): the launch lists planned for the ASN aug / dropout modes have the structure the
+    reference forward prescribes (models/asn_stacked_hg.py:159-190,308-322)."""
+    C = 32
+    net = M.create_hg(2, 1, 16, C)
+    dev = torch.device("cpu")
+
+    def build(asn, **kw):
+        stores = [ParamStore(net, dev)] + ([ParamStore(asn, dev)] if asn is not None else [])
+        plan = Plan(stores, dev, True, True)
+        img = plan.input_image(2, 256, 256)
+        outs, agent = net._build(plan, img, asn, **kw)
+        for o in outs:
+            plan.output_nchw(o)
+        if agent is not None:
+            for a in agent:
+                (plan.output_plain if kw.get("is_dropout") else plan.output_rows)(a)
+        plan.finish()
+        return plan, outs, agent
+
+    names = lambda lst: [r[2] for r in lst]
+    # aug, half hourglass: no up path, two [N,7] logits, gradients only inside the agent
+    aug = M.create_asn(C, C, 7, 7, is_aug=True)
+    plan, outs, agent = build(aug, is_half_hg=True)
+    assert outs == [] and len(agent) == 2 and (agent[0].N, agent[0].C) == (2, 7)
+    assert names(plan.fwd).count("linear_fwd") == 2 and names(plan.fwd).count("avgpool_fwd") == 1
+    assert "add_fwd" in names(plan.fwd) and "mask_mul_fwd" not in names(plan.fwd)
+    # dropout, half hourglass: one [N,4,4,1] map of mask logits
+    drop = M.create_asn(C, C, is_dropout=True)
+    plan, outs, agent = build(drop, is_half_hg=True, is_dropout=True)
+    assert outs == [] and len(agent) == 1 and (agent[0].H, agent[0].W, agent[0].C) == (4, 4, 1)
+    assert "softmax_sample" not in names(plan.fwd)
+    # dropout, whole net: softmax -> host sampling -> 5 masked tensors in EACH of the two hourglasses (ref:179-190,320-322)
+    plan, outs, agent = build(drop, is_dropout=True)
+    f = names(plan.fwd)
+    assert len(outs) == 2 and f.count("softmax_sample") == 1 and f.count("host_sample_mask") == 1
+    assert f.count("mask_mul_fwd") == 10 and names(plan.bwd).count("mask_mul_bwd") == 10
+    assert f.index("softmax_sample") < f.index("host_sample_mask") < f.index("mask_mul_fwd")
+    assert tuple(plan.mask_indexes.shape) == (2, 2)
+    with torch.no_grad():
+        assert M.create_asn(C, C, 7, 7, is_aug=True)({"x": 0}, is_aug=False, is_dropout=False) is None   # ref:430-439
