@@ -173,6 +173,32 @@ def cpu_sample(args, sd, x, t, budget_s, steps, warmup):
             "s_per_step": dt, "sample_batch": sb}
 
 
+def cpu_config1(steps=5):
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case: 1-stack hourglass, nFeat=128, bs=2, 64x64,
+    forward + MSE on the host cores (reference model when oracle/_ref travelled, else the oracle port)."""
+    import argparse as _ap
+    import torch
+    a = _ap.Namespace(stacks=1, chan=128, batch=2, res=64)
+    sd = make_weights(a)
+    x, t = build_inputs(a, 0)
+    cpu = CpuStep(a, sd)
+
+    def fwd_mse():
+        with torch.no_grad():
+            if cpu.kind == "reference":
+                outs = cpu.net(x)
+            else:
+                outs, _ = cpu.O.hg_forward(cpu.sd, x, 1, 1, training=True)
+            return float(sum(((o - t) ** 2).sum() / o.numel() for o in outs))
+    fwd_mse()
+    t0 = time.time()
+    for _ in range(steps):
+        loss = fwd_mse()
+    dt = (time.time() - t0) / steps
+    return {"images_per_s": a.batch / dt, "ms": dt * 1e3, "loss": loss, "kind": cpu.kind, "cores": cpu.cores,
+            "workload": "1-stack hourglass nFeat=128, bs=2, 64x64 synthetic, CPU fwd+MSE"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -334,6 +360,10 @@ def run_ours(args):
             r = cpu_sample(args, sd, x, t, budget_s=25.0, steps=2, warmup=0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["parity"] = parity_vs_cpu(args, sd, x, t, torch, dev)
+            try:
+                line["cpu_baseline"]["config1"] = cpu_config1()
+            except Exception as e:
+                line["cpu_baseline"]["config1"] = {"failed": str(e)}
         except Exception as e:      # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % e}
