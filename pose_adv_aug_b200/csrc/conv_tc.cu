@@ -1020,6 +1020,8 @@ bool conv_tc2_eligible(const TcArgs& ta);                             // conv_tc
 int wgrad_tc2_try(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W, int Cin,
                   const float* dz, int Cout, int ksize, float* dw, float* dbias, void* stream);   // wgrad_tc2.cu (MN-major)
 int conv_tc2_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream);
+bool conv_tc3_eligible(const TcArgs& ta);                             // conv_tc3.cu (persistent, phase-overlapped tile kernel)
+int conv_tc3_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream);
 }
 
 using namespace hgk;
@@ -1044,6 +1046,16 @@ static bool use_tile_kernel() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("HGK_TC2_OFF");
+        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// HGK_TC3_OFF=1 disables the persistent tile kernel of conv_tc3.cu (A/B comparisons against conv_tc2.cu)
+static bool use_tc3() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HGK_TC3_OFF");
         v = (e != nullptr && e[0] == '1') ? 0 : 1;
     }
     return v == 1;
@@ -1077,7 +1089,8 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     ta.c.bfin = bfin != nullptr ? *bfin : BnBwdFin{};
     ta.c.ap = ap != nullptr ? *ap : BnApply{};
     if (ap != nullptr)
-        HGK_REQUIRE(w_lo == nullptr && use_tile_kernel() && conv_tc2_eligible(ta), "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
+        HGK_REQUIRE(w_lo == nullptr && ((use_tc3() && conv_tc3_eligible(ta)) || (use_tile_kernel() && conv_tc2_eligible(ta))),
+                    "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
                     "image-tile kernel (see hgk_conv_tc_bnapply_supported)");
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
@@ -1086,7 +1099,8 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     const bool split = w_lo != nullptr;
     if (bz != nullptr)
         HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
-    if (use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
+    if (use_tc3() && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
+    else if (use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
     else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
                         : (Cout == 128 ? launch_tc<128, false, true>(ta, st) : launch_tc<256, false, true>(ta, st));
@@ -1153,11 +1167,12 @@ extern "C" int hgk_conv_tc_dgrad_bnfin_nhwc(const float* dz, int N, int H, int W
 }
 
 extern "C" int hgk_conv_tc_bnapply_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
-    if (!hgk_conv_tc_supported(Cin, Cout, ksize) || !use_tile_kernel() || N <= 0 || H <= 0 || W <= 0) return 0;
-    TcArgs ta;
+    if (!hgk_conv_tc_supported(Cin, Cout, ksize) || N <= 0 || H <= 0 || W <= 0) return 0;
+    TcArgs ta{};
     ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
     ta.c.P = (long long)N * H * W;
-    return conv_tc2_eligible(ta) ? 1 : 0;
+    if (use_tc3() && conv_tc3_eligible(ta)) return 1;
+    return (use_tile_kernel() && conv_tc2_eligible(ta)) ? 1 : 0;
 }
 
 extern "C" int hgk_conv_tc_dgrad_bnapply_nhwc(const float* g, const float* gz, const float* gscale, const float* gshift, int grelu,
