@@ -1,24 +1,30 @@
-// Persistent, phase-overlapped tcgen05 implicit-GEMM convolution over 16x8-pixel image tiles.
+// Persistent, phase-overlapped tcgen05 implicit-GEMM convolution, CHANNELS ON THE TMEM LANES.
 //
 // Same contract as conv_tc2_kernel (conv_tc2.cu): BN+ReLU on load, 3xTF32 (forward) or plain TF32 (data gradient),
 // optional BatchNorm-backward apply on load (BNAPPLY), bias / shortcut / accumulate epilogue with the BatchNorm
 // statistics (or the fused BatchNorm-backward reduction, BWDSTATS) and the last-CTA finaliser.  What changed is the
-// execution structure (profiles/r2_tile_kernel_timeline.md: prologue + epilogue were 40-55 % of a CTA's life and the
-// two CTAs of an SM ran in lock-step):
+// execution structure (profiles/r2_tile_kernel_timeline.md: prologue + epilogue were 40-55 % of a CTA's life, the two
+// CTAs of an SM ran in lock-step; profiles/r3_persistent_kernel.md: the first persistent version was bound by shared-
+// memory bandwidth and by its transpose-through-shared-memory epilogue):
 //   * ONE CTA per SM walks over its tiles (tile = blockIdx.x + i * gridDim.x); nothing drains between tiles;
+//   * the GEMM is computed TRANSPOSED: D[channel][pixel] = W[channel][k] * X[pixel][k]^T, i.e. the packed weights are the
+//     M = 128 operand (two MMAs for 256 output channels) and the activation tile is the N = 128-pixel operand.  TMEM lanes
+//     are output channels, so an epilogue thread owns ONE channel: per-channel bias / BatchNorm vectors are scalars, the
+//     BatchNorm statistics are plain per-thread sums (no cross-lane reduction, no shared memory), and the NHWC stores
+//     of a warp are 32 consecutive channels of one pixel = one full 128-byte line;
 //   * the activation halo tile of a 16-channel chunk is fetched by TMA (cp.async.bulk.tensor, 4-D tensor map over
 //     [N][H][W][C], out-of-bounds rows / columns zero-filled by the hardware) DIRECTLY into the K-major 64-byte-swizzle
-//     UMMA layout (CU_TENSOR_MAP_SWIZZLE_64B is that layout), several chunks ahead -- no address generation, no
-//     register staging, the bytes in flight are bounded by shared memory instead of registers;
+//     UMMA layout (CU_TENSOR_MAP_SWIZZLE_64B is that layout), several chunks ahead;
 //   * eight transform warps turn the landed tile IN PLACE into the TF32 "hi" operand (BN+ReLU, round) and write the
 //     "lo" operand (3xTF32) next to it; for BNAPPLY the second plane receives the raw z tile (second tensor map) and
 //     the transform forms dz = cA*((g*mask - cC) - (z - mean)*cB), writes it back to global once, and rounds it;
 //   * one thread issues tcgen05.mma.kind::tf32 into one of TWO TMEM accumulator sets; the nine taps of a 3x3 are nine
 //     descriptors into the same halo tile (start address shifted by (dh*HWD + dw)*64 bytes);
-//   * eight epilogue warps drain accumulator set i&1 (tcgen05.ld -> per-warp 32x32 transpose patch -> coalesced
-//     128-bit stores, shortcut / accumulate loads issued one block ahead) while the main loop of tile i+1 runs;
-//     BatchNorm statistics are kept in shared memory (fp64) across tiles: one global atomic per channel per CTA.
-// 1x1 convolutions see the tensor as [1][P/8][8][C] (any H, W with P % 128 == 0: also the 8x8 / 4x4 rungs).
+//   * eight epilogue warps drain accumulator set i&1 (tcgen05.ld -> registers -> coalesced stores) while the main loop
+//     of tile i+1 runs; the shortcut / accumulate / BN-backward input tiles of the NEXT tile are pulled into L2 by
+//     cp.async.bulk.prefetch one tile ahead.
+// 1x1 convolutions see the tensor as [1][P/8][8][C] (any H, W with P % 8 == 0: also the 8x8 / 4x4 rungs; the ragged last
+// tile is zero-filled by TMA and masked by the epilogue).  Output channels: 128 or 256 (64-channel layers: conv_tc2.cu).
 #include <cuda.h>
 #include <stdlib.h>
 #include <type_traits>
@@ -40,7 +46,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -48,8 +58,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // developer diagnostics (tools/dbg_timeline3.py): cycles a role spends waiting on a barrier, accumulated per CTA into
 // args.dbg[cta][slot]; a predicated-off branch in production (args.dbg == nullptr)
@@ -74,44 +84,45 @@ constexpr int T3_WMMA = T3_NTW, T3_WLDA = T3_NTW + 1, T3_WLDB = T3_NTW + 2, T3_W
 constexpr int T3_WEPI = T3_NTW + 4;                         // first epilogue warp (multiple of 4: TMEM lane quarter = warp % 4)
 constexpr int T3_THREADS = (T3_WEPI + T3_NEW) * 32;         // 640
 constexpr int T3_NTT = T3_NTW * 32;                         // transform threads
-constexpr int T3_PATCH = 32 * 36 * 4;                       // per-epilogue-warp transpose patch (row stride 36 floats)
 static_assert(T3_WEPI % 4 == 0, "epilogue warps must start at a multiple of four");
 
 template <int BN, bool SPLIT, int KS, bool BNAPPLY>
 struct T3Cfg {
-    static constexpr int TH = 16, TW = 8;
+    static constexpr int NM = BN / 128;                                      // M = 128-channel halves of the output
+    // accumulators per (half, pixel sub-tile), see conv_tc.cu (the tensor core truncates its fp32 accumulator): the long 3x3
+    // 3xTF32 chain keeps hi*hi and the cross terms apart; the epilogue sums them in fp32
+    static constexpr int NACC = (SPLIT && KS == 3) ? 2 : 1;
+    static constexpr int NSUBS = 512 / (256 * NM * NACC);                    // 128-pixel sub-tiles per tile (two accumulator sets fit)
+    static constexpr int TH = KS == 1 ? 16 * NSUBS : 16, TW = KS == 1 ? 8 : 8 * NSUBS;
+    static constexpr int NPX = TH * TW;
     static constexpr int PAD = KS / 2;
     static constexpr int HH = TH + 2 * PAD, HWD = TW + 2 * PAD;
     static constexpr int NPIX = HH * HWD;
+    static constexpr int SUB_OFF = KS == 1 ? 128 * 64 : 8 * 64;              // byte offset of sub-tile 1 inside a plane
     static constexpr int TAPS = KS * KS;
     static constexpr int NITEM = NPIX * 4;
     static constexpr int NJ = (NITEM + T3_NTT - 1) / T3_NTT;
-    static constexpr int SBO_A = HWD * 64;
+    static constexpr int SBO_X = HWD * 64;
     static constexpr int A_BOX = NPIX * 64;                                  // bytes one tensor-map box delivers
     static constexpr int A_PLANE = (A_BOX + 1023) / 1024 * 1024;
     static constexpr int NPLANE = (SPLIT || BNAPPLY) ? 2 : 1;                // plane 1: lo operand (SPLIT) or raw z (BNAPPLY)
-    static constexpr int A_STAGE = NPLANE * A_PLANE;
-    static constexpr int A_TX = (BNAPPLY ? 2 : 1) * A_BOX;
+    static constexpr int CPS = (KS == 1 && NSUBS == 1) ? 2 : 1;              // 16-channel chunks per activation stage
+    static constexpr int A_STAGE = NPLANE * CPS * A_PLANE;
+    static constexpr int A_TX = (BNAPPLY ? 2 : 1) * CPS * A_BOX;
     static constexpr int B_HALF = BN * 16 * 4;
     static constexpr int B_STAGE = (SPLIT ? 2 : 1) * B_HALF;
-    // accumulators per tile, see conv_tc.cu (the tensor core truncates its fp32 accumulator): long 3xTF32 chains are
-    // split over hi*hi / cross-term accumulators and summed in fp32 by the epilogue
-    static constexpr int NMAIN = (SPLIT && KS == 3 && BN <= 64) ? 2 : 1;
-    static constexpr int NACC = (!SPLIT || KS == 1 || BN >= 256) ? 1 : NMAIN + 1;
-    static constexpr int SUBCOLS = NACC * BN;
-    static constexpr int TMEM_COLS = (2 * SUBCOLS <= 64) ? 64 : (2 * SUBCOLS <= 128) ? 128 : (2 * SUBCOLS <= 256) ? 256 : 512;
-    static constexpr int CPW = BN / 2;                                       // columns per epilogue warp
-    static constexpr int NBLK = CPW / 32;                                    // 32-column blocks per epilogue warp
-    static constexpr int EPI_BYTES = T3_NEW * T3_PATCH + T3_NEW * CPW * 2 * 8;
-    static constexpr int AVAIL = 227 * 1024 - 1024 - EPI_BYTES - 1024;
-    static constexpr int NSB = KS == 3 ? (B_STAGE <= 8192 ? 9 : 6) : (B_STAGE >= 32768 ? 3 : 4);
+    static constexpr int SETCOLS = NM * NACC * NSUBS * 128;                  // TMEM columns of one accumulator set
+    static constexpr int TMEM_COLS = (2 * SETCOLS <= 256) ? 256 : 512;
+    static constexpr int AVAIL = 227 * 1024 - 1024 - 1024;
+    static constexpr int NSB = KS == 3 ? 9 : (B_STAGE >= 32768 ? 3 : 4);
     static constexpr int NSA_FIT = (AVAIL - NSB * B_STAGE) / A_STAGE;
-    static constexpr int NSA = NSA_FIT > 8 ? 8 : NSA_FIT;
+    static constexpr int NSA = NSA_FIT > 6 ? 6 : NSA_FIT;
     static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
-    static constexpr int SMEM = PIPE + EPI_BYTES + 1024;
-    static_assert(2 * SUBCOLS <= 512, "TMEM capacity (two accumulator sets)");
-    static_assert(NSA >= 2, "activation ring needs two stages");
-    static_assert(BN % 64 == 0, "two epilogue warps per lane quarter split the columns in 32-column blocks");
+    static constexpr int SMEM = PIPE + 1024;
+    static constexpr int NSTEP = NM * NSUBS * 8 / 2;                         // 16-pixel x 32-channel steps per epilogue warp and tile
+    static_assert(BN == 128 || BN == 256, "output channels on the TMEM lanes: multiples of 128");
+    static_assert(NSUBS >= 1 && 2 * SETCOLS <= 512, "TMEM capacity (two accumulator sets)");
+    static_assert(NSA >= 3, "activation ring: one stage in the tensor core, one in the transform, one in flight");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -120,12 +131,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z) {
     static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
     using Cfg = T3Cfg<BN, SPLIT, KS, BNAPPLY>;
-    constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
-    constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
-    constexpr uint32_t SBO_A = Cfg::SBO_A, LBO_B = BN * 16, SBO_B = 128;
+    constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NACC = Cfg::NACC, NM = Cfg::NM, NSUBS = Cfg::NSUBS, CPS = Cfg::CPS;
+    constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SETCOLS = Cfg::SETCOLS, TH = Cfg::TH, TW = Cfg::TW;
+    constexpr uint32_t SBO_X = Cfg::SBO_X, LBO_W = BN * 16, SBO_W = 128;
     constexpr uint32_t A_PLANE = Cfg::A_PLANE, A_STAGE = Cfg::A_STAGE, B_HALF = Cfg::B_HALF, B_STAGE = Cfg::B_STAGE;
     constexpr uint32_t B_OFF = NSA * A_STAGE;
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    // D = f32 (bit 4), A = B = tf32 (2 << 7, 2 << 10), both K-major, N = 128 pixels (>> 3 at bit 17), M = 128 channels (>> 4 at bit 24)
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const ConvArgs& a = args.c;
 
     extern __shared__ uint8_t smem_raw[];
@@ -137,9 +149,9 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles_w = a.W >> 3, tiles_hw = (a.H >> 4) * tiles_w;
+    const int tiles_w = a.W / TW, tiles_hw = ((a.H + TH - 1) / TH) * tiles_w;      // KS == 1: the last row tile may be ragged
     const int ntiles = a.N * tiles_hw;
-    const int KC = a.Cin >> 4;
+    const int KR = a.Cin / (16 * CPS);                                              // activation stages (rounds) per tile
     const uint32_t bar_raw = smem_u32(&bars[0]), bar_fa = smem_u32(&bars[NSA]), bar_ea = smem_u32(&bars[2 * NSA]);
     const uint32_t bar_fb = smem_u32(&bars[3 * NSA]), bar_eb = smem_u32(&bars[3 * NSA + NSB]);
     const uint32_t bar_accf = smem_u32(&bars[3 * NSA + 2 * NSB]), bar_acce = smem_u32(&bars[3 * NSA + 2 * NSB + 2]);
@@ -147,7 +159,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
     if (tid == 0) {
         for (int s = 0; s < NSA; ++s) {
             mbar_init(bar_raw + 8 * s, 1);
-            mbar_init(bar_fa + 8 * s, T3_NTT);
+            mbar_init(bar_fa + 8 * s, T3_NTW);
             mbar_init(bar_ea + 8 * s, 1);
         }
         for (int s = 0; s < NSB; ++s) {
@@ -156,7 +168,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_accf + 8 * b, 1);
-            mbar_init(bar_acce + 8 * b, T3_NEW * 32);
+            mbar_init(bar_acce + 8 * b, T3_NEW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -196,78 +208,105 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             s_off[j] = (unsigned)hp * 64u + (((unsigned)quad ^ (((unsigned)hp >> 1) & 3u)) << 4);
             if (idx < Cfg::NITEM) {
                 smask |= 1u << j;
-                if (hh >= PAD && hh < PAD + 16 && ww >= PAD && ww < PAD + 8) imask |= 1u << j;
+                if (hh >= PAD && hh < PAD + TH && ww >= PAD && ww < PAD + TW) imask |= 1u << j;
             }
         }
-        const bool has_aff = a.x.scale != nullptr;
-        const float x_clamp = a.x.relu ? 0.f : -INFINITY;
+        constexpr bool ALLV = (Cfg::NITEM % T3_NTT) == 0;       // every item slot of every thread is a real item
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            if (!ALLV && !((smask >> j) & 1u)) s_off[j] = s_off[0];     // idle slots re-read item 0 (never stored)
+        // identity affine = (1, 0, clamp -inf): exact, so the on-load activation is applied without a branch
+        const float x_clamp = (a.x.scale != nullptr && a.x.relu) ? 0.f : -INFINITY;
         const BnApply& ap = a.ap;
+        const float ap_thr = ap.relu ? 0.f : -INFINITY;
         int sa = 0;
         unsigned par = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int n_img = tile / tiles_hw;
             const int trem = tile - n_img * tiles_hw;
-            const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) << 3;
-            unsigned vmask = smask;             // pixel inside the image (zero padding is a zero of the ACTIVATED tensor)
+            const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
+            unsigned vmask = 0;                 // pixel inside the image (zero padding is a zero of the ACTIVATED tensor)
             unsigned g_off[BNAPPLY ? NJ : 1];
-            if (KS == 3 || BNAPPLY) {
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int h = th0 - PAD + (hw_j[j] & 255), w = tw0 - PAD + (hw_j[j] >> 8);
-                    if (KS == 3 && !((unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W)) vmask &= ~(1u << j);
-                    if (BNAPPLY) g_off[j] = (unsigned)((n_img * a.H + h) * a.W + w) * (unsigned)a.Cin + (unsigned)quad * 4u;
-                }
+            for (int j = 0; j < NJ; ++j) {
+                const int h = th0 - PAD + (hw_j[j] & 255), w = tw0 - PAD + (hw_j[j] >> 8);
+                if (((smask >> j) & 1u) && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W) vmask |= 1u << j;
+                if (BNAPPLY) g_off[j] = (unsigned)((n_img * a.H + h) * a.W + w) * (unsigned)a.Cin + (unsigned)quad * 4u;
             }
-            for (int kc = 0; kc < KC; ++kc) {
-                float4 sc, sh;
-                load_affine4(a.x.scale, a.x.shift, kc * 16 + quad * 4, sc, sh);
-                float4 bs, bt, bmu, bA, bB, bC;
-                if (BNAPPLY) {
-                    const int c = kc * 16 + quad * 4;
-                    bs = ldg4(ap.scale + c); bt = ldg4(ap.shift + c); bmu = ldg4(ap.mean + c);
-                    bA = ldg4(ap.cA + c); bB = ldg4(ap.cB + c); bC = ldg4(ap.cC + c);
-                }
+            const unsigned wmask = vmask & imask;       // BNAPPLY: items whose dz this tile writes back
+            for (int kr = 0; kr < KR; ++kr) {
                 T3_WAIT(bar_raw + 8 * sa, par, w0);
                 const long long tc0 = dbg_on ? clock64() : 0;
-                uint8_t* base = sgen + sa * A_STAGE;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    if (!((smask >> j) & 1u)) continue;
-                    float4 v = ld4(reinterpret_cast<const float*>(base + s_off[j]));
-                    const bool in_img = (vmask >> j) & 1u;
-                    if (has_aff && in_img) v = actc4(v, sc, sh, x_clamp);
+                for (int cc = 0; cc < CPS; ++cc) {
+                    const int kc = kr * CPS + cc;
+                    float4 sc, sh;
+                    load_affine4(a.x.scale, a.x.shift, kc * 16 + quad * 4, sc, sh);
+                    float4 bs, bt, bmu, bA, bB, bC;
                     if (BNAPPLY) {
-                        // dz = cA * ((g * relu-mask - cC) - (z - mean) * cB)   (bn_bwd_apply_kernel, bn.cu)
-                        const float4 z = ld4(reinterpret_cast<const float*>(base + A_PLANE + s_off[j]));
-                        if (in_img) {
-                            const float gx = (ap.relu && fmaf(z.x, bs.x, bt.x) <= 0.f) ? 0.f : v.x;
-                            const float gy = (ap.relu && fmaf(z.y, bs.y, bt.y) <= 0.f) ? 0.f : v.y;
-                            const float gz = (ap.relu && fmaf(z.z, bs.z, bt.z) <= 0.f) ? 0.f : v.z;
-                            const float gw = (ap.relu && fmaf(z.w, bs.w, bt.w) <= 0.f) ? 0.f : v.w;
-                            v.x = bA.x * ((gx - bC.x) - (z.x - bmu.x) * bB.x);
-                            v.y = bA.y * ((gy - bC.y) - (z.y - bmu.y) * bB.y);
-                            v.z = bA.z * ((gz - bC.z) - (z.z - bmu.z) * bB.z);
-                            v.w = bA.w * ((gw - bC.w) - (z.w - bmu.w) * bB.w);
-                            if ((imask >> j) & 1u) st4(ap.dz + (g_off[BNAPPLY ? j : 0] + (unsigned)kc * 16u), v);
-                        }
+                        const int c = kc * 16 + quad * 4;
+                        bs = ldg4(ap.scale + c); bt = ldg4(ap.shift + c); bmu = ldg4(ap.mean + c);
+                        bA = ldg4(ap.cA + c); bB = ldg4(ap.cB + c); bC = ldg4(ap.cC + c);
                     }
-                    const float4 hi = tf32_rna4(v);
-                    *reinterpret_cast<float4*>(base + s_off[j]) = hi;
-                    if (SPLIT) {
-                        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                        *reinterpret_cast<float4*>(base + A_PLANE + s_off[j]) = lo;
+                    uint8_t* base = sgen + sa * A_STAGE + cc * A_PLANE;
+                    uint8_t* base2 = base + CPS * A_PLANE;
+                    // items in batches of JB: shared-memory loads first, then the arithmetic (BNAPPLY: small batches, the six
+                    // per-channel vectors already take 24 registers)
+                    constexpr int JB = BNAPPLY ? 2 : NJ;
+#pragma unroll
+                    for (int j0 = 0; j0 < NJ; j0 += JB) {
+                        float4 vv[JB], zz[BNAPPLY ? JB : 1];
+#pragma unroll
+                        for (int jj = 0; jj < JB; ++jj) {
+                            const int j = j0 + jj;
+                            if (j >= NJ) break;
+                            vv[jj] = ld4(reinterpret_cast<const float*>(base + s_off[j]));
+                            if (BNAPPLY) zz[BNAPPLY ? jj : 0] = ld4(reinterpret_cast<const float*>(base2 + s_off[j]));
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < JB; ++jj) {
+                            const int j = j0 + jj;
+                            if (j >= NJ) break;
+                            const bool in_img = (vmask >> j) & 1u;
+                            float4 v = vv[jj];
+                            if (!BNAPPLY) {
+                                const float4 t = actc4(v, sc, sh, x_clamp);
+                                v.x = in_img ? t.x : 0.f; v.y = in_img ? t.y : 0.f; v.z = in_img ? t.z : 0.f; v.w = in_img ? t.w : 0.f;
+                            } else {
+                                // dz = cA * ((g * relu-mask - cC) - (z - mean) * cB)   (bn_bwd_apply_kernel, bn.cu)
+                                const float4 z = zz[BNAPPLY ? jj : 0];
+                                const float gx = fmaf(z.x, bs.x, bt.x) <= ap_thr ? 0.f : v.x;
+                                const float gy = fmaf(z.y, bs.y, bt.y) <= ap_thr ? 0.f : v.y;
+                                const float gz = fmaf(z.z, bs.z, bt.z) <= ap_thr ? 0.f : v.z;
+                                const float gw = fmaf(z.w, bs.w, bt.w) <= ap_thr ? 0.f : v.w;
+                                v.x = in_img ? bA.x * ((gx - bC.x) - (z.x - bmu.x) * bB.x) : 0.f;
+                                v.y = in_img ? bA.y * ((gy - bC.y) - (z.y - bmu.y) * bB.y) : 0.f;
+                                v.z = in_img ? bA.z * ((gz - bC.z) - (z.z - bmu.z) * bB.z) : 0.f;
+                                v.w = in_img ? bA.w * ((gw - bC.w) - (z.w - bmu.w) * bB.w) : 0.f;
+                                if ((wmask >> j) & 1u) st4(ap.dz + (g_off[BNAPPLY ? j : 0] + (unsigned)kc * 16u), v);
+                            }
+                            const float4 hi = tf32_rna4(v);
+                            if (ALLV || ((smask >> j) & 1u)) {
+                                *reinterpret_cast<float4*>(base + s_off[j]) = hi;
+                                if (SPLIT) {
+                                    const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                                    *reinterpret_cast<float4*>(base2 + s_off[j]) = lo;
+                                }
+                            }
+                        }
                     }
                 }
                 const long long tc1 = dbg_on ? clock64() : 0;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(bar_fa + 8 * sa);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_fa + 8 * sa);                   // one arrival per warp
                 if (dbg_on) { w1 += tc1 - tc0; w2 += clock64() - tc1; }
                 if (++sa == NSA) { sa = 0; par ^= 1u; }
             }
         }
         if (tid == 0) { T3_DBG(0, clock64() - t_begin); T3_DBG(1, w0); T3_DBG(12, w1); T3_DBG(13, w2); }
     } else if (warp == T3_WMMA) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: D[channel][pixel] += W[channel][k] * X[pixel][k] =====
         if (lane == 0) {
             int sa = 0, sb = 0;
             unsigned fa_par = 0, fb_par = 0;
@@ -276,41 +315,52 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                 const int b = i & 1;
                 if (i >= 2) T3_WAIT(bar_acce + 8 * b, (unsigned)((i >> 1) - 1) & 1u, w2);   // epilogue drained this accumulator set
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t t_set = tmem + (uint32_t)(b * SUBCOLS);
-                int it = 0;
-                for (int kc = 0; kc < KC; ++kc) {
+                const uint32_t t_set = tmem + (uint32_t)(b * SETCOLS);
+                bool first = true;                                             // first k-step of the tile overwrites the accumulators
+                for (int kr = 0; kr < KR; ++kr) {
                     T3_WAIT(bar_fa + 8 * sa, fa_par, w0);
-                    const uint32_t a_stage = sbase + sa * A_STAGE;
 #pragma unroll 1
-                    for (int tap = 0; tap < TAPS; ++tap, ++it) {
-                        T3_WAIT(bar_fb + 8 * sb, fb_par, w1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
-                        const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
+                    for (int cc = 0; cc < CPS; ++cc) {
+                        const uint32_t x_hi0 = sbase + sa * A_STAGE + cc * A_PLANE;
+#pragma unroll 1
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            T3_WAIT(bar_fb + 8 * sb, fb_par, w1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t x_tap = x_hi0 + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
+                            const uint32_t w_hi0 = sbase + B_OFF + sb * B_STAGE;
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const uint64_t da = umma_desc_k64_3(a_tap + k * 32, SBO_A);
-                            const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO_B);
-                            if (SPLIT) {
-                                const uint64_t dal = umma_desc_k64_3(a_tap + A_PLANE + k * 32, SBO_A);
-                                const uint64_t dbl = umma_desc(b_hi + B_HALF + k * 2 * LBO_B, LBO_B, SBO_B);
-                                if (NACC == 1) {
-                                    umma_tf32(t_set, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-                                    umma_tf32(t_set, da, dbl, IDESC, 1u);
-                                    umma_tf32(t_set, da, db, IDESC, 1u);
-                                } else {
-                                    const uint32_t t_small = t_set + NMAIN * BN;
-                                    const uint32_t t_main = t_set + (NMAIN > 1 ? (it & 1) * BN : 0);
-                                    umma_tf32(t_small, dal, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-                                    umma_tf32(t_small, da, dbl, IDESC, 1u);
-                                    umma_tf32(t_main, da, db, IDESC, (it >= NMAIN || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t acc_flag = (first && k == 0) ? 0u : 1u;
+#pragma unroll
+                                for (int s = 0; s < NSUBS; ++s) {
+                                    const uint64_t dx = umma_desc_k64_3(x_tap + s * Cfg::SUB_OFF + k * 32, SBO_X);
+                                    const uint64_t dxl = umma_desc_k64_3(x_tap + CPS * A_PLANE + s * Cfg::SUB_OFF + k * 32, SBO_X);
+#pragma unroll
+                                    for (int mh = 0; mh < NM; ++mh) {
+                                        const uint64_t dw = umma_desc(w_hi0 + mh * (128 * 16) + k * 2 * LBO_W, LBO_W, SBO_W);
+                                        const uint32_t t_main = t_set + (uint32_t)(((mh * NACC) * NSUBS + s) * 128);
+                                        if (SPLIT) {
+                                            const uint64_t dwl = umma_desc(w_hi0 + B_HALF + mh * (128 * 16) + k * 2 * LBO_W, LBO_W, SBO_W);
+                                            const uint32_t t_small = t_set + (uint32_t)(((mh * NACC + (NACC - 1)) * NSUBS + s) * 128);
+                                            if (NACC == 1) {
+                                                umma_tf32(t_main, dw, dxl, IDESC, acc_flag);
+                                                umma_tf32(t_main, dwl, dx, IDESC, 1u);
+                                                umma_tf32(t_main, dw, dx, IDESC, 1u);
+                                            } else {
+                                                umma_tf32(t_small, dw, dxl, IDESC, acc_flag);
+                                                umma_tf32(t_small, dwl, dx, IDESC, 1u);
+                                                umma_tf32(t_main, dw, dx, IDESC, acc_flag);
+                                            }
+                                        } else {
+                                            umma_tf32(t_main, dw, dx, IDESC, acc_flag);
+                                        }
+                                    }
                                 }
-                            } else {
-                                umma_tf32(t_set, da, db, IDESC, (it > 0 || k > 0) ? 1u : 0u);
                             }
+                            first = false;
+                            umma_commit(bar_eb + 8 * sb);                      // weight stage free
+                            if (++sb == NSB) { sb = 0; fb_par ^= 1u; }
                         }
-                        umma_commit(bar_eb + 8 * sb);                          // weight stage free
-                        if (++sb == NSB) { sb = 0; fb_par ^= 1u; }
                     }
                     umma_commit(bar_ea + 8 * sa);                              // activation stage free
                     if (++sa == NSA) { sa = 0; fa_par ^= 1u; }
@@ -329,14 +379,18 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int n_img = tile / tiles_hw;
                 const int trem = tile - n_img * tiles_hw;
-                const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) << 3;
-                for (int kc = 0; kc < KC; ++kc, ++g) {
+                const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
+                for (int kr = 0; kr < KR; ++kr, ++g) {
                     if (g >= NSA) T3_WAIT(bar_ea + 8 * sa, ea_par, w0);
                     const uint32_t bb = bar_raw + 8 * sa;
                     const uint32_t dst = sbase + sa * A_STAGE;
                     mbar_expect_tx(bb, Cfg::A_TX);
-                    tma_load_4d(dst, &tm_x, kc * 16, tw0 - PAD, th0 - PAD, n_img, bb);
-                    if (BNAPPLY) tma_load_4d(dst + A_PLANE, &tm_z, kc * 16, tw0 - PAD, th0 - PAD, n_img, bb);
+#pragma unroll
+                    for (int cc = 0; cc < CPS; ++cc) {
+                        const int c0 = (kr * CPS + cc) * 16;
+                        tma_load_4d(dst + cc * A_PLANE, &tm_x, c0, tw0 - PAD, th0 - PAD, n_img, bb);
+                        if (BNAPPLY) tma_load_4d(dst + (CPS + cc) * A_PLANE, &tm_z, c0, tw0 - PAD, th0 - PAD, n_img, bb);
+                    }
                     if (++sa == NSA) { sa = 0; ea_par ^= 1u; }
                 }
             }
@@ -346,7 +400,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
     } else if (warp == T3_WLDB) {
         // ===== weight stream: one cp.async.bulk per (chunk, tap) stage; packed blocks are [tap][Cin/32][8 quads][BN][4] =====
         if (lane == 0) {
-            const int KC32 = a.Cin >> 5;
+            const int KC = a.Cin >> 4, KC32 = a.Cin >> 5;
             int sb = 0;
             unsigned eb_par = 1;
             long long g = 0;
@@ -367,145 +421,154 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             T3_DBG(8, clock64() - t_begin); T3_DBG(9, w0);
         }
         __syncwarp();
-    } else if (warp >= T3_WEPI) {
-        // ===== epilogue warps: TMEM -> registers -> 32x32 patch -> bias / shortcut / accumulate -> coalesced store, statistics =====
+    } else if (warp == T3_WAUX) {
+        // ===== L2 prefetch of the epilogue's input tiles (shortcut / previous output / BN-backward z), one tile ahead =====
+        const float* src = lane == 0 ? a.res.z : (lane == 1 ? (a.accumulate ? a.y : nullptr) : (lane == 2 && BWDSTATS ? a.bz : nullptr));
+        if (lane < 3 && src != nullptr) {
+            int i = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+                // pace: the rows of tile i are requested when the main loop of tile i-1 has finished
+                if (i >= 1) mbar_wait(bar_accf + 8 * ((i - 1) & 1), (unsigned)((i - 1) >> 1) & 1u);
+                const int n_img = tile / tiles_hw;
+                const int trem = tile - n_img * tiles_hw;
+                const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
+                if (KS == 1) {
+                    const long long p0 = (long long)tile * Cfg::NPX;
+                    long long np = a.P - p0;
+                    if (np > Cfg::NPX) np = Cfg::NPX;
+                    l2_prefetch(src + p0 * a.Cout, (uint32_t)(np * a.Cout * 4));
+                } else {
+                    for (int r = 0; r < TH; ++r)
+                        l2_prefetch(src + ((size_t)(n_img * a.H + th0 + r) * a.W + tw0) * a.Cout, (uint32_t)(TW * a.Cout * 4));
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: thread = output channel; 16 pixels (TMEM columns) per step =====
         const int we = warp - T3_WEPI;
-        const int lq = warp & 3;                 // TMEM lane quarter this warp may access = 32 tile rows
-        const int half = we >> 2;                // column half of the tile
-        constexpr int CPW = Cfg::CPW, NBLK = Cfg::NBLK;
-        float* patch = reinterpret_cast<float*>(sgen + Cfg::PIPE + we * T3_PATCH);
-        double* stat = reinterpret_cast<double*>(sgen + Cfg::PIPE + T3_NEW * T3_PATCH) + (size_t)we * CPW * 2;
+        const int lq = warp & 3;                 // TMEM lane quarter this warp may access = 32 channels of a 128-channel half
+        const int hsel = we >> 2;                // the two warps of a lane quarter alternate over the 16-pixel steps
+        constexpr int NSTEP = Cfg::NSTEP;
         const bool do_stats = a.stat_sum != nullptr;
         const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
         const bool has_acc = a.accumulate != 0;
-        for (int c = lane; c < CPW * 2; c += 32) stat[c] = 0.0;
-        __syncwarp();
-        const int rsub = lane >> 3, cq = lane & 7;   // row loop: lane -> (row rsub + 4 i, column quad cq)
-        const unsigned uW = (unsigned)a.W, uCout = (unsigned)a.Cout;
-        const unsigned col_base = (unsigned)(half * CPW + cq * 4);
+        const float* __restrict__ resp = a.res.z;
+        const float* __restrict__ bzp = a.bz;
+        float* __restrict__ yp = a.y;
+        const unsigned uCout = (unsigned)a.Cout;
+        const unsigned row_stride = (unsigned)a.W * uCout;
+        // shortcut activation as a branch-free (scale, shift, clamp): identity = (1, 0, -inf)
+        const float r_clamp = (res_aff && a.res.relu) ? 0.f : -INFINITY;
+        const float b_thr = a.brelu ? 0.f : -INFINITY;       // BN-backward ReLU mask: g = (bz*scale+shift <= thr) ? 0 : dy
+        double d1[NM], d2[NM];
+        float bv[NM], rs[NM], rt[NM], bsc[NM], bsh[NM], bmu[NM], biv[NM];
+#pragma unroll
+        for (int mh = 0; mh < NM; ++mh) {
+            const int ch = mh * 128 + lq * 32 + lane;
+            d1[mh] = 0.0; d2[mh] = 0.0;
+            bv[mh] = a.bias != nullptr ? __ldg(a.bias + ch) : 0.f;
+            rs[mh] = res_aff ? __ldg(a.res.scale + ch) : 1.f;
+            rt[mh] = res_aff ? __ldg(a.res.shift + ch) : 0.f;
+            bsc[mh] = 1.f; bsh[mh] = 0.f; bmu[mh] = 0.f; biv[mh] = 1.f;
+            if (BWDSTATS) { bsc[mh] = __ldg(a.bscale + ch); bsh[mh] = __ldg(a.bshift + ch); bmu[mh] = __ldg(a.bmean + ch); biv[mh] = __ldg(a.binvstd + ch); }
+        }
 
         auto tile_loop = [&](auto r_tag, auto a_tag) {
             constexpr bool R = decltype(r_tag)::value, A = decltype(a_tag)::value;
             constexpr int NL = (R ? 1 : 0) + (A ? 1 : 0) + (BWDSTATS ? 1 : 0);
-            constexpr int RB = NL <= 1 ? 8 : (NL == 2 ? 4 : 2);     // rows per step (prefetch registers: NL * RB float4)
-            constexpr int SPB = 8 / RB, NSTEP = NBLK * SPB;
             int i = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
                 const int b = i & 1;
                 const int n_img = tile / tiles_hw;
                 const int trem = tile - n_img * tiles_hw;
-                const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) << 3;
-                // tile row r = lq*32 + rsub + 4*ri -> pixel (th0 + lq*4 + (ri>>1), tw0 + rsub + 4*(ri&1))
-                const unsigned pix_base = (unsigned)((n_img * a.H + th0 + lq * 4) * a.W + tw0 + rsub);
-                float4 rr[R ? RB : 1], oo[A ? RB : 1], zz[BWDSTATS ? RB : 1];
-                auto off_of = [&](int st, int k) -> unsigned {
-                    const int blk = st / SPB, ri = (st % SPB) * RB + k;
-                    return (pix_base + (unsigned)(ri >> 1) * uW + (unsigned)((ri & 1) * 4)) * uCout + col_base + (unsigned)(blk * 32);
-                };
-                auto issue = [&](int st, int k) {
-                    const unsigned off = off_of(st, k);
-                    if (R) rr[R ? k : 0] = ldg4(a.res.z + off);
-                    if (A) oo[A ? k : 0] = ld4(a.y + off);
-                    if (BWDSTATS) zz[BWDSTATS ? k : 0] = ldg4(a.bz + off);
-                };
-                if (NL > 0) {
-#pragma unroll
-                    for (int k = 0; k < RB; ++k) issue(0, k);
+                const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
+                const unsigned pix0 = (unsigned)((n_img * a.H + th0) * a.W + tw0);
+                // KS == 1: pixels of the tile that exist (the last tile of the linear view may be ragged)
+                int npx = Cfg::NPX;
+                if (KS == 1) {
+                    const long long left = a.P - (long long)tile * Cfg::NPX;
+                    if (left < Cfg::NPX) npx = (int)left;
                 }
+                float rr[R ? 16 : 1], oo[A ? 16 : 1], zz[BWDSTATS ? 16 : 1];
+                // step -> (channel half mh, pixel sub-tile s, 16-pixel group j): this warp takes every other group
+                auto step_base = [&](int st, int& mh, unsigned& col, unsigned& off, int& lp0) {
+                    const int per_mh = NSUBS * 4;                  // steps of this warp per channel half
+                    mh = st / per_mh;
+                    const int rem = st - mh * per_mh;
+                    const int s = rem >> 2, j = ((rem & 3) << 1) + hsel;      // 16-pixel group j of sub-tile s: MMA rows 16j..16j+15
+                    col = (unsigned)(((mh * NACC) * NSUBS + s) * 128 + j * 16);
+                    // MMA row r of sub-tile s -> tile pixel (KS==1: row s*16 + r/8, column r%8; KS==3: row r/8, column s*8 + r%8)
+                    const int trow = (KS == 1 ? s * 16 : 0) + j * 2, tcol = (KS == 1 ? 0 : s * 8);
+                    lp0 = trow * 8;                                // KS == 1: linear index of the group's first pixel inside the tile
+                    off = (pix0 + (unsigned)trow * (unsigned)a.W + (unsigned)tcol) * uCout + (unsigned)(mh * 128 + lq * 32 + lane);
+                };
+                auto issue = [&](int st) {
+                    int mh, lp0; unsigned col, off;
+                    step_base(st, mh, col, off, lp0);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const unsigned o = off + (KS == 1 ? (unsigned)q * uCout : (unsigned)(q >> 3) * row_stride + (unsigned)(q & 7) * uCout);
+                        const bool ok = KS != 1 || lp0 + q < npx;
+                        if (R) rr[R ? q : 0] = ok ? __ldg(resp + o) : 0.f;
+                        if (A) oo[A ? q : 0] = ok ? yp[o] : 0.f;
+                        if (BWDSTATS) zz[BWDSTATS ? q : 0] = ok ? __ldg(bzp + o) : 0.f;
+                    }
+                };
+                if (NL > 0) issue(0);
                 T3_WAIT(bar_accf + 8 * b, (unsigned)(i >> 1) & 1u, w0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rs, rt;
-                float4 bsc = make_float4(1.f, 1.f, 1.f, 1.f), bsh = make_float4(0.f, 0.f, 0.f, 0.f), bmu = bsh, biv = bsc;
-                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int st = 0; st < NSTEP; ++st) {
-                    const int blk = st / SPB;
-                    if (st % SPB == 0) {
-                        // accumulator block (32 rows x 32 columns) -> transpose patch
-                        const long long te0 = dbg_on ? clock64() : 0;
-                        const int c0 = half * CPW + blk * 32;
+                    int mh, lp0; unsigned col, off;
+                    step_base(st, mh, col, off, lp0);
+                    const long long te0 = dbg_on ? clock64() : 0;
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SETCOLS) + col;
+                    tmem_ld16_nowait(taddr, r);
+                    tmem_ld_wait();
+                    float acc[16];
 #pragma unroll
-                        for (int h16 = 0; h16 < 2; ++h16) {
-                            uint32_t r[16];
-                            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SUBCOLS + c0 + h16 * 16);
-                            tmem_ld16(taddr, r);
-                            float acc[16];
+                    for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(r[q]);
+                    if (NACC > 1) {
+                        tmem_ld16_nowait(taddr + (uint32_t)((NACC - 1) * NSUBS * 128), r);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(r[q]);
-#pragma unroll
-                            for (int e = 1; e < NACC; ++e) {
-                                tmem_ld16(taddr + (uint32_t)(e * BN), r);
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r[q]);
-                            }
-                            float* dst = patch + lane * 36 + h16 * 16;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                st4(dst + q * 4, make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
-                        }
-                        if (blk == NBLK - 1) {       // accumulator set fully read: hand it back to the MMA warp
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            mbar_arrive(bar_acce + 8 * b);
-                        }
-                        const int n = c0 + cq * 4;
-                        if (a.bias != nullptr) bv = ldg4(a.bias + n);
-                        if (R) load_affine4(a.res.scale, a.res.shift, n, rs, rt);
-                        if (BWDSTATS) { bsc = ldg4(a.bscale + n); bsh = ldg4(a.bshift + n); bmu = ldg4(a.bmean + n); biv = ldg4(a.binvstd + n); }
+                        for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r[q]);
+                    }
+                    if (st == NSTEP - 1) {       // accumulator set fully read: hand it back to the MMA warp
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (dbg_on) w1 += clock64() - te0;
+                        if (lane == 0) mbar_arrive(bar_acce + 8 * b);
                     }
+                    if (dbg_on) w1 += clock64() - te0;
+                    const float bias = NM > 1 ? (mh ? bv[NM - 1] : bv[0]) : bv[0];
+                    const float rsc = NM > 1 ? (mh ? rs[NM - 1] : rs[0]) : rs[0], rsh = NM > 1 ? (mh ? rt[NM - 1] : rt[0]) : rt[0];
+                    const float s_c = NM > 1 ? (mh ? bsc[NM - 1] : bsc[0]) : bsc[0], s_h = NM > 1 ? (mh ? bsh[NM - 1] : bsh[0]) : bsh[0];
+                    const float s_m = NM > 1 ? (mh ? bmu[NM - 1] : bmu[0]) : bmu[0], s_i = NM > 1 ? (mh ? biv[NM - 1] : biv[0]) : biv[0];
+                    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < RB; ++k) {
-                        const int ri = (st % SPB) * RB + k;
-                        const unsigned off = off_of(st, k);
-                        float4 v = ld4(patch + (rsub + 4 * ri) * 36 + cq * 4);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        if (R) {
-                            float4 q = rr[R ? k : 0];
-                            if (res_aff) q = act4(q, rs, rt, a.res.relu);
-                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    for (int q = 0; q < 16; ++q) {
+                        const unsigned o = off + (KS == 1 ? (unsigned)q * uCout : (unsigned)(q >> 3) * row_stride + (unsigned)(q & 7) * uCout);
+                        const bool ok = KS != 1 || lp0 + q < npx;
+                        float v = acc[q] + bias;
+                        if (R) v += fmaxf(fmaf(rr[R ? q : 0], rsc, rsh), r_clamp);
+                        if (A) v += oo[A ? q : 0];
+                        if (ok) yp[o] = v;
+                        float gv = v, gx = v;                       // statistics: sum gv, sum gv*gx
+                        if (BWDSTATS) {
+                            const float z = zz[BWDSTATS ? q : 0];
+                            gv = fmaf(z, s_c, s_h) <= b_thr ? 0.f : v;
+                            gx = (z - s_m) * s_i;
                         }
-                        if (A) { const float4 o = oo[A ? k : 0]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                        st4(a.y + off, v);
-                        if (do_stats) {
-                            if (BWDSTATS) {
-                                const float4 z = zz[BWDSTATS ? k : 0];
-                                const float gx = (a.brelu && fmaf(z.x, bsc.x, bsh.x) <= 0.f) ? 0.f : v.x;
-                                const float gy = (a.brelu && fmaf(z.y, bsc.y, bsh.y) <= 0.f) ? 0.f : v.y;
-                                const float gz = (a.brelu && fmaf(z.z, bsc.z, bsh.z) <= 0.f) ? 0.f : v.z;
-                                const float gw = (a.brelu && fmaf(z.w, bsc.w, bsh.w) <= 0.f) ? 0.f : v.w;
-                                s1[0] += gx; s2[0] = fmaf(gx, (z.x - bmu.x) * biv.x, s2[0]);
-                                s1[1] += gy; s2[1] = fmaf(gy, (z.y - bmu.y) * biv.y, s2[1]);
-                                s1[2] += gz; s2[2] = fmaf(gz, (z.z - bmu.z) * biv.z, s2[2]);
-                                s1[3] += gw; s2[3] = fmaf(gw, (z.w - bmu.w) * biv.w, s2[3]);
-                            } else {
-                                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-                                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-                                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-                                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
-                            }
-                        }
-                        if (NL > 0 && st + 1 < NSTEP) issue(st + 1, k);      // next step's loads behind this row's use
+                        if (KS == 1) gv = ok ? gv : 0.f;
+                        s1 += gv;
+                        s2 = fmaf(gv, gx, s2);
                     }
-                    if (st % SPB == SPB - 1) {
-                        __syncwarp();                    // the patch is rewritten by the next block
-                        if (do_stats) {
-                            // fp32 partial sums over this lane's 8 rows; 4 lanes (rsub) share a column quad: shuffle, then fp64
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-                                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-                                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-                                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
-                            }
-                            if (rsub == 0) {
-                                double* sp = stat + (size_t)(blk * 32 + cq * 4) * 2;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) { sp[j * 2 + 0] += (double)s1[j]; sp[j * 2 + 1] += (double)s2[j]; }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-                        }
+                    if (NL > 0 && st + 1 < NSTEP) issue(st + 1);     // one batch, behind every use of the previous one
+                    if (do_stats) {              // fp32 partial sums over 16 pixels, fp64 from here on
+                        if (NM > 1 && mh) { d1[NM - 1] += (double)s1; d2[NM - 1] += (double)s2; }
+                        else { d1[0] += (double)s1; d2[0] += (double)s2; }
                     }
                 }
             }
@@ -515,29 +578,22 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         } else {
             if (has_acc) tile_loop(std::false_type{}, std::true_type{}); else tile_loop(std::false_type{}, std::false_type{});
         }
+        if (do_stats) {
+#pragma unroll
+            for (int mh = 0; mh < NM; ++mh) {
+                const int ch = mh * 128 + lq * 32 + lane;
+                atomicAdd(a.stat_sum + ch, d1[mh]);
+                atomicAdd(a.stat_sq + ch, d2[mh]);
+            }
+        }
         if (we == 0 && lane == 0) { T3_DBG(10, clock64() - t_begin); T3_DBG(11, w0); T3_DBG(16, w1); }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == T3_WAUX)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
-    // ---- statistics: per-warp fp64 partial sums (shared memory) -> one global atomic per channel per CTA; last CTA finalises ----
+    // ---- the CTA that arrives last turns the complete sums into the per-channel BatchNorm vectors ----
     if (a.stat_sum != nullptr) {
-        const double* stat0 = reinterpret_cast<const double*>(sgen + Cfg::PIPE + T3_NEW * T3_PATCH);
-        if (blockIdx.x < ntiles) {
-            for (int c = tid; c < BN; c += T3_THREADS) {
-                const int hf = c / Cfg::CPW, cl = c - hf * Cfg::CPW;
-                double x1 = 0.0, x2 = 0.0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double* sp = stat0 + ((size_t)(hf * 4 + q) * Cfg::CPW + cl) * 2;
-                    x1 += sp[0];
-                    x2 += sp[1];
-                }
-                atomicAdd(a.stat_sum + c, x1);
-                atomicAdd(a.stat_sq + c, x2);
-            }
-        }
         if (!BWDSTATS && a.ffin.ticket != nullptr) {
             if (last_cta_arrives(a.ffin.ticket, gridDim.x)) bn_fwd_finalize_cta(a.ffin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
         } else if (BWDSTATS && a.bfin.ticket != nullptr) {
@@ -599,7 +655,7 @@ static int launch_tc3(TcArgs ta, cudaStream_t st) {
         }
         configured = true;
     }
-    if (KS == 1) {          // a 1x1 convolution has no neighbourhood: any 128 consecutive pixels are a tile
+    if (KS == 1) {          // a 1x1 convolution has no neighbourhood: any run of consecutive pixels is a tile
         ta.c.H = (int)(ta.c.P / 8);
         ta.c.W = 8;
         ta.c.N = 1;
@@ -613,7 +669,7 @@ static int launch_tc3(TcArgs ta, cudaStream_t st) {
     } else {
         mz = mx;
     }
-    const long long tiles = (long long)ta.c.N * (ta.c.H >> 4) * (ta.c.W >> 3);
+    const long long tiles = (long long)ta.c.N * ((ta.c.H + Cfg::TH - 1) / Cfg::TH) * (ta.c.W / Cfg::TW);
     const long long rounds = (tiles + kNumSMs - 1) / kNumSMs;
     const unsigned grid = (unsigned)((tiles + rounds - 1) / rounds);
     conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY><<<grid, T3_THREADS, smem, st>>>(ta, mx, mz);
@@ -632,27 +688,23 @@ static int launch_tc3_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream
 // true when the persistent tile kernel covers this problem
 bool conv_tc3_eligible(const TcArgs& ta) {
     const ConvArgs& c = ta.c;
+    if (c.Cout != 128 && c.Cout != 256) return false;
     if (c.ksize == 3) {
-        if (c.H % 16 || c.W % 8) return false;
+        if (c.H % 16 || c.W % 16) return false;
         if (c.Cout > 128) return false;                                   // 3x3 with 256 outputs: no instantiation
     } else {
-        if (c.P % 128) return false;
+        if (c.P % 8) return false;
     }
     const long long cmax = c.Cin > c.Cout ? c.Cin : c.Cout;
-    if (c.P * cmax >= (1LL << 32)) return false;                          // 32-bit element offsets
+    if ((c.P + 256) * cmax >= (1LL << 32)) return false;                  // 32-bit element offsets
     if (((uintptr_t)c.x.z & 15) || (c.ap.z != nullptr && ((uintptr_t)c.ap.z & 15))) return false;   // tensor-map base alignment
     return true;
 }
 
 int conv_tc3_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    const int BN = ta.c.Cout;
-    if (ta.c.ksize == 3) {
-        if (BN == 64) return launch_tc3_bn<64, 3>(ta, split, bwdstats, st);
-        return launch_tc3_bn<128, 3>(ta, split, bwdstats, st);
-    }
-    if (BN == 64) return launch_tc3_bn<64, 1>(ta, split, bwdstats, st);
-    if (BN == 128) return launch_tc3_bn<128, 1>(ta, split, bwdstats, st);
+    if (ta.c.ksize == 3) return launch_tc3_bn<128, 3>(ta, split, bwdstats, st);
+    if (ta.c.Cout == 128) return launch_tc3_bn<128, 1>(ta, split, bwdstats, st);
     return launch_tc3_bn<256, 1>(ta, split, bwdstats, st);
 }
 

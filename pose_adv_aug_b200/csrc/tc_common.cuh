@@ -41,17 +41,19 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Blocking wait.  The suspend-time hint matters: without it try_wait returns after a very short hardware nap and the
+// waiting warps (a whole role of a warp-specialised kernel) spin through the loop, taking issue slots from the warps of the
+// same scheduler that have work (profiles/r3_persistent_kernel.md: the epilogue warps ran at a third of their speed).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "HGK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra HGK_DONE_%=;\n\t"
+        "bra HGK_WAIT_%=;\n\t"
+        "HGK_DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
