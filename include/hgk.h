@@ -219,6 +219,9 @@ int hgk_criterion_bwd(int kind, const float* pred, const float* gt, const float*
  * one launch over the flat buffers: g' = g*grad_scale; v = alpha v + (1-alpha) g'^2; p -= lr g'/(sqrt(v)+eps) */
 int hgk_rmsprop_flat(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
                      float grad_scale, void* stream);
+/* The same update with (lr, alpha, eps, grad_scale) read from a 4-float DEVICE array at execution time, so a captured CUDA
+ * graph follows the reference's learning-rate schedule (adjust_lr, utils/util.py:105; stack-hg.py:106) without re-capture. */
+int hgk_rmsprop_flat_dev(float* p, const float* g, float* v, long long n, const float* hyper, void* stream);
 /* y[i] = (float)x[i]  (double loss accumulators -> fp32 scalars) */
 int hgk_f64_to_f32(const double* x, float* y, int n, float mul, void* stream);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "hgk_criterion_fwd": [I, P, P, P, L, P, P],
     "hgk_criterion_bwd": [I, P, P, P, L, P, P, P],
     "hgk_rmsprop_flat": [P, P, P, L, F, F, F, F, P],
+    "hgk_rmsprop_flat_dev": [P, P, P, L, P, P],
     "hgk_f64_to_f32": [P, P, I, F, P],
     "hgk_heatmap_peaks": [P, I, I, I, I, I, I, I, P, P, P, P],
     "hgk_pts2heatmap": [P, I, I, I, P, I, P, P, P],

@@ -113,12 +113,14 @@ struct T3Cfg {
     static constexpr int B_STAGE = (SPLIT ? 2 : 1) * B_HALF;
     static constexpr int SETCOLS = NM * NACC * NSUBS * 128;                  // TMEM columns of one accumulator set
     static constexpr int TMEM_COLS = (2 * SETCOLS <= 256) ? 256 : 512;
-    static constexpr int AVAIL = 227 * 1024 - 1024 - 1024;
+    static constexpr int NVEC = BNAPPLY ? 6 : 2;                             // per-input-channel vectors staged in shared memory
+    static constexpr int VEC_BYTES = NVEC * 256 * 4;                         // Cin <= 256
+    static constexpr int AVAIL = 227 * 1024 - 1024 - 1024 - VEC_BYTES;
     static constexpr int NSB = KS == 3 ? 9 : (B_STAGE >= 32768 ? 3 : 4);
     static constexpr int NSA_FIT = (AVAIL - NSB * B_STAGE) / A_STAGE;
     static constexpr int NSA = NSA_FIT > 6 ? 6 : NSA_FIT;
     static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
-    static constexpr int SMEM = PIPE + 1024;
+    static constexpr int SMEM = PIPE + VEC_BYTES + 1024;
     static constexpr int NSTEP = NM * NSUBS * 8 / 2;                         // 16-pixel x 32-channel steps per epilogue warp and tile
     static_assert(BN == 128 || BN == 256, "output channels on the TMEM lanes: multiples of 128");
     static_assert(NSUBS >= 1 && 2 * SETCOLS <= 512, "TMEM capacity (two accumulator sets)");
@@ -182,6 +184,22 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
         if (BNAPPLY) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_z)) : "memory");
     }
+    // per-input-channel vectors of the on-load transform, staged once (with 227 KB of shared memory the L1 has no room
+    // for them: read through __ldg they cost an L2 round trip per 16-channel chunk on the transform's critical path)
+    float* svec = reinterpret_cast<float*>(sgen + Cfg::PIPE);               // [NVEC][256]
+    for (int c = tid; c < a.Cin; c += T3_THREADS) {
+        if (!BNAPPLY) {
+            svec[c] = a.x.scale != nullptr ? __ldg(a.x.scale + c) : 1.f;
+            svec[256 + c] = a.x.scale != nullptr ? __ldg(a.x.shift + c) : 0.f;
+        } else {
+            svec[c] = __ldg(a.ap.scale + c);
+            svec[256 + c] = __ldg(a.ap.shift + c);
+            svec[512 + c] = __ldg(a.ap.mean + c);
+            svec[768 + c] = __ldg(a.ap.cA + c);
+            svec[1024 + c] = __ldg(a.ap.cB + c);
+            svec[1280 + c] = __ldg(a.ap.cC + c);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -240,13 +258,13 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
 #pragma unroll
                 for (int cc = 0; cc < CPS; ++cc) {
                     const int kc = kr * CPS + cc;
-                    float4 sc, sh;
-                    load_affine4(a.x.scale, a.x.shift, kc * 16 + quad * 4, sc, sh);
-                    float4 bs, bt, bmu, bA, bB, bC;
-                    if (BNAPPLY) {
-                        const int c = kc * 16 + quad * 4;
-                        bs = ldg4(ap.scale + c); bt = ldg4(ap.shift + c); bmu = ldg4(ap.mean + c);
-                        bA = ldg4(ap.cA + c); bB = ldg4(ap.cB + c); bC = ldg4(ap.cC + c);
+                    const float* vp = svec + kc * 16 + quad * 4;
+                    float4 sc, sh, bs, bt, bmu, bA, bB, bC;
+                    if (!BNAPPLY) {
+                        sc = ld4(vp); sh = ld4(vp + 256);
+                    } else {
+                        bs = ld4(vp); bt = ld4(vp + 256); bmu = ld4(vp + 512);
+                        bA = ld4(vp + 768); bB = ld4(vp + 1024); bC = ld4(vp + 1280);
                     }
                     uint8_t* base = sgen + sa * A_STAGE + cc * A_PLANE;
                     uint8_t* base2 = base + CPS * A_PLANE;
@@ -456,8 +474,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         const float* __restrict__ resp = a.res.z;
         const float* __restrict__ bzp = a.bz;
         float* __restrict__ yp = a.y;
-        const unsigned uCout = (unsigned)a.Cout;
-        const unsigned row_stride = (unsigned)a.W * uCout;
+        const unsigned row_stride = (unsigned)a.W * (unsigned)BN;      // Cout == BN: per-pixel offsets are immediates
         // shortcut activation as a branch-free (scale, shift, clamp): identity = (1, 0, -inf)
         const float r_clamp = (res_aff && a.res.relu) ? 0.f : -INFINITY;
         const float b_thr = a.brelu ? 0.f : -INFINITY;       // BN-backward ReLU mask: g = (bz*scale+shift <= thr) ? 0 : dy
@@ -473,6 +490,9 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             bsc[mh] = 1.f; bsh[mh] = 0.f; bmu[mh] = 0.f; biv[mh] = 1.f;
             if (BWDSTATS) { bsc[mh] = __ldg(a.bscale + ch); bsh[mh] = __ldg(a.bshift + ch); bmu[mh] = __ldg(a.bmean + ch); biv[mh] = __ldg(a.binvstd + ch); }
         }
+        // element offset of pixel q (0..15) of a step relative to the step's first pixel: compile-time for a 1x1 (consecutive
+        // pixels), one runtime row stride for a 3x3 (two image rows of 8 pixels)
+#define T3_QOFF(q) (KS == 1 ? (unsigned)((q) * BN) : ((q) >> 3) * row_stride + (unsigned)(((q) & 7) * BN))
 
         auto tile_loop = [&](auto r_tag, auto a_tag) {
             constexpr bool R = decltype(r_tag)::value, A = decltype(a_tag)::value;
@@ -484,7 +504,8 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                 const int trem = tile - n_img * tiles_hw;
                 const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
                 const unsigned pix0 = (unsigned)((n_img * a.H + th0) * a.W + tw0);
-                // KS == 1: pixels of the tile that exist (the last tile of the linear view may be ragged)
+                // KS == 1: pixels of the tile that exist (the last tile of the linear view may be ragged; P % 16 == 0, so a
+                // 16-pixel step is either complete or absent)
                 int npx = Cfg::NPX;
                 if (KS == 1) {
                     const long long left = a.P - (long long)tile * Cfg::NPX;
@@ -501,18 +522,20 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                     // MMA row r of sub-tile s -> tile pixel (KS==1: row s*16 + r/8, column r%8; KS==3: row r/8, column s*8 + r%8)
                     const int trow = (KS == 1 ? s * 16 : 0) + j * 2, tcol = (KS == 1 ? 0 : s * 8);
                     lp0 = trow * 8;                                // KS == 1: linear index of the group's first pixel inside the tile
-                    off = (pix0 + (unsigned)trow * (unsigned)a.W + (unsigned)tcol) * uCout + (unsigned)(mh * 128 + lq * 32 + lane);
+                    off = (pix0 + (unsigned)trow * (unsigned)a.W + (unsigned)tcol) * (unsigned)BN + (unsigned)(mh * 128 + lq * 32 + lane);
                 };
                 auto issue = [&](int st) {
                     int mh, lp0; unsigned col, off;
                     step_base(st, mh, col, off, lp0);
+                    if (KS == 1 && lp0 >= npx) return;
+                    const float* pr = resp + off;
+                    const float* po = yp + off;
+                    const float* pz = bzp + off;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        const unsigned o = off + (KS == 1 ? (unsigned)q * uCout : (unsigned)(q >> 3) * row_stride + (unsigned)(q & 7) * uCout);
-                        const bool ok = KS != 1 || lp0 + q < npx;
-                        if (R) rr[R ? q : 0] = ok ? __ldg(resp + o) : 0.f;
-                        if (A) oo[A ? q : 0] = ok ? yp[o] : 0.f;
-                        if (BWDSTATS) zz[BWDSTATS ? q : 0] = ok ? __ldg(bzp + o) : 0.f;
+                        if (R) rr[R ? q : 0] = __ldg(pr + T3_QOFF(q));
+                        if (A) oo[A ? q : 0] = po[T3_QOFF(q)];
+                        if (BWDSTATS) zz[BWDSTATS ? q : 0] = __ldg(pz + T3_QOFF(q));
                     }
                 };
                 if (NL > 0) issue(0);
@@ -522,19 +545,22 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                 for (int st = 0; st < NSTEP; ++st) {
                     int mh, lp0; unsigned col, off;
                     step_base(st, mh, col, off, lp0);
+                    const bool present = KS != 1 || lp0 < npx;      // warp-uniform
                     const long long te0 = dbg_on ? clock64() : 0;
-                    uint32_t r[16];
-                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SETCOLS) + col;
-                    tmem_ld16_nowait(taddr, r);
-                    tmem_ld_wait();
                     float acc[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(r[q]);
-                    if (NACC > 1) {
-                        tmem_ld16_nowait(taddr + (uint32_t)((NACC - 1) * NSUBS * 128), r);
+                    if (present) {
+                        uint32_t r[16];
+                        const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SETCOLS) + col;
+                        tmem_ld16_nowait(taddr, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r[q]);
+                        for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(r[q]);
+                        if (NACC > 1) {
+                            tmem_ld16_nowait(taddr + (uint32_t)((NACC - 1) * NSUBS * 128), r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r[q]);
+                        }
                     }
                     if (st == NSTEP - 1) {       // accumulator set fully read: hand it back to the MMA warp
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -542,37 +568,39 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                         if (lane == 0) mbar_arrive(bar_acce + 8 * b);
                     }
                     if (dbg_on) w1 += clock64() - te0;
-                    const float bias = NM > 1 ? (mh ? bv[NM - 1] : bv[0]) : bv[0];
-                    const float rsc = NM > 1 ? (mh ? rs[NM - 1] : rs[0]) : rs[0], rsh = NM > 1 ? (mh ? rt[NM - 1] : rt[0]) : rt[0];
-                    const float s_c = NM > 1 ? (mh ? bsc[NM - 1] : bsc[0]) : bsc[0], s_h = NM > 1 ? (mh ? bsh[NM - 1] : bsh[0]) : bsh[0];
-                    const float s_m = NM > 1 ? (mh ? bmu[NM - 1] : bmu[0]) : bmu[0], s_i = NM > 1 ? (mh ? biv[NM - 1] : biv[0]) : biv[0];
-                    float s1 = 0.f, s2 = 0.f;
+                    if (present) {
+                        const float bias = NM > 1 ? (mh ? bv[NM - 1] : bv[0]) : bv[0];
+                        const float rsc = NM > 1 ? (mh ? rs[NM - 1] : rs[0]) : rs[0], rsh = NM > 1 ? (mh ? rt[NM - 1] : rt[0]) : rt[0];
+                        const float s_c = NM > 1 ? (mh ? bsc[NM - 1] : bsc[0]) : bsc[0], s_h = NM > 1 ? (mh ? bsh[NM - 1] : bsh[0]) : bsh[0];
+                        const float s_m = NM > 1 ? (mh ? bmu[NM - 1] : bmu[0]) : bmu[0], s_i = NM > 1 ? (mh ? biv[NM - 1] : biv[0]) : biv[0];
+                        float* py = yp + off;
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const unsigned o = off + (KS == 1 ? (unsigned)q * uCout : (unsigned)(q >> 3) * row_stride + (unsigned)(q & 7) * uCout);
-                        const bool ok = KS != 1 || lp0 + q < npx;
-                        float v = acc[q] + bias;
-                        if (R) v += fmaxf(fmaf(rr[R ? q : 0], rsc, rsh), r_clamp);
-                        if (A) v += oo[A ? q : 0];
-                        if (ok) yp[o] = v;
-                        float gv = v, gx = v;                       // statistics: sum gv, sum gv*gx
-                        if (BWDSTATS) {
-                            const float z = zz[BWDSTATS ? q : 0];
-                            gv = fmaf(z, s_c, s_h) <= b_thr ? 0.f : v;
-                            gx = (z - s_m) * s_i;
+                        for (int q = 0; q < 16; ++q) {
+                            float v = acc[q] + bias;
+                            if (R) v += fmaxf(fmaf(rr[R ? q : 0], rsc, rsh), r_clamp);
+                            if (A) v += oo[A ? q : 0];
+                            py[T3_QOFF(q)] = v;
+                            if (BWDSTATS) {          // sum g, sum g * xhat
+                                const float z = zz[BWDSTATS ? q : 0];
+                                const float gv = fmaf(z, s_c, s_h) <= b_thr ? 0.f : v;
+                                s1 += gv;
+                                s2 = fmaf(gv, (z - s_m) * s_i, s2);
+                            } else {                 // sum y, sum y^2
+                                s1 += v;
+                                s2 = fmaf(v, v, s2);
+                            }
                         }
-                        if (KS == 1) gv = ok ? gv : 0.f;
-                        s1 += gv;
-                        s2 = fmaf(gv, gx, s2);
+                        if (do_stats) {              // fp32 partial sums over 16 pixels, fp64 from here on
+                            if (NM > 1 && mh) { d1[NM - 1] += (double)s1; d2[NM - 1] += (double)s2; }
+                            else { d1[0] += (double)s1; d2[0] += (double)s2; }
+                        }
                     }
                     if (NL > 0 && st + 1 < NSTEP) issue(st + 1);     // one batch, behind every use of the previous one
-                    if (do_stats) {              // fp32 partial sums over 16 pixels, fp64 from here on
-                        if (NM > 1 && mh) { d1[NM - 1] += (double)s1; d2[NM - 1] += (double)s2; }
-                        else { d1[0] += (double)s1; d2[0] += (double)s2; }
-                    }
                 }
             }
         };
+#undef T3_QOFF
         if (has_res) {
             if (has_acc) tile_loop(std::true_type{}, std::true_type{}); else tile_loop(std::true_type{}, std::false_type{});
         } else {
@@ -693,8 +721,9 @@ bool conv_tc3_eligible(const TcArgs& ta) {
         if (c.H % 16 || c.W % 16) return false;
         if (c.Cout > 128) return false;                                   // 3x3 with 256 outputs: no instantiation
     } else {
-        if (c.P % 8) return false;
+        if (c.P % 16) return false;                                       // a 16-pixel epilogue step is complete or absent
     }
+    if (c.Cin > 256) return false;                                        // per-channel vectors staged in shared memory
     const long long cmax = c.Cin > c.Cout ? c.Cin : c.Cout;
     if ((c.P + 256) * cmax >= (1LL << 32)) return false;                  // 32-bit element offsets
     if (((uintptr_t)c.x.z & 15) || (c.ap.z != nullptr && ((uintptr_t)c.ap.z & 15))) return false;   // tensor-map base alignment

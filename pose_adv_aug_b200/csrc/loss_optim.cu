@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(256) criterion_bwd_kernel(int kind, const floa
     }
 }
 
-__global__ void __launch_bounds__(256) rmsprop_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
-                                                           long long n, float lr, float alpha, float eps, float gscale) {
+__device__ __forceinline__ void rmsprop_flat_body(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n,
+                                                  float lr, float alpha, float eps, float gscale) {
     const long long n4 = n >> 2;
     const float oma = 1.f - alpha;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -118,6 +118,18 @@ __global__ void __launch_bounds__(256) rmsprop_flat_kernel(float* __restrict__ p
             p[i] -= lr * (gg / (sqrtf(vv) + eps));
         }
     }
+}
+
+__global__ void __launch_bounds__(256) rmsprop_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
+                                                           long long n, float lr, float alpha, float eps, float gscale) {
+    rmsprop_flat_body(p, g, v, n, lr, alpha, eps, gscale);
+}
+
+// hyper-parameters read from device memory: a CUDA graph that captured this launch follows later changes of the learning
+// rate (the reference's adjust_lr, utils/util.py) without being re-captured
+__global__ void __launch_bounds__(256) rmsprop_flat_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
+                                                               long long n, const float* __restrict__ hyper) {
+    rmsprop_flat_body(p, g, v, n, hyper[0], hyper[1], hyper[2], hyper[3]);
 }
 
 __global__ void f64_to_f32_kernel(const double* __restrict__ x, float* __restrict__ y, int n, float mul) {
@@ -182,6 +194,15 @@ extern "C" int hgk_rmsprop_flat(float* p, const float* g, float* v, long long n,
                 "hgk_rmsprop_flat: flat buffers must be 16-byte aligned");
     rmsprop_flat_kernel<<<lo_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, v, n, lr, alpha, eps, grad_scale);
     HGK_CHECK_LAUNCH("hgk_rmsprop_flat");
+    return HGK_OK;
+}
+
+extern "C" int hgk_rmsprop_flat_dev(float* p, const float* g, float* v, long long n, const float* hyper, void* stream) {
+    HGK_REQUIRE(p && g && v && hyper && n > 0, "hgk_rmsprop_flat_dev: bad arguments");
+    HGK_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)v % 16 == 0),
+                "hgk_rmsprop_flat_dev: flat buffers must be 16-byte aligned");
+    rmsprop_flat_dev_kernel<<<lo_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, v, n, hyper);
+    HGK_CHECK_LAUNCH("hgk_rmsprop_flat_dev");
     return HGK_OK;
 }
 

@@ -120,7 +120,10 @@ def _run(root, extra_roots, key, inputs, build):
     shapes = tuple(tuple(x.shape) for x in inputs)
     modes = tuple(m.training for m in mods)
     ids = tuple(id(s) for s in stores)
-    pkey = (key, shapes, modes, need_grad, ids, CONV_PATH, PRECISE_GRADS)
+    # which inputs want a gradient is baked into the plan (input_nchw(needs_grad=...)): it is part of the key, so a module
+    # first called on a constant input and later inside a larger autograd graph gets a plan with the input-gradient path
+    in_grad = tuple(bool(x.requires_grad) and need_grad for x in inputs)
+    pkey = (key, shapes, modes, need_grad, in_grad, ids, CONV_PATH, PRECISE_GRADS)
     cache = _state(root).plans
     plan = cache.get(pkey)
     if plan is None:
@@ -386,6 +389,9 @@ class _Hourglass_Wrapper(nn.Module):
         _check_input(x)
         if x.shape[1] != 3 or x.shape[2] % 64 or x.shape[3] % 64:
             raise ValueError("expected [N,3,H,W] images with H, W multiples of 64 (got %s)" % (tuple(x.shape),))
+        if x.requires_grad and torch.is_grad_enabled():
+            # the stem kernel has no image-gradient path (no script of the reference differentiates w.r.t. the image)
+            raise HGKError("the input image requires grad, but this path produces no image gradient; pass x.detach()")
 
         def build(plan):
             img = plan.input_image(x.shape[0], x.shape[2], x.shape[3])

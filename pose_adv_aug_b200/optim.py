@@ -52,18 +52,45 @@ class FlatRMSprop(object):
                   "hgk_rmsprop_flat")
 
     def state_dict(self):
-        st = self._sync()
-        state = {}
-        for i, (p, o) in enumerate(zip(st.params, st.offsets)):
-            state[i] = {"square_avg": self.square_avg[o:o + p.numel()].view(p.shape).clone()}
-        return {"state": state, "param_groups": [dict(self.param_groups[0], params=list(range(len(st.params))))]}
+        return pack_state(self._sync(), self.square_avg, self.param_groups[0])
 
     def load_state_dict(self, sd):
-        st = self._sync()
-        for i, (p, o) in enumerate(zip(st.params, st.offsets)):
-            s = sd["state"].get(i)
-            if s is not None and "square_avg" in s:
-                self.square_avg[o:o + p.numel()].view(p.shape).copy_(s["square_avg"])
-        for k in ("lr", "alpha", "eps"):
-            if k in sd["param_groups"][0]:
-                self.param_groups[0][k] = sd["param_groups"][0][k]
+        unpack_state(self._sync(), self.square_avg, sd, self.param_groups[0])
+
+
+def pack_state(store, square_avg, group):
+    """torch.optim-style state dict of the flat square-average buffer: state[i]['square_avg'] per parameter i (the order
+    of module.parameters()), param_groups[0] = hyper-parameters + 'params': [0..n-1]."""
+    state = {}
+    for i, (p, o) in enumerate(zip(store.params, store.offsets)):
+        state[i] = {"square_avg": square_avg[o:o + p.numel()].view(p.shape).clone()}
+    g = dict((k, group[k]) for k in ("lr", "alpha", "eps"))
+    g["params"] = list(range(len(store.params)))
+    return {"state": state, "param_groups": [g]}
+
+
+def unpack_state(store, square_avg, sd, group):
+    """Inverse of pack_state.  Saved state keys are mapped through param_groups[0]['params'] BY POSITION, as
+    torch.optim.Optimizer.load_state_dict does (so checkpoints keyed by id(p), e.g. the reference's torch-0.3 files, load
+    too); missing entries and shape mismatches raise instead of leaving square_avg silently at zero."""
+    groups = sd.get("param_groups") or [{}]
+    keys = groups[0].get("params")
+    if keys is None:
+        keys = sorted(sd["state"].keys(), key=lambda k: (str(type(k)), k))
+    if len(keys) != len(store.params):
+        raise HGKError("optimizer state has %d parameters, the model has %d" % (len(keys), len(store.params)))
+    for key, p, o in zip(keys, store.params, store.offsets):
+        s = sd["state"].get(key)
+        if s is None:
+            if sd["state"]:          # a partially filled state would silently reset some square averages
+                raise HGKError("optimizer state has no entry for parameter key %r" % (key,))
+            continue
+        v = s.get("square_avg")
+        if v is None:
+            raise HGKError("optimizer state entry %r has no 'square_avg' (not an RMSprop checkpoint?)" % (key,))
+        if v.numel() != p.numel():
+            raise HGKError("square_avg of parameter key %r has %d elements, the parameter has %d" % (key, v.numel(), p.numel()))
+        square_avg[o:o + p.numel()].view(p.shape).copy_(v.reshape(p.shape))
+    for k in ("lr", "alpha", "eps"):
+        if k in groups[0]:
+            group[k] = groups[0][k]

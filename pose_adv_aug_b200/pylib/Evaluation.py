@@ -49,41 +49,35 @@ def get_preds(scores):
 
 
 def GetTransform(center, scale, rot, res, size):
-    """ref:211-237 (host, fp64)."""
+    """Crop transform (original image -> res x res crop) as a 3x3 homogeneous matrix (host, fp64); the map of ref:211-237 in
+    closed form: a similarity p -> k*(p - center) + res/2 with k = res / (size*scale), followed -- when rot != 0 -- by a
+    rotation of -rot degrees about the crop centre (res/2, res/2).  With q = k*(p - center) the crop-centred point, the whole
+    map is  p -> R(-rot) q + res/2,  i.e. linear part k*R and translation R*(k*(-center) ... ) + res/2."""
     h = size * scale
-    t = np.zeros((3, 3))
-    t[0, 0] = float(res) / h
-    t[1, 1] = float(res) / h
-    t[0, 2] = res * (-float(center[0]) / h + .5)
-    t[1, 2] = res * (-float(center[1]) / h + .5)
-    t[2, 2] = 1
-    if not rot == 0:
-        rot = -rot
-        rot_mat = np.zeros((3, 3))
-        rot_rad = rot * np.pi / 180
-        sn, cs = np.sin(rot_rad), np.cos(rot_rad)
-        rot_mat[0, :2] = [cs, -sn]
-        rot_mat[1, :2] = [sn, cs]
-        rot_mat[2, 2] = 1
-        t_mat = np.eye(3)
-        t_mat[0, 2] = -res / 2
-        t_mat[1, 2] = -res / 2
-        t_inv = t_mat.copy()
-        t_inv[:2, 2] *= -1
-        t = np.dot(t_inv, np.dot(rot_mat, np.dot(t_mat, t)))
-    return t
+    k = float(res) / h
+    half = res / 2
+    # crop-centred image of the origin: k*(0 - center) = res*(-center/h + 1/2) - res/2
+    ox = res * (-float(center[0]) / h + .5)
+    oy = res * (-float(center[1]) / h + .5)
+    if rot == 0:
+        return np.array([[k, 0., ox], [0., k, oy], [0., 0., 1.]])
+    ang = -rot * np.pi / 180
+    sn, cs = np.sin(ang), np.cos(ang)
+    qx, qy = ox - half, oy - half
+    return np.array([[cs * k, -sn * k, (cs * qx - sn * qy) + half],
+                     [sn * k, cs * k, (sn * qx + cs * qy) + half],
+                     [0., 0., 1.]])
 
 
 def TransformPts(pts, center, scale, rot, res, size, invert=0):
-    """ref:239-247 (host numpy; kept for callers that transform ground-truth points)."""
-    NLMK, DIM = pts.shape
+    """ref:239-247 -- 1-based [M,2] points through the crop transform (or its inverse), truncated to integers as the
+    reference does (host numpy; kept for callers that transform ground-truth points)."""
     t = GetTransform(center, scale, rot, res, size)
     if invert:
         t = np.linalg.inv(t)
-    new_pt = np.concatenate((pts - 1, np.ones((NLMK, 1))), axis=1).T
-    new_pt = np.dot(t, new_pt)
-    new_pt = new_pt[0:2, :].T
-    return new_pt.astype(int) + 1
+    p0 = np.asarray(pts, dtype=np.float64) - 1
+    mapped = (p0[:, 0:1] * t[:2, 0] + p0[:, 1:2] * t[:2, 1]) + t[:2, 2]
+    return mapped.astype(int) + 1
 
 
 def transform_preds(coords, center, scale, res, rot):

@@ -11,13 +11,32 @@ from .models import asn_stacked_hg as M
 from . import dist as hdist
 
 
+class _HyperGroup(dict):
+    """param_groups[0] of the trainer: a dict whose 'lr' / 'alpha' / 'eps' writes go straight to the 4-float device array the
+    update kernel reads (no graph re-capture, no host synchronisation beyond the small copy)."""
+    _SLOT = {"lr": 0, "alpha": 1, "eps": 2}
+
+    def __init__(self, owner, lr, alpha, eps):
+        dict.__init__(self, lr=lr, alpha=alpha, eps=eps)
+        self._owner = owner
+
+    def __setitem__(self, key, value):
+        dict.__setitem__(self, key, value)
+        slot = self._SLOT.get(key)
+        if slot is not None:
+            self._owner.hyper[slot:slot + 1].fill_(float(value))
+
+    def update(self, *a, **kw):
+        for k, v in dict(*a, **kw).items():
+            self[k] = v
+
+
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
                  distributed=None, n_streams=8, n_low=3):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
-        self.lr, self.alpha, self.eps = lr, alpha, eps
         self.lib = get_lib()
         self.world = hdist.world_size() if distributed is None else (hdist.world_size() if distributed else 1)
         net.to(self.device)
@@ -26,6 +45,10 @@ class HourglassTrainer(object):
         if self.world > 1:
             hdist.broadcast_flat_params(self.store.flat)
         self.square_avg = torch.zeros_like(self.store.flat)
+        # (lr, alpha, eps, 1/world) live in DEVICE memory and are read by the update kernel at execution time: the captured
+        # CUDA graph follows later changes (the reference's adjust_lr, stack-hg.py:106 / utils/util.py:105) without re-capture
+        self.hyper = torch.tensor([lr, alpha, eps, 1.0 / self.world], device=self.device, dtype=torch.float32)
+        self.param_groups = [_HyperGroup(self, lr, alpha, eps)]      # torch.optim-style access: param_groups[0]['lr'] = ...
         K = net.num_classes
         self.x = torch.zeros(batch, 3, res, res, device=self.device)
         self.t = torch.zeros(batch, K, res // 4, res // 4, device=self.device)
@@ -133,9 +156,8 @@ class HourglassTrainer(object):
         """flat RMSprop (1/world folded in) + loss accumulator -> fp32 scalar."""
         st = self.store
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.lib.check(self.lib.rmsprop_flat(st.flat.data_ptr(), st.grad.data_ptr(), self.square_avg.data_ptr(),
-                                             st.numel, self.lr, self.alpha, self.eps, 1.0 / self.world, stream),
-                       "hgk_rmsprop_flat")
+        self.lib.check(self.lib.rmsprop_flat_dev(st.flat.data_ptr(), st.grad.data_ptr(), self.square_avg.data_ptr(),
+                                                 st.numel, self.hyper.data_ptr(), stream), "hgk_rmsprop_flat_dev")
         self.lib.check(self.lib.f64_to_f32(self.loss_acc.data_ptr(), self.loss.data_ptr(), 1, 1.0, stream),
                        "hgk_f64_to_f32")
 
@@ -238,6 +260,32 @@ class HourglassTrainer(object):
         self._staging_free.record(main)
         self._has_staged = False
         return self.step_resident()
+
+    # ---- optimizer protocol of the reference loop (stack-hg.py:51-52,106; utils/checkpoint.py) ----
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        self.param_groups[0]["lr"] = value
+
+    @property
+    def alpha(self):
+        return self.param_groups[0]["alpha"]
+
+    @property
+    def eps(self):
+        return self.param_groups[0]["eps"]
+
+    def state_dict(self):
+        """checkpoint['optimizer'] of the reference: per-parameter square_avg + hyper-parameters (torch.optim layout)."""
+        from .optim import pack_state
+        return pack_state(self.store, self.square_avg, self.param_groups[0])
+
+    def load_state_dict(self, sd):
+        from .optim import unpack_state
+        unpack_state(self.store, self.square_avg, sd, self.param_groups[0])
 
     def heatmaps(self):
         """Per-stack NCHW heat-maps of the last step (views of the plan's static output buffers)."""

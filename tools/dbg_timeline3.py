@@ -89,6 +89,12 @@ def run_dgrad(N, H, W, Cin, Cout, k, red=1, acc=0):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "one":          # a single layer (ncu capture)
+    run_fwd(24, 64, 64, 128, 256, 1, res=1)
+if which == "one3":
+    run_fwd(24, 64, 64, 128, 128, 3)
+if which == "oned":
+    run_dgrad(24, 64, 64, 256, 128, 1, red=1)
 if which in ("fwd", "all"):
     run_fwd(24, 64, 64, 128, 256, 1, res=1)
     run_fwd(24, 64, 64, 256, 128, 1)
