@@ -77,7 +77,7 @@ def test_schedule_respects_every_dependency():
                 readers[p] = []
             if name in barriers:
                 barrier = i
-        assert n_dep > 800
+        assert n_dep > 600      # sanity: the recomputed dependency set is not trivially empty
         # and there is real parallelism: no stream holds more than 60 % of the launches
         assert max(so.count(k) for k in range(ns)) < 0.6 * len(L) or ns == 2
 
