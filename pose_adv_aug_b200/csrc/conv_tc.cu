@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
             HGK_TRACE(4, it);
         }
     }
+    __syncwarp();      // the single-lane role reconverges before the CTA-wide barrier
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // every producer has observed the last commit: accumulator complete, smem reusable
 
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgTcArgs 
             umma_commit(bar_empty + 8 * s);
         }
     }
+    __syncwarp();      // the single-lane role reconverges before the CTA-wide barrier
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // producers have observed the last commit: accumulator complete, smem reusable
 
@@ -853,6 +855,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad3_tc_kernel(const WgTcArgs
             umma_commit(bar_empty + 8 * s);
         }
     }
+    __syncwarp();      // the single-lane role reconverges before the CTA-wide barrier
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
 
@@ -1051,14 +1054,20 @@ static bool use_tile_kernel() {
     return v == 1;
 }
 
-// HGK_TC3_OFF=1 disables the persistent tile kernel of conv_tc3.cu (A/B comparisons against conv_tc2.cu)
-static bool use_tc3() {
+// Which layer classes take the persistent kernel of conv_tc3.cu: bit 0 forward 1x1, bit 1 forward 3x3, bit 2 data gradient
+// 1x1, bit 3 data gradient 3x3.  Default 13: the 3x3 forward (3xTF32, tensor-bound) is faster on the two-CTAs-per-SM kernel
+// of conv_tc2.cu (profiles/r3_persistent_kernel.md).  HGK_TC3_MASK overrides (0 = conv_tc2.cu everywhere; A/B comparisons).
+static int tc3_mask() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("HGK_TC3_OFF");
-        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("HGK_TC3_MASK");
+        v = e != nullptr ? atoi(e) : 13;
     }
-    return v == 1;
+    return v;
+}
+static bool use_tc3(int ksize, bool split) {
+    const int bit = (split ? 0 : 2) + (ksize == 3 ? 1 : 0);
+    return (tc3_mask() >> bit) & 1;
 }
 
 static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shift, int x_relu,
@@ -1089,7 +1098,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     ta.c.bfin = bfin != nullptr ? *bfin : BnBwdFin{};
     ta.c.ap = ap != nullptr ? *ap : BnApply{};
     if (ap != nullptr)
-        HGK_REQUIRE(w_lo == nullptr && ((use_tc3() && conv_tc3_eligible(ta)) || (use_tile_kernel() && conv_tc2_eligible(ta))),
+        HGK_REQUIRE(w_lo == nullptr && ((use_tc3(ksize, false) && conv_tc3_eligible(ta)) || (use_tile_kernel() && conv_tc2_eligible(ta))),
                     "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
                     "image-tile kernel (see hgk_conv_tc_bnapply_supported)");
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
@@ -1099,7 +1108,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     const bool split = w_lo != nullptr;
     if (bz != nullptr)
         HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
-    if (use_tc3() && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
+    if (use_tc3(ksize, split) && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
     else if (use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
     else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
@@ -1171,7 +1180,7 @@ extern "C" int hgk_conv_tc_bnapply_supported(int N, int H, int W, int Cin, int C
     TcArgs ta{};
     ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
     ta.c.P = (long long)N * H * W;
-    if (use_tc3() && conv_tc3_eligible(ta)) return 1;
+    if (use_tc3(ksize, false) && conv_tc3_eligible(ta)) return 1;
     return (use_tile_kernel() && conv_tc2_eligible(ta)) ? 1 : 0;
 }
 

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
 #define T2_RENDEZVOUS()                                                           \
     do {                                                                          \
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");          \
-        asm volatile("bar.sync 1, 320;" ::: "memory");                            \
+        asm volatile("barrier.sync 1, 320;" ::: "memory");   /* non-aligned form: reached from different code */  \
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");           \
     } while (0)
     static_assert(T2_THREADS == 320, "T2_RENDEZVOUS counts 320 threads");
@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
             }
             umma_commit(bar_done);
         }
+        __syncwarp();
     } else {
         // ===== weight stream: one cp.async.bulk per (chunk, tap) stage; packed blocks are [tap][Cin/32][8 quads][BN][4] =====
         T2_RENDEZVOUS();
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                 }
             }
         }
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();

@@ -323,7 +323,12 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             }
         }
         if (tid == 0) { T3_DBG(0, clock64() - t_begin); T3_DBG(1, w0); T3_DBG(12, w1); T3_DBG(13, w2); }
-    } else if (warp == T3_WMMA) {
+    } else if (warp < T3_WEPI) {
+    // register budget per role (setmaxnreg acts on aligned groups of four warps and the compiler budgets the code that follows
+    // it on every path, so it sits inside the role branch): 640 x 96 registers are allocated at launch; the four support warps
+    // keep 48, the eight epilogue warps take 120 (two prefetch register sets): 128*48 + 256*96 + 256*120 = 61440
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
+    if (warp == T3_WMMA) {
         // ===== MMA issuer: D[channel][pixel] += W[channel][k] * X[pixel][k] =====
         if (lane == 0) {
             int sa = 0, sb = 0;
@@ -462,8 +467,10 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             }
         }
         __syncwarp();
+    }
     } else {
         // ===== epilogue warps: thread = output channel; 16 pixels (TMEM columns) per step =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;" ::: "memory");
         const int we = warp - T3_WEPI;
         const int lq = warp & 3;                 // TMEM lane quarter this warp may access = 32 channels of a 128-channel half
         const int hsel = we >> 2;                // the two warps of a lane quarter alternate over the 16-pixel steps
@@ -497,106 +504,146 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         auto tile_loop = [&](auto r_tag, auto a_tag) {
             constexpr bool R = decltype(r_tag)::value, A = decltype(a_tag)::value;
             constexpr int NL = (R ? 1 : 0) + (A ? 1 : 0) + (BWDSTATS ? 1 : 0);
-            int i = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-                const int b = i & 1;
+            // The epilogue's global inputs (shortcut / previous output / BN-backward z) are fetched in BATCHES of KB steps: all
+            // loads of a batch are issued together and nothing is issued until the whole batch has been consumed.  (Loads that
+            // are issued between the issue and the use of an older set share the warp's six scoreboard slots with it, so the
+            // wait for the old set also waits for the new one: register double-buffering gained nothing, ncu showed the warps
+            // in long-scoreboard stalls half of the time.)  The first batch of a tile is issued before the tile's accumulator
+            // is awaited -- at the end of the previous tile -- so per tile only the later batch boundaries expose a latency.
+            constexpr int KB = NL == 1 ? 2 : 1;
+            constexpr int NBATCH = NSTEP / KB;
+            static_assert(NSTEP % KB == 0, "steps per tile are a multiple of the prefetch batch");
+            float rr[R ? KB * 16 : 1], oo[A ? KB * 16 : 1], zz[BWDSTATS ? KB * 16 : 1];
+            // tile -> first pixel and number of pixels that exist (KS == 1: the last tile of the linear view may be ragged;
+            // P % 16 == 0, so a 16-pixel step is either complete or absent)
+            auto tile_setup = [&](int tile, unsigned& pix0, int& npx) {
                 const int n_img = tile / tiles_hw;
                 const int trem = tile - n_img * tiles_hw;
                 const int th0 = (trem / tiles_w) * TH, tw0 = (trem % tiles_w) * TW;
-                const unsigned pix0 = (unsigned)((n_img * a.H + th0) * a.W + tw0);
-                // KS == 1: pixels of the tile that exist (the last tile of the linear view may be ragged; P % 16 == 0, so a
-                // 16-pixel step is either complete or absent)
-                int npx = Cfg::NPX;
+                pix0 = (unsigned)((n_img * a.H + th0) * a.W + tw0);
+                npx = Cfg::NPX;
                 if (KS == 1) {
                     const long long left = a.P - (long long)tile * Cfg::NPX;
                     if (left < Cfg::NPX) npx = (int)left;
                 }
-                float rr[R ? 16 : 1], oo[A ? 16 : 1], zz[BWDSTATS ? 16 : 1];
-                // step -> (channel half mh, pixel sub-tile s, 16-pixel group j): this warp takes every other group
-                auto step_base = [&](int st, int& mh, unsigned& col, unsigned& off, int& lp0) {
-                    const int per_mh = NSUBS * 4;                  // steps of this warp per channel half
-                    mh = st / per_mh;
-                    const int rem = st - mh * per_mh;
-                    const int s = rem >> 2, j = ((rem & 3) << 1) + hsel;      // 16-pixel group j of sub-tile s: MMA rows 16j..16j+15
-                    col = (unsigned)(((mh * NACC) * NSUBS + s) * 128 + j * 16);
-                    // MMA row r of sub-tile s -> tile pixel (KS==1: row s*16 + r/8, column r%8; KS==3: row r/8, column s*8 + r%8)
-                    const int trow = (KS == 1 ? s * 16 : 0) + j * 2, tcol = (KS == 1 ? 0 : s * 8);
-                    lp0 = trow * 8;                                // KS == 1: linear index of the group's first pixel inside the tile
-                    off = (pix0 + (unsigned)trow * (unsigned)a.W + (unsigned)tcol) * (unsigned)BN + (unsigned)(mh * 128 + lq * 32 + lane);
-                };
-                auto issue = [&](int st) {
+            };
+            // step -> (channel half mh, pixel sub-tile s, 16-pixel group j): this warp takes every other group
+            auto step_base = [&](int st, unsigned pix0, int& mh, unsigned& col, unsigned& off, int& lp0) {
+                const int per_mh = NSUBS * 4;                  // steps of this warp per channel half
+                mh = st / per_mh;
+                const int rem = st - mh * per_mh;
+                const int s = rem >> 2, j = ((rem & 3) << 1) + hsel;      // 16-pixel group j of sub-tile s: MMA rows 16j..16j+15
+                col = (unsigned)(((mh * NACC) * NSUBS + s) * 128 + j * 16);
+                // MMA row r of sub-tile s -> tile pixel (KS==1: row s*16 + r/8, column r%8; KS==3: row r/8, column s*8 + r%8)
+                const int trow = (KS == 1 ? s * 16 : 0) + j * 2, tcol = (KS == 1 ? 0 : s * 8);
+                lp0 = trow * 8;                                // KS == 1: linear index of the group's first pixel inside the tile
+                off = (pix0 + (unsigned)trow * (unsigned)a.W + (unsigned)tcol) * (unsigned)BN + (unsigned)(mh * 128 + lq * 32 + lane);
+            };
+            auto issue_batch = [&](int bi, unsigned pix0, int npx) {
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
                     int mh, lp0; unsigned col, off;
-                    step_base(st, mh, col, off, lp0);
-                    if (KS == 1 && lp0 >= npx) return;
+                    step_base(bi * KB + k, pix0, mh, col, off, lp0);
+                    if (KS == 1 && lp0 >= npx) continue;
                     const float* pr = resp + off;
                     const float* po = yp + off;
                     const float* pz = bzp + off;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        if (R) rr[R ? q : 0] = __ldg(pr + T3_QOFF(q));
-                        if (A) oo[A ? q : 0] = po[T3_QOFF(q)];
-                        if (BWDSTATS) zz[BWDSTATS ? q : 0] = __ldg(pz + T3_QOFF(q));
+                        if (R) rr[R ? k * 16 + q : 0] = __ldg(pr + T3_QOFF(q));
+                        if (A) oo[A ? k * 16 + q : 0] = po[T3_QOFF(q)];
+                        if (BWDSTATS) zz[BWDSTATS ? k * 16 + q : 0] = __ldg(pz + T3_QOFF(q));
                     }
-                };
-                if (NL > 0) issue(0);
+                }
+            };
+            unsigned pix0 = 0;
+            int npx = 0;
+            if (blockIdx.x < ntiles) {
+                tile_setup(blockIdx.x, pix0, npx);
+                if (NL > 0) issue_batch(0, pix0, npx);
+            }
+            int i = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+                const int b = i & 1;
                 T3_WAIT(bar_accf + 8 * b, (unsigned)(i >> 1) & 1u, w0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int st = 0; st < NSTEP; ++st) {
+                // TMEM loads run ONE STEP AHEAD of their use: next to the tensor core's accumulator traffic of the following
+                // tile's main loop a tcgen05.ld takes ~1000 cycles (ncu: half of the epilogue's samples sat on its scoreboard)
+                uint32_t r[16], r2[16];              // r2: second accumulator (NACC == 2 only)
+                auto tmem_issue = [&](int st) {
                     int mh, lp0; unsigned col, off;
-                    step_base(st, mh, col, off, lp0);
-                    const bool present = KS != 1 || lp0 < npx;      // warp-uniform
-                    const long long te0 = dbg_on ? clock64() : 0;
-                    float acc[16];
-                    if (present) {
-                        uint32_t r[16];
-                        const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SETCOLS) + col;
-                        tmem_ld16_nowait(taddr, r);
+                    step_base(st, pix0, mh, col, off, lp0);
+                    if (KS == 1 && lp0 >= npx) return;
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * SETCOLS) + col;
+                    tmem_ld16_nowait(taddr, r);
+                    if (NACC > 1) tmem_ld16_nowait(taddr + (uint32_t)((NACC - 1) * NSUBS * 128), r2);
+                };
+                tmem_issue(0);
+#pragma unroll 1
+                for (int bi = 0; bi < NBATCH; ++bi) {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+                        const int st = bi * KB + k;
+                        int mh, lp0; unsigned col, off;
+                        step_base(st, pix0, mh, col, off, lp0);
+                        const bool present = KS != 1 || lp0 < npx;      // warp-uniform
+                        const long long te0 = dbg_on ? clock64() : 0;
                         tmem_ld_wait();
+                        float acc[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(r[q]);
                         if (NACC > 1) {
-                            tmem_ld16_nowait(taddr + (uint32_t)((NACC - 1) * NSUBS * 128), r);
-                            tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r[q]);
+                            for (int q = 0; q < 16; ++q) acc[q] += __uint_as_float(r2[q]);
                         }
-                    }
-                    if (st == NSTEP - 1) {       // accumulator set fully read: hand it back to the MMA warp
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_acce + 8 * b);
-                    }
-                    if (dbg_on) w1 += clock64() - te0;
-                    if (present) {
-                        const float bias = NM > 1 ? (mh ? bv[NM - 1] : bv[0]) : bv[0];
-                        const float rsc = NM > 1 ? (mh ? rs[NM - 1] : rs[0]) : rs[0], rsh = NM > 1 ? (mh ? rt[NM - 1] : rt[0]) : rt[0];
-                        const float s_c = NM > 1 ? (mh ? bsc[NM - 1] : bsc[0]) : bsc[0], s_h = NM > 1 ? (mh ? bsh[NM - 1] : bsh[0]) : bsh[0];
-                        const float s_m = NM > 1 ? (mh ? bmu[NM - 1] : bmu[0]) : bmu[0], s_i = NM > 1 ? (mh ? biv[NM - 1] : biv[0]) : biv[0];
-                        float* py = yp + off;
-                        float s1 = 0.f, s2 = 0.f;
+                        if (st + 1 < NSTEP) {
+                            tmem_issue(st + 1);
+                        } else {                     // accumulator set fully read: hand it back to the MMA warp
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_acce + 8 * b);
+                        }
+                        if (dbg_on) w1 += clock64() - te0;
+                        if (present) {
+                            const float bias = NM > 1 ? (mh ? bv[NM - 1] : bv[0]) : bv[0];
+                            const float rsc = NM > 1 ? (mh ? rs[NM - 1] : rs[0]) : rs[0], rsh = NM > 1 ? (mh ? rt[NM - 1] : rt[0]) : rt[0];
+                            const float s_c = NM > 1 ? (mh ? bsc[NM - 1] : bsc[0]) : bsc[0], s_h = NM > 1 ? (mh ? bsh[NM - 1] : bsh[0]) : bsh[0];
+                            const float s_m = NM > 1 ? (mh ? bmu[NM - 1] : bmu[0]) : bmu[0], s_i = NM > 1 ? (mh ? biv[NM - 1] : biv[0]) : biv[0];
+                            float* py = yp + off;
+                            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            float v = acc[q] + bias;
-                            if (R) v += fmaxf(fmaf(rr[R ? q : 0], rsc, rsh), r_clamp);
-                            if (A) v += oo[A ? q : 0];
-                            py[T3_QOFF(q)] = v;
-                            if (BWDSTATS) {          // sum g, sum g * xhat
-                                const float z = zz[BWDSTATS ? q : 0];
-                                const float gv = fmaf(z, s_c, s_h) <= b_thr ? 0.f : v;
-                                s1 += gv;
-                                s2 = fmaf(gv, (z - s_m) * s_i, s2);
-                            } else {                 // sum y, sum y^2
-                                s1 += v;
-                                s2 = fmaf(v, v, s2);
+                            for (int q = 0; q < 16; ++q) {
+                                float v = acc[q] + bias;
+                                if (R) v += fmaxf(fmaf(rr[R ? k * 16 + q : 0], rsc, rsh), r_clamp);
+                                if (A) v += oo[A ? k * 16 + q : 0];
+                                py[T3_QOFF(q)] = v;
+                                if (BWDSTATS) {          // sum g, sum g * xhat
+                                    const float z = zz[BWDSTATS ? k * 16 + q : 0];
+                                    const float gv = fmaf(z, s_c, s_h) <= b_thr ? 0.f : v;
+                                    s1 += gv;
+                                    s2 = fmaf(gv, (z - s_m) * s_i, s2);
+                                } else {                 // sum y, sum y^2
+                                    s1 += v;
+                                    s2 = fmaf(v, v, s2);
+                                }
+                            }
+                            if (do_stats) {              // fp32 partial sums over 16 pixels, fp64 from here on
+                                if (NM > 1 && mh) { d1[NM - 1] += (double)s1; d2[NM - 1] += (double)s2; }
+                                else { d1[0] += (double)s1; d2[0] += (double)s2; }
                             }
                         }
-                        if (do_stats) {              // fp32 partial sums over 16 pixels, fp64 from here on
-                            if (NM > 1 && mh) { d1[NM - 1] += (double)s1; d2[NM - 1] += (double)s2; }
-                            else { d1[0] += (double)s1; d2[0] += (double)s2; }
-                        }
                     }
-                    if (NL > 0 && st + 1 < NSTEP) issue(st + 1);     // one batch, behind every use of the previous one
+                    // the whole batch is consumed: fetch the next one (of this tile, or the first of this CTA's next tile)
+                    if (NL > 0) {
+                        if (bi + 1 < NBATCH) {
+                            issue_batch(bi + 1, pix0, npx);
+                        } else if (tile + (int)gridDim.x < ntiles) {
+                            tile_setup(tile + gridDim.x, pix0, npx);
+                            issue_batch(0, pix0, npx);
+                        }
+                    } else if (bi + 1 == NBATCH && tile + (int)gridDim.x < ntiles) {
+                        tile_setup(tile + gridDim.x, pix0, npx);
+                    }
                 }
             }
         };

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args
         }
         umma_commit(bar_done);
     }
+    __syncwarp();      // the single-lane role reconverges before the CTA-wide barrier
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // accumulators complete, shared memory reusable
 

@@ -293,19 +293,29 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
     a.train()
     opt = FlatRMSprop(a, lr=2.5e-4)
     losses_a = []
+    grad_a = None
     for _ in range(3):
         outs = a(x.to(DEV))
         loss = O.mse_loss(outs, t.to(DEV))
         opt.zero_grad()
         loss.backward()
+        if grad_a is None:
+            grad_a = opt.store.grad.clone()
         opt.step()
         losses_a.append(float(loss))
     # (b) fused trainer without graph, (c) with graph
     for net, use_graph in ((nets[1], False), (nets[2], True)):
         tr = HourglassTrainer(net, N, R, lr=2.5e-4, use_graph=use_graph)
-        losses = [float(tr.step(x.pin_memory(), t.pin_memory())) for _ in range(3)]
-        for la, lb in zip(losses_a, losses):
-            assert abs(la - lb) < 1e-4 * abs(la), (losses_a, losses)
+        losses = [float(tr.step(x.pin_memory(), t.pin_memory()))]
+        # same kernels on both paths: the first step's flat gradient agrees to rounding (dL/dout comes from torch ops on one
+        # side and from the fused MSE kernel on the other; weight gradients are float atomics)
+        g_b = tr.store.grad
+        assert float((g_b - grad_a).norm() / grad_a.norm()) < 1e-4
+        losses += [float(tr.step(x.pin_memory(), t.pin_memory())) for _ in range(2)]
+        # ... after which RMSprop's first steps (~lr*10*sign(g) per weight whatever |g| is) turn that rounding noise into
+        # visible loss differences on this tiny, ill-conditioned net: tight on steps 0-1, loose on step 2
+        for i, (la, lb) in enumerate(zip(losses_a, losses)):
+            assert abs(la - lb) < (1e-4 if i < 2 else 1e-2) * abs(la), (losses_a, losses)
         # Parameters: the two paths differ only by rounding of dL/dout (torch ops vs the fused MSE kernel)
         # and atomics order, but that 1e-7 noise is amplified towards the stem by the BN chain
         # and RMSprop's first steps move a weight by ~lr*10*sign(g) whatever |g| is.  So: the heads agree

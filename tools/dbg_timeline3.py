@@ -36,11 +36,15 @@ def pack(w, mode, BN):
     return dst[:w.numel()], dst[w.numel():]
 
 
+WARM = False
+
+
 def timed(fn):
     ms = 0.0
     for rep in range(3):
         buf.zero_()
-        flush = torch.empty(64 << 20, device=DEV).fill_(1.0); del flush
+        if not WARM:
+            flush = torch.empty(64 << 20, device=DEV).fill_(1.0); del flush
         L.cdll.hgk_debug_set_timeline(buf.data_ptr() if rep == 2 else 0)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -89,6 +93,13 @@ def run_dgrad(N, H, W, Cin, Cout, k, red=1, acc=0):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "warm":         # everything L2-resident (no flush, small batch): separates HBM latency from the rest
+    WARM = True
+    run_fwd(6, 64, 64, 128, 256, 1, res=1)
+    run_fwd(6, 64, 64, 256, 128, 1)
+    WARM = False
+    run_fwd(6, 64, 64, 128, 256, 1, res=1)
+    run_fwd(6, 64, 64, 256, 128, 1)
 if which == "one":          # a single layer (ncu capture)
     run_fwd(24, 64, 64, 128, 256, 1, res=1)
 if which == "one3":
