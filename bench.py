@@ -20,7 +20,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "images/sec 2-stack HG bs24 256x256 train step"
-BYTES_PER_IMAGE_STEP = 0.892e9      # algorithmic HBM bytes / image / train step
+BYTES_PER_IMAGE_STEP = 0.892e9      # algorithmic HBM bytes / image / train step at S=2
+
+
+def bytes_per_image_step(stacks):
+    """0.892 GB/image at S=2 and 3.15 GB/image at S=8 (the 7.81 ms floor of configs[4] at bs 16); the stem and
+    the three residuals in front of the stacks are the constant part, every stack adds the same amount."""
+    per_stack = (3.15e9 - BYTES_PER_IMAGE_STEP) / 6.0
+    return BYTES_PER_IMAGE_STEP + (stacks - 2) * per_stack
 FLOP_PER_IMAGE_STEP = 50.0e9
 
 
@@ -147,30 +154,35 @@ class CpuStep(object):
 
 
 def cpu_sample(args, sd, x, t, budget_s, steps, warmup):
-    """Times `steps` reference steps (after `warmup`) on a sample batch sized to fit budget_s."""
+    """Times reference train steps on the host cores at the FULL per-GPU batch of the workload (the batch size changes the
+    BatchNorm statistics and the per-image cost, so a smaller sample batch would be a different workload); the sample is
+    bounded through the NUMBER of steps: at most `steps` timed steps after `warmup`, fewer when budget_s would be exceeded
+    (never fewer than one).  Returns the measured rate and what the sample was."""
     cpu = CpuStep(args, sd)
-    b = min(2, args.batch)
+    sb = args.batch
+    b = min(2, sb)
+    cpu.step(x[:b], t[:b])                      # thread pool / allocator warm-up on a tiny batch (untimed)
     t0 = time.time()
-    cpu.step(x[:b], t[:b])
-    per_img = (time.time() - t0) / b
-    total = steps + warmup
-    sb = b
-    while sb * 2 <= args.batch and per_img * (sb * 2) * total <= budget_s:
-        sb *= 2
-    if sb == 16 and args.batch == 24 and per_img * 24 * total <= budget_s:
-        sb = 24
-    for _ in range(warmup):
+    outs, loss = cpu.step(x[:sb], t[:sb])       # first full-batch step: timed, counts as warm-up unless it is all we can afford
+    first = time.time() - t0
+    n_warm = max(0, min(warmup, int(budget_s / max(first, 1e-6)) - 1) - 1)
+    for _ in range(n_warm):
         cpu.step(x[:sb], t[:sb])
-    t0 = time.time()
-    outs = None
-    for _ in range(steps):
-        outs, loss = cpu.step(x[:sb], t[:sb])
-    dt = (time.time() - t0) / max(steps, 1)
+    left = budget_s - first * (1 + n_warm)
+    n_timed = max(0, min(steps, int(left / max(first, 1e-6))))
+    if n_timed == 0:
+        dt, n_timed, n_warm_total = first, 1, 0
+    else:
+        t0 = time.time()
+        for _ in range(n_timed):
+            outs, loss = cpu.step(x[:sb], t[:sb])
+        dt = (time.time() - t0) / n_timed
+        n_warm_total = 1 + n_warm
     return {"value": sb / dt, "unit": "images/s", "cores": cpu.cores, "kind": cpu.kind,
-            "sample": "%d timed train steps (fwd+MSE+bwd+RMSprop, %d warm-up) at batch %d of the same "
+            "sample": "%d timed train steps (fwd+MSE+bwd+RMSprop, %d full-batch warm-up) at batch %d of the same "
                       "S=%d C=%d %dx%d workload, torch CPU fp32, %d threads" %
-                      (steps, warmup + 1, sb, args.stacks, args.chan, args.res, args.res, cpu.cores),
-            "s_per_step": dt, "sample_batch": sb}
+                      (n_timed, n_warm_total, sb, args.stacks, args.chan, args.res, args.res, cpu.cores),
+            "s_per_step": dt, "sample_batch": sb, "timed_steps": n_timed}
 
 
 def cpu_config1(steps=5):
@@ -209,7 +221,7 @@ def run_reference(args):
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
     r = cpu_sample(args, sd, x, t, budget_s=150.0, steps=steps, warmup=warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
+            "steps": r["timed_steps"], "warmup": warmup, "steps_requested": steps, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, 1),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -219,9 +231,9 @@ def run_reference(args):
 
 
 def config_dict(args, world):
-    return {"workload": "2-stack hourglass train step (fwd + sum-of-stacks MSE + bwd + RMSprop%s), S=%d C=%d, "
+    return {"workload": "%d-stack hourglass train step (fwd + sum-of-stacks MSE + bwd + RMSprop%s), S=%d C=%d, "
                         "bs=%d/GPU, %dx%d synthetic MPII-shaped batch" %
-                        (" + 1 NCCL grad all-reduce" if world > 1 else "", args.stacks, args.chan, args.batch,
+                        (args.stacks, " + 1 NCCL grad all-reduce" if world > 1 else "", args.stacks, args.chan, args.batch,
                          args.res, args.res),
             "stacks": args.stacks, "chan": args.chan, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "res": args.res, "parallelism": "dp%d" % world,
@@ -341,10 +353,11 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
             "roofline": roof,
-            "step_roofline": {"bound": "hbm", "achieved": args.batch * BYTES_PER_IMAGE_STEP / (ms_step / 1e3) / 1e9,
+            "step_roofline": {"bound": "hbm", "achieved": args.batch * bytes_per_image_step(args.stacks) / (ms_step / 1e3) / 1e9,
                               "peak": pk["hbm_gbs"], "unit": "GB/s",
-                              "frac": args.batch * BYTES_PER_IMAGE_STEP / (ms_step / 1e3) / 1e9 / pk["hbm_gbs"],
-                              "note": "whole step, algorithmic 0.892 GB/image/step of the fused plan; peak %s" % pk["src"]},
+                              "frac": args.batch * bytes_per_image_step(args.stacks) / (ms_step / 1e3) / 1e9 / pk["hbm_gbs"],
+                              "note": "whole step, algorithmic %.3f GB/image/step of the fused plan; peak %s"
+                                      % (bytes_per_image_step(args.stacks) / 1e9, pk["src"])},
             "e2e": {"value": world * args.batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/s",
                     "h2d_bytes_per_step": int(xp.numel() * 4 + tp.numel() * 4), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "serial_value": world * args.batch * e2e_steps / (e2e_serial_ms / 1e3),
@@ -434,12 +447,24 @@ def dominant_kernel_roofline(tr, pk, torch):
     tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc")
     achieved = top / (ms / 1e3) / 1e12
     tile = tc and H % 16 == 0 and W % 16 == 0
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch: read from the newest committed `ncu --set full`
+    # summary (profiles/ncu_traffic.json, written by tools/ncu_summary.py with the commit it was captured at); None when
+    # no capture of this layer shape is committed
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for ent in tj.get("entries", []):
+            if ent.get("shape") == [N, H, W, Cin, Cout] and ent.get("ksize") == 3 and ent.get("direction") == "fwd":
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_src = "%s @ %s (%s)" % (ent.get("file"), ent.get("commit"), ent.get("kernel"))
+    except Exception:
+        pass
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the committed ncu --set full
             # capture profiles/r2z_kernels_ncu.txt (24x64x64, 128->128: 51.6 MB read + 7.3 MB written back before the
             # kernel ended; the 50 MB output largely stays dirty in the 126 MB L2)
-            "traffic": 58.8e6 if (tile and (N, H, W, Cin, Cout) == (24, 64, 64, 128, 128)) else None,
+            "traffic": traffic, "traffic_src": traffic_src,
             "kernel": "%s 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this FLOP class/step)" %
                       (("conv_tc2_kernel (tcgen05 image-tile kernel, 3xTF32)" if tile else "conv_tc_kernel (tcgen05, 3xTF32)")
                        if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
@@ -450,8 +475,86 @@ def dominant_kernel_roofline(tr, pk, torch):
                         "per product at 1/2 the bf16 rate, so its own ceiling is peak/6)"}
 
 
+def run_config3(args):
+    """BASELINE.json configs[2]: one agent-augmented joint-train iteration (joint-train-pose-s-r-agent.py:245-296) at bs 24:
+    half-hourglass forward (hg.train(), agent.eval()) -> ASN (scale, rotation) distributions -> on-GPU sampling ->
+    [CPU data pipeline of the reference: out of scope; the targets of the re-augmented batch are rendered on the GPU from
+    joint coordinates] -> full hourglass train step (CUDA graph) -> PCK on the GPU; plus the agent update
+    (train_agent_sr, :323-410: hg.eval(), agent.train(), KL loss, ASN backward, flat RMSprop) timed separately."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from pose_adv_aug_b200 import synth, HourglassTrainer, FlatRMSprop, agent
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    from pose_adv_aug_b200.pylib import Evaluation, HumanPts
+    dev = torch.device("cuda", 0)
+    S, C, N, R = 2, 256, 24, 256
+    net = M.create_hg(S, 1, 16, C)
+    net.load_state_dict(synth.make_state_dict(synth.schema_of(net), seed=1, perturb_bn=False))
+    asn = M.create_asn(C, C, 7, 7, is_aug=True)
+    asn.load_state_dict(synth.make_state_dict(synth.schema_of(asn), seed=2, perturb_bn=False))
+    asn.to(dev)
+    tr = HourglassTrainer(net, N, R, device=dev, use_graph=True)
+    x = synth.make_images(N, R, seed=100).to(dev)
+    tr.x.copy_(x)
+    tr.t.copy_(synth.make_heatmaps(N, R, 16, seed=200))
+    pts = torch.randint(4, 60, (N, 16, 2), device=dev).float()
+    np.random.seed(0)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def iteration():
+        net.train(); asn.eval()
+        with torch.no_grad():
+            ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
+        agent.sample_scale_rotation(ps, pr)
+        hm, _ = HumanPts.pts2heatmap(pts, [64, 64])
+        tr.t.copy_(hm)
+        tr.step_resident()
+        return Evaluation.accuracy(tr.heatmaps()[-1], tr.t, list(range(16)))
+
+    opt = FlatRMSprop(asn, lr=2.5e-4)
+    tgt = torch.softmax(torch.randn(N, 7, device=dev), dim=1)
+
+    def agent_update():
+        net.eval(); asn.train()
+        ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
+        loss = F.kl_div(torch.log(F.softmax(ps, dim=1) + 1e-7), tgt, reduction="mean") * 7 + \
+            F.kl_div(torch.log(F.softmax(pr, dim=1) + 1e-7), tgt, reduction="mean") * 7
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    ms = timed(iteration, steps, warmup)
+    ms_up = timed(agent_update, steps, warmup)
+    print(json.dumps({
+        "metric": "images/sec 2-stack HG + ASN agent joint-train iteration bs24 256x256", "value": N / ms * 1e3,
+        "unit": "images/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: half-hg(train BN)+ASN(eval) forward, on-GPU (s, r) sampling, GPU target "
+                               "rendering, full 2-stack train step (CUDA graph), GPU PCK; S=2 C=256 bs=24 256x256",
+                   "batch_per_gpu": N, "parallelism": "dp1"},
+        "agent_update": {"ms_per_update": ms_up, "images_per_s": N / ms_up * 1e3,
+                         "what": "train_agent_sr: half-hg(eval) + ASN(train) forward + KL + ASN backward + flat RMSprop (module path)"},
+        "gpu_launches": None, "launches_per_train_step": tr.launches_per_step}))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
+                    help="BASELINE.json configuration (1-based): 2 = the bench line (default), 3 = agent-augmented joint-train "
+                         "iteration, 5 = 8-stack hourglass bs 16")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
@@ -466,6 +569,15 @@ def main():
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--low-streams", type=int, default=3, help="of --streams, low-priority streams reserved for weight gradients")
     args = ap.parse_args()
+    if args.config == 5:
+        global METRIC
+        METRIC = "images/sec 8-stack HG bs16 256x256 train step"
+        args.stacks, args.batch = 8, 16
+    if args.config == 3 and args.impl == "ours":
+        args.steps = 10 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        run_config3(args)
+        return
     if args.impl == "reference":
         args.steps = 2 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup

@@ -191,6 +191,16 @@ int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, in
 /* dst = [accumulate ? dst : 0] + src  (gradient fan-in of `x + y + tmp_in`, :334) */
 int hgk_add_into(const float* src, float* dst, long long n, int accumulate, void* stream);
 
+/* ---- inter-stack head `x = x + forth_conv(y) + in_conv(out_conv(y))` (models/asn_stacked_hg.py:329-334) ----
+ * in_conv(out_conv(y)) is linear in y: the J->C and the C->C 1x1 convolutions are folded into ONE C->C convolution with
+ * Wc = Wf + Wi Wo, bc = bf + bi + Wi bo (OIHW fp32, Wf [C,C], Wi [C,J], Wo [J,C]); the pair below is the weight-space part
+ * (forward combination; exact chain rule back: dWf += dWc, dWi += dWc Wo^T, dWo += Wi^T dWc, dbf/dbi += dbc, dbo += Wi^T dbc). */
+int hgk_head_combine_fwd(const float* w_forth, const float* b_forth, const float* w_in, const float* b_in,
+                         const float* w_out, const float* b_out, float* w_comb, float* b_comb, int C, int J, void* stream);
+int hgk_head_combine_bwd(const float* dw_comb, const float* db_comb, const float* w_in, const float* w_out,
+                         float* dw_forth, float* db_forth, float* dw_in, float* db_in, float* dw_out, float* db_out,
+                         int C, int J, void* stream);
+
 /* ---- layout at the module boundary (the reference API is NCHW) ---- */
 int hgk_nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, void* stream);
 int hgk_nhwc_to_nchw(const float* x, const float* x_scale, const float* x_shift, int x_relu,

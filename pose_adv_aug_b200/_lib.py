@@ -40,6 +40,8 @@ SIGNATURES = {
     "hgk_add_fwd": [P, P, P, I, I, P, P, P, I, I, I, I, I, P, P],
     "hgk_upsample2_bwd": [P, I, I, I, I, P, I, P],
     "hgk_add_into": [P, P, L, I, P],
+    "hgk_head_combine_fwd": [P, P, P, P, P, P, P, P, I, I, P],
+    "hgk_head_combine_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "hgk_nchw_to_nhwc": [P, I, I, I, I, P, P],
     "hgk_nhwc_to_nchw": [P, P, P, I, I, I, I, I, P, P],
     "hgk_avgpool_fwd": [P, P, P, I, I, I, I, I, I, P, P],

@@ -42,7 +42,7 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ gamma, const fl
 }
 
 // One block = 256 threads = rows_par pixel rows x (C/4) channel quads; grid-strided over pixels.
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
                                                             int relu, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, long long P, int C,
@@ -60,18 +60,35 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         long long p1 = p0 + rows_per_blk < P ? p0 + rows_per_blk : P;
         float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
         int cnt = 0;
-        for (long long p = p0 + row; p < p1; p += rows_par) {
-            float4 d = ldg4(dy + p * C + c);
-            float4 v = ldg4(z + p * C + c);
-            float gx = (relu && fmaf(v.x, s.x, t.x) <= 0.f) ? 0.f : d.x;
-            float gy = (relu && fmaf(v.y, s.y, t.y) <= 0.f) ? 0.f : d.y;
-            float gz = (relu && fmaf(v.z, s.z, t.z) <= 0.f) ? 0.f : d.z;
-            float gw = (relu && fmaf(v.w, s.w, t.w) <= 0.f) ? 0.f : d.w;
-            f1[0] += gx; f2[0] = fmaf(gx, (v.x - mu.x) * is.x, f2[0]);
-            f1[1] += gy; f2[1] = fmaf(gy, (v.y - mu.y) * is.y, f2[1]);
-            f1[2] += gz; f2[2] = fmaf(gz, (v.z - mu.z) * is.z, f2[2]);
-            f1[3] += gw; f2[3] = fmaf(gw, (v.w - mu.w) * is.w, f2[3]);
-            if (++cnt == 16) {           // flush short fp32 partials into fp64
+        // four rows per trip, all eight 16-byte loads issued before the arithmetic (the kernel is a pure HBM stream: with
+        // one row per trip a thread had 32 bytes in flight and the launch ran at a third of the copy bandwidth)
+        constexpr int UR = 4;
+        const long long rstep = (long long)rows_par * UR;
+        for (long long p = p0 + row; p < p1; p += rstep) {
+            float4 d[UR], v[UR];
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const long long pp = p + (long long)u * rows_par;
+                if (pp < p1) {
+                    d[u] = ldg4(dy + pp * C + c);
+                    v[u] = ldg4(z + pp * C + c);
+                } else {                      // absent row: g = 0 contributes nothing to either sum
+                    d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u] = mu;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const float gx = (relu && fmaf(v[u].x, s.x, t.x) <= 0.f) ? 0.f : d[u].x;
+                const float gy = (relu && fmaf(v[u].y, s.y, t.y) <= 0.f) ? 0.f : d[u].y;
+                const float gz = (relu && fmaf(v[u].z, s.z, t.z) <= 0.f) ? 0.f : d[u].z;
+                const float gw = (relu && fmaf(v[u].w, s.w, t.w) <= 0.f) ? 0.f : d[u].w;
+                f1[0] += gx; f2[0] = fmaf(gx, (v[u].x - mu.x) * is.x, f2[0]);
+                f1[1] += gy; f2[1] = fmaf(gy, (v[u].y - mu.y) * is.y, f2[1]);
+                f1[2] += gz; f2[2] = fmaf(gz, (v[u].z - mu.z) * is.z, f2[2]);
+                f1[3] += gw; f2[3] = fmaf(gw, (v[u].w - mu.w) * is.w, f2[3]);
+            }
+            if (++cnt == 4) {            // flush short fp32 partials (16 rows) into fp64
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     g1[j] += (double)f1[j]; g2[j] += (double)f2[j];
@@ -138,13 +155,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            int relu, const float* __restrict__ mean,
                                                            const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, long long total4, int C4) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C4) * 4;
-        float4 d = ld4(dy + i * 4);
-        float4 v = ldg4(z + i * 4);
-        float4 s = ldg4(scale + c), t = ldg4(shift + c), a = ldg4(cA + c), b = ldg4(cB + c), cc = ldg4(cC + c);
-        float4 mu = ldg4(mean + c);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    auto one = [&](long long i, float4 d, float4 v, float4 s, float4 t, float4 a, float4 b, float4 cc, float4 mu) {
         float gx = (relu && fmaf(v.x, s.x, t.x) <= 0.f) ? 0.f : d.x;
         float gy = (relu && fmaf(v.y, s.y, t.y) <= 0.f) ? 0.f : d.y;
         float gz = (relu && fmaf(v.z, s.z, t.z) <= 0.f) ? 0.f : d.z;
@@ -155,6 +168,36 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
         o.z = a.z * ((gz - cc.z) - (v.z - mu.z) * b.z);
         o.w = a.w * ((gw - cc.w) - (v.w - mu.w) * b.w);
         st4(dy + i * 4, o);
+    };
+    if (stride % C4 == 0) {
+        // the grid stride is a multiple of the channel-quad count: a thread stays on ONE channel quad, its seven per-channel
+        // vectors are loaded once and four items are in flight per trip
+        const int c = (int)(i0 % C4) * 4;
+        const float4 s = ldg4(scale + c), t = ldg4(shift + c), a = ldg4(cA + c), b = ldg4(cB + c), cc = ldg4(cC + c);
+        const float4 mu = ldg4(mean + c);
+        constexpr int UR = 4;
+        for (long long i = i0; i < total4; i += stride * UR) {
+            float4 d[UR], v[UR];
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const long long ii = i + u * stride;
+                if (ii < total4) { d[u] = ld4(dy + ii * 4); v[u] = ldg4(z + ii * 4); }
+            }
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const long long ii = i + u * stride;
+                if (ii < total4) one(ii, d[u], v[u], s, t, a, b, cc, mu);
+            }
+        }
+        return;
+    }
+    for (long long i = i0; i < total4; i += stride) {
+        int c = (int)(i % C4) * 4;
+        float4 d = ld4(dy + i * 4);
+        float4 v = ldg4(z + i * 4);
+        float4 s = ldg4(scale + c), t = ldg4(shift + c), a = ldg4(cA + c), b = ldg4(cB + c), cc = ldg4(cC + c);
+        float4 mu = ldg4(mean + c);
+        one(i, d, v, s, t, a, b, cc, mu);
     }
 }
 
@@ -196,7 +239,7 @@ static int bn_bwd_reduce_impl(const float* dy, const float* z, const float* scal
     int cq_per_blk = cq < 64 ? cq : 64;                   // up to 256 channels per block column
     int ngrp = (cq + cq_per_blk - 1) / cq_per_blk;
     int rows_par = 256 / cq_per_blk;
-    long long want_blocks = (4LL * kNumSMs + ngrp - 1) / ngrp;
+    long long want_blocks = (3LL * kNumSMs + ngrp - 1) / ngrp;      // three resident CTAs per SM (85 registers)
     long long rows_per_blk = (P + want_blocks - 1) / want_blocks;
     if (rows_per_blk < 64) rows_per_blk = 64;
     long long nblk = (P + rows_per_blk - 1) / rows_per_blk;

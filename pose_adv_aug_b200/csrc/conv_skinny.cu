@@ -21,10 +21,12 @@ __device__ __forceinline__ void pair_sync(int wp) {
     else asm volatile("bar.sync 2, %0;" ::"n"(32 * CQ) : "memory");
 }
 
-// ---- C -> 16.  CQ = warps cooperating on one pixel (Cin = 128 * CQ); CTA = 4 warps, 2 pixels per warp step ----
+// ---- C -> 16.  CQ = warps cooperating on one pixel (Cin = 128 * CQ); CTA = 4 warps, N16_PX pixels per warp step (with the
+// prefetched next step: 2 * N16_PX * 512 bytes in flight per warp -- with two pixels the kernel ran at a quarter of the HBM rate)
+constexpr int N16_PX = 4;
 template <int CQ>
 __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
-    __shared__ float part[4][2][16];                // [warp][pixel of the step][output]: partial sums when CQ > 1
+    __shared__ float part[4][N16_PX][16];           // [warp][pixel of the step][output]: partial sums when CQ > 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cq = warp % CQ;                       // which 128-channel slice of the pixel this warp owns
     const int wp = warp / CQ;                       // pixel-group slot of the warp inside the CTA
@@ -40,28 +42,30 @@ __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
     load_affine4(a.x.scale, a.x.shift, c0, sc, sh);
     const bool has_aff = a.x.scale != nullptr;
     const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
-    const long long groups = (a.P + 1) / 2;         // 2 pixels per warp step
+    const long long groups = (a.P + N16_PX - 1) / N16_PX;
     const long long gstride = (long long)gridDim.x * WPB;
     const float* xz = a.x.z + c0;
-    auto load2 = [&](long long g, float4 (&xv)[2]) {
+    auto load2 = [&](long long g, float4 (&xv)[N16_PX]) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N16_PX; ++i) {
             xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const long long p = g * 2 + i;
+            const long long p = g * N16_PX + i;
             if (p < a.P) xv[i] = ldg4(xz + p * a.Cin);
         }
     };
-    float4 xn[2];
+    float4 xn[N16_PX];
     long long g = (long long)blockIdx.x * WPB + wp;
     load2(g, xn);
     // the warps of a pixel group run the same number of steps (same g): named barriers pair them up
     for (; g < groups; g += gstride) {
-        float4 xv[2] = {xn[0], xn[1]};
-        load2(g + gstride, xn);                      // prefetch the next step while this one computes
-        const long long p0 = g * 2;
-        float out[2];                                // after the reduce-scatter: output (lane & 15) of pixel i
+        float4 xv[N16_PX];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N16_PX; ++i) xv[i] = xn[i];
+        load2(g + gstride, xn);                      // prefetch the next step while this one computes
+        const long long p0 = g * N16_PX;
+        float out[N16_PX];                           // after the reduce-scatter: output (lane & 15) of pixel i
+#pragma unroll
+        for (int i = 0; i < N16_PX; ++i) {
             if (has_aff && p0 + i < a.P) xv[i] = act4(xv[i], sc, sh, a.x.relu);
             float acc[16];
 #pragma unroll
@@ -89,14 +93,14 @@ __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
         const int o = lane & 15;
         if (CQ > 1) {
             if (lane < 16) {
-                part[warp][0][o] = out[0];
-                part[warp][1][o] = out[1];
+#pragma unroll
+                for (int i = 0; i < N16_PX; ++i) part[warp][i][o] = out[i];
             }
             pair_sync<CQ>(wp);
         }
         if (cq == 0 && lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < N16_PX; ++i) {
                 if (p0 + i >= a.P) break;
                 float v = out[i];
                 if (CQ > 1) {
@@ -118,7 +122,11 @@ __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
     }
 }
 
-// ---- 16 -> C.  A warp covers 128 output channels of one pixel per step (software-pipelined); CTA = 8 warps ----
+// ---- 16 -> C.  A warp covers 128 output channels of NPX consecutive pixels per step; CTA = 8 warps.  The NPX x 16 input values
+// of a step are ONE coalesced 16-byte load per lane (lane = pixel (lane >> 2), channel quad (lane & 3)) and reach the FMAs by
+// warp shuffles; the shortcut / previous-output rows of all NPX pixels are requested before the arithmetic starts (NPX x 512
+// bytes per operand and warp in flight: with one pixel per step the launch ran at a fifth of the HBM rate).
+template <int NPX, bool RES, bool ACC>
 __global__ void __launch_bounds__(256, 2) conv_k16_kernel(const ConvArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nq = a.Cout >> 7;                      // 128-channel slices per pixel
@@ -132,48 +140,50 @@ __global__ void __launch_bounds__(256, 2) conv_k16_kernel(const ConvArgs a) {
     if (a.bias != nullptr) bv = ldg4(a.bias + n0);
     float4 rs, rt;
     load_affine4(a.res.scale, a.res.shift, n0, rs, rt);
-    const bool has_aff = a.x.scale != nullptr;
-    const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
-    const long long pstride = (long long)gridDim.x * WPB;
-    struct Px { float4 x[4], r, o; };
-    auto load1 = [&](long long p, Px& d) {
-        d.r = make_float4(0.f, 0.f, 0.f, 0.f);
-        d.o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < a.P) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) d.x[q] = ldg4(a.x.z + p * 16 + q * 4);       // warp-uniform address: one broadcast transaction
-            if (has_res) d.r = ldg4(a.res.z + p * a.Cout + n0);
-            if (a.accumulate) d.o = ld4(a.y + p * a.Cout + n0);
+    const bool has_aff = a.x.scale != nullptr, res_aff = a.res.scale != nullptr;
+    float4 xsc, xsh;
+    load_affine4(a.x.scale, a.x.shift, (lane & 3) * 4, xsc, xsh);
+    const long long groups = (a.P + NPX - 1) / NPX;
+    const long long gstride = (long long)gridDim.x * WPB;
+    for (long long g = (long long)blockIdx.x * WPB + wp; g < groups; g += gstride) {
+        const long long p0 = g * NPX;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < NPX * 4 && p0 + (lane >> 2) < a.P) {
+            xv = ldg4(a.x.z + (p0 + (lane >> 2)) * 16 + (lane & 3) * 4);
+            if (has_aff) xv = act4(xv, xsc, xsh, a.x.relu);
         }
-    };
-    long long p = (long long)blockIdx.x * WPB + wp;
-    Px nx;
-    load1(p, nx);
-    for (; p < a.P; p += pstride) {
-        Px cur = nx;
-        load1(p + pstride, nx);                      // prefetch the next pixel while this one computes
-        float4 v = bv;
+        float4 rr[RES ? NPX : 1], oo[ACC ? NPX : 1];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 x4 = cur.x[q];
-            if (has_aff) {
-                float4 xsc, xsh;
-                load_affine4(a.x.scale, a.x.shift, q * 4, xsc, xsh);
-                x4 = act4(x4, xsc, xsh, a.x.relu);
+        for (int i = 0; i < NPX; ++i) {
+            const bool ok = p0 + i < a.P;
+            if (RES) rr[RES ? i : 0] = ok ? ldg4(a.res.z + (p0 + i) * a.Cout + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ACC) oo[ACC ? i : 0] = ok ? ld4(a.y + (p0 + i) * a.Cout + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            float4 v = bv;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int src = i * 4 + q;
+                const float x0 = __shfl_sync(0xffffffffu, xv.x, src), x1 = __shfl_sync(0xffffffffu, xv.y, src);
+                const float x2 = __shfl_sync(0xffffffffu, xv.z, src), x3 = __shfl_sync(0xffffffffu, xv.w, src);
+                const float4 w0 = wr[q * 4 + 0], w1 = wr[q * 4 + 1], w2 = wr[q * 4 + 2], w3 = wr[q * 4 + 3];
+                v.x += x0 * w0.x + x1 * w1.x + x2 * w2.x + x3 * w3.x;
+                v.y += x0 * w0.y + x1 * w1.y + x2 * w2.y + x3 * w3.y;
+                v.z += x0 * w0.z + x1 * w1.z + x2 * w2.z + x3 * w3.z;
+                v.w += x0 * w0.w + x1 * w1.w + x2 * w2.w + x3 * w3.w;
             }
-            const float4 w0 = wr[q * 4 + 0], w1 = wr[q * 4 + 1], w2 = wr[q * 4 + 2], w3 = wr[q * 4 + 3];
-            v.x += x4.x * w0.x + x4.y * w1.x + x4.z * w2.x + x4.w * w3.x;
-            v.y += x4.x * w0.y + x4.y * w1.y + x4.z * w2.y + x4.w * w3.y;
-            v.z += x4.x * w0.z + x4.y * w1.z + x4.z * w2.z + x4.w * w3.z;
-            v.w += x4.x * w0.w + x4.y * w1.w + x4.z * w2.w + x4.w * w3.w;
+            if (RES) {
+                float4 q = rr[RES ? i : 0];
+                if (res_aff) q = act4(q, rs, rt, a.res.relu);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            if (ACC) {
+                const float4 o = oo[ACC ? i : 0];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            if (p0 + i < a.P) st4(a.y + (p0 + i) * a.Cout + n0, v);
         }
-        if (has_res) {
-            float4 q = cur.r;
-            if (res_aff) q = act4(q, rs, rt, a.res.relu);
-            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-        }
-        v.x += cur.o.x; v.y += cur.o.y; v.z += cur.o.z; v.w += cur.o.w;
-        st4(a.y + p * a.Cout + n0, v);
     }
 }
 
@@ -192,7 +202,12 @@ int conv_skinny_try(const ConvArgs& a, cudaStream_t st) {
         return 1;
     }
     if (a.Cin == 16 && (a.Cout == 128 || a.Cout == 256)) {
-        conv_k16_kernel<<<kNumSMs * 4, 256, 0, st>>>(a);
+        const bool res = a.res.z != nullptr, acc = a.accumulate != 0;
+        const int grid = kNumSMs * 4;
+        if (res && acc) conv_k16_kernel<4, true, true><<<grid, 256, 0, st>>>(a);
+        else if (res) conv_k16_kernel<8, true, false><<<grid, 256, 0, st>>>(a);
+        else if (acc) conv_k16_kernel<8, false, true><<<grid, 256, 0, st>>>(a);
+        else conv_k16_kernel<8, false, false><<<grid, 256, 0, st>>>(a);
         return 1;
     }
     return 0;

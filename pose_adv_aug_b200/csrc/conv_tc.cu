@@ -1018,7 +1018,6 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
 }  // namespace hgk
 
 namespace hgk {
-int conv_tcp_launch(const TcArgs& ta, bool split, void* stream);      // conv_tcp.cu (persistent kernel)
 bool conv_tc2_eligible(const TcArgs& ta);                             // conv_tc2.cu (16x16 image-tile kernel)
 int wgrad_tc2_try(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W, int Cin,
                   const float* dz, int Cout, int ksize, float* dw, float* dbias, void* stream);   // wgrad_tc2.cu (MN-major)
@@ -1028,17 +1027,6 @@ int conv_tc3_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream);
 }
 
 using namespace hgk;
-
-// HGK_TC_PERSIST=1 selects the persistent warp-specialised kernel of conv_tcp.cu (experimental: its
-// 4-warp epilogue is currently the bottleneck, so the two-CTAs-per-SM kernel above is the default)
-static bool use_persistent() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("HGK_TC_PERSIST");
-        v = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
 
 extern "C" int hgk_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin > 0 && Cin % 32 == 0 && (Cout == 64 || Cout == 128 || Cout == 256) && (ksize == 1 || ksize == 3)) ? 1 : 0;
@@ -1113,8 +1101,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
                         : (Cout == 128 ? launch_tc<128, false, true>(ta, st) : launch_tc<256, false, true>(ta, st));
-    } else if (use_persistent()) rc = conv_tcp_launch(ta, split, stream);
-    else if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
+    } else if (Cout == 64) rc = split ? launch_tc<64, true>(ta, st) : launch_tc<64, false>(ta, st);
     else if (Cout == 128) rc = split ? launch_tc<128, true>(ta, st) : launch_tc<128, false>(ta, st);
     else rc = split ? launch_tc<256, true>(ta, st) : launch_tc<256, false>(ta, st);
     if (rc != HGK_OK) return rc;

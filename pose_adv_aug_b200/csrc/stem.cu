@@ -27,37 +27,69 @@ __device__ __forceinline__ void stem_load_patch(float* patch, const float* img, 
     }
 }
 
-// grid: (tiles_x, tiles_y, N); 256 threads: tx = tid&15 -> 4 couts, ty = tid>>4 -> 8 pixels
-__global__ void __launch_bounds__(256) stem_conv7_fwd_kernel(const float* __restrict__ img, int N, int H, int W,
-                                                             const float* __restrict__ w, const float* __restrict__ bias,
-                                                             float* __restrict__ y, double* stat_sum, double* stat_sq) {
+// Persistent CTAs (3 per SM) walk over the output tiles; 256 threads: tx = tid&15 -> 4 couts, ty = tid>>4 -> 8 pixels of one
+// tile row.  The [k][co] weight tile is staged ONCE per CTA (a per-tile transposing store with a 64-float stride was a
+// 32-way bank conflict: ~9 400 LSU cycles per tile, 40 % of the kernel), and a thread reads the 21 consecutive patch floats
+// its eight stride-2 windows cover as six LDS.128 per (channel, kh) row instead of one scalar load per tap and pixel
+// (13 shared-memory loads per 224 FFMA; it was 9 per 32, LSU-bound).  Patch rows are padded to 40 floats (alignment).
+constexpr int ST_PWF = 40;
+
+__global__ void __launch_bounds__(256, 3) stem_conv7_fwd_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                                float* __restrict__ y, double* stat_sum, double* stat_sq,
+                                                                int tiles_x, int tiles_y) {
     __shared__ __align__(16) float Ws[ST_K * ST_CO];          // [k][co]
-    __shared__ float patch[3 * ST_PH * ST_PW];
+    __shared__ __align__(16) float patch[3 * ST_PH * ST_PWF];
     const int tid = threadIdx.x;
     const int OH = H / 2, OW = W / 2;
-    const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH, n = blockIdx.z;
-    for (int i = tid; i < ST_K * ST_CO; i += 256) {           // coalesced over k, transposed store
-        int co = i / ST_K, k = i - co * ST_K;
-        Ws[k * ST_CO + co] = __ldg(w + i);
+    for (int i = tid; i < ST_K * ST_CO; i += 256) {           // consecutive threads -> consecutive co: conflict-free stores
+        const int k = i >> 6, co = i & 63;
+        Ws[i] = __ldg(w + co * ST_K + k);
     }
-    stem_load_patch(patch, img, n, H, W, oy0, ox0, tid);
-    __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;
     const int oy = ty >> 1, oxb = (ty & 1) * 8;
-    float acc[8][4];
+    const float4 bv = bias ? ldg4(bias + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+    const int total = tiles_x * tiles_y * N;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n = t / (tiles_x * tiles_y);
+        const int r = t - n * (tiles_x * tiles_y);
+        const int tyi = r / tiles_x, txi = r - tyi * tiles_x;
+        const int oy0 = tyi * ST_TH, ox0 = txi * ST_TW;
+        const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+        __syncthreads();                                      // previous tile's patch fully consumed (first trip: Ws staged)
+        for (int i = tid; i < 3 * ST_PH * ST_PWF; i += 256) {
+            const int cc = i / (ST_PH * ST_PWF);
+            const int rr = i - cc * (ST_PH * ST_PWF);
+            const int py = rr / ST_PWF, px = rr - py * ST_PWF;
+            const int iy = iy0 + py, ix = ix0 + px;
+            float v = 0.f;
+            if (px < ST_PW && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+                v = __ldg(img + ((size_t)(n * 3 + cc) * H + iy) * W + ix);
+            patch[i] = v;
+        }
+        __syncthreads();
+        float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int c = 0; c < 3; ++c)
-        for (int kh = 0; kh < 7; ++kh) {
-            const float* prow = patch + (c * ST_PH + oy * 2 + kh) * ST_PW + oxb * 2;
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+        for (int ck = 0; ck < 21; ++ck) {                     // (channel, kh) patch rows
+            const int c = ck / 7, kh = ck - c * 7;
+            const float* prow = patch + (c * ST_PH + oy * 2 + kh) * ST_PWF + oxb * 2;
+            float pv[24];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const float4 v = ld4(prow + 4 * q);
+                pv[4 * q] = v.x; pv[4 * q + 1] = v.y; pv[4 * q + 2] = v.z; pv[4 * q + 3] = v.w;
+            }
 #pragma unroll
             for (int kw = 0; kw < 7; ++kw) {
-                float4 b = ld4(Ws + ((c * 7 + kh) * 7 + kw) * ST_CO + tx * 4);
+                const float4 b = ld4(Ws + (ck * 7 + kw) * ST_CO + tx * 4);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float av = prow[i * 2 + kw];
+                    const float av = pv[i * 2 + kw];
                     acc[i][0] = fmaf(av, b.x, acc[i][0]);
                     acc[i][1] = fmaf(av, b.y, acc[i][1]);
                     acc[i][2] = fmaf(av, b.z, acc[i][2]);
@@ -65,20 +97,22 @@ __global__ void __launch_bounds__(256) stem_conv7_fwd_kernel(const float* __rest
                 }
             }
         }
-    float4 bv = bias ? ldg4(bias + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    const int gy = oy0 + oy;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        const int gy = oy0 + oy;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int gx = ox0 + oxb + i;
-        if (gy < OH && gx < OW) {
-            float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
-            st4(y + (((size_t)n * OH + gy) * OW + gx) * ST_CO + tx * 4, v);
-            s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-            s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-            s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-            s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+        for (int i = 0; i < 8; ++i) {
+            const int gx = ox0 + oxb + i;
+            if (gy < OH && gx < OW) {
+                const float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+                st4(y + (((size_t)n * OH + gy) * OW + gx) * ST_CO + tx * 4, v);
+                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
+                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
+                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
+                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+            }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }   // fp32 over 8 pixels, fp64 from here on
     }
     if (stat_sum != nullptr) {
         __syncthreads();
@@ -86,24 +120,24 @@ __global__ void __launch_bounds__(256) stem_conv7_fwd_kernel(const float* __rest
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double d1 = (double)s1[j], d2 = (double)s2[j];
-            d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
-            d2 += __shfl_xor_sync(0xffffffffu, d2, 16);
+            double e1 = d1[j], e2 = d2[j];
+            e1 += __shfl_xor_sync(0xffffffffu, e1, 16);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, 16);
             if (lane < 16) {
-                red[(warp * 64 + tx * 4 + j) * 2 + 0] = d1;
-                red[(warp * 64 + tx * 4 + j) * 2 + 1] = d2;
+                red[(warp * 64 + tx * 4 + j) * 2 + 0] = e1;
+                red[(warp * 64 + tx * 4 + j) * 2 + 1] = e2;
             }
         }
         __syncthreads();
         if (tid < 64) {
-            double d1 = 0.0, d2 = 0.0;
+            double e1 = 0.0, e2 = 0.0;
 #pragma unroll
             for (int wv = 0; wv < 8; ++wv) {
-                d1 += red[(wv * 64 + tid) * 2 + 0];
-                d2 += red[(wv * 64 + tid) * 2 + 1];
+                e1 += red[(wv * 64 + tid) * 2 + 0];
+                e2 += red[(wv * 64 + tid) * 2 + 1];
             }
-            atomicAdd(stat_sum + tid, d1);
-            atomicAdd(stat_sq + tid, d2);
+            atomicAdd(stat_sum + tid, e1);
+            atomicAdd(stat_sq + tid, e2);
         }
     }
 }
@@ -277,8 +311,11 @@ extern "C" int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const f
     HGK_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hgk_stem_conv7_fwd: H, W must be even and positive");
     HGK_REQUIRE((stat_sum == nullptr) == (stat_sq == nullptr), "hgk_stem_conv7_fwd: stat_sum/stat_sq must both be set");
     HGK_REQUIRE(N <= 65535, "hgk_stem_conv7_fwd: batch too large");
-    dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
-    stem_conv7_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, w, bias, y, stat_sum, stat_sq);
+    const int tiles_x = (W / 2 + ST_TW - 1) / ST_TW, tiles_y = (H / 2 + ST_TH - 1) / ST_TH;
+    const long long total = (long long)tiles_x * tiles_y * N;
+    HGK_REQUIRE(total < (1LL << 31), "hgk_stem_conv7_fwd: too many tiles");
+    const int grid = (int)(total < 3 * kNumSMs ? total : 3 * kNumSMs);
+    stem_conv7_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, w, bias, y, stat_sum, stat_sq, tiles_x, tiles_y);
     HGK_CHECK_LAUNCH("hgk_stem_conv7_fwd");
     return HGK_OK;
 }

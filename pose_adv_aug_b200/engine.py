@@ -222,6 +222,9 @@ class Plan(object):
         self.bytes_alloc = 0
         self.finished = False
         self.low_recs = set()      # id() of forward launches built inside a low_scope() (off the critical path)
+        self.pre = []              # launches that run BEFORE the weight repack (derived weights: Plan.head_comb)
+        self.aux_grad = {}         # id(derived weight / bias tensor) -> its gradient tensor (not part of any flat store)
+        self.aux_zero = []         # ... which are zeroed at the start of every backward pass
         self.after = {}            # id(launch) -> id(earlier launch) it must additionally wait for (scheduling-only edge)
 
     # ---- allocation helpers ----
@@ -308,6 +311,9 @@ class Plan(object):
         return p.data_ptr()
 
     def param_grad_ptr(self, p):
+        g = self.aux_grad.get(id(p))
+        if g is not None:
+            return g.data_ptr()
         for st in self.stores:
             i = st.index.get(id(p))
             if i is not None:
@@ -452,6 +458,14 @@ class Plan(object):
         self.tape.append(op)
         return op.out
 
+    def head_comb(self, forth_conv, in_conv, out_conv):
+        """`forth_conv(y) + in_conv(out_conv(y))` (models/asn_stacked_hg.py:332-334) folded into ONE C->C convolution:
+        returns a conv-like object (weight Wc = Wf + Wi Wo, bias bc = bf + bi + Wi bo, recomputed by a launch in front of the
+        weight repack) to be passed to `conv(y, comb, res=x)`; the backward redistributes dWc / dbc exactly (csrc/heads.cu)."""
+        op = _HeadCombOp(self, forth_conv, in_conv, out_conv)
+        self.tape.append(op)
+        return op
+
     def maxpool(self, x):
         op = _PoolOp(self, x)
         self.tape.append(op)
@@ -564,8 +578,8 @@ class Plan(object):
             base = min(st.flat.data_ptr() for st in self.stores)
             rows = []
             for (w, off, O, I, taps, mode) in self.pack_entries:
-                d = w.data_ptr() - base
-                assert d >= 0 and d % 4 == 0, "weight outside the flat stores"
+                d = w.data_ptr() - base            # signed: derived weights (Plan.head_comb) live outside the flat stores
+                assert d % 4 == 0
                 rows.append([d // 4, off, O, I, taps, mode])
             self.pack_table = torch.tensor(rows, dtype=torch.long, device=self.device)
             self.pack_launch = [self.lib.pack_weights,
@@ -580,8 +594,8 @@ class Plan(object):
             base = min(st.flat.data_ptr() for st in self.stores)
             rows = []
             for (w, mode, BN, hi, lo) in self.tc_entries:
-                d = w.data_ptr() - base
-                assert d >= 0 and d % 4 == 0, "weight outside the flat stores"
+                d = w.data_ptr() - base            # signed, see above
+                assert d % 4 == 0
                 O, I, taps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
                 N, K = (O, I) if mode == 0 else (I, O)
                 rows.append([d // 4, hi, lo, N, K, taps, mode, BN])
@@ -601,6 +615,15 @@ class Plan(object):
                 self.nbt_bufs = [b for b in self.nbt_bufs if id(b) not in mine]
         self.finished = True
 
+    def head_launches(self):
+        """The launches in front of the forward list: derived weights, then the two weight repacks."""
+        lst = list(self.pre)
+        if self.pack_launch is not None:
+            lst.append(self.pack_launch)
+        if self.tc_launch is not None:
+            lst.append(self.tc_launch)
+        return lst
+
     def _run(self, lst, stream):
         for fn, args, name in lst:
             rc = fn(*args, stream)
@@ -618,10 +641,7 @@ class Plan(object):
             self.patch(key, x.data_ptr())
         if self.stat_f_used:
             self.stat_f[:self.stat_f_used].zero_()
-        if self.pack_launch is not None:
-            self._run([self.pack_launch], stream)
-        if self.tc_launch is not None:
-            self._run([self.tc_launch], stream)
+        self._run(self.head_launches(), stream)
         self._run(self.fwd, stream)
         for f in self.nbt_flat:
             f.add_(1)
@@ -638,6 +658,8 @@ class Plan(object):
             self.stat_b[:self.stat_b_used].zero_()
         if self.wg_buf is not None:
             self.wg_buf.zero_()
+        for a in self.aux_zero:
+            a.zero_()
         held = []
         for op, g in zip(self.outputs, gouts):
             if op.no_grad:
@@ -668,6 +690,7 @@ _WRITES = {
     "maxpool2_fwd": (8,), "maxpool2_bwd": (9,), "add_fwd": (13,), "upsample2_bwd": (5,), "add_into": (1,),
     "nchw_to_nhwc": (5,), "nhwc_to_nchw": (8,),
     "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7),
+    "head_combine_fwd": (6, 7), "head_combine_bwd": (4, 5, 6, 7, 8, 9),
     "mse_fwd_bwd": (5, 7), "avgpool_fwd": (9,), "avgpool_bwd": (6,), "linear_fwd": (6,), "linear_bwd": (6, 7, 8),
 }
 
@@ -983,6 +1006,38 @@ class _ConvOp(object):
         # shortcut: d/d res = dz (donated: this op never touches the buffer again)
         if self.res is not None:
             p.contribute(self.res, dzb, True)
+
+
+class _HeadCombOp(object):
+    """Derived 1x1 convolution Wc = Wf + Wi Wo, bc = bf + bi + Wi bo (see Plan.head_comb); quacks like nn.Conv2d for
+    _ConvOp (.weight, .bias).  Sits in the tape BEFORE the convolution that uses it, so that its backward (which turns the
+    accumulated dWc / dbc into the gradients of the three real layers) is emitted AFTER that convolution's weight gradient."""
+
+    def __init__(self, plan, forth_conv, in_conv, out_conv):
+        self.plan, self.forth, self.inc, self.outc = plan, forth_conv, in_conv, out_conv
+        C, J = forth_conv.weight.shape[0], out_conv.weight.shape[0]
+        if (tuple(forth_conv.weight.shape) != (C, C, 1, 1) or tuple(in_conv.weight.shape) != (C, J, 1, 1)
+                or tuple(out_conv.weight.shape) != (J, C, 1, 1)):
+            raise ValueError("head_comb expects 1x1 convolutions C->C, J->C and C->J")
+        self.C, self.J = C, J
+        dev = plan.device
+        self.weight = torch.empty(C, C, 1, 1, device=dev, dtype=torch.float32)
+        self.bias = torch.empty(C, device=dev, dtype=torch.float32)
+        plan.keep += [self.weight, self.bias]
+        plan.launch(plan.pre, "head_combine_fwd", _ptr(forth_conv.weight), _ptr(forth_conv.bias), _ptr(in_conv.weight),
+                    _ptr(in_conv.bias), _ptr(out_conv.weight), _ptr(out_conv.bias), _ptr(self.weight), _ptr(self.bias), C, J)
+        if plan.need_grad:
+            self.dweight, self.dbias = torch.zeros_like(self.weight), torch.zeros_like(self.bias)
+            plan.aux_grad[id(self.weight)] = self.dweight
+            plan.aux_grad[id(self.bias)] = self.dbias
+            plan.aux_zero += [self.dweight, self.dbias]
+
+    def emit_bwd(self):
+        p = self.plan
+        g = lambda t: p.param_grad_ptr(t) if t is not None else 0
+        p.launch(p.bwd, "head_combine_bwd", _ptr(self.dweight), _ptr(self.dbias), _ptr(self.inc.weight), _ptr(self.outc.weight),
+                 g(self.forth.weight), g(self.forth.bias), g(self.inc.weight), g(self.inc.bias), g(self.outc.weight),
+                 g(self.outc.bias), self.C, self.J)
 
 
 class _PoolOp(object):

@@ -28,6 +28,10 @@ PRECISE_GRADS = False
 # streams, 3 of them low priority).  HGK_DEFER_SKIPS=0 restores the reference's build order.
 import os as _os
 DEFER_SKIPS = _os.environ.get("HGK_DEFER_SKIPS", "1") == "1"
+# Inter-stack head: forth_conv(y) + in_conv(out_conv(y)) as ONE C->C convolution with the combined weights Wf + Wi Wo
+# (engine.Plan.head_comb, csrc/heads.cu): the 16->C pass over the activation, its data gradient and its weight gradient
+# become weight-space products.  HGK_FUSE_HEAD=0 restores the three separate convolutions of ref:332-334.
+FUSE_HEAD = _os.environ.get("HGK_FUSE_HEAD", "1") == "1"
 
 
 def _reference_init(root):
@@ -123,7 +127,7 @@ def _run(root, extra_roots, key, inputs, build):
     # which inputs want a gradient is baked into the plan (input_nchw(needs_grad=...)): it is part of the key, so a module
     # first called on a constant input and later inside a larger autograd graph gets a plan with the input-gradient path
     in_grad = tuple(bool(x.requires_grad) and need_grad for x in inputs)
-    pkey = (key, shapes, modes, need_grad, in_grad, ids, CONV_PATH, PRECISE_GRADS)
+    pkey = (key, shapes, modes, need_grad, in_grad, ids, CONV_PATH, PRECISE_GRADS, FUSE_HEAD)
     cache = _state(root).plans
     plan = cache.get(pkey)
     if plan is None:
@@ -379,8 +383,12 @@ class _Hourglass_Wrapper(nn.Module):
             o = plan.conv(y, self.out_conv[i])                          # ref:329
             outs.append(o)
             if i < self.num_stacks - 1:
-                t = plan.conv(y, self.forth_conv[i], res=x)             # ref:332,334
-                x = plan.conv(o, self.in_conv[i], res=t)                # ref:333-334
+                if FUSE_HEAD:
+                    comb = plan.head_comb(self.forth_conv[i], self.in_conv[i], self.out_conv[i])
+                    x = plan.conv(y, comb, res=x)                       # ref:332-334 as one convolution
+                else:
+                    t = plan.conv(y, self.forth_conv[i], res=x)         # ref:332,334
+                    x = plan.conv(o, self.in_conv[i], res=t)            # ref:333-334
         return outs, agent
 
     def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False):

@@ -74,8 +74,7 @@ class HourglassTrainer(object):
     # number of libhgk kernel launches per step (for bench.py's gpu_launches)
     @property
     def launches_per_step(self):
-        return (len(self.plan.fwd) + len(self.plan.bwd) + (1 if self.plan.pack_launch else 0)
-                + (1 if self.plan.tc_launch else 0) + 2)
+        return len(self.plan.head_launches()) + len(self.plan.fwd) + len(self.plan.bwd) + 2
 
     def _body_grads(self):
         """zero grads/loss -> forward -> fused MSE -> backward (local gradients in the flat buffer)."""
@@ -106,12 +105,9 @@ class HourglassTrainer(object):
             if not op.no_grad and op.gsrc is not None:
                 op.gsrc.zero_()
                 plan.patch("gout%d" % op.index, op.gsrc.data_ptr())
-        launches = []
-        if plan.pack_launch is not None:
-            launches.append(plan.pack_launch)
-        if plan.tc_launch is not None:
-            launches.append(plan.tc_launch)
-        launches += plan.fwd + plan.bwd
+        for a in plan.aux_zero:
+            a.zero_()
+        launches = plan.head_launches() + plan.fwd + plan.bwd
         n_low = min(self.n_low, n_streams - 1)
         if self._sched is None:
             import os

@@ -92,13 +92,17 @@ def test_plan_builds_and_covers_every_parameter():
         plan.output_nchw(o, no_grad=True)
     plan.finish()
     names = [r[2] for r in plan.fwd]
-    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + names.count("conv_nhwc") == 101
+    # 101 convolutions in the reference graph; the inter-stack in_conv is folded into forth_conv (Plan.head_comb)
+    n_conv = 100 if M.FUSE_HEAD else 101
+    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + names.count("conv_nhwc") == n_conv
             and names.count("stem_conv7_fwd") == 1)
+    assert [r[2] for r in plan.pre] == (["head_combine_fwd"] if M.FUSE_HEAD else [])
     # 96 BatchNorms: 95 finalised by the last CTA of their tensor-core convolution, the stem's by its own launch
     assert names.count("conv_tc_bn_nhwc") == 95 and names.count("bn_finalize") == 1
     assert names.count("maxpool2_fwd") == 9 and names.count("add_fwd") == 8
     bnames = [r[2] for r in plan.bwd]
-    assert bnames.count("conv_wgrad_tc_nhwc") + bnames.count("conv_wgrad_nhwc") == 101
+    assert bnames.count("conv_wgrad_tc_nhwc") + bnames.count("conv_wgrad_nhwc") == n_conv
+    assert bnames.count("head_combine_bwd") == (1 if M.FUSE_HEAD else 0)
     assert "add_into" not in bnames                                             # all gradient fan-ins are aliased/fused
     # 96 BatchNorm backwards: the apply is evaluated on load by the image-tile data-gradient kernel wherever that
     # kernel runs (H, W multiples of 16), a bn_bwd_apply launch remains for the 8x8 / 4x4 layers and the stem

@@ -22,7 +22,7 @@ def _plan():
     keep = (torch.zeros(2, 3, 256, 256), torch.zeros(2, 16, 64, 64))
     plan.patch("image", keep[0].data_ptr())
     plan.patch("target", keep[1].data_ptr())
-    return plan, keep, [plan.pack_launch, plan.tc_launch] + plan.fwd + plan.bwd
+    return plan, keep, plan.head_launches() + plan.fwd + plan.bwd
 
 
 def test_schedule_respects_every_dependency():

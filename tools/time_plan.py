@@ -34,12 +34,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 plan = tr.plan
 stream = torch.cuda.current_stream().cuda_stream
-recs = []
-if plan.pack_launch:
-    recs.append(plan.pack_launch)
-if plan.tc_launch:
-    recs.append(plan.tc_launch)
-recs += plan.fwd + plan.bwd
+recs = plan.head_launches() + plan.fwd + plan.bwd
+for a in plan.aux_zero:
+    a.zero_()
 plan.stat_f[:plan.stat_f_used].zero_()
 plan.stat_b[:plan.stat_b_used].zero_()
 tr.store.grad.zero_()
