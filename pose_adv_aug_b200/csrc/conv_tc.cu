@@ -15,6 +15,13 @@
 //     commits to the stage's mbarrier, which frees the stage for the producers;
 //   * epilogue: tcgen05.ld -> shared staging tile -> coalesced bias/residual/accumulate/store and
 //     fp64 per-channel statistics.
+//
+// SPLIT-K OVER A THREAD-BLOCK CLUSTER (the 16x16 / 8x8 / 4x4 rungs of the hourglass): a 3x3 128->128 layer at 4x4 has
+// P = 384 pixels = 3 CTAs, each of which used to walk all 36 (tap, channel-chunk) stages alone -- a 48 us latency chain
+// on 3 of 148 SMs, four of them per residual block on the critical path of every hourglass.  Launched with a cluster of
+// S CTAs along grid.z, CTA `rank` runs stages [rank*T/S, (rank+1)*T/S) into its own TMEM accumulator, stages the partial
+// 128 x BN tile in its shared memory, and after a cluster barrier every CTA sums ITS 128/S pixel rows over the S partial
+// tiles through distributed shared memory (fixed order: rank 0 .. S-1) and runs the usual epilogue on them.
 #include <stdlib.h>
 #include "common.cuh"
 #include "conv_args.cuh"
@@ -55,6 +62,32 @@ struct TcCfg {
     static_assert(NST >= 2, "pipeline needs two stages");
 };
 
+__device__ __forceinline__ uint32_t cluster_nctaid_z() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.z;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t cluster_ctaid_z() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%cluster_ctaid.z;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in the CTA with rank `rank`
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int BN, bool SPLIT, bool BWDSTATS, bool BIG>
 __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const TcArgs args) {
     using Cfg = TcCfg<BN, SPLIT, BIG>;
@@ -76,7 +109,10 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
     const int n0 = blockIdx.y * BN;
     const int taps = a.ksize * a.ksize;
     const int KC = a.Cin / BK;
-    const int T = taps * KC;
+    // split-K: this CTA runs stages [it0, it0 + T) of the taps * KC stages (host guarantees divisibility)
+    const int SK = (int)cluster_nctaid_z(), sk_rank = (int)cluster_ctaid_z();
+    const int T = taps * KC / SK;
+    const int it0 = sk_rank * T;
     const int HW = a.H * a.W;
     // full_a: 256 producer arrivals; full_b: weight bulk copy (expect_tx); empty: tcgen05.commit
     const uint32_t bar_fa = smem_u32(&bars[0]), bar_fb = smem_u32(&bars[4]), bar_em = smem_u32(&bars[8]);
@@ -105,8 +141,8 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         // ===== producers (activation transform + weight bulk copies) =====
         // packed weights: [n-tile][tap][k] blocks in UMMA canonical layout; one stage = BN*BK contiguous floats
         const size_t wblk = (size_t)BN * BK;
-        const float* wsrc_hi = args.w_hi + (size_t)blockIdx.y * T * wblk;
-        const float* wsrc_lo = SPLIT ? args.w_lo + (size_t)blockIdx.y * T * wblk : nullptr;
+        const float* wsrc_hi = args.w_hi + ((size_t)blockIdx.y * T * SK + it0) * wblk;
+        const float* wsrc_lo = SPLIT ? args.w_lo + ((size_t)blockIdx.y * T * SK + it0) * wblk : nullptr;
         // thread -> NJ pixels x one 4-channel quad of the stage; a warp covers 8 pixels x 4 quads so that global
         // loads are full 32-byte sectors and shared stores are conflict-free 128-byte runs
         const int p_low = lane & 7, q_low = lane >> 3;
@@ -146,8 +182,9 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         float4 a_reg[2][NJ];
         unsigned a_msk[2];
         // running (tap, k-chunk) counters of the load stream (two stages ahead) and of the store stream
-        int l_tap = 0, l_kc = 0, l_toff = (a.ksize == 3) ? -(a.W + 1) * a.Cin : 0;
-        int s_kc = 0;
+        int l_tap = it0 / KC, l_kc = it0 % KC;
+        int l_toff = (a.ksize == 3) ? ((l_tap / 3 - 1) * a.W + (l_tap % 3 - 1)) * a.Cin : 0;
+        int s_kc = it0 % KC;
         auto load_a = [&](int set) {
             const int coff = l_toff + l_kc * BK;
             unsigned m = 0;
@@ -271,6 +308,11 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
     const int cg = (epi ? tid : 0) % CG, r0 = (epi ? tid : 0) / CG;
     const bool do_stats = a.stat_sum != nullptr;
     const bool has_res = a.res.z != nullptr, res_aff = a.res.scale != nullptr;
+    // split-K: this CTA finishes rows [row_base, row_base + TBM / SK) of the tile (rows_t per thread), summed over the SK
+    // partial tiles of the cluster
+    const int rows_t = ROWS / SK;
+    const int row_base = sk_rank * (TBM / SK);
+    const uint32_t stg_s = sbase;            // shared::cta address of the staging tile (same offset in every CTA of the cluster)
 #pragma unroll 1
     for (int ch = 0; ch < BN / CH; ++ch) {
         if (warp < 8) {
@@ -302,6 +344,7 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        if (SK > 1) cluster_sync_all();          // every partial tile of the cluster is staged
         if (ch == BN / CH - 1) {
             if (tid == 0) HGK_STAMP(6);
             if (warp == 0)
@@ -320,15 +363,15 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
         // rows are processed 4 at a time with all global loads (residual / previous output / BN input) issued
         // first, so their latency is paid once per batch instead of once per row
 #pragma unroll 1
-        for (int g = 0; epi && g < ROWS; g += 4) {
+        for (int g = 0; epi && g < rows_t; g += 4) {
             float4 rr[4], oo[4], zz[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const long long p = m0 + r0 + (g + i) * RL;
+                const long long p = m0 + row_base + r0 + (g + i) * RL;
                 rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 oo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 zz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p < a.P) {
+                if (g + i < rows_t && p < a.P) {
                     if (has_res) rr[i] = ldg4(a.res.z + p * a.Cout + n);
                     if (a.accumulate) oo[i] = ld4(a.y + p * a.Cout + n);
                     if (bwd_stats) zz[i] = ldg4(a.bz + p * a.Cout + n);
@@ -336,10 +379,20 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = r0 + (g + i) * RL;
+                const int r = row_base + r0 + (g + i) * RL;
                 const long long p = m0 + r;
-                if (p >= a.P) break;
-                float4 v = ld4(stg + r * SROW + cg * 4);
+                if (g + i >= rows_t || p >= a.P) break;
+                float4 v;
+                if (SK == 1) {
+                    v = ld4(stg + r * SROW + cg * 4);
+                } else {                         // fixed-order sum of the cluster's partial tiles
+                    const uint32_t off = stg_s + (uint32_t)(r * SROW + cg * 4) * 4u;
+                    v = ld_dsmem4(dsmem_addr(off, 0));
+                    for (int c = 1; c < SK; ++c) {
+                        const float4 q = ld_dsmem4(dsmem_addr(off, (uint32_t)c));
+                        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    }
+                }
                 v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                 if (has_res) {
                     float4 q = rr[i];
@@ -392,16 +445,19 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
                 atomicAdd(a.stat_sq + n0 + ch * CH + tid, x2);
             }
         }
-        if (ch + 1 < BN / CH) __syncthreads();       // staging tile is rewritten by the next chunk
+        // the staging tile is rewritten by the next chunk -- and, with split-K, read by the other CTAs of the cluster, which
+        // must be done with it before it is rewritten or this CTA exits
+        if (SK > 1) cluster_sync_all();
+        else if (ch + 1 < BN / CH) __syncthreads();
     }
     if (tid == 0) HGK_STAMP(7);
     // fused BatchNorm finaliser: the CTA that arrives last turns the complete sums into per-channel vectors
     if (do_stats) {
         if (!BWDSTATS && a.ffin.ticket != nullptr) {
-            if (last_cta_arrives(a.ffin.ticket, gridDim.x * gridDim.y))
+            if (last_cta_arrives(a.ffin.ticket, gridDim.x * gridDim.y * gridDim.z))
                 bn_fwd_finalize_cta(a.ffin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
         } else if (BWDSTATS && a.bfin.ticket != nullptr) {
-            if (last_cta_arrives(a.bfin.ticket, gridDim.x * gridDim.y))
+            if (last_cta_arrives(a.bfin.ticket, gridDim.x * gridDim.y * gridDim.z))
                 bn_bwd_finalize_cta(a.bfin, a.stat_sum, a.stat_sq, (double)a.P, a.Cout);
         }
     }
@@ -985,7 +1041,7 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
 }
 
 template <int BN, bool SPLIT, bool BWDSTATS, bool BIG>
-static int launch_tc_cfg(const TcArgs& ta, cudaStream_t st) {
+static int launch_tc_cfg(const TcArgs& ta, cudaStream_t st, int sk = 1) {
     static bool configured = false;
     constexpr int smem = TcCfg<BN, SPLIT, BIG>::SMEM;
     if (!configured) {
@@ -997,9 +1053,49 @@ static int launch_tc_cfg(const TcArgs& ta, cudaStream_t st) {
         configured = true;
     }
     long long mt = (ta.c.P + TBM - 1) / TBM;
-    dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN));
-    conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG><<<grid, TNT + 32, smem, st>>>(ta);
+    dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN), (unsigned)sk);
+    if (sk <= 1) {
+        conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG><<<grid, TNT + 32, smem, st>>>(ta);
+        return HGK_OK;
+    }
+    // split-K: the sk CTAs along grid.z form one thread-block cluster (partial tiles are summed through distributed shared memory)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TNT + 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)sk;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG>, ta);
+    if (e != cudaSuccess) {
+        set_error("hgk_conv_tc_nhwc: cluster launch (split-K %d): %s", sk, cudaGetErrorString(e));
+        return HGK_ECUDA;
+    }
     return HGK_OK;
+}
+
+// Split-K factor for a small layer (0 = not a split-K shape): the largest cluster size in {8, 4, 2} that divides the stage
+// count of the one-CTA-per-SM configuration (32-channel stages) and keeps the whole grid in one wave.  HGK_SPLITK=0 disables
+// it, HGK_SPLITK_MT sets the largest layer (in 128-pixel tiles) that takes this path (default 12: the 8x8 and 4x4 rungs at batch 24;
+// measured 10.66 ms/step against 10.73 with 24, 10.80 with 48 and 11.26 without split-K, gpurun_out/r4c_ab.txt).
+static int splitk_factor(long long P, int Cin, int Cout, int ksize) {
+    static int on = -1, max_mt = 12;
+    if (on < 0) {
+        const char* e = getenv("HGK_SPLITK");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        const char* m = getenv("HGK_SPLITK_MT");
+        if (m != nullptr) max_mt = atoi(m);
+    }
+    if (!on || (Cout != 128 && Cout != 256) || Cin % 32) return 0;
+    const long long mt = (P + TBM - 1) / TBM;
+    if (mt > max_mt) return 0;
+    const int stages = ksize * ksize * (Cin / 32);
+    for (int sk = 8; sk >= 2; sk >>= 1)
+        if (stages % sk == 0 && mt * sk <= kNumSMs) return sk;
+    return 0;
 }
 
 template <int BN, bool SPLIT, bool BWDSTATS = false>
@@ -1011,7 +1107,10 @@ static int launch_tc(const TcArgs& ta, cudaStream_t st) {
         const char* e = getenv("HGK_TC_BIG_OFF");
         big_off = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
-    if (ctas <= kNumSMs && !big_off) return launch_tc_cfg<BN, SPLIT, BWDSTATS, true>(ta, st);
+    if (ctas <= kNumSMs && !big_off) {
+        const int sk = (BN == ta.c.Cout) ? splitk_factor(ta.c.P, ta.c.Cin, ta.c.Cout, ta.c.ksize) : 0;
+        return launch_tc_cfg<BN, SPLIT, BWDSTATS, true>(ta, st, sk > 1 ? sk : 1);
+    }
     return launch_tc_cfg<BN, SPLIT, BWDSTATS, false>(ta, st);
 }
 
@@ -1096,8 +1195,9 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     const bool split = w_lo != nullptr;
     if (bz != nullptr)
         HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
-    if (use_tc3(ksize, split) && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
-    else if (use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
+    const bool small = ap == nullptr && splitk_factor(ta.c.P, Cin, Cout, ksize) > 1;      // cluster split-K (conv_tc_kernel)
+    if (!small && use_tc3(ksize, split) && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
+    else if (!small && use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
     else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)
                         : (Cout == 128 ? launch_tc<128, false, true>(ta, st) : launch_tc<256, false, true>(ta, st));
@@ -1167,6 +1267,9 @@ extern "C" int hgk_conv_tc_bnapply_supported(int N, int H, int W, int Cin, int C
     TcArgs ta{};
     ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
     ta.c.P = (long long)N * H * W;
+    // small layers take the cluster split-K kernel, which has no apply-on-load: their BatchNorm-backward apply is a launch of
+    // its own (a few microseconds at that size)
+    if (splitk_factor(ta.c.P, Cin, Cout, ksize) > 1) return 0;
     if (use_tc3(ksize, false) && conv_tc3_eligible(ta)) return 1;
     return (use_tile_kernel() && conv_tc2_eligible(ta)) ? 1 : 0;
 }

@@ -571,13 +571,17 @@ def test_bn_bwd_fused_finalizers(shape):
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (1, 64, 64, 128, 128, 3), (2, 32, 48, 64, 128, 1),
                                    (1, 16, 32, 256, 256, 1), (1, 128, 128, 64, 64, 3), (10, 64, 64, 128, 128, 3),
-                                   (10, 64, 64, 256, 128, 1)])
+                                   (10, 64, 64, 256, 128, 1), (8, 16, 16, 128, 128, 3), (4, 16, 32, 256, 256, 1)])
 @pytest.mark.parametrize("with_red", [0, 1])
 def test_conv_tc_dgrad_bnapply(shape, with_red):
     """BatchNorm-backward apply evaluated on load by the image-tile data-gradient kernel == bn_bwd_apply followed by the
     plain data-gradient kernel; the dz side output equals bn_bwd_apply's result exactly."""
     N, H, W, Ci, Co, k = shape           # conv Ci -> Co; g, gz live on the Co side
-    assert lib().conv_tc_bnapply_supported(N, H, W, Co, Ci, k)
+    # "supported" is the planner's answer: layers of at most 12 tiles of 128 pixels take the cluster split-K kernel (no apply on
+    # load) for their plain data gradient.  The fused kernel still accepts them; the reference chain below then runs a
+    # different kernel (other summation order), so the data gradient is compared to rounding instead of bit for bit.
+    same_kernel = lib().conv_tc_bnapply_supported(N, H, W, Co, Ci, k)
+    assert same_kernel or N * H * W <= 12 * 128
     w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
     g, gz = nhwc(rnd("g", (N, Co, H, W))), nhwc(rnd("gz", (N, Co, H, W)))
     v = {n: dev32(rnd(n, (Co,), lo, hi)) for n, lo, hi in (("sc", 0.5, 1.5), ("sh", -0.3, 0.3), ("mu", -0.2, 0.2),
@@ -614,7 +618,10 @@ def test_conv_tc_dgrad_bnapply(shape, with_red):
          ptr(v["cC"]), ptr(dz), N, H, W, Co, ptr(hi), k, Ci, ptr(extra), ptr(gx), 0, *red)
     torch.cuda.synchronize()
     assert torch.equal(dz, dz_ref)               # same fp32 expression, every pixel written exactly once
-    assert torch.equal(gx, gx_ref)               # same operand values -> bit-identical accumulation
+    if same_kernel:
+        assert torch.equal(gx, gx_ref)           # same operand values -> bit-identical accumulation
+    else:
+        assert relerr(gx, gx_ref) < 1e-5
     if with_red:
         assert int(ticket.item()) == 0
         for key in ("dgamma", "dbeta", "cA", "cB", "cC"):

@@ -323,9 +323,13 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
         for (k, pa), (_, pb) in zip(a.state_dict().items(), net.state_dict().items()):
             if pa.is_floating_point():
                 d = (pa - pb).abs()
-                # running statistics are not O(1) quantities (a variance of 5 moves by 0.04 when the activations move by 0.4 %):
-                # the bound scales with the tensor's magnitude
-                assert float(d.max()) < 2e-2 * max(1.0, float(pa.abs().max())), k
+                # parameters travel at most ~3 * lr * 10 = 7.5e-3 in three RMSprop steps whatever the gradient is, which bounds
+                # their difference; BatchNorm running statistics are batch statistics of a diverging (chaotic) pair of nets --
+                # 64 samples per channel at the 4x4 rung of this 4-image batch -- and only have to stay in the same ballpark
+                if "running_" in k:
+                    assert float(d.max()) < 1e-1 * max(1.0, float(pa.abs().max())), k
+                else:
+                    assert float(d.max()) < 2e-2, k
                 if k.startswith("out_conv.1") and k.endswith("weight"):
                     # (1e-4 = 4 % of one RMSprop step: observed differences are 3e-6 .. 1e-5 depending on the
                     # atomics order of the run, so a 1e-5 gate was flaky)
