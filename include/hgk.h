@@ -34,6 +34,11 @@ const char* hgk_last_error(void);
 int hgk_version(void);
 /* 1 if the library was compiled for sm_100a and the current device is compute capability 10.x */
 int hgk_device_ok(void);
+/* Programmatic dependent launch: the NEXT launch of this thread may start its prologue under the tail of the kernel in front
+ * of it in its stream (cudaLaunchAttributeProgrammaticStreamSerialization; every libhgk kernel on the chain waits with
+ * griddepcontrol.wait before its first global access).  Only legal when that predecessor is a kernel launch: the caller arms
+ * it per launch; unarmed launches keep plain stream order. */
+int hgk_pdl_arm(int on);
 
 /* ---- convolution (nn.Conv2d 1x1 / 3x3 p1, models/asn_stacked_hg.py:17,20,23,242-248,279) ----
  * y = [accumulate ? y : 0] + conv(T(x), w) + bias + T_res(res)
@@ -147,6 +152,13 @@ int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const float* w, co
                        float* y, double* stat_sum, double* stat_sq, void* stream);
 int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const float* dz, int Cout,
                          float* dw, float* dbias, void* stream);
+/* The same with bn1's BatchNorm-backward apply evaluated on load: g = dL/d relu(bn1(z)), z = the stem's pre-BN output;
+ * dz = cA*((g*[z*scale+shift > 0] - cC) - (z - mean)*cB) is formed in shared memory (the expression of hgk_bn_bwd_apply) and
+ * never written to global memory. */
+int hgk_stem_conv7_wgrad_bnapply(const float* img, int N, int H, int W, const float* g, const float* z,
+                                 const float* scale, const float* shift, int relu, const float* mean,
+                                 const float* cA, const float* cB, const float* cC, int Cout,
+                                 float* dw, float* dbias, void* stream);
 
 /* ---- nn.BatchNorm2d (eps 1e-5, momentum 0.1), models/asn_stacked_hg.py:19,22,25,224,243 ----
  * train: (sum, sumsq, count) -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "hgk_unpack_add_grads": [P, P, P, I, P],
     "hgk_stem_conv7_fwd": [P, I, I, I, P, P, I, P, P, P, P],
     "hgk_stem_conv7_wgrad": [P, I, I, I, P, I, P, P, P],
+    "hgk_stem_conv7_wgrad_bnapply": [P, I, I, I, P, P, P, P, I, P, P, P, P, I, P, P, P],
     "hgk_bn_finalize": [P, P, L, P, P, F, F, P, P, P, P, P, P, I, P],
     "hgk_bn_eval_prepare": [P, P, P, P, F, P, P, P, P, I, P],
     "hgk_bn_bwd_reduce": [P, P, P, P, I, P, P, L, I, P, P, P],
@@ -82,6 +83,9 @@ class _Lib(object):
         self.cdll.hgk_last_error.argtypes = []
         self.cdll.hgk_version.restype = I
         self.cdll.hgk_device_ok.restype = I
+        self.cdll.hgk_pdl_arm.restype = I
+        self.cdll.hgk_pdl_arm.argtypes = [I]
+        self.pdl_arm = self.cdll.hgk_pdl_arm
         self.cdll.hgk_conv_tc_supported.restype = I
         self.cdll.hgk_conv_tc_supported.argtypes = [I, I, I]
         self.cdll.hgk_conv_tc_bnapply_supported.restype = I

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const float* __re
                                                             const float* __restrict__ invstd, long long P, int C,
                                                             double* sum_g, double* sum_gx, int cq_per_blk, int rows_par,
                                                             long long rows_per_blk, BnBwdFin fin) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     extern __shared__ double red[];      // [rows_par][cq_per_blk*4][2]
     const int tid = threadIdx.x;
     const int cq = tid % cq_per_blk, row = tid / cq_per_blk;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            int relu, const float* __restrict__ mean,
                                                            const float* __restrict__ cA, const float* __restrict__ cB,
                                                            const float* __restrict__ cC, long long total4, int C4) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     auto one = [&](long long i, float4 d, float4 v, float4 s, float4 t, float4 a, float4 b, float4 cc, float4 mu) {
@@ -245,7 +247,7 @@ static int bn_bwd_reduce_impl(const float* dy, const float* z, const float* scal
     long long nblk = (P + rows_per_blk - 1) / rows_per_blk;
     dim3 grid((unsigned)nblk, (unsigned)ngrp);
     size_t smem = (size_t)rows_par * cq_per_blk * 4 * 2 * sizeof(double);
-    bn_bwd_reduce_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, mean, invstd, P, C, sum_g,
+    launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), smem, (cudaStream_t)stream, dy, z, scale, shift, relu, mean, invstd, P, C, sum_g,
                                                                     sum_gx, cq_per_blk, rows_par, rows_per_blk, fin);
     HGK_CHECK_LAUNCH("hgk_bn_bwd_reduce");
     return HGK_OK;
@@ -285,7 +287,7 @@ extern "C" int hgk_bn_bwd_apply(float* dy, const float* z, const float* scale, c
     long long total4 = P * (C / 4);
     long long blocks = (total4 + 255) / 256;
     if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
-    bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, relu, mean, cA, cB, cC, total4, C / 4);
+    launch_pdl(bn_bwd_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dy, z, scale, shift, relu, mean, cA, cB, cC, total4, C / 4);
     HGK_CHECK_LAUNCH("hgk_bn_bwd_apply");
     return HGK_OK;
 }

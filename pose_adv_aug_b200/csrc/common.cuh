@@ -85,4 +85,34 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// The train step is a chain of ~190 dependent kernels per direction, most of them short: with plain stream order kernel
+// N+1's grid is launched only after kernel N has drained, so every boundary pays launch latency + the new kernel's prologue
+// (barrier init, TMEM allocation, tensor-map prefetch, index set-up).  Kernels launched through launch_pdl() carry
+// cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident as soon as every CTA of the
+// predecessor has executed pdl_launch_dependents() (SM resources permitting) and run their prologue under the predecessor's
+// tail; pdl_wait() (griddepcontrol.wait) then blocks until the predecessor grid has COMPLETED and its writes are visible.
+// Rule for every kernel launched this way: no global-memory access of any kind before pdl_wait().
+// Under stream capture the same-stream edge becomes a programmatic graph edge; cross-stream (event) edges stay full edges.
+// HGK_PDL=0 launches everything with plain stream order (A/B comparisons).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace hgk

@@ -26,6 +26,7 @@ __device__ __forceinline__ void pair_sync(int wp) {
 constexpr int N16_PX = 4;
 template <int CQ>
 __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     __shared__ float part[4][N16_PX][16];           // [warp][pixel of the step][output]: partial sums when CQ > 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cq = warp % CQ;                       // which 128-channel slice of the pixel this warp owns
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(128, 4) conv_n16_kernel(const ConvArgs a) {
 // bytes per operand and warp in flight: with one pixel per step the launch ran at a fifth of the HBM rate).
 template <int NPX, bool RES, bool ACC>
 __global__ void __launch_bounds__(256, 2) conv_k16_kernel(const ConvArgs a) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nq = a.Cout >> 7;                      // 128-channel slices per pixel
     const int slice = warp % nq;                     // host guarantees 8 % nq == 0
@@ -197,17 +199,17 @@ int conv_skinny_try(const ConvArgs& a, cudaStream_t st) {
     if (off || a.ksize != 1 || a.stat_sum != nullptr) return 0;
     if (a.Cout == 16 && (a.Cin == 128 || a.Cin == 256)) {
         const int grid = kNumSMs * 8;
-        if (a.Cin == 128) conv_n16_kernel<1><<<grid, 128, 0, st>>>(a);
-        else conv_n16_kernel<2><<<grid, 128, 0, st>>>(a);
+        if (a.Cin == 128) launch_pdl(conv_n16_kernel<1>, dim3(grid), dim3(128), 0, st, a);
+        else launch_pdl(conv_n16_kernel<2>, dim3(grid), dim3(128), 0, st, a);
         return 1;
     }
     if (a.Cin == 16 && (a.Cout == 128 || a.Cout == 256)) {
         const bool res = a.res.z != nullptr, acc = a.accumulate != 0;
         const int grid = kNumSMs * 4;
-        if (res && acc) conv_k16_kernel<4, true, true><<<grid, 256, 0, st>>>(a);
-        else if (res) conv_k16_kernel<8, true, false><<<grid, 256, 0, st>>>(a);
-        else if (acc) conv_k16_kernel<8, false, true><<<grid, 256, 0, st>>>(a);
-        else conv_k16_kernel<8, false, false><<<grid, 256, 0, st>>>(a);
+        if (res && acc) launch_pdl(conv_k16_kernel<4, true, true>, dim3(grid), dim3(256), 0, st, a);
+        else if (res) launch_pdl(conv_k16_kernel<8, true, false>, dim3(grid), dim3(256), 0, st, a);
+        else if (acc) launch_pdl(conv_k16_kernel<8, false, true>, dim3(grid), dim3(256), 0, st, a);
+        else launch_pdl(conv_k16_kernel<8, false, false>, dim3(grid), dim3(256), 0, st, a);
         return 1;
     }
     return 0;

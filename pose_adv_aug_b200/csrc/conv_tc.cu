@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
     if (tid == 0) HGK_STAMP(1);
+    // programmatic dependent launch (common.cuh): no global access above this point
+    pdl_wait();
 
     if (warp < 8) {
         // ===== producers (activation transform + weight bulk copies) =====
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(TNT + 32, BIG ? 1 : 2) conv_tc_kernel(const Tc
     __syncwarp();      // the single-lane role reconverges before the CTA-wide barrier
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();       // every producer has observed the last commit: accumulator complete, smem reusable
+    pdl_launch_dependents();   // main loop done: the next kernel of the chain may start its prologue under this epilogue
 
     // ---- epilogue, in column chunks of CH: TMEM -> registers -> staging tile -> coalesced
     //      bias / residual / accumulate / store + BN statistics ----
@@ -1054,24 +1057,23 @@ static int launch_tc_cfg(const TcArgs& ta, cudaStream_t st, int sk = 1) {
     }
     long long mt = (ta.c.P + TBM - 1) / TBM;
     dim3 grid((unsigned)mt, (unsigned)(ta.c.Cout / BN), (unsigned)sk);
-    if (sk <= 1) {
-        conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG><<<grid, TNT + 32, smem, st>>>(ta);
-        return HGK_OK;
-    }
-    // split-K: the sk CTAs along grid.z form one thread-block cluster (partial tiles are summed through distributed shared memory)
+    // the sk CTAs along grid.z form one thread-block cluster (split-K: partial tiles are summed through distributed shared
+    // memory); programmatic dependent launch as everywhere on the chain (common.cuh)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(TNT + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)sk;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = (unsigned)(sk > 1 ? sk : 1);
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = sk > 1 ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, BWDSTATS, BIG>, ta);
     if (e != cudaSuccess) {
-        set_error("hgk_conv_tc_nhwc: cluster launch (split-K %d): %s", sk, cudaGetErrorString(e));
+        set_error("hgk_conv_tc_nhwc: launch (split-K %d): %s", sk, cudaGetErrorString(e));
         return HGK_ECUDA;
     }
     return HGK_OK;

@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     } while (0)
     static_assert(T2_THREADS == 320, "T2_RENDEZVOUS counts 320 threads");
     uint32_t tmem = 0;
+    // programmatic dependent launch (common.cuh): barrier initialisation and the TMEM allocation above overlap the previous
+    // kernel's tail; no global access before this point
+    pdl_wait();
 
     if (warp < 8) {
         // ===== producers: halo tile of one 16-channel chunk -> registers -> BN+ReLU, hi/lo -> shared memory =====
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         }
         if (tid == 0) HGK_STAMP(4);
         mbar_wait(bar_done, 0);              // every MMA retired: accumulators complete, shared memory reusable
+        pdl_launch_dependents();             // main loop done: the next kernel of the chain may start its prologue
         if (tid == 0) HGK_STAMP(5);
     } else if (warp == 8) {
         // ===== MMA issuer =====
@@ -519,7 +523,11 @@ static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
         configured = true;
     }
     const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W / (8 * NSUB)));
-    conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB><<<grid, T2_THREADS, smem, st>>>(ta);
+    cudaError_t le = launch_pdl(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB>, dim3(grid), dim3(T2_THREADS), (size_t)smem, st, ta);
+    if (le != cudaSuccess) {
+        set_error("hgk_conv_tc_nhwc (image-tile kernel): launch: %s", cudaGetErrorString(le));
+        return HGK_ECUDA;
+    }
     return HGK_OK;
 }
 

@@ -184,6 +184,9 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
         if (BNAPPLY) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_z)) : "memory");
     }
+    // programmatic dependent launch: everything above ran under the previous kernel's tail; nothing below may start before
+    // that kernel has completed (first global reads: the per-channel vectors)
+    pdl_wait();
     // per-input-channel vectors of the on-load transform, staged once (with 227 KB of shared memory the L1 has no room
     // for them: read through __ldg they cost an L2 round trip per 16-channel chunk on the transform's critical path)
     float* svec = reinterpret_cast<float*>(sgen + Cfg::PIPE);               // [NVEC][256]
@@ -665,6 +668,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    pdl_launch_dependents();      // every tile of this CTA is stored: the next kernel of the chain may start its prologue
     if (warp == T3_WAUX)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
     // ---- the CTA that arrives last turns the complete sums into the per-channel BatchNorm vectors ----
@@ -747,7 +751,11 @@ static int launch_tc3(TcArgs ta, cudaStream_t st) {
     const long long tiles = (long long)ta.c.N * ((ta.c.H + Cfg::TH - 1) / Cfg::TH) * (ta.c.W / Cfg::TW);
     const long long rounds = (tiles + kNumSMs - 1) / kNumSMs;
     const unsigned grid = (unsigned)((tiles + rounds - 1) / rounds);
-    conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY><<<grid, T3_THREADS, smem, st>>>(ta, mx, mz);
+    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY>, dim3(grid), dim3(T3_THREADS), (size_t)smem, st, ta, mx, mz);
+    if (le != cudaSuccess) {
+        set_error("hgk_conv_tc_nhwc (persistent tile kernel): launch: %s", cudaGetErrorString(le));
+        return HGK_ECUDA;
+    }
     return HGK_OK;
 }
 

@@ -1,5 +1,6 @@
 // Per-joint heat-map MSE (inline loss of reference stack-hg.py:156-159), the pylib/Criterion.py
 // helpers, the flat multi-tensor RMSprop (stack-hg.py:51-52,165) and the library's error state.
+#include <stdlib.h>
 #include "common.cuh"
 #include <string.h>
 
@@ -31,6 +32,7 @@ __device__ __forceinline__ void block_add_double(double v, double* dst) {
 __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const float* __restrict__ out, const float* __restrict__ target,
                                                           long long n, float inv_numel, float gscale, float* dout,
                                                           int accumulate, double* loss) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     float part = 0.f;
     double acc = 0.0;
     const float gs = 2.f * inv_numel * gscale;
@@ -149,6 +151,29 @@ static inline unsigned lo_blocks(long long items) {
 using namespace hgk;
 
 extern "C" const char* hgk_last_error(void) { return g_err; }
+namespace hgk {
+// A launch may carry the programmatic-serialization attribute only when the operation in front of it IN ITS STREAM is a kernel
+// launch (under stream capture a programmatic edge out of a memset / event node invalidates the capture).  The host knows
+// that, the library does not: the caller arms the flag (hgk_pdl_arm) for the launches that directly follow another libhgk
+// launch on the same stream; it is consumed by the next launch.  HGK_PDL=0 switches the mechanism off altogether.
+static thread_local int g_pdl_armed = 0;
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HGK_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const bool on = v == 1 && g_pdl_armed != 0;
+    g_pdl_armed = 0;
+    return on;
+}
+}  // namespace hgk
+
+extern "C" int hgk_pdl_arm(int on) {
+    hgk::g_pdl_armed = on;
+    return HGK_OK;
+}
+
 extern "C" int hgk_version(void) { return 100; }
 
 extern "C" int hgk_device_ok(void) {
@@ -164,7 +189,7 @@ extern "C" int hgk_mse_fwd_bwd(const float* out, const float* target, long long 
     HGK_REQUIRE(out && target && loss && n > 0, "hgk_mse_fwd_bwd: bad arguments");
     HGK_REQUIRE(((uintptr_t)out % 16 == 0) && ((uintptr_t)target % 16 == 0) && ((uintptr_t)dout % 16 == 0),
                 "hgk_mse_fwd_bwd: pointers must be 16-byte aligned");
-    mse_fwd_bwd_kernel<<<lo_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(out, target, n, inv_numel, gscale, dout, accumulate, loss);
+    launch_pdl(mse_fwd_bwd_kernel, dim3(lo_blocks(n / 4)), dim3(256), 0, (cudaStream_t)stream, out, target, n, inv_numel, gscale, dout, accumulate, loss);
     HGK_CHECK_LAUNCH("hgk_mse_fwd_bwd");
     return HGK_OK;
 }

@@ -15,6 +15,7 @@ static inline unsigned stream_blocks(long long work_items) {
 }
 
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(Act x, int N, int H, int W, int C4, float* __restrict__ y) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)N * OH * OW * C4;
     const int C = C4 * 4;
@@ -54,6 +55,7 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
 
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, int W, int C4,
                                                            const float* __restrict__ dy, float* __restrict__ dx, int accumulate) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)N * OH * OW * C4;
     const int C = C4 * 4;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
 }
 
 __global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, int N, int H, int W, int C4, float* __restrict__ y) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const long long total = (long long)N * H * W * C4;
     const int C = C4 * 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, in
 
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C4,
                                                             float* __restrict__ da, int accumulate) {
+    pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)N * OH * OW * C4;
     const int C = C4 * 4;
@@ -281,7 +285,7 @@ extern "C" int hgk_maxpool2_fwd(const float* x, const float* x_scale, const floa
     HGK_NHWC_CHECK("hgk_maxpool2_fwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_fwd: H and W must be even (H=%d W=%d)", H, W);
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    maxpool2_fwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
+    launch_pdl(maxpool2_fwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
     HGK_CHECK_LAUNCH("hgk_maxpool2_fwd");
     return HGK_OK;
 }
@@ -292,7 +296,7 @@ extern "C" int hgk_maxpool2_bwd(const float* x, const float* x_scale, const floa
     HGK_NHWC_CHECK("hgk_maxpool2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_bwd: H and W must be even (H=%d W=%d)", H, W);
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    maxpool2_bwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
+    launch_pdl(maxpool2_bwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
                                                                                 dy, dx, accumulate);
     HGK_CHECK_LAUNCH("hgk_maxpool2_bwd");
     return HGK_OK;
@@ -305,7 +309,7 @@ extern "C" int hgk_add_fwd(const float* a, const float* a_scale, const float* a_
     HGK_NHWC_CHECK("hgk_add_fwd");
     HGK_REQUIRE(!a_up || (H % 2 == 0 && W % 2 == 0), "hgk_add_fwd: up-sampled output must have even H, W");
     long long total = (long long)N * H * W * (C / 4);
-    add_fwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(Act{a, a_scale, a_shift, a_relu}, a_up,
+    launch_pdl(add_fwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{a, a_scale, a_shift, a_relu}, a_up,
                                                                            Act{b, b_scale, b_shift, b_relu}, N, H, W, C / 4, y);
     HGK_CHECK_LAUNCH("hgk_add_fwd");
     return HGK_OK;
@@ -316,7 +320,7 @@ extern "C" int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, fl
     HGK_NHWC_CHECK("hgk_upsample2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_upsample2_bwd: H and W must be even");
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    upsample2_bwd_kernel<<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, N, H, W, C / 4, da, accumulate);
+    launch_pdl(upsample2_bwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
     HGK_CHECK_LAUNCH("hgk_upsample2_bwd");
     return HGK_OK;
 }

@@ -300,6 +300,168 @@ __global__ void __launch_bounds__(ST_WG2_THREADS, 2) stem_conv7_wgrad2_kernel(co
     if (dbias != nullptr && tid < ST_CO) atomicAdd(dbias + tid, bsum);
 }
 
+// Third-generation weight gradient: the stem is the LAST layer of the backward pass, so this kernel (and the BatchNorm-backward
+// apply in front of it) ran alone on the GPU for 0.36 ms.  Two changes:
+//   * the BatchNorm-backward apply is evaluated here: the kernel reads g = dL/d relu(bn1(z)) and z, forms
+//     dz = cA*((g*[z*scale+shift > 0] - cC) - (z - mean)*cB) in shared memory (bn_bwd_apply_kernel's expression) -- the
+//     stand-alone pass over the 100 MB tensor (read g, read z, write dz) and the re-read of dz disappear;
+//   * tiles of 4 x 16 output pixels, double-buffered with cp.async (the next tile's g, z and image patch stream in while
+//     the current one is in the FFMA loop; the old kernel alternated a load phase and a compute phase per CTA).
+// Thread -> 4 couts x the 7 kw taps of one (channel, kh) patch row, as in the second generation.
+constexpr int ST3_TH = 4, ST3_TW = 16;
+constexpr int ST3_PH = 2 * ST3_TH + 5;                     // 13 input rows
+constexpr int ST3_PX = ST3_TH * ST3_TW;                    // 64 output pixels per tile
+constexpr int ST3_THREADS = 352;                           // 21 x 16 workers + 16 idle lanes
+constexpr int ST3_BUF_FLOATS = 2 * ST3_PX * ST_CO + 3 * ST3_PH * ST_PWP;       // g | z | patch
+constexpr int ST3_SMEM = 2 * ST3_BUF_FLOATS * 4 + 6 * ST_CO * 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;                         // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                                         const float* __restrict__ g, const float* __restrict__ z,
+                                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                         int relu, const float* __restrict__ mean,
+                                                                         const float* __restrict__ cA, const float* __restrict__ cB,
+                                                                         const float* __restrict__ cC, float* dw, float* dbias,
+                                                                         int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) float st3_smem[];
+    float* vecs = st3_smem + 2 * ST3_BUF_FLOATS;           // scale | shift | mean | cA | cB | cC, 64 each
+    const int tid = threadIdx.x;
+    const int OH = H / 2, OW = W / 2;
+    const int tx = tid & 15, ty = tid >> 4;
+    const bool worker = ty < 21;
+    const int c = worker ? ty / 7 : 0, kh = worker ? ty - (ty / 7) * 7 : 0;
+    if (tid < ST_CO) {
+        vecs[tid] = __ldg(scale + tid); vecs[64 + tid] = __ldg(shift + tid); vecs[128 + tid] = __ldg(mean + tid);
+        vecs[192 + tid] = __ldg(cA + tid); vecs[256 + tid] = __ldg(cB + tid); vecs[320 + tid] = __ldg(cC + tid);
+    }
+    float acc[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);          // bias gradient of channel quad (tid & 15), this thread's share
+    const int total = tiles_x * tiles_y * N;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(st3_smem);
+
+    auto issue = [&](int t, int b) {                        // asynchronous copies of tile t into buffer b
+        const int n = t / (tiles_x * tiles_y);
+        const int r = t - n * (tiles_x * tiles_y);
+        const int tyi = r / tiles_x, txi = r - tyi * tiles_x;
+        const int oy0 = tyi * ST3_TH, ox0 = txi * ST3_TW;
+        const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+        const uint32_t gb = sbase + (uint32_t)(b * ST3_BUF_FLOATS) * 4u;
+        for (int i = tid; i < ST3_PX * (ST_CO / 4); i += ST3_THREADS) {
+            const int q = i >> 4, cv = i & 15;
+            const int gy = oy0 + q / ST3_TW, gx = ox0 + (q % ST3_TW);
+            const bool ok = gy < OH && gx < OW;
+            const size_t off = ok ? ((((size_t)n * OH + gy) * OW + gx) * ST_CO + cv * 4) : 0;
+            cp_async16(gb + (uint32_t)(q * ST_CO + cv * 4) * 4u, g + off, ok);
+            cp_async16(gb + (uint32_t)(ST3_PX * ST_CO + q * ST_CO + cv * 4) * 4u, z + off, ok);
+        }
+        const uint32_t pb = gb + (uint32_t)(2 * ST3_PX * ST_CO) * 4u;
+        for (int i = tid; i < 3 * ST3_PH * ST_PWP; i += ST3_THREADS) {
+            const int cc = i / (ST3_PH * ST_PWP);
+            const int rr = i - cc * (ST3_PH * ST_PWP);
+            const int py = rr / ST_PWP, px = rr - py * ST_PWP;
+            const int iy = iy0 + py, ix = ix0 + px;
+            const bool ok = px < ST_PW && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            const size_t off = ok ? (((size_t)(n * 3 + cc) * H + iy) * W + ix) : 0;
+            cp_async4(pb + (uint32_t)i * 4u, img + off, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int t = blockIdx.x, b = 0;
+    if (t < total) issue(t, 0);
+    for (; t < total; t += gridDim.x, b ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < total) {
+            issue(tn, b ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                    // tile t has landed (and the vectors are staged)
+        float* gs = st3_smem + b * ST3_BUF_FLOATS;
+        const float* zs = gs + ST3_PX * ST_CO;
+        const float* patch = gs + 2 * ST3_PX * ST_CO;
+        {   // BatchNorm-backward apply in place: g -> dz (this thread always meets channel quad tid & 15: 352 % 16 == 0)
+            const int cv = tid & 15;
+            const float4 s4 = ld4(vecs + cv * 4), t4 = ld4(vecs + 64 + cv * 4), mu = ld4(vecs + 128 + cv * 4);
+            const float4 a4 = ld4(vecs + 192 + cv * 4), b4 = ld4(vecs + 256 + cv * 4), c4 = ld4(vecs + 320 + cv * 4);
+            const int n = t / (tiles_x * tiles_y);
+            const int r = t - n * (tiles_x * tiles_y);
+            const int oy0 = (r / tiles_x) * ST3_TH, ox0 = (r % tiles_x) * ST3_TW;
+            for (int i = tid; i < ST3_PX * (ST_CO / 4); i += ST3_THREADS) {
+                const int q = i >> 4;
+                const bool ok = oy0 + q / ST3_TW < OH && ox0 + (q % ST3_TW) < OW;
+                const float4 gv = ld4(gs + q * ST_CO + cv * 4), zv = ld4(zs + q * ST_CO + cv * 4);
+                const float gx = (relu && fmaf(zv.x, s4.x, t4.x) <= 0.f) ? 0.f : gv.x;
+                const float gy = (relu && fmaf(zv.y, s4.y, t4.y) <= 0.f) ? 0.f : gv.y;
+                const float gz = (relu && fmaf(zv.z, s4.z, t4.z) <= 0.f) ? 0.f : gv.z;
+                const float gw = (relu && fmaf(zv.w, s4.w, t4.w) <= 0.f) ? 0.f : gv.w;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {                                   // pixels outside the image contribute nothing (their dz is not defined)
+                    o.x = a4.x * ((gx - c4.x) - (zv.x - mu.x) * b4.x);
+                    o.y = a4.y * ((gy - c4.y) - (zv.y - mu.y) * b4.y);
+                    o.z = a4.z * ((gz - c4.z) - (zv.z - mu.z) * b4.z);
+                    o.w = a4.w * ((gw - c4.w) - (zv.w - mu.w) * b4.w);
+                }
+                st4(gs + q * ST_CO + cv * 4, o);
+                bsum.x += o.x; bsum.y += o.y; bsum.z += o.z; bsum.w += o.w;
+            }
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 1
+            for (int oy = 0; oy < ST3_TH; ++oy) {
+                const float* prow = patch + (c * ST3_PH + 2 * oy + kh) * ST_PWP;
+                const float* arow = gs + (oy * ST3_TW) * ST_CO + tx * 4;
+#pragma unroll 2
+                for (int p = 0; p < ST3_TW / 2; ++p) {
+                    const float4 a0 = ld4(arow + (2 * p) * ST_CO);
+                    const float4 a1 = ld4(arow + (2 * p + 1) * ST_CO);
+                    const float4 b0 = ld4(prow + 4 * p), b1 = ld4(prow + 4 * p + 4);
+                    const float b8 = prow[4 * p + 8];
+                    const float bb[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b8};
+#pragma unroll
+                    for (int kw = 0; kw < 7; ++kw) {
+                        acc[0][kw] = fmaf(a0.x, bb[kw], acc[0][kw]);
+                        acc[1][kw] = fmaf(a0.y, bb[kw], acc[1][kw]);
+                        acc[2][kw] = fmaf(a0.z, bb[kw], acc[2][kw]);
+                        acc[3][kw] = fmaf(a0.w, bb[kw], acc[3][kw]);
+                        acc[0][kw] = fmaf(a1.x, bb[kw + 2], acc[0][kw]);
+                        acc[1][kw] = fmaf(a1.y, bb[kw + 2], acc[1][kw]);
+                        acc[2][kw] = fmaf(a1.z, bb[kw + 2], acc[2][kw]);
+                        acc[3][kw] = fmaf(a1.w, bb[kw + 2], acc[3][kw]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                    // buffer b is free for the tile after next
+    }
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw)
+                atomicAdd(dw + (size_t)(tx * 4 + i) * ST_K + (c * 7 + kh) * 7 + kw, acc[i][kw]);
+    }
+    if (dbias != nullptr) {
+        const int cv = tid & 15;
+        atomicAdd(dbias + cv * 4 + 0, bsum.x); atomicAdd(dbias + cv * 4 + 1, bsum.y);
+        atomicAdd(dbias + cv * 4 + 2, bsum.z); atomicAdd(dbias + cv * 4 + 3, bsum.w);
+    }
+}
+
 }  // namespace hgk
 
 using namespace hgk;
@@ -338,5 +500,32 @@ extern "C" int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const
     else
         stem_conv7_wgrad2_kernel<<<grid, ST_WG2_THREADS, 0, (cudaStream_t)stream>>>(img, N, H, W, dz, dw, dbias, tiles_x, tiles_y);
     HGK_CHECK_LAUNCH("hgk_stem_conv7_wgrad");
+    return HGK_OK;
+}
+
+extern "C" int hgk_stem_conv7_wgrad_bnapply(const float* img, int N, int H, int W, const float* g, const float* z,
+                                            const float* scale, const float* shift, int relu, const float* mean,
+                                            const float* cA, const float* cB, const float* cC, int Cout,
+                                            float* dw, float* dbias, void* stream) {
+    HGK_REQUIRE(img && g && z && scale && shift && mean && cA && cB && cC && dw, "hgk_stem_conv7_wgrad_bnapply: null pointer");
+    HGK_REQUIRE(Cout == ST_CO, "hgk_stem_conv7_wgrad_bnapply: Cout must be 64 (got %d)", Cout);
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hgk_stem_conv7_wgrad_bnapply: H, W must be even and positive");
+    HGK_REQUIRE((((uintptr_t)g | (uintptr_t)z) & 15) == 0, "hgk_stem_conv7_wgrad_bnapply: g and z must be 16-byte aligned");
+    const int tiles_x = (W / 2 + ST3_TW - 1) / ST3_TW, tiles_y = (H / 2 + ST3_TH - 1) / ST3_TH;
+    const long long total = (long long)tiles_x * tiles_y * N;
+    HGK_REQUIRE(total < (1LL << 31), "hgk_stem_conv7_wgrad_bnapply: too many tiles");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_conv7_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST3_SMEM);
+        if (e != cudaSuccess) {
+            set_error("hgk_stem_conv7_wgrad_bnapply: cudaFuncSetAttribute(%d bytes): %s", ST3_SMEM, cudaGetErrorString(e));
+            return HGK_ECUDA;
+        }
+        configured = true;
+    }
+    const int grid = (int)(total < 2 * kNumSMs ? total : 2 * kNumSMs);
+    stem_conv7_wgrad3_kernel<<<grid, ST3_THREADS, ST3_SMEM, (cudaStream_t)stream>>>(img, N, H, W, g, z, scale, shift, relu, mean,
+                                                                                  cA, cB, cC, dw, dbias, tiles_x, tiles_y);
+    HGK_CHECK_LAUNCH("hgk_stem_conv7_wgrad_bnapply");
     return HGK_OK;
 }

@@ -625,7 +625,12 @@ class Plan(object):
         return lst
 
     def _run(self, lst, stream):
+        arm = self.lib.pdl_arm
+        prev_kernel = False
         for fn, args, name in lst:
+            # programmatic dependent launch is only legal behind another kernel launch of the same stream (hgk.h)
+            arm(1 if prev_kernel else 0)           # (always set: a launch that does not consume the flag must not leak it)
+            prev_kernel = name != "host_sample_mask"
             rc = fn(*args, stream)
             if rc != 0:
                 raise HGKError("%s failed (%d): %s" % (name, rc, self.lib.last_error()))
@@ -689,7 +694,7 @@ _WRITES = {
     "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
     "maxpool2_fwd": (8,), "maxpool2_bwd": (9,), "add_fwd": (13,), "upsample2_bwd": (5,), "add_into": (1,),
     "nchw_to_nhwc": (5,), "nhwc_to_nchw": (8,),
-    "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7),
+    "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7), "stem_conv7_wgrad_bnapply": (14, 15),
     "head_combine_fwd": (6, 7), "head_combine_bwd": (4, 5, 6, 7, 8, 9),
     "mse_fwd_bwd": (5, 7), "avgpool_fwd": (9,), "avgpool_bwd": (6,), "linear_fwd": (6,), "linear_bwd": (6, 7, 8),
 }
@@ -852,9 +857,17 @@ class _StemOp(object):
         g = p.finalize_grad(o)
         if g is None:
             return
-        _emit_bn_bwd(p, o, r, g)
-        rec = p.launch(p.bwd, "stem_conv7_wgrad", 0, self.img.N, self.img.H, self.img.W, _ptr(g), o.C,
-                       p.param_grad_ptr(self.conv.weight), p.param_grad_ptr(self.conv.bias))
+        if p.fuse_bn_apply:
+            # BatchNorm-backward apply evaluated on load by the weight-gradient kernel (it is the only reader of dz: the stem
+            # has no data gradient)
+            _emit_bn_bwd(p, o, r, g, with_apply=False)
+            rec = p.launch(p.bwd, "stem_conv7_wgrad_bnapply", 0, self.img.N, self.img.H, self.img.W, _ptr(g), _ptr(o.z),
+                           _ptr(r.scale), _ptr(r.shift), int(o.relu), _ptr(r.mean), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), o.C,
+                           p.param_grad_ptr(self.conv.weight), p.param_grad_ptr(self.conv.bias))
+        else:
+            _emit_bn_bwd(p, o, r, g)
+            rec = p.launch(p.bwd, "stem_conv7_wgrad", 0, self.img.N, self.img.H, self.img.W, _ptr(g), o.C,
+                           p.param_grad_ptr(self.conv.weight), p.param_grad_ptr(self.conv.bias))
         p.dynamic("image", rec, 0)
 
 

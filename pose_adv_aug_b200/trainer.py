@@ -115,7 +115,7 @@ class HourglassTrainer(object):
             low_ids = plan.low_recs if low_on else ()
             self._sched = schedule_streams(launches, n_streams, n_low=n_low, low_ids=low_ids,
                                            after=plan.after if M.DEFER_SKIPS else None,
-                                           low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad"))
+                                           low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad", "stem_conv7_wgrad_bnapply"))
         stream_of, cross = self._sched
         # with a low-priority pool the other side streams are high priority (-1); the capture stream keeps priority 0
         side = [torch.cuda.Stream(self.device, priority=(0 if (n_low and i >= n_streams - 1 - n_low) else (-1 if n_low else 0)))
@@ -127,10 +127,17 @@ class HourglassTrainer(object):
             s_.wait_event(fork)
         events = {}
         users = set(d for c in cross for d in c)
+        last_on = [False] * n_streams          # the last operation on stream k was a libhgk kernel launch
+        arm = self.lib.pdl_arm
         for i, (fn, args, name) in enumerate(launches):
-            sk = streams[stream_of[i]]
+            k = stream_of[i]
+            sk = streams[k]
             for d in cross[i]:
                 sk.wait_event(events[d])
+            # programmatic dependent launch (hgk.h): only directly behind another launch of the same stream; a launch that
+            # also waits for events of other streams keeps plain (full) dependencies
+            arm(1 if (last_on[k] and not cross[i]) else 0)
+            last_on[k] = True
             rc = fn(*args, sk.cuda_stream)
             if rc != 0:
                 raise HGKError("%s failed (%d): %s" % (name, rc, self.lib.last_error()))
@@ -194,16 +201,26 @@ class HourglassTrainer(object):
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         grads = self._body_grads if self.n_streams <= 1 else (lambda: self._body_grads_multistream(self.n_streams))
-        if self.world > 1:
-            with torch.cuda.graph(self.graph):
-                grads()
-            self.graph_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_update):
-                self._body_update()
-        else:
-            with torch.cuda.graph(self.graph):
-                grads()
-                self._body_update()
+        # Python's cyclic garbage collector must not run inside the capture: a finaliser of an unrelated CUDA object (an old
+        # plan's graph, streams, events) that calls into the driver invalidates a global-mode stream capture
+        import gc
+        gc_was_on = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            if self.world > 1:
+                with torch.cuda.graph(self.graph):
+                    grads()
+                self.graph_update = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_update):
+                    self._body_update()
+            else:
+                with torch.cuda.graph(self.graph):
+                    grads()
+                    self._body_update()
+        finally:
+            if gc_was_on:
+                gc.enable()
         # restore the state consumed by the warm-up step
         self.store.flat.copy_(saved[0])
         self.square_avg.copy_(saved[1])

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     # every entry point that launches work is bound with a signature
     launching = [n for n in names if n not in ("hgk_last_error", "hgk_version", "hgk_device_ok", "hgk_conv_tc_supported",
                                                "hgk_conv_wgrad_tc_supported", "hgk_debug_set_timeline",
-                                               "hgk_conv_tc_bnapply_supported")]
+                                               "hgk_conv_tc_bnapply_supported", "hgk_pdl_arm")]
     assert sorted(launching) == sorted(SIGNATURES.keys())
     assert lib.cdll.hgk_version() >= 100
 
@@ -105,10 +105,10 @@ def test_plan_builds_and_covers_every_parameter():
     assert bnames.count("head_combine_bwd") == (1 if M.FUSE_HEAD else 0)
     assert "add_into" not in bnames                                             # all gradient fan-ins are aliased/fused
     # 96 BatchNorm backwards: the apply is evaluated on load by the image-tile data-gradient kernels on the large layers;
-    # a bn_bwd_apply launch remains for the stem and for the small layers, which take the cluster split-K kernel (at this
-    # dry plan's batch of 2 the 16x16 .. 4x4 rungs are small: <= 12 tiles of 128 pixels)
-    n_ap = bnames.count("conv_tc_dgrad_bnapply_nhwc")
-    assert n_ap + bnames.count("bn_bwd_apply") == 96 and n_ap >= 20
+    # the stem's by its weight-gradient kernel; a bn_bwd_apply launch remains for the small layers, which take the cluster
+    # split-K kernel (at this dry plan's batch of 2 the 16x16 .. 4x4 rungs are small: <= 12 tiles of 128 pixels)
+    n_ap = bnames.count("conv_tc_dgrad_bnapply_nhwc") + bnames.count("stem_conv7_wgrad_bnapply")
+    assert n_ap + bnames.count("bn_bwd_apply") == 96 and n_ap >= 20 and bnames.count("stem_conv7_wgrad_bnapply") == 1
     # every BN-backward finaliser rides on the kernel that produced its sums
     n_ap_red = sum(1 for r in plan.bwd if r[2] == "conv_tc_dgrad_bnapply_nhwc" and r[1][20] != 0)
     assert bnames.count("conv_tc_dgrad_bnfin_nhwc") + bnames.count("bn_bwd_reduce_fin") + n_ap_red == 96

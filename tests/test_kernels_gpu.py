@@ -166,6 +166,23 @@ def test_stem_fwd_and_wgrad(shape):
     torch.cuda.synchronize()
     assert relerr(gw, w.grad) < 2e-5
     assert relerr(gb, b.grad) < 2e-5
+    # the same with bn1's BatchNorm-backward apply evaluated on load (hgk_stem_conv7_wgrad_bnapply) == hgk_bn_bwd_apply
+    # followed by hgk_stem_conv7_wgrad on the dz it wrote
+    OHW = (N, H // 2, W // 2, 64)
+    g, zz = nhwc(rnd("g", (N, 64, H // 2, W // 2))), nhwc(rnd("zz", (N, 64, H // 2, W // 2), -2.0, 2.0))
+    v = {n: dev32(rnd(n, (64,), lo, hi)) for n, lo, hi in (("sc", 0.5, 1.5), ("sh", -0.3, 0.3), ("mu", -0.2, 0.2),
+                                                           ("cA", 0.5, 1.5), ("cB", -0.2, 0.2), ("cC", -0.1, 0.1))}
+    dz_ref = g.clone()
+    call("bn_bwd_apply", ptr(dz_ref), ptr(zz), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["cA"]), ptr(v["cB"]), ptr(v["cC"]),
+         OHW[0] * OHW[1] * OHW[2], 64)
+    gw_ref, gb_ref = torch.zeros(64, 3, 7, 7, device=DEV), torch.zeros(64, device=DEV)
+    call("stem_conv7_wgrad", ptr(dimg), N, H, W, ptr(dz_ref), 64, ptr(gw_ref), ptr(gb_ref))
+    gw2, gb2 = torch.zeros(64, 3, 7, 7, device=DEV), torch.zeros(64, device=DEV)
+    call("stem_conv7_wgrad_bnapply", ptr(dimg), N, H, W, ptr(g), ptr(zz), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["cA"]),
+         ptr(v["cB"]), ptr(v["cC"]), 64, ptr(gw2), ptr(gb2))
+    torch.cuda.synchronize()
+    assert relerr(gw2, gw_ref) < 2e-5
+    assert relerr(gb2, gb_ref) < 2e-5
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 8, 64), (3, 5, 7, 12), (2, 1, 1, 128), (4, 16, 16, 256), (2, 4, 4, 320)])

@@ -299,9 +299,12 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
         loss = O.mse_loss(outs, t.to(DEV))
         opt.zero_grad()
         loss.backward()
-        if grad_a is None:
+        first = grad_a is None
+        if first:
             grad_a = opt.store.grad.clone()
         opt.step()
+        if first:
+            head_a = a.out_conv[1].weight.detach().clone()       # after ONE update: the two paths have not diverged yet
         losses_a.append(float(loss))
     # (b) fused trainer without graph, (c) with graph
     for net, use_graph in ((nets[1], False), (nets[2], True)):
@@ -311,6 +314,10 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
         # side and from the fused MSE kernel on the other; weight gradients are float atomics)
         g_b = tr.store.grad
         assert float((g_b - grad_a).norm() / grad_a.norm()) < 1e-4
+        # one RMSprop update later the last head agrees tightly: an element moves by ~lr*10*sign(g), so only elements whose
+        # gradient is at the rounding-noise level (sign flips) may differ (1e-4 = 4 % of one step)
+        d1 = (net.out_conv[1].weight.detach() - head_a).abs()
+        assert float((d1 > 1e-4).float().mean()) < 0.02
         losses += [float(tr.step(x.pin_memory(), t.pin_memory())) for _ in range(2)]
         # ... after which RMSprop's first steps (~lr*10*sign(g) per weight whatever |g| is) turn that rounding noise into
         # visible loss differences on this tiny, ill-conditioned net: tight on steps 0-1, loose on step 2
@@ -330,10 +337,6 @@ def test_trainer_matches_module_path_and_graph_replay(monkeypatch):
                     assert float(d.max()) < 1e-1 * max(1.0, float(pa.abs().max())), k
                 else:
                     assert float(d.max()) < 2e-2, k
-                if k.startswith("out_conv.1") and k.endswith("weight"):
-                    # (1e-4 = 4 % of one RMSprop step: observed differences are 3e-6 .. 1e-5 depending on the
-                    # atomics order of the run, so a 1e-5 gate was flaky)
-                    assert float((d > 1e-4).float().mean()) < 0.02, k
         hm = tr.heatmaps()
         assert len(hm) == S and tuple(hm[0].shape) == (N, K, R // 4, R // 4)
     # oracle: same three steps on CPU fp32.  Step 0 (before any update) must agree tightly; after that every
@@ -536,3 +539,108 @@ def test_prefetched_step_equals_serial_step():
     for a, b in zip(la, lb):
         assert abs(a - b) < 1e-5 * abs(a), (la, lb)
     assert len(set(round(v, 6) for v in la)) == 4
+
+
+def test_headline_shape_train_step_vs_fp64_oracle():
+    """BASELINE configs[1] shapes (2 stacks, nFeat 256, 256x256; 4 images so that the CPU oracle finishes in seconds): one
+    full train step on the SHIPPING path (3xTF32 forward, plain-TF32 backward, tcgen05 instantiations <128|256, ...>) against
+    the fp64 oracle.  Heat-maps and loss within 1e-3 (north_star); gradients by the noise-floor rule: our distance to fp64 is
+    at most twice the fp32 reference arithmetic's own distance to fp64 (1.2e-2 rel-L2 at this config)."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer
+    S, Mo, K, C, N, R = 2, 1, 16, 256, 4, 256
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=71)
+    x, t = synth.make_images(N, R, seed=72), synth.make_heatmaps(N, R, K, seed=73)
+    sd64 = OrderedDict((k, v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items())
+    outs64, loss64, g64, _ = O.train_step(sd64, x.double(), t.double(), S, Mo)
+    sd32 = OrderedDict((k, v.clone()) for k, v in sd.items())
+    outs32, loss32, g32, _ = O.train_step(sd32, x, t, S, Mo)
+    net = _load(M.create_hg(S, Mo, K, C), sd)
+    tr = HourglassTrainer(net, N, R, device=DEV, use_graph=False)
+    loss = float(tr.step(x.pin_memory(), t.pin_memory()))
+    torch.cuda.synchronize()
+    for h, o64 in zip(tr.heatmaps(), outs64):
+        assert float((h.cpu().double() - o64).abs().max() / o64.abs().max()) < 1e-3
+    assert abs(loss - float(loss64)) < 1e-3 * abs(float(loss64))
+    grads = dict((k, p.grad.detach().cpu().double()) for k, p in net.named_parameters())
+    num = den = num32 = 0.0
+    dot = n1 = 0.0
+    for k, g in g64.items():
+        num += float((grads[k] - g).pow(2).sum())
+        num32 += float((g32[k].double() - g).pow(2).sum())
+        den += float(g.pow(2).sum())
+        dot += float((grads[k] * g).sum())
+        n1 += float(grads[k].pow(2).sum())
+    ours, floor = (num / den) ** 0.5, (num32 / den) ** 0.5
+    cosine = dot / (n1 ** 0.5 * den ** 0.5)
+    print("headline-shape gradient rel-L2 vs fp64: ours %.3e, fp32 oracle %.3e, cosine %.6f" % (ours, floor, cosine))
+    assert ours < 2.0 * floor + 1e-3, (ours, floor)
+    assert cosine > 0.999
+
+
+def test_virtual_rank_data_parallel_step():
+    """nn.DataParallel semantics of stack-hg.py:49 without a second GPU: W virtual ranks run their shard one after the other
+    on this device (each with its OWN BatchNorm batch statistics, as the reference's replicas), the flat gradient buffers are
+    summed on the device -- what the one ncclAllReduce(sum) of the step produces -- and the flat RMSprop kernel applies the
+    update with 1/W folded in.  Checked against the oracle: per-shard fp32 gradients, averaged."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer
+    S, Mo, K, C, Nloc, R, W = 2, 1, 16, 64, 2, 128, 2
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=81)
+    xs = [synth.make_images(Nloc, R, seed=82 + r) for r in range(W)]
+    ts = [synth.make_heatmaps(Nloc, R, K, seed=92 + r) for r in range(W)]
+    net = _load(M.create_hg(S, Mo, K, C), sd)
+    monkey = M.PRECISE_GRADS
+    M.PRECISE_GRADS = True                      # fp32-class gradients: the comparison below is on the data-parallel arithmetic
+    try:
+        tr = HourglassTrainer(net, Nloc, R, device=DEV, use_graph=False, distributed=False)
+        acc = torch.zeros_like(tr.store.grad)
+        losses = []
+        for r in range(W):
+            tr.x.copy_(xs[r]); tr.t.copy_(ts[r])
+            tr._body_grads()                    # zero grads/loss -> forward -> MSE -> backward of this rank's shard
+            acc += tr.store.grad
+            losses.append(float(tr.loss_acc))
+        # oracle gradients of the W shards on the same (not yet updated) weights, in fp32 (the reference's arithmetic) and fp64
+        gsum = gsum64 = None
+        sd64 = OrderedDict((k, v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items())
+        for r in range(W):
+            _, l_ref, g, _ = O.train_step(OrderedDict((k, v.clone()) for k, v in sd.items()), xs[r], ts[r], S, Mo)
+            assert abs(losses[r] - float(l_ref)) < 1e-3 * abs(float(l_ref))
+            _, _, g64, _ = O.train_step(OrderedDict((k, v.clone()) for k, v in sd64.items()), xs[r].double(), ts[r].double(), S, Mo)
+            gsum = g if gsum is None else OrderedDict((k, gsum[k] + g[k]) for k in g)
+            gsum64 = g64 if gsum64 is None else OrderedDict((k, gsum64[k] + g64[k]) for k in g64)
+        tr.store.grad.copy_(acc)                # == the all-reduced buffer
+        # noise-floor rule (SURVEY 0.5): the summed gradient is about as close to fp64 as the fp32 reference arithmetic is (factor
+        # 3 instead of the usual 2: two images per virtual rank, the ReLU-mask flips behind the whole-net noise do not average)
+        num = num32 = den = 0.0
+        for k, p in net.named_parameters():
+            num += float((p.grad.detach().cpu().double() - gsum64[k]).pow(2).sum())
+            num32 += float((gsum[k].double() - gsum64[k]).pow(2).sum())
+            den += float(gsum64[k].pow(2).sum())
+        assert (num / den) ** 0.5 < 3.0 * (num32 / den) ** 0.5 + 1e-3, ((num / den) ** 0.5, (num32 / den) ** 0.5)
+        # update with 1/W folded into the kernel: p -= lr * (g/W) / (sqrt((1-alpha) (g/W)^2) + eps)
+        before = tr.store.flat.clone()
+        tr.hyper[3:4].fill_(1.0 / W)
+        tr._body_update()
+        torch.cuda.synchronize()
+        gbar = acc / W
+        want = before - 2.5e-4 * gbar / ((0.01 * gbar * gbar).sqrt() + 1e-8)
+        assert float((tr.store.flat - want).abs().max()) < 1e-6
+    finally:
+        M.PRECISE_GRADS = monkey
+
+
+def test_two_rank_nccl_equals_sum_of_local_gradients():
+    """tools/check_dp.py under torchrun (2 ranks, NCCL): identical parameters on every rank after 3 steps and all-reduced
+    gradient == sum of the local gradients.  Needs two GPUs; skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_dp.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "DP CHECK OK" in out, out[-2000:]
