@@ -34,6 +34,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("HGK_NVCC_EXTRA", "").split()      # developer experiments (-DKNOB=value)
     if verbose:
         flags = flags + ["-Xptxas", "-v"]
     procs = []

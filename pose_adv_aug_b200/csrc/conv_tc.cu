@@ -1309,7 +1309,7 @@ extern "C" int hgk_pack_weights_tc(const float* src_base, float* dst_base, const
     HGK_REQUIRE(src_base && dst_base && table, "hgk_pack_weights_tc: null pointer");
     if (n_entries <= 0) return HGK_OK;
     HGK_REQUIRE(n_entries <= 65535, "hgk_pack_weights_tc: too many entries");
-    dim3 grid(16, (unsigned)n_entries);
+    dim3 grid(72, (unsigned)n_entries);      // (16 blocks per entry: 85 us, latency-bound scattered 4-byte reads, alone at the head of the step)
     pack_weights_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_base, dst_base, table, n_entries);
     HGK_CHECK_LAUNCH("hgk_pack_weights_tc");
     return HGK_OK;
@@ -1383,7 +1383,8 @@ extern "C" int hgk_unpack_add_grads(const float* src_base, float* dst_base, cons
     HGK_REQUIRE(src_base && dst_base && table, "hgk_unpack_add_grads: null pointer");
     if (n_entries <= 0) return HGK_OK;
     HGK_REQUIRE(n_entries <= 65535, "hgk_unpack_add_grads: too many entries");
-    dim3 grid(8, (unsigned)n_entries);
+    dim3 grid(72, (unsigned)n_entries);      // 8 elements per thread for a 128x128x9 tensor (8 blocks per entry left the launch
+                                             // latency-bound: 50 us for 18 MB, alone at the end of the step)
     unpack_add_grads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_base, dst_base, table, n_entries);
     HGK_CHECK_LAUNCH("hgk_unpack_add_grads");
     return HGK_OK;

@@ -78,6 +78,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
         if (dbg_on && blockIdx.x < 256) args.dbg[blockIdx.x * 32 + (slot)] = (long long)(val); \
     } while (0)
 
+#ifndef T3_KB1
+#define T3_KB1 2
+#endif
 constexpr int T3_NTW = 8;                                   // transform warps
 constexpr int T3_NEW = 8;                                   // epilogue warps
 constexpr int T3_WMMA = T3_NTW, T3_WLDA = T3_NTW + 1, T3_WLDB = T3_NTW + 2, T3_WAUX = T3_NTW + 3;
@@ -513,7 +516,7 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
             // wait for the old set also waits for the new one: register double-buffering gained nothing, ncu showed the warps
             // in long-scoreboard stalls half of the time.)  The first batch of a tile is issued before the tile's accumulator
             // is awaited -- at the end of the previous tile -- so per tile only the later batch boundaries expose a latency.
-            constexpr int KB = NL == 1 ? 2 : 1;
+            constexpr int KB = NL == 1 ? T3_KB1 : 1;
             constexpr int NBATCH = NSTEP / KB;
             static_assert(NSTEP % KB == 0, "steps per tile are a multiple of the prefetch batch");
             float rr[R ? KB * 16 : 1], oo[A ? KB * 16 : 1], zz[BWDSTATS ? KB * 16 : 1];

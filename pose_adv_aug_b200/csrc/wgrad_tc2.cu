@@ -67,15 +67,26 @@ struct Wg2Cfg {
     static constexpr int TMEM_COLS = ACC <= 64 ? 64 : ACC <= 128 ? 128 : ACC <= 256 ? 256 : 512;
     static constexpr int CH = CIN > 128 ? 128 : CIN;
     static constexpr int STG_BYTES = TBM * (CH + 4) * 4;
-    static constexpr int NST = (200 * 1024 / STAGE) > 4 ? 4 : (200 * 1024 / STAGE);
+    // Two CTAs per SM wherever the accumulators leave room for it (<= 256 TMEM columns): the producer chain of a stage
+    // (wait -> transform -> proxy fence -> arrive -> MMA -> commit) is ~1 700 cycles for 32 pixels whatever the channel
+    // counts are, so a lone CTA per SM left the SM idle most of the time (ncu: 14 % warps active); the second CTA's chain
+    // runs in the gaps.  Shared memory is then split in two (<= 110 KB each).
+    // Only the variants whose two register-prefetch sets fit under the 96-register cap of two 288-thread CTAs
+    // (NJA + NJB <= 8 float4 per set).  Measured for the larger ones (128->256, 256->128 at 64x64): two CTAs with ONE
+    // prefetch set are 10 % slower than one CTA with two (45.8 -> 51.4 us, 49.9 -> 54.5 us), two CTAs with two sets spill.
+    static constexpr bool OCC2 = TMEM_COLS <= 256 && NJA + NJB <= 8;
+    static constexpr int NSET = 2;
+    static constexpr int SMEM_BUDGET = OCC2 ? 108 * 1024 : 200 * 1024;
+    static constexpr int NST = (SMEM_BUDGET / STAGE) > 4 ? 4 : (SMEM_BUDGET / STAGE);
     static constexpr int SMEM = (NST * STAGE > STG_BYTES + 4096 ? NST * STAGE : STG_BYTES + 4096) + 1024;
+    static_assert(!OCC2 || SMEM <= 113 * 1024, "two CTAs per SM share 227 KB");
     static_assert(ACC <= 512, "TMEM capacity");
     static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle atoms need 512-byte aligned tiles");
     static_assert(NST >= 2, "pipeline needs two stages");
 };
 
 template <int CIN, int MT, int TAPS>
-__global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args a) {
+__global__ void __launch_bounds__(WG2_THREADS, (Wg2Cfg<CIN, MT, TAPS>::OCC2 ? 2 : 1)) wgrad2_tc_kernel(const Wg2Args a) {
     using Cfg = Wg2Cfg<CIN, MT, TAPS>;
     constexpr int QA = Cfg::QA, QB = Cfg::QB, NJA = Cfg::NJA, NJB = Cfg::NJB, NST = Cfg::NST, UPX = Cfg::UPX;
     constexpr uint32_t LBO_A = Cfg::LBO_A, LBO_B = Cfg::LBO_B, A_BYTES = Cfg::A_BYTES, STAGE = Cfg::STAGE;
@@ -125,8 +136,9 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args
         const float x_clamp = a.x.relu ? 0.f : -INFINITY;
         const float* dzp = a.dz + qa * 4;
         const float* xzp = a.x.z + qb * 4;
-        float4 ra[2][NJA], rb[2][NJB];
-        unsigned bm[2] = {0u, 0u};
+        constexpr int NSET = Cfg::NSET;
+        float4 ra[NSET][NJA], rb[NSET][NJB];
+        unsigned bm[NSET] = {};
         // all index arithmetic in 32 bits (host guarantees P * max(Cin, Cout) < 2^31); H and W are powers of two for 3x3
         int l_u = (int)u_begin;                                  // first unit of the stage the next load() fetches
         const int i_end = (int)u_end;
@@ -190,15 +202,15 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wgrad2_tc_kernel(const Wg2Args
             }
         };
         load(0);
-        if (T > 1) load(1);
+        if (NSET > 1 && T > 1) load(NSET - 1);
         int s = 0;
         unsigned em_par = 1;
         for (int it = 0; it < T; ++it) {
             if (it >= NST) mbar_wait(bar_empty + 8 * s, em_par);
-            if (it & 1) store(s, 1); else store(s, 0);
+            if (NSET > 1 && (it & 1)) store(s, NSET - 1); else store(s, 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_full + 8 * s);
-            if (it + 2 < T) { if (it & 1) load(1); else load(0); }
+            if (it + NSET < T) { if (NSET > 1 && (it & 1)) load(NSET - 1); else load(0); }
             if (++s == NST) { s = 0; em_par ^= 1u; }
         }
         mbar_wait(bar_done, 0);
@@ -335,7 +347,11 @@ int wgrad_tc2_try(const float* x, const float* x_scale, const float* x_shift, in
     a.units = P / 8;
     a.lw8 = lw8;
     const int groups = ksize == 3 ? 3 : 1;
-    long long want = kNumSMs / groups;
+    // two CTAs per SM for the variants with Wg2Cfg::OCC2 (same predicate)
+    const int acc_cols = MT * (ksize == 3 ? 3 : 1) * Cin;
+    const int nja = 4 * MT, njb = (4 * (ksize == 3 ? 10 : 8) * (Cin / 4) + 255) / 256;
+    const bool occ2 = acc_cols <= 256 && nja + njb <= 8;
+    long long want = (long long)kNumSMs * (occ2 ? 2 : 1) / groups;
     long long max_ctas = (a.units + 15) / 16;                  // at least 4 stages per CTA
     long long ctas = want < max_ctas ? want : max_ctas;
     if (ctas < 1) ctas = 1;
