@@ -1020,24 +1020,27 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
     const long long* t = table + (size_t)e * 8;
     const long long so = t[0], dhi = t[1], dlo = t[2];
     const int N = (int)t[3], K = (int)t[4], taps = (int)t[5], mode = (int)t[6], BN = (int)t[7];
-    const long long total = (long long)N * K * taps;
-    const int KC = K / 32;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int el = (int)(i & 3);
-        long long r = i >> 2;
-        int nn = (int)(r % BN);
-        r /= BN;
-        int q = (int)(r & 7);
-        long long blk = r >> 3;
-        int kc = (int)(blk % KC);
+    // 32-bit index arithmetic (a weight tensor has at most a few hundred thousand elements; the five 64-bit divisions per
+    // element of the first version made this launch compute-bound: 85 us alone at the head of every step)
+    const unsigned total = (unsigned)N * (unsigned)K * (unsigned)taps;
+    const unsigned KC = (unsigned)K / 32u, uBN = (unsigned)BN, utaps = (unsigned)taps;
+    const float* sp = src + so;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned el = i & 3u;
+        unsigned r = i >> 2;
+        const unsigned nn = r % uBN;
+        r /= uBN;
+        const unsigned q = r & 7u;
+        unsigned blk = r >> 3;
+        const unsigned kc = blk % KC;
         blk /= KC;
-        int tap = (int)(blk % taps);
-        int ntile = (int)(blk / taps);
-        int n = ntile * BN + nn, k = kc * 32 + q * 4 + el;
+        const unsigned tap = blk % utaps;
+        const unsigned ntile = blk / utaps;
+        const unsigned n = ntile * uBN + nn, k = kc * 32u + q * 4u + el;
         float v;
-        if (mode == 0) v = __ldg(src + so + ((long long)n * K + k) * taps + tap);
-        else v = __ldg(src + so + ((long long)k * N + n) * taps + (taps - 1 - tap));
-        float hi = tf32_rna(v);
+        if (mode == 0) v = __ldg(sp + (n * (unsigned)K + k) * utaps + tap);
+        else v = __ldg(sp + (k * (unsigned)N + n) * utaps + (utaps - 1u - tap));
+        const float hi = tf32_rna(v);
         dst[dhi + i] = hi;
         if (dlo >= 0) dst[dlo + i] = v - hi;
     }

@@ -14,22 +14,23 @@ static inline unsigned stream_blocks(long long work_items) {
     return (unsigned)b;
 }
 
+template <typename idx_t>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(Act x, int N, int H, int W, int C4, float* __restrict__ y) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
-    const long long total = (long long)N * OH * OW * C4;
+    const idx_t total = (idx_t)N * OH * OW * C4;
     const int C = C4 * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int cq = (int)(i % C4);
-        long long q = i / C4;
-        int ow = (int)(q % OW);
-        long long r = q / OW;
-        int oh = (int)(r % OH);
-        int n = (int)(r / OH);
+    for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
+        int cq = (int)(i % (idx_t)C4);
+        idx_t q = i / (idx_t)C4;
+        int ow = (int)(q % (idx_t)OW);
+        idx_t r = q / (idx_t)OW;
+        int oh = (int)(r % (idx_t)OH);
+        int n = (int)(r / (idx_t)OH);
         float4 s, t;
         load_affine4(x.scale, x.shift, cq * 4, s, t);
-        const float* base = x.z + (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
-        float4 v00 = ldg4(base), v01 = ldg4(base + C), v10 = ldg4(base + (long long)W * C), v11 = ldg4(base + (long long)W * C + C);
+        const float* base = x.z + (((idx_t)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        float4 v00 = ldg4(base), v01 = ldg4(base + C), v10 = ldg4(base + (idx_t)W * C), v11 = ldg4(base + (idx_t)W * C + C);
         if (x.scale != nullptr) {
             v00 = act4(v00, s, t, x.relu); v01 = act4(v01, s, t, x.relu);
             v10 = act4(v10, s, t, x.relu); v11 = act4(v11, s, t, x.relu);
@@ -53,23 +54,24 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
     return k;
 }
 
+template <typename idx_t>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, int W, int C4,
                                                            const float* __restrict__ dy, float* __restrict__ dx, int accumulate) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
-    const long long total = (long long)N * OH * OW * C4;
+    const idx_t total = (idx_t)N * OH * OW * C4;
     const int C = C4 * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int cq = (int)(i % C4);
-        long long q = i / C4;
-        int ow = (int)(q % OW);
-        long long r = q / OW;
-        int oh = (int)(r % OH);
-        int n = (int)(r / OH);
+    for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
+        int cq = (int)(i % (idx_t)C4);
+        idx_t q = i / (idx_t)C4;
+        int ow = (int)(q % (idx_t)OW);
+        idx_t r = q / (idx_t)OW;
+        int oh = (int)(r % (idx_t)OH);
+        int n = (int)(r / (idx_t)OH);
         float4 s, t;
         load_affine4(x.scale, x.shift, cq * 4, s, t);
-        const long long off = (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
-        const long long o01 = C, o10 = (long long)W * C, o11 = (long long)W * C + C;
+        const idx_t off = (((idx_t)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        const idx_t o01 = C, o10 = (idx_t)W * C, o11 = (idx_t)W * C + C;
         float4 v00 = ldg4(x.z + off), v01 = ldg4(x.z + off + o01), v10 = ldg4(x.z + off + o10), v11 = ldg4(x.z + off + o11);
         if (x.scale != nullptr) {
             v00 = act4(v00, s, t, x.relu); v01 = act4(v01, s, t, x.relu);
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             d[k] = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f, kw == k ? g.w : 0.f);
-        const long long offs[4] = {0, o01, o10, o11};
+        const idx_t offs[4] = {0, o01, o10, o11};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float* p = dx + off + offs[k];
@@ -98,23 +100,24 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
     }
 }
 
+template <typename idx_t>
 __global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, int N, int H, int W, int C4, float* __restrict__ y) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
-    const long long total = (long long)N * H * W * C4;
+    const idx_t total = (idx_t)N * H * W * C4;
     const int C = C4 * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int cq = (int)(i % C4);
-        long long q = i / C4;
+    for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
+        int cq = (int)(i % (idx_t)C4);
+        idx_t q = i / (idx_t)C4;
         float4 sa, ta, sb, tb;
         load_affine4(a.scale, a.shift, cq * 4, sa, ta);
         load_affine4(b.scale, b.shift, cq * 4, sb, tb);
-        long long ai = i * 4;
+        idx_t ai = i * 4;
         if (a_up) {
-            int w = (int)(q % W);
-            long long r = q / W;
-            int h = (int)(r % H);
-            int n = (int)(r / H);
-            ai = ((((long long)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C) + cq * 4;
+            int w = (int)(q % (idx_t)W);
+            idx_t r = q / (idx_t)W;
+            int h = (int)(r % (idx_t)H);
+            int n = (int)(r / (idx_t)H);
+            ai = ((((idx_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C) + cq * 4;
         }
         float4 va = ldg4(a.z + ai);
         float4 vb = ldg4(b.z + i * 4);
@@ -124,21 +127,22 @@ __global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, in
     }
 }
 
+template <typename idx_t>
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C4,
                                                             float* __restrict__ da, int accumulate) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
-    const long long total = (long long)N * OH * OW * C4;
+    const idx_t total = (idx_t)N * OH * OW * C4;
     const int C = C4 * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int cq = (int)(i % C4);
-        long long q = i / C4;
-        int ow = (int)(q % OW);
-        long long r = q / OW;
-        int oh = (int)(r % OH);
-        int n = (int)(r / OH);
-        const float* base = dy + (((long long)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
-        float4 a = ldg4(base), b = ldg4(base + C), c = ldg4(base + (long long)W * C), d = ldg4(base + (long long)W * C + C);
+    for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
+        int cq = (int)(i % (idx_t)C4);
+        idx_t q = i / (idx_t)C4;
+        int ow = (int)(q % (idx_t)OW);
+        idx_t r = q / (idx_t)OW;
+        int oh = (int)(r % (idx_t)OH);
+        int n = (int)(r / (idx_t)OH);
+        const float* base = dy + (((idx_t)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
+        float4 a = ldg4(base), b = ldg4(base + C), c = ldg4(base + (idx_t)W * C), d = ldg4(base + (idx_t)W * C + C);
         float4 o = make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
         if (accumulate) {
             float4 old = ld4(da + i * 4);
@@ -276,6 +280,9 @@ __global__ void linear_bwd_kernel(const float* __restrict__ x, const float* __re
 
 using namespace hgk;
 
+// 32-bit index arithmetic whenever the largest element index fits (every layer of the hourglass): the four 64-bit divisions
+// per float4 item made these streams instruction-bound (add_fwd at 64x64x256: 57 us for 225 MB, 60 % of the copy rate)
+#define HGK_SMALL_IDX() ((long long)N * H * W * C < (1LL << 31))
 #define HGK_NHWC_CHECK(name)                                                                      \
     HGK_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, name ": need positive dims and C %% 4 == 0 (C=%d)", C)
 
@@ -285,7 +292,10 @@ extern "C" int hgk_maxpool2_fwd(const float* x, const float* x_scale, const floa
     HGK_NHWC_CHECK("hgk_maxpool2_fwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_fwd: H and W must be even (H=%d W=%d)", H, W);
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    launch_pdl(maxpool2_fwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
+    if (HGK_SMALL_IDX())
+        launch_pdl(maxpool2_fwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
+    else
+        launch_pdl(maxpool2_fwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4, y);
     HGK_CHECK_LAUNCH("hgk_maxpool2_fwd");
     return HGK_OK;
 }
@@ -296,7 +306,11 @@ extern "C" int hgk_maxpool2_bwd(const float* x, const float* x_scale, const floa
     HGK_NHWC_CHECK("hgk_maxpool2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_bwd: H and W must be even (H=%d W=%d)", H, W);
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    launch_pdl(maxpool2_bwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
+    if (HGK_SMALL_IDX())
+        launch_pdl(maxpool2_bwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
+                                                                                dy, dx, accumulate);
+    else
+        launch_pdl(maxpool2_bwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
                                                                                 dy, dx, accumulate);
     HGK_CHECK_LAUNCH("hgk_maxpool2_bwd");
     return HGK_OK;
@@ -309,7 +323,11 @@ extern "C" int hgk_add_fwd(const float* a, const float* a_scale, const float* a_
     HGK_NHWC_CHECK("hgk_add_fwd");
     HGK_REQUIRE(!a_up || (H % 2 == 0 && W % 2 == 0), "hgk_add_fwd: up-sampled output must have even H, W");
     long long total = (long long)N * H * W * (C / 4);
-    launch_pdl(add_fwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{a, a_scale, a_shift, a_relu}, a_up,
+    if (HGK_SMALL_IDX())
+        launch_pdl(add_fwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{a, a_scale, a_shift, a_relu}, a_up,
+                                                                           Act{b, b_scale, b_shift, b_relu}, N, H, W, C / 4, y);
+    else
+        launch_pdl(add_fwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{a, a_scale, a_shift, a_relu}, a_up,
                                                                            Act{b, b_scale, b_shift, b_relu}, N, H, W, C / 4, y);
     HGK_CHECK_LAUNCH("hgk_add_fwd");
     return HGK_OK;
@@ -320,7 +338,10 @@ extern "C" int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, fl
     HGK_NHWC_CHECK("hgk_upsample2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_upsample2_bwd: H and W must be even");
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    launch_pdl(upsample2_bwd_kernel, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
+    if (HGK_SMALL_IDX())
+        launch_pdl(upsample2_bwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
+    else
+        launch_pdl(upsample2_bwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
     HGK_CHECK_LAUNCH("hgk_upsample2_bwd");
     return HGK_OK;
 }
