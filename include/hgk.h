@@ -200,6 +200,18 @@ int hgk_add_fwd(const float* a, const float* a_scale, const float* a_shift, int 
                 int N, int H, int W, int C, float* y, void* stream);
 /* da[N,H/2,W/2,C] = [accumulate ? da : 0] + 2x2 window sums of dy[N,H,W,C] */
 int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, int accumulate, void* stream);
+/* The same two kernels writing the LAST contribution to dL/d relu(bn(z)) of a tensor with several consumers (hourglass level
+ * inputs: skip branch + pool; up-path sums): the BatchNorm-backward reduction (sum g, sum g*xhat; hgk_bn_bwd_reduce_fin) and its
+ * last-CTA finaliser ride on the launch instead of a pass of their own over g and z.  maxpool: the reduction is over the pooled
+ * tensor x itself (its own scale/shift/relu); upsample: over z [N,H/2,W/2,C] next to da.  C/4 must divide 256. */
+int hgk_maxpool2_bwd_bnred(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W, int C,
+                           const float* dy, float* dx, int accumulate, const float* mean, const float* invstd,
+                           double* sum_g, double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                           float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
+int hgk_upsample2_bwd_bnred(const float* dy, int N, int H, int W, int C, float* da, int accumulate, const float* z,
+                            const float* scale, const float* shift, int relu, const float* mean, const float* invstd,
+                            double* sum_g, double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                            float* cA, float* cB, float* cC, unsigned int* ticket, void* stream);
 /* dst = [accumulate ? dst : 0] + src  (gradient fan-in of `x + y + tmp_in`, :334) */
 int hgk_add_into(const float* src, float* dst, long long n, int accumulate, void* stream);
 

@@ -40,6 +40,8 @@ SIGNATURES = {
     "hgk_maxpool2_bwd": [P, P, P, I, I, I, I, I, P, P, I, P],
     "hgk_add_fwd": [P, P, P, I, I, P, P, P, I, I, I, I, I, P, P],
     "hgk_upsample2_bwd": [P, I, I, I, I, P, I, P],
+    "hgk_maxpool2_bwd_bnred": [P, P, P, I, I, I, I, I, P, P, I, P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "hgk_upsample2_bwd_bnred": [P, I, I, I, I, P, I, P, P, P, I, P, P, P, P, P, I, P, P, P, P, P, P, P],
     "hgk_add_into": [P, P, L, I, P],
     "hgk_head_combine_fwd": [P, P, P, P, P, P, P, P, I, I, P],
     "hgk_head_combine_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],

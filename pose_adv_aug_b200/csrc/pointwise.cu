@@ -3,6 +3,8 @@
 // load), nearest 2x up-sample + skip add, their backward passes, NCHW<->NHWC boundary
 // transposes, AvgPool2d and the tiny nn.Linear heads.  All are 128-bit coalesced NHWC streams.
 #include "common.cuh"
+#include "conv_args.cuh"
+#include "bn_fin.cuh"
 
 namespace hgk {
 
@@ -44,6 +46,48 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(Act x, int N, int H, 
     }
 }
 
+// BatchNorm-backward reduction fused into the kernel that writes the LAST contribution to dL/d relu(bn(z)) of a tensor with
+// several consumers (the hourglass level inputs: skip branch + pool; the up-path sums): sum g and sum g*xhat with
+// g = dy*[z*scale+shift > 0], xhat = (z - mean)*invstd -- what bn_bwd_reduce_kernel (bn.cu) computes in a pass of its own over
+// both tensors (22 launches, 0.8 ms per step before this).  z == nullptr disables it.
+struct BnRed {
+    const float* z;          // pre-BN tensor the gradient belongs to (same shape as the gradient)
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    int relu;
+    double* sum_g;
+    double* sum_gx;
+    BnBwdFin fin;            // last-CTA finaliser (ticket == nullptr: none)
+    long long P;             // pixels of the tensor (statistics count)
+};
+
+// per-thread partial sums (channel quad fixed per thread) -> shared memory -> fp64 atomics -> last-CTA finaliser.
+// Every thread of the CTA must call it.  blockDim.x == 256, 256 % C4 == 0.
+__device__ __forceinline__ void bn_red_flush(const BnRed& br, int C4, const float (&s1)[4], const float (&s2)[4], double (&d1)[4],
+                                             double (&d2)[4], bool last) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }
+    if (!last) return;
+    __shared__ double red[256][8];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[tid][j] = d1[j]; red[tid][4 + j] = d2[j]; }
+    __syncthreads();
+    const int C = C4 * 4;
+    if (tid < C) {                                  // channel tid: quad tid / 4 lives in threads (tid / 4) + k * C4
+        const int q = tid >> 2, e = tid & 3;
+        double a = 0.0, b = 0.0;
+        for (int r = q; r < 256; r += C4) { a += red[r][e]; b += red[r][4 + e]; }
+        atomicAdd(br.sum_g + tid, a);
+        atomicAdd(br.sum_gx + tid, b);
+    }
+    if (br.fin.ticket != nullptr) {
+        if (last_cta_arrives(br.fin.ticket, gridDim.x)) bn_bwd_finalize_cta(br.fin, br.sum_g, br.sum_gx, (double)br.P, C);
+    }
+}
+
 // first-maximum-in-scan-order wins (torch max_pool2d: `val > maxval`), so ties route like the reference
 __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
     int k = 0;
@@ -54,13 +98,24 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
     return k;
 }
 
-template <typename idx_t>
+template <typename idx_t, bool RED>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, int W, int C4,
-                                                           const float* __restrict__ dy, float* __restrict__ dx, int accumulate) {
+                                                           const float* __restrict__ dy, float* __restrict__ dx, int accumulate,
+                                                           const BnRed br) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
     const idx_t total = (idx_t)N * OH * OW * C4;
     const int C = C4 * 4;
+    // RED: the grid stride is a multiple of C4 (host), so a thread stays on ONE channel quad
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
+    if (RED) {
+        const int cq0 = (int)(((idx_t)blockIdx.x * blockDim.x + threadIdx.x) % (idx_t)C4);
+        mu = ldg4(br.mean + cq0 * 4);
+        is = ldg4(br.invstd + cq0 * 4);
+    }
+    int trips = 0;
     for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
         int cq = (int)(i % (idx_t)C4);
         idx_t q = i / (idx_t)C4;
@@ -72,7 +127,8 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
         load_affine4(x.scale, x.shift, cq * 4, s, t);
         const idx_t off = (((idx_t)n * H + oh * 2) * W + ow * 2) * C + cq * 4;
         const idx_t o01 = C, o10 = (idx_t)W * C, o11 = (idx_t)W * C + C;
-        float4 v00 = ldg4(x.z + off), v01 = ldg4(x.z + off + o01), v10 = ldg4(x.z + off + o10), v11 = ldg4(x.z + off + o11);
+        const float4 z00 = ldg4(x.z + off), z01 = ldg4(x.z + off + o01), z10 = ldg4(x.z + off + o10), z11 = ldg4(x.z + off + o11);
+        float4 v00 = z00, v01 = z01, v10 = z10, v11 = z11;
         if (x.scale != nullptr) {
             v00 = act4(v00, s, t, x.relu); v01 = act4(v01, s, t, x.relu);
             v10 = act4(v10, s, t, x.relu); v11 = act4(v11, s, t, x.relu);
@@ -87,6 +143,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
         for (int k = 0; k < 4; ++k)
             d[k] = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f, kw == k ? g.w : 0.f);
         const idx_t offs[4] = {0, o01, o10, o11};
+        const float4 zz[4] = {z00, z01, z10, z11};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float* p = dx + off + offs[k];
@@ -96,8 +153,26 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(Act x, int N, int H, 
                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
             st4(p, o);
+            if (RED) {            // o is the COMPLETE gradient w.r.t. relu(bn(z)) at this pixel
+                const float4 zv = zz[k];
+                const float gx = (br.relu && fmaf(zv.x, s.x, t.x) <= 0.f) ? 0.f : o.x;
+                const float gy = (br.relu && fmaf(zv.y, s.y, t.y) <= 0.f) ? 0.f : o.y;
+                const float gz = (br.relu && fmaf(zv.z, s.z, t.z) <= 0.f) ? 0.f : o.z;
+                const float gw = (br.relu && fmaf(zv.w, s.w, t.w) <= 0.f) ? 0.f : o.w;
+                s1[0] += gx; s2[0] = fmaf(gx, (zv.x - mu.x) * is.x, s2[0]);
+                s1[1] += gy; s2[1] = fmaf(gy, (zv.y - mu.y) * is.y, s2[1]);
+                s1[2] += gz; s2[2] = fmaf(gz, (zv.z - mu.z) * is.z, s2[2]);
+                s1[3] += gw; s2[3] = fmaf(gw, (zv.w - mu.w) * is.w, s2[3]);
+            }
+        }
+        if (RED && ++trips == 4) {            // 16 values per fp32 partial, fp64 from there on
+            bn_red_flush(br, C4, s1, s2, d1, d2, false);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            trips = 0;
         }
     }
+    if (RED) bn_red_flush(br, C4, s1, s2, d1, d2, true);
 }
 
 template <typename idx_t>
@@ -127,13 +202,22 @@ __global__ void __launch_bounds__(256) add_fwd_kernel(Act a, int a_up, Act b, in
     }
 }
 
-template <typename idx_t>
+template <typename idx_t, bool RED>
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C4,
-                                                            float* __restrict__ da, int accumulate) {
+                                                            float* __restrict__ da, int accumulate, const BnRed br) {
     pdl_wait();               // programmatic dependent launch (common.cuh): no global access above
     const int OH = H / 2, OW = W / 2;
     const idx_t total = (idx_t)N * OH * OW * C4;
     const int C = C4 * 4;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, bs = mu, bt = mu;
+    if (RED) {                // the grid stride is a multiple of C4 (host): a thread stays on one channel quad
+        const int cq0 = (int)(((idx_t)blockIdx.x * blockDim.x + threadIdx.x) % (idx_t)C4);
+        mu = ldg4(br.mean + cq0 * 4); is = ldg4(br.invstd + cq0 * 4);
+        bs = ldg4(br.scale + cq0 * 4); bt = ldg4(br.shift + cq0 * 4);
+    }
+    int trips = 0;
     for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (idx_t)gridDim.x * blockDim.x) {
         int cq = (int)(i % (idx_t)C4);
         idx_t q = i / (idx_t)C4;
@@ -149,7 +233,25 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restr
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         st4(da + i * 4, o);
+        if (RED) {                // o is the COMPLETE gradient w.r.t. relu(bn(z)) at this pixel
+            const float4 zv = ldg4(br.z + i * 4);
+            const float gx = (br.relu && fmaf(zv.x, bs.x, bt.x) <= 0.f) ? 0.f : o.x;
+            const float gy = (br.relu && fmaf(zv.y, bs.y, bt.y) <= 0.f) ? 0.f : o.y;
+            const float gz = (br.relu && fmaf(zv.z, bs.z, bt.z) <= 0.f) ? 0.f : o.z;
+            const float gw = (br.relu && fmaf(zv.w, bs.w, bt.w) <= 0.f) ? 0.f : o.w;
+            s1[0] += gx; s2[0] = fmaf(gx, (zv.x - mu.x) * is.x, s2[0]);
+            s1[1] += gy; s2[1] = fmaf(gy, (zv.y - mu.y) * is.y, s2[1]);
+            s1[2] += gz; s2[2] = fmaf(gz, (zv.z - mu.z) * is.z, s2[2]);
+            s1[3] += gw; s2[3] = fmaf(gw, (zv.w - mu.w) * is.w, s2[3]);
+            if (++trips == 16) {
+                bn_red_flush(br, C4, s1, s2, d1, d2, false);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+                trips = 0;
+            }
+        }
     }
+    if (RED) bn_red_flush(br, C4, s1, s2, d1, d2, true);
 }
 
 __global__ void __launch_bounds__(256) add_into_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4,
@@ -300,20 +402,45 @@ extern "C" int hgk_maxpool2_fwd(const float* x, const float* x_scale, const floa
     return HGK_OK;
 }
 
-extern "C" int hgk_maxpool2_bwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
-                                int C, const float* dy, float* dx, int accumulate, void* stream) {
+// grid of a kernel with the fused BatchNorm-backward reduction: the stride (gridDim * 256) must be a multiple of C / 4 so that a
+// thread keeps its channel quad; 256 % (C / 4) == 0 is required by the caller
+static unsigned red_blocks(long long total) { return stream_blocks(total); }
+
+static int maxpool2_bwd_impl(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                             int C, const float* dy, float* dx, int accumulate, const BnRed& br, void* stream) {
     HGK_REQUIRE(x && dy && dx, "hgk_maxpool2_bwd: null pointer");
     HGK_NHWC_CHECK("hgk_maxpool2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_maxpool2_bwd: H and W must be even (H=%d W=%d)", H, W);
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    if (HGK_SMALL_IDX())
-        launch_pdl(maxpool2_bwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
-                                                                                dy, dx, accumulate);
-    else
-        launch_pdl(maxpool2_bwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, Act{x, x_scale, x_shift, x_relu}, N, H, W, C / 4,
-                                                                                dy, dx, accumulate);
+    const dim3 grid(red_blocks(total)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Act ax{x, x_scale, x_shift, x_relu};
+    if (br.z != nullptr) {
+        HGK_REQUIRE(C <= 1024 && 256 % (C / 4) == 0, "hgk_maxpool2_bwd_bnred: C / 4 must divide 256 (C=%d)", C);
+        HGK_REQUIRE(br.z == x && x_scale != nullptr, "hgk_maxpool2_bwd_bnred: the reduction is over the pooled tensor's own BatchNorm");
+        if (HGK_SMALL_IDX()) launch_pdl(maxpool2_bwd_kernel<unsigned, true>, grid, block, 0, st, ax, N, H, W, C / 4, dy, dx, accumulate, br);
+        else launch_pdl(maxpool2_bwd_kernel<long long, true>, grid, block, 0, st, ax, N, H, W, C / 4, dy, dx, accumulate, br);
+    } else {
+        if (HGK_SMALL_IDX()) launch_pdl(maxpool2_bwd_kernel<unsigned, false>, grid, block, 0, st, ax, N, H, W, C / 4, dy, dx, accumulate, br);
+        else launch_pdl(maxpool2_bwd_kernel<long long, false>, grid, block, 0, st, ax, N, H, W, C / 4, dy, dx, accumulate, br);
+    }
     HGK_CHECK_LAUNCH("hgk_maxpool2_bwd");
     return HGK_OK;
+}
+
+extern "C" int hgk_maxpool2_bwd(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                                int C, const float* dy, float* dx, int accumulate, void* stream) {
+    return maxpool2_bwd_impl(x, x_scale, x_shift, x_relu, N, H, W, C, dy, dx, accumulate, BnRed{}, stream);
+}
+
+extern "C" int hgk_maxpool2_bwd_bnred(const float* x, const float* x_scale, const float* x_shift, int x_relu, int N, int H, int W,
+                                      int C, const float* dy, float* dx, int accumulate, const float* mean, const float* invstd,
+                                      double* sum_g, double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                                      float* cA, float* cB, float* cC, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(mean && invstd && sum_g && sum_gx && gamma && cA && cB && cC && ticket, "hgk_maxpool2_bwd_bnred: null pointer");
+    BnRed br{x, x_scale, x_shift, mean, invstd, x_relu, sum_g, sum_gx,
+             BnBwdFin{gamma, mean, invstd, dgamma, dbeta, cA, cB, cC, ticket, training}, (long long)N * H * W};
+    return maxpool2_bwd_impl(x, x_scale, x_shift, x_relu, N, H, W, C, dy, dx, accumulate, br, stream);
 }
 
 extern "C" int hgk_add_fwd(const float* a, const float* a_scale, const float* a_shift, int a_relu, int a_up, const float* b,
@@ -333,17 +460,40 @@ extern "C" int hgk_add_fwd(const float* a, const float* a_scale, const float* a_
     return HGK_OK;
 }
 
-extern "C" int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, int accumulate, void* stream) {
+static int upsample2_bwd_impl(const float* dy, int N, int H, int W, int C, float* da, int accumulate, const BnRed& br, void* stream) {
     HGK_REQUIRE(dy && da, "hgk_upsample2_bwd: null pointer");
     HGK_NHWC_CHECK("hgk_upsample2_bwd");
     HGK_REQUIRE(H % 2 == 0 && W % 2 == 0, "hgk_upsample2_bwd: H and W must be even");
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    if (HGK_SMALL_IDX())
-        launch_pdl(upsample2_bwd_kernel<unsigned>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
-    else
-        launch_pdl(upsample2_bwd_kernel<long long>, dim3(stream_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dy, N, H, W, C / 4, da, accumulate);
+    const dim3 grid(red_blocks(total)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (br.z != nullptr) {
+        HGK_REQUIRE(C <= 1024 && 256 % (C / 4) == 0, "hgk_upsample2_bwd_bnred: C / 4 must divide 256 (C=%d)", C);
+        if (HGK_SMALL_IDX()) launch_pdl(upsample2_bwd_kernel<unsigned, true>, grid, block, 0, st, dy, N, H, W, C / 4, da, accumulate, br);
+        else launch_pdl(upsample2_bwd_kernel<long long, true>, grid, block, 0, st, dy, N, H, W, C / 4, da, accumulate, br);
+    } else {
+        if (HGK_SMALL_IDX()) launch_pdl(upsample2_bwd_kernel<unsigned, false>, grid, block, 0, st, dy, N, H, W, C / 4, da, accumulate, br);
+        else launch_pdl(upsample2_bwd_kernel<long long, false>, grid, block, 0, st, dy, N, H, W, C / 4, da, accumulate, br);
+    }
     HGK_CHECK_LAUNCH("hgk_upsample2_bwd");
     return HGK_OK;
+}
+
+extern "C" int hgk_upsample2_bwd(const float* dy, int N, int H, int W, int C, float* da, int accumulate, void* stream) {
+    return upsample2_bwd_impl(dy, N, H, W, C, da, accumulate, BnRed{}, stream);
+}
+
+/* da receives the LAST contribution to dL/d relu(bn(z)) of its tensor (z: [N,H/2,W/2,C]): the BatchNorm-backward reduction and
+ * its finaliser ride on this launch */
+extern "C" int hgk_upsample2_bwd_bnred(const float* dy, int N, int H, int W, int C, float* da, int accumulate, const float* z,
+                                       const float* scale, const float* shift, int relu, const float* mean, const float* invstd,
+                                       double* sum_g, double* sum_gx, const float* gamma, int training, float* dgamma, float* dbeta,
+                                       float* cA, float* cB, float* cC, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(z && scale && shift && mean && invstd && sum_g && sum_gx && gamma && cA && cB && cC && ticket,
+                "hgk_upsample2_bwd_bnred: null pointer");
+    BnRed br{z, scale, shift, mean, invstd, relu, sum_g, sum_gx,
+             BnBwdFin{gamma, mean, invstd, dgamma, dbeta, cA, cB, cC, ticket, training}, (long long)N * (H / 2) * (W / 2)};
+    return upsample2_bwd_impl(dy, N, H, W, C, da, accumulate, br, stream);
 }
 
 extern "C" int hgk_add_into(const float* src, float* dst, long long n, int accumulate, void* stream) {

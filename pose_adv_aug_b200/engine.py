@@ -693,6 +693,7 @@ _WRITES = {
     "bn_finalize": (7, 8, 9, 10, 11, 12), "bn_eval_prepare": (5, 6, 7, 8),
     "bn_bwd_reduce": (9, 10), "bn_bwd_finalize": (7, 8, 9, 10, 11), "bn_bwd_apply": (0,),
     "maxpool2_fwd": (8,), "maxpool2_bwd": (9,), "add_fwd": (13,), "upsample2_bwd": (5,), "add_into": (1,),
+    "maxpool2_bwd_bnred": (9, 13, 14, 17, 18, 19, 20, 21, 22), "upsample2_bwd_bnred": (5, 13, 14, 17, 18, 19, 20, 21, 22),
     "nchw_to_nhwc": (5,), "nhwc_to_nchw": (8,),
     "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7), "stem_conv7_wgrad_bnapply": (14, 15),
     "head_combine_fwd": (6, 7), "head_combine_bwd": (4, 5, 6, 7, 8, 9),
@@ -1053,6 +1054,19 @@ class _HeadCombOp(object):
                  g(self.outc.bias), self.C, self.J)
 
 
+def _last_contribution(p, t):
+    """True when the launch about to be emitted writes the LAST contribution to the gradient of the BatchNorm-carrying tensor t
+    (every consumer has contributed, nothing is pending) and the BatchNorm-backward reduction can ride on it."""
+    return (t.bn is not None and t.scale is not None and t.n_done == t.n_cons and not t.contribs and p.fuse_bn_bwd
+            and p.fuse_bn_fin and t.C % 4 == 0 and 256 % (t.C // 4) == 0)
+
+
+def _bn_red_args(p, t):
+    r = t.bn
+    return [_ptr(r.mean), _ptr(r.invstd), _ptr(r.sum_g), _ptr(r.sum_gx), _ptr(r.gamma), int(r.training),
+            p.param_grad_ptr(r.gamma), p.param_grad_ptr(r.beta), _ptr(r.cA), _ptr(r.cB), _ptr(r.cC), p.ticket_alloc()]
+
+
 class _PoolOp(object):
     """nn.MaxPool2d(2, 2) of a virtual activation, models/asn_stacked_hg.py:69,142-154,287."""
 
@@ -1072,7 +1086,12 @@ class _PoolOp(object):
         if g is None or not x.needs_grad:
             return
         gx, acc, _ = p.grad_target(x, allow_res=False)
-        p.launch(p.bwd, "maxpool2_bwd", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(g), _ptr(gx), acc]))
+        if _last_contribution(p, x):
+            # this launch completes dL/d relu(bn(z)) of the pooled tensor: its BatchNorm-backward reduction + finaliser ride along
+            p.launch(p.bwd, "maxpool2_bwd_bnred", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(g), _ptr(gx), acc] + _bn_red_args(p, x)))
+            x.bwd_stats_fused = x.bwd_fin_fused = True
+        else:
+            p.launch(p.bwd, "maxpool2_bwd", *(x.act_args() + [x.N, x.H, x.W, x.C, _ptr(g), _ptr(gx), acc]))
 
 
 class _AddOp(object):
@@ -1096,7 +1115,11 @@ class _AddOp(object):
             return
         if a.needs_grad:
             ga, acc, _ = p.grad_target(a, allow_res=False)
-            if self.up:
+            if self.up and _last_contribution(p, a):
+                p.launch(p.bwd, "upsample2_bwd_bnred", _ptr(g), b.N, b.H, b.W, b.C, _ptr(ga), acc, _ptr(a.z), _ptr(a.scale),
+                         _ptr(a.shift), int(a.relu), *_bn_red_args(p, a))
+                a.bwd_stats_fused = a.bwd_fin_fused = True
+            elif self.up:
                 p.launch(p.bwd, "upsample2_bwd", _ptr(g), b.N, b.H, b.W, b.C, _ptr(ga), acc)
             else:
                 p.launch(p.bwd, "add_into", _ptr(g), _ptr(ga), a.P * a.C, acc)

@@ -380,15 +380,17 @@ class _Hourglass_Wrapper(nn.Module):
                 y, _, _ = self.hg[i]._build(plan, x, mask=mask)         # ref:320-322: later stacks reuse the masks
             y = _build_stack(self.post_res[i], plan, y)                 # ref:327
             y = plan.conv(y, self.linear[i][0], bn=self.linear[i][1])   # ref:328
+            fused = FUSE_HEAD and i < self.num_stacks - 1
+            if fused:
+                # ref:332-334 as one convolution, built BEFORE out_conv: the backward then meets out_conv's (SIMT) data gradient
+                # first and this tensor-core one last, which carries y's BatchNorm-backward reduction in its epilogue
+                comb = plan.head_comb(self.forth_conv[i], self.in_conv[i], self.out_conv[i])
+                x = plan.conv(y, comb, res=x)
             o = plan.conv(y, self.out_conv[i])                          # ref:329
             outs.append(o)
-            if i < self.num_stacks - 1:
-                if FUSE_HEAD:
-                    comb = plan.head_comb(self.forth_conv[i], self.in_conv[i], self.out_conv[i])
-                    x = plan.conv(y, comb, res=x)                       # ref:332-334 as one convolution
-                else:
-                    t = plan.conv(y, self.forth_conv[i], res=x)         # ref:332,334
-                    x = plan.conv(o, self.in_conv[i], res=t)            # ref:333-334
+            if i < self.num_stacks - 1 and not fused:
+                t = plan.conv(y, self.forth_conv[i], res=x)             # ref:332,334
+                x = plan.conv(o, self.in_conv[i], res=t)                # ref:333-334
         return outs, agent
 
     def forward(self, x, asn=None, is_half_hg=False, is_aug=False, is_dropout=False):

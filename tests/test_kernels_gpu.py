@@ -295,6 +295,50 @@ def test_add_upsample_fwd_bwd(up):
         assert relerr(from_nhwc(ga), ref_g) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64), (3, 16, 32, 256), (24, 8, 8, 128)])
+@pytest.mark.parametrize("which", ["maxpool", "upsample"])
+def test_pool_upsample_bwd_with_fused_bn_reduction(shape, which):
+    """hgk_maxpool2_bwd_bnred / hgk_upsample2_bwd_bnred == the plain kernel followed by hgk_bn_bwd_reduce_fin over the gradient it
+    completed: same gradient bit for bit, same sums / dgamma / dbeta / cA / cB / cC to rounding, ticket re-armed."""
+    N, H, W, C = shape
+    v = {n: dev32(rnd(n, (C,), lo, hi)) for n, lo, hi in (("sc", 0.5, 1.5), ("sh", -0.3, 0.3), ("mu", -0.2, 0.2),
+                                                           ("iv", 0.5, 2.0), ("gamma", 0.5, 1.5))}
+
+    def fresh():
+        return dict(sg=torch.zeros(C, device=DEV, dtype=torch.float64), sgx=torch.zeros(C, device=DEV, dtype=torch.float64),
+                    dgamma=torch.zeros(C, device=DEV), dbeta=torch.zeros(C, device=DEV),
+                    cA=torch.zeros(C, device=DEV), cB=torch.zeros(C, device=DEV), cC=torch.zeros(C, device=DEV))
+    r, f = fresh(), fresh()
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    if which == "maxpool":
+        x = nhwc(rnd("x", (N, C, H, W), -2.0, 2.0))                      # pooled tensor (pre-BN), its gradient has the same shape
+        dy = nhwc(rnd("dy", (N, C, H // 2, W // 2)))
+        g0 = nhwc(rnd("g0", (N, C, H, W)))
+        g_ref, g_fus = g0.clone(), g0.clone()
+        call("maxpool2_bwd", ptr(x), ptr(v["sc"]), ptr(v["sh"]), 1, N, H, W, C, ptr(dy), ptr(g_ref), 1)
+        z, P = x, N * H * W
+        call("maxpool2_bwd_bnred", ptr(x), ptr(v["sc"]), ptr(v["sh"]), 1, N, H, W, C, ptr(dy), ptr(g_fus), 1, ptr(v["mu"]), ptr(v["iv"]),
+             ptr(f["sg"]), ptr(f["sgx"]), ptr(v["gamma"]), 1, ptr(f["dgamma"]), ptr(f["dbeta"]), ptr(f["cA"]), ptr(f["cB"]), ptr(f["cC"]),
+             ptr(ticket))
+    else:
+        z = nhwc(rnd("z", (N, C, H // 2, W // 2), -2.0, 2.0))            # tensor the up-sampled branch came from
+        dy = nhwc(rnd("dy", (N, C, H, W)))
+        g0 = nhwc(rnd("g0", (N, C, H // 2, W // 2)))
+        g_ref, g_fus = g0.clone(), g0.clone()
+        call("upsample2_bwd", ptr(dy), N, H, W, C, ptr(g_ref), 1)
+        P = N * (H // 2) * (W // 2)
+        call("upsample2_bwd_bnred", ptr(dy), N, H, W, C, ptr(g_fus), 1, ptr(z), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["iv"]),
+             ptr(f["sg"]), ptr(f["sgx"]), ptr(v["gamma"]), 1, ptr(f["dgamma"]), ptr(f["dbeta"]), ptr(f["cA"]), ptr(f["cB"]), ptr(f["cC"]),
+             ptr(ticket))
+    call("bn_bwd_reduce_fin", ptr(g_ref), ptr(z), ptr(v["sc"]), ptr(v["sh"]), 1, ptr(v["mu"]), ptr(v["iv"]), P, C, ptr(r["sg"]),
+         ptr(r["sgx"]), ptr(v["gamma"]), 1, ptr(r["dgamma"]), ptr(r["dbeta"]), ptr(r["cA"]), ptr(r["cB"]), ptr(r["cC"]), ptr(ticket))
+    torch.cuda.synchronize()
+    assert torch.equal(g_fus, g_ref)
+    assert int(ticket.item()) == 0
+    for key in ("sg", "sgx", "dgamma", "dbeta", "cA", "cB", "cC"):
+        assert relerr(f[key].float(), r[key].float()) < 1e-5, key
+
+
 def test_add_into_and_layout():
     for n in (1024, 1030, 7):
         a, b = rnd("a", (n,)), rnd("b", (n,))
