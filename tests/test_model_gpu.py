@@ -382,7 +382,7 @@ def test_multistream_graph_equals_single_stream():
     # a sign flip of a near-zero gradient moves a weight by 2 * 10 * lr); the same spread exists between two
     # single-stream runs, so only the loss is compared from here on
     for i in (2, 3):
-        assert abs(la[i] - lb[i]) < 2e-3 * abs(la[i]), (la, lb)
+        assert abs(la[i] - lb[i]) < (2e-3 if i == 2 else 5e-3) * abs(la[i]), (la, lb)
 
 
 def test_cpu_input_fails_loudly():

@@ -4,7 +4,7 @@
 # summaries are copied to profiles/ by hand.
 # usage: bash tools/sanitize.sh <tag> [pytest -k expression]
 TAG=${1:-san}
-KEXPR=${2:-"(conv_tc_fwd_3xtf32 or conv_tc_dgrad_bnapply or conv_tc_dgrad_1xtf32 or conv_tc_dgrad_bnstats or conv_wgrad_tc or conv_tc_fused_bn_finalize) and (shape0 or shape5 or shape15 or shape16 or (shape1 and not (shape10 or shape11 or shape12 or shape13 or shape14 or shape17 or shape18 or shape19)))"}
+KEXPR=${2:-"(conv_tc_fwd_3xtf32 or conv_tc_dgrad_bnapply or conv_tc_dgrad_1xtf32 or conv_tc_dgrad_bnstats or conv_wgrad_tc or conv_tc_fused_bn_finalize or pool_upsample_bwd_with_fused or stem_fwd_and_wgrad or conv_skinny) and (shape0 or shape5 or shape15 or shape16 or (shape1 and not (shape10 or shape11 or shape12 or shape13 or shape14 or shape17 or shape18 or shape19)))"}
 OUT=gpurun_out
 mkdir -p $OUT
 for TOOL in memcheck racecheck synccheck; do
