@@ -414,7 +414,7 @@ def dominant_kernel_roofline(tr, pk, torch):
         a = rec[1]
         if rec[2] == "conv_nhwc":
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[9], a[12]
-        elif rec[2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc"):
+        elif rec[2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc"):
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[10], a[12]
         else:
             continue
@@ -444,7 +444,8 @@ def dominant_kernel_roofline(tr, pk, torch):
     ms = e0.elapsed_time(e1) / (reps * len(recs))
     a = recs[0][1]
     N, H, W, Cin, Cout = a[4], a[5], a[6], a[7], a[12]
-    tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc")
+    tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc")
+    x2 = recs[0][2] == "conv_tc_bn_x2_nhwc"
     achieved = top / (ms / 1e3) / 1e12
     tile = tc and H % 16 == 0 and W % 16 == 0
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch: read from the newest committed `ncu --set full`
@@ -466,13 +467,16 @@ def dominant_kernel_roofline(tr, pk, torch):
             # kernel ended; the 50 MB output largely stays dirty in the 126 MB L2)
             "traffic": traffic, "traffic_src": traffic_src,
             "kernel": "%s 3x3 %d->%d @ %dx%dx%d (fwd, %d launches of this FLOP class/step)" %
-                      (("conv_tc2_kernel (tcgen05 image-tile kernel, 3xTF32)" if tile else "conv_tc_kernel (tcgen05, 3xTF32)")
+                      ((("conv_tc2_kernel (tcgen05 image-tile kernel, TF32 + 2xBF16)" if x2 else
+                         "conv_tc2_kernel (tcgen05 image-tile kernel, 3xTF32)") if tile else "conv_tc_kernel (tcgen05, 3xTF32)")
                        if tc else "conv_igemm_simt (fp32 FFMA)", Cin, Cout, N, H, W, len(recs)),
             "ms_per_launch": ms, "flop_per_launch": top, "algorithmic_bytes_per_launch": 4.0 * N * H * W * (Cin + Cout),
-            "mma_flop_per_launch": top * (3 if tc else 1),
-            "frac_of_3xtf32_ceiling": achieved / (pk["bf16_tflops"] / 6.0) if tc else None,
-            "peak_src": pk["src"] + " dense bf16 burst; achieved counts algorithmic fp32 FLOPs (the kernel issues 3 TF32 MMAs "
-                        "per product at 1/2 the bf16 rate, so its own ceiling is peak/6)"}
+            # tensor-core work in TF32-equivalents: 3 TF32 MMAs per product (3xTF32), or 1 TF32 + 2 BF16 at twice the rate = 2
+            "mma_flop_per_launch": top * ((2 if x2 else 3) if tc else 1),
+            "frac_of_own_tensor_ceiling": achieved / (pk["bf16_tflops"] / (4.0 if x2 else 6.0)) if tc else None,
+            "peak_src": pk["src"] + " dense bf16 burst; achieved counts algorithmic fp32 FLOPs (per fp32-class product the kernel "
+                        "issues " + ("one TF32 MMA at 1/2 the bf16 rate and two bf16 MMAs: its own ceiling is peak/4)" if x2 else
+                                     "3 TF32 MMAs at 1/2 the bf16 rate: its own ceiling is peak/6)")}
 
 
 def run_config3(args):

@@ -20,6 +20,8 @@ SIGNATURES = {
     "hgk_conv_tc_dgrad_bnstats_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P, P],
     "hgk_conv_tc_bn_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P,
                             P, P, F, F, P, P, P, P, P, P, P, P],
+    "hgk_conv_tc_bn_x2_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P,
+                               P, P, F, F, P, P, P, P, P, P, P, P],
     "hgk_conv_tc_dgrad_bnfin_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P,
                                      P, I, P, P, P, P, P, P, P],
     "hgk_conv_tc_dgrad_bnapply_nhwc": [P, P, P, P, I, P, P, P, P, P, I, I, I, I, P, I, I, P, P, I,
@@ -92,6 +94,8 @@ class _Lib(object):
         self.cdll.hgk_conv_tc_supported.argtypes = [I, I, I]
         self.cdll.hgk_conv_tc_bnapply_supported.restype = I
         self.cdll.hgk_conv_tc_bnapply_supported.argtypes = [I, I, I, I, I, I]
+        self.cdll.hgk_conv_tc_x2_supported.restype = I
+        self.cdll.hgk_conv_tc_x2_supported.argtypes = [I, I, I, I, I, I]
         self.cdll.hgk_conv_wgrad_tc_supported.restype = I
         self.cdll.hgk_conv_wgrad_tc_supported.argtypes = [I, I, I]
         for name, args in SIGNATURES.items():
@@ -105,6 +109,9 @@ class _Lib(object):
 
     def conv_tc_bnapply_supported(self, n, h, w, cin, cout, k):
         return bool(self.cdll.hgk_conv_tc_bnapply_supported(n, h, w, cin, cout, k))
+
+    def conv_tc_x2_supported(self, n, h, w, cin, cout, k):
+        return bool(self.cdll.hgk_conv_tc_x2_supported(n, h, w, cin, cout, k))
 
     def conv_wgrad_tc_supported(self, cin, cout, k):
         return bool(self.cdll.hgk_conv_wgrad_tc_supported(cin, cout, k))

@@ -23,6 +23,7 @@
 // 128 x BN tile in its shared memory, and after a cluster barrier every CTA sums ITS 128/S pixel rows over the S partial
 // tiles through distributed shared memory (fixed order: rank 0 .. S-1) and runs the usual epilogue on them.
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
@@ -1011,6 +1012,9 @@ static int launch_wg(const WgTcArgs& a, dim3 grid, cudaStream_t st) {
 // table rows (8 x int64): {src_off, dst_hi_off, dst_lo_off (-1: none), N, K, taps, mode, BN}
 //   mode 0 (forward) : B[n][k; tap] = W[o=n][i=k][tap]              (OIHW source, O=N, I=K)
 //   mode 1 (dgrad)   : B[n][k; tap] = W[o=k][i=n][taps-1-tap]       (O=K, I=N; taps pre-flipped)
+//   mode 2 (forward, TF32 + 2xBF16 products): hi as mode 0; the "lo" buffer holds, per 16-channel chunk (the footprint of the
+//                      fp32 lo half-block: BN x 64 bytes), the two bf16 cross-term operands in the K-major no-swizzle
+//                      core-matrix layout [k/8 (2)][n (BN)][8 x bf16]: first bf16(wh), then bf16(w - wh)
 // destination: [n-tile][tap][k/32] blocks, each block [quad(8)][n(BN)][4]
 // ------------------------------------------------------------------------------------------
 __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __restrict__ dst,
@@ -1038,11 +1042,23 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ src, float* __r
         const unsigned ntile = blk / utaps;
         const unsigned n = ntile * uBN + nn, k = kc * 32u + q * 4u + el;
         float v;
-        if (mode == 0) v = __ldg(sp + (n * (unsigned)K + k) * utaps + tap);
+        if (mode != 1) v = __ldg(sp + (n * (unsigned)K + k) * utaps + tap);
         else v = __ldg(sp + (k * (unsigned)N + n) * utaps + (utaps - 1u - tap));
         const float hi = tf32_rna(v);
         dst[dhi + i] = hi;
-        if (dlo >= 0) dst[dlo + i] = v - hi;
+        if (dlo >= 0) {
+            if (mode == 2) {
+                // half-block of this 16-channel chunk (in floats from the lo base), then bf16 positions inside it
+                const unsigned hb = ((ntile * utaps + tap) * KC + kc) * uBN * 32u + (q >> 2) * uBN * 16u;
+                const unsigned k16 = (q & 3u) * 4u + el;                 // channel inside the chunk
+                const unsigned pos = (k16 >> 3) * uBN * 8u + nn * 8u + (k16 & 7u);     // [k/8][n][8]
+                __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(dst + dlo + hb);
+                lb[pos] = __float2bfloat16_rn(hi);
+                lb[uBN * 16u + pos] = __float2bfloat16_rn(v - hi);
+            } else {
+                dst[dlo + i] = v - hi;
+            }
+        }
     }
 }
 
@@ -1162,6 +1178,8 @@ static bool use_tc3(int ksize, bool split) {
     return (tc3_mask() >> bit) & 1;
 }
 
+extern "C" int hgk_conv_tc_x2_supported(int N, int H, int W, int Cin, int Cout, int ksize);
+
 static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shift, int x_relu,
                         int N, int H, int W, int Cin,
                         const float* w_hi, const float* w_lo, int ksize, const float* bias, int Cout,
@@ -1169,7 +1187,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
                         float* y, int accumulate, double* stat_sum, double* stat_sq,
                         const float* bz, const float* bscale, const float* bshift, const float* bmean,
                         const float* binvstd, int brelu, const BnFwdFin* ffin, const BnBwdFin* bfin, void* stream,
-                        const BnApply* ap = nullptr) {
+                        const BnApply* ap = nullptr, int lo_bf16 = 0) {
     HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
     HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
     HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
@@ -1193,7 +1211,10 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
         HGK_REQUIRE(w_lo == nullptr && ((use_tc3(ksize, false) && conv_tc3_eligible(ta)) || (use_tile_kernel() && conv_tc2_eligible(ta))),
                     "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
                     "image-tile kernel (see hgk_conv_tc_bnapply_supported)");
-    ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf;
+    ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf; ta.lo_bf16 = lo_bf16;
+    if (lo_bf16)
+        HGK_REQUIRE(w_lo != nullptr && ap == nullptr && hgk_conv_tc_x2_supported(N, H, W, Cin, Cout, ksize),
+                    "hgk_conv_tc_bn_x2_nhwc: shape not covered by the TF32 + 2xBF16 tile kernel (see hgk_conv_tc_x2_supported)");
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
@@ -1239,6 +1260,41 @@ extern "C" int hgk_conv_tc_bn_nhwc(const float* x, const float* x_scale, const f
     return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_lo, ksize, bias, Cout, res, res_scale, res_shift,
                         res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &f, nullptr,
                         stream);
+}
+
+// 1 when a forward convolution of this shape runs on the image-tile kernel with TF32 + 2xBF16 products (3x3, H and W multiples
+// of 16, 64 / 128 output channels, not one of the small split-K layers, 3x3 forward not routed to conv_tc3).  HGK_X2=0 disables it.
+extern "C" int hgk_conv_tc_x2_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HGK_X2");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (!on || ksize != 3 || !hgk_conv_tc_supported(Cin, Cout, ksize) || (Cout != 64 && Cout != 128) || N <= 0 || H <= 0 || W <= 0)
+        return 0;
+    TcArgs ta{};
+    ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
+    ta.c.P = (long long)N * H * W;
+    if (splitk_factor(ta.c.P, Cin, Cout, ksize) > 1) return 0;
+    if (use_tc3(ksize, true) && conv_tc3_eligible(ta)) return 0;
+    return (use_tile_kernel() && conv_tc2_eligible(ta)) ? 1 : 0;
+}
+
+extern "C" int hgk_conv_tc_bn_x2_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                      int N, int H, int W, int Cin,
+                                      const float* w_hi, const float* w_x2, int ksize, const float* bias, int Cout,
+                                      const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                                      float* y, int accumulate, double* stat_sum, double* stat_sq,
+                                      const float* gamma, const float* beta, float eps, float momentum,
+                                      float* running_mean, float* running_var, float* scale, float* shift,
+                                      float* save_mean, float* save_invstd, unsigned int* ticket, void* stream) {
+    HGK_REQUIRE(stat_sum && stat_sq && gamma && beta && scale && shift && save_mean && save_invstd && ticket && w_x2,
+                "hgk_conv_tc_bn_x2_nhwc: null pointer");
+    HGK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "hgk_conv_tc_bn_x2_nhwc: running stats must both be set");
+    BnFwdFin f{gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, ticket, eps, momentum};
+    return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_x2, ksize, bias, Cout, res, res_scale, res_shift,
+                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &f, nullptr,
+                        stream, nullptr, 1);
 }
 
 extern "C" int hgk_conv_tc_dgrad_bnstats_nhwc(const float* dz, int N, int H, int W, int Cin,

@@ -28,6 +28,14 @@
 #include "tc_common.cuh"
 #include "bn_fin.cuh"
 
+// TF32 + 2xBF16 forward products (template parameter XBF; 3x3 forward, the tensor-bound launches of the step).  The fp32-class
+// product x*w ~= xh*wh + xl*wh + xh*wl keeps its main term in TF32 (kind::tf32, K = 8) and evaluates the two cross terms --
+// each 2^-11 of the main term -- with bf16 operands (kind::f16, K = 16): bf16(xl)*bf16(wh) + bf16(xh)*bf16(wl), error
+// ~3 * 2^-20 per product.  Four MMAs per 16-channel chunk and tap instead of six, same shared-memory bytes: the fp32 lo plane
+// of the activation stage is replaced by two bf16 tiles (xl, xh) in the K-major NO-swizzle core-matrix layout
+// [k/8 (2 planes)][halo pixel][8 x bf16 = 16 B] (pixel rows 16 bytes apart, so a 3x3 tap is again a shifted start address:
+// (dh*HWD + dw) * 16 bytes; 8-pixel row group -> next image row = SBO = HWD * 16), the fp32 lo half of the weight stage by
+// [wh_bf16 | wl_bf16] in [k/8][n][8 x bf16] (pack mode 2, conv_tc.cu).
 namespace hgk {
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B (layout type 4 in bits 61-63): rows of 64 bytes, 8-row groups
@@ -84,9 +92,16 @@ struct T2Cfg {
     static_assert(SMEM <= (OCC2 ? 113 : 227) * 1024, "shared memory");
 };
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB>
+template <int BN, bool SPLIT, int KS, int NSUB>
+__host__ __device__ constexpr uint32_t Cfg_NPIX16() { return (uint32_t)T2Cfg<BN, SPLIT, KS, NSUB>::NPIX * 16u; }
+
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB, bool XBF = false>
 __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 ? 2 : 1)) conv_tc2_kernel(const TcArgs args) {
     static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
+    static_assert(!XBF || SPLIT, "bf16 cross terms belong to the error-compensated forward");
+    // XBF: second half of an activation stage = xl tile (2 planes of NPIX x 16 B) followed by the xh tile
+    constexpr uint32_t XPLANE = Cfg_NPIX16<BN, SPLIT, KS, NSUB>();
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
     using Cfg = T2Cfg<BN, SPLIT, KS, NSUB>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NMAIN = Cfg::NMAIN, NACC = Cfg::NACC;
     constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SUBCOLS = Cfg::SUBCOLS;
@@ -221,9 +236,18 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                 }
                 const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
                 *reinterpret_cast<float4*>(base + s_off[j]) = hi;
-                if (SPLIT) {
+                if (SPLIT && !XBF) {
                     const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
                     *reinterpret_cast<float4*>(base + A_HALF + s_off[j]) = lo;
+                }
+                if (XBF) {
+                    // bf16 tiles: plane = channel quad / 2 (8-channel K group), row = halo pixel (16 B), 8-byte half = quad & 1
+                    const uint32_t boff = (uint32_t)(quad >> 1) * XPLANE + (uint32_t)((tid + 256 * j) >> 2) * 16u + (uint32_t)(quad & 1) * 8u;
+                    uint2 xl, xh;
+                    xl.x = pack_bf16x2(v.x - hi.x, v.y - hi.y); xl.y = pack_bf16x2(v.z - hi.z, v.w - hi.w);
+                    xh.x = pack_bf16x2(hi.x, hi.y); xh.y = pack_bf16x2(hi.z, hi.w);
+                    *reinterpret_cast<uint2*>(base + A_HALF + boff) = xl;
+                    *reinterpret_cast<uint2*>(base + A_HALF + 2u * XPLANE + boff) = xh;
                 }
             }
         };
@@ -293,11 +317,26 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
 #pragma unroll
                     for (int sub = 0; sub < NSUB; ++sub) {
                         const uint32_t t_sub = tmem + sub * SUBCOLS;
+                        if (XBF) {
+                            // cross terms, one K = 16 bf16 MMA each: xl * wh_bf16 and xh_bf16 * wl_bf16
+                            const uint32_t x_tap = a_stage + A_HALF + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 16u : 0u) + sub * 128;
+                            const uint64_t dxl = umma_desc(x_tap, XPLANE, (uint32_t)HWD * 16u);
+                            const uint64_t dxh = umma_desc(x_tap + 2u * XPLANE, XPLANE, (uint32_t)HWD * 16u);
+                            const uint64_t dwh = umma_desc(b_hi + B_HALF, LBO_B, SBO_B);
+                            const uint64_t dwl = umma_desc(b_hi + B_HALF + BN * 32, LBO_B, SBO_B);
+                            const uint32_t t_x = NACC == 1 ? t_sub : t_sub + NMAIN * BN;
+                            umma_bf16(t_x, dxl, dwh, IDESC_BF, (NACC == 1 || it > 0) ? (it > 0 ? 1u : 0u) : 0u);
+                            umma_bf16(t_x, dxh, dwl, IDESC_BF, 1u);
+                        }
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             const uint64_t da = umma_desc_k64(a_tap + sub * 512 + k * 32, SBO_A);
                             const uint64_t db = umma_desc(b_hi + k * 2 * LBO_B, LBO_B, SBO_B);
-                            if (SPLIT) {
+                            if (XBF) {
+                                const uint32_t t_main = NACC == 1 ? t_sub : t_sub + (NMAIN > 1 ? (it & 1) * BN : 0);
+                                // (NACC == 1: the bf16 MMA above already initialised the accumulator of this stage)
+                                umma_tf32(t_main, da, db, IDESC, NACC == 1 ? 1u : ((it >= NMAIN || k > 0) ? 1u : 0u));
+                            } else if (SPLIT) {
                                 const uint64_t dal = umma_desc_k64(a_tap + A_HALF + sub * 512 + k * 32, SBO_A);
                                 const uint64_t dbl = umma_desc(b_hi + B_HALF + k * 2 * LBO_B, LBO_B, SBO_B);
                                 if (NACC == 1) {
@@ -510,12 +549,12 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     }
 }
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB>
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, int NSUB, bool XBF = false>
 static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
     static bool configured = false;
     constexpr int smem = T2Cfg<BN, SPLIT, KS, NSUB>::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc (tile kernel): cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
@@ -523,7 +562,7 @@ static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
         configured = true;
     }
     const unsigned grid = (unsigned)(ta.c.N * (ta.c.H >> 4) * (ta.c.W / (8 * NSUB)));
-    cudaError_t le = launch_pdl(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB>, dim3(grid), dim3(T2_THREADS), (size_t)smem, st, ta);
+    cudaError_t le = launch_pdl(conv_tc2_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, NSUB, XBF>, dim3(grid), dim3(T2_THREADS), (size_t)smem, st, ta);
     if (le != cudaSuccess) {
         set_error("hgk_conv_tc_nhwc (image-tile kernel): launch: %s", cudaGetErrorString(le));
         return HGK_ECUDA;
@@ -531,7 +570,7 @@ static int launch_tc2_sub(const TcArgs& ta, cudaStream_t st) {
     return HGK_OK;
 }
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false>
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY = false, bool XBF = false>
 static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
     // 16x8 tiles (twice the CTAs, two per SM: prologue / epilogue of one overlaps the main loop of the other) up to the
     // 64x64 layers; 16x16 tiles (half the weight stream per pixel) for the 128x128 layers.  Measured on the config-2
@@ -542,8 +581,8 @@ static int launch_tc2_cfg(const TcArgs& ta, cudaStream_t st) {
         const char* e = getenv("HGK_TC2_SUB1_BELOW");
         below = e != nullptr ? atoll(e) : 400;
     }
-    if (tiles16 < below) return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 1>(ta, st);
-    return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 2>(ta, st);
+    if (tiles16 < below) return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 1, XBF>(ta, st);
+    return launch_tc2_sub<BN, SPLIT, KS, BWDSTATS, BNAPPLY, 2, XBF>(ta, st);
 }
 
 template <int BN, int KS>
@@ -551,7 +590,15 @@ static int launch_tc2_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream
     if (ta.c.ap.z != nullptr)        // data gradient with the BatchNorm-backward apply evaluated on load
         return bwdstats ? launch_tc2_cfg<BN, false, KS, true, true>(ta, st) : launch_tc2_cfg<BN, false, KS, false, true>(ta, st);
     if (bwdstats) return launch_tc2_cfg<BN, false, KS, true>(ta, st);
-    if (split) return launch_tc2_cfg<BN, true, KS, false>(ta, st);
+    if (split) {
+        // TF32 + 2xBF16 products (w_lo in pack mode 2): 3x3 forward with 64 / 128 output channels only
+        if (ta.lo_bf16) {
+            if (KS == 3 && BN <= 128) return launch_tc2_cfg<BN, true, KS == 3 ? 3 : 1, false, false, (KS == 3 && BN <= 128)>(ta, st);
+            set_error("hgk_conv_tc_bn_x2_nhwc: no TF32 + 2xBF16 instantiation for k=%d Cout=%d", KS, BN);
+            return HGK_EINVAL;
+        }
+        return launch_tc2_cfg<BN, true, KS, false>(ta, st);
+    }
     return launch_tc2_cfg<BN, false, KS, false>(ta, st);
 }
 

@@ -10,6 +10,7 @@ struct TcArgs {
     const float* w_hi;
     const float* w_lo;
     long long* dbg;      // optional timeline buffer (developer diagnostics): [cta][16] globaltimer stamps
+    int lo_bf16;         // w_lo holds the bf16 cross-term operands [wh_bf16 | wl_bf16] (pack mode 2) instead of fp32 w - wh
 };
 
 extern long long* g_dbg_buf;
@@ -67,6 +68,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
+}
+// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulation in TMEM
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// two fp32 -> one register of two bf16 (round to nearest even), low half = first argument
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

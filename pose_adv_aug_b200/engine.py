@@ -341,9 +341,10 @@ class Plan(object):
 
     def packed_weight_tc(self, w, mode, need_lo):
         """(hi, lo) references of the UMMA-layout copy of OIHW weight `w` (see hgk_pack_weights_tc).
-        mode 0: forward operand (N=O, K=I); mode 1: data-gradient operand (N=I, K=O, taps flipped)."""
+        mode 0: forward operand (N=O, K=I); mode 1: data-gradient operand (N=I, K=O, taps flipped); mode 2: forward operand
+        whose "lo" buffer holds the bf16 cross-term operands of the TF32 + 2xBF16 kernel (hgk_conv_tc_bn_x2_nhwc)."""
         O, I = w.shape[0], w.shape[1]
-        BN = O if mode == 0 else I
+        BN = O if mode != 1 else I
         n = (w.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         for e in self.tc_entries:
             if e[0] is w and e[1] == mode:
@@ -597,7 +598,7 @@ class Plan(object):
                 d = w.data_ptr() - base            # signed, see above
                 assert d % 4 == 0
                 O, I, taps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
-                N, K = (O, I) if mode == 0 else (I, O)
+                N, K = (O, I) if mode != 1 else (I, O)
                 rows.append([d // 4, hi, lo, N, K, taps, mode, BN])
             self.tc_table = torch.tensor(rows, dtype=torch.long, device=self.device)
             self.tc_launch = [self.lib.pack_weights_tc,
@@ -685,7 +686,7 @@ class Plan(object):
 # argument positions written by each entry point (everything else is read-only); used by schedule_streams
 _WRITES = {
     "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20), "conv_tc_dgrad_bnstats_nhwc": (10, 18, 19),
-    "conv_tc_bn_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31),
+    "conv_tc_bn_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31), "conv_tc_bn_x2_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31),
     "conv_tc_dgrad_bnfin_nhwc": (10, 18, 19, 22, 23, 24, 25, 26, 27),
     "bn_bwd_reduce_fin": (9, 10, 13, 14, 15, 16, 17, 18),
     "conv_tc_dgrad_bnapply_nhwc": (9, 18, 26, 27, 30, 31, 32, 33, 34, 35),
@@ -921,11 +922,15 @@ class _ConvOp(object):
         fin_fused = False
         if p.use_tc and p.lib.conv_tc_supported(Cin, Cout, k):
             # tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class accuracy)
-            hi, lo = p.packed_weight_tc(w, 0, True)
+            # 3x3 layers on the image-tile kernel: TF32 + 2xBF16 products (4 instead of 6 tensor-core instructions per product
+            # group, same fp32-class accuracy class; csrc/conv_tc2.cu)
+            x2 = (stats and p.fuse_bn_fin and not p.precise_grads     # (PRECISE_GRADS: the all-3xTF32 / fp32 mode)
+                  and p.lib.conv_tc_x2_supported(x.N, x.H, x.W, Cin, Cout, k))
+            hi, lo = p.packed_weight_tc(w, 2 if x2 else 0, True)
             base = x.act_args() + [x.N, x.H, x.W, Cin, hi, lo, k, p.param_ptr(conv.bias), Cout] + ra
             if stats and p.fuse_bn_fin:
                 # the last CTA of the convolution finalises the BatchNorm (scale/shift, running statistics)
-                p.launch(p.fwd, "conv_tc_bn_nhwc", *(base + [_ptr(z), 0, _ptr(r.sum), _ptr(r.sq), _ptr(r.gamma), _ptr(r.beta),
+                p.launch(p.fwd, "conv_tc_bn_x2_nhwc" if x2 else "conv_tc_bn_nhwc", *(base + [_ptr(z), 0, _ptr(r.sum), _ptr(r.sq), _ptr(r.gamma), _ptr(r.beta),
                                                              BN_EPS, BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale),
                                                              _ptr(r.shift), _ptr(r.mean), _ptr(r.invstd), p.ticket_alloc()]))
                 fin_fused = True

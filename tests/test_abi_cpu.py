@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     # every entry point that launches work is bound with a signature
     launching = [n for n in names if n not in ("hgk_last_error", "hgk_version", "hgk_device_ok", "hgk_conv_tc_supported",
                                                "hgk_conv_wgrad_tc_supported", "hgk_debug_set_timeline",
-                                               "hgk_conv_tc_bnapply_supported", "hgk_pdl_arm")]
+                                               "hgk_conv_tc_bnapply_supported", "hgk_pdl_arm", "hgk_conv_tc_x2_supported")]
     assert sorted(launching) == sorted(SIGNATURES.keys())
     assert lib.cdll.hgk_version() >= 100
 
@@ -94,11 +94,12 @@ def test_plan_builds_and_covers_every_parameter():
     names = [r[2] for r in plan.fwd]
     # 101 convolutions in the reference graph; the inter-stack in_conv is folded into forth_conv (Plan.head_comb)
     n_conv = 100 if M.FUSE_HEAD else 101
-    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + names.count("conv_nhwc") == n_conv
+    n_x2 = names.count("conv_tc_bn_x2_nhwc")          # 3x3 layers on the image-tile kernel: TF32 + 2xBF16 products
+    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + n_x2 + names.count("conv_nhwc") == n_conv
             and names.count("stem_conv7_fwd") == 1)
     assert [r[2] for r in plan.pre] == (["head_combine_fwd"] if M.FUSE_HEAD else [])
     # 96 BatchNorms: 95 finalised by the last CTA of their tensor-core convolution, the stem's by its own launch
-    assert names.count("conv_tc_bn_nhwc") == 95 and names.count("bn_finalize") == 1
+    assert names.count("conv_tc_bn_nhwc") + n_x2 == 95 and names.count("bn_finalize") == 1 and n_x2 >= 10
     assert names.count("maxpool2_fwd") == 9 and names.count("add_fwd") == 8
     bnames = [r[2] for r in plan.bwd]
     assert bnames.count("conv_wgrad_tc_nhwc") + bnames.count("conv_wgrad_nhwc") == n_conv

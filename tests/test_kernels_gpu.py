@@ -581,6 +581,61 @@ def test_conv_tc_fused_bn_finalize(shape):
     assert relerr(drm.cpu(), rm1) < 2e-5 and relerr(drv.cpu(), rv1) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(8, 16, 16, 128, 128, 3), (3, 32, 48, 128, 128, 3), (2, 64, 64, 64, 64, 3),
+                                   (10, 64, 64, 128, 128, 3), (2, 128, 128, 64, 64, 3), (8, 16, 16, 256, 128, 3)])
+@pytest.mark.parametrize("variant", ["plain", "full"])
+def test_conv_tc_fwd_tf32_plus_2xbf16(shape, variant):
+    """hgk_conv_tc_bn_x2_nhwc: x*w ~= xh*wh (TF32) + bf16(xl)*bf16(wh) + bf16(xh)*bf16(wl) on the image-tile kernel (pack mode 2)
+    against the fp64 convolution: same tolerance as the 3xTF32 kernel (error ~3 * 2^-20 per product), BN+ReLU on load,
+    shortcut, accumulate, fused BatchNorm statistics / finaliser."""
+    N, H, W, Ci, Co, k = shape
+    assert lib().cdll.hgk_conv_tc_x2_supported(N, H, W, Ci, Co, k) == 1
+    x = rnd("x", (N, Ci, H, W))
+    w = rnd("w", (Co, Ci, k, k), -0.2, 0.2)
+    b = rnd("b", (Co,))
+    full = variant == "full"
+    xs, xt = (rnd("xs", (Ci,), 0.5, 1.5), rnd("xt", (Ci,), -0.3, 0.3)) if full else (None, None)
+    res = rnd("res", (N, Co, H, W)) if full else None
+    rs, rt = (rnd("rs", (Co,), 0.5, 1.5), rnd("rt", (Co,), -0.3, 0.3)) if full else (None, None)
+    y0 = rnd("y0", (N, Co, H, W)) if full else None
+    ref = _conv_ref(affine_act(x, xs, xt, True), w, b, k)
+    if full:
+        ref = ref + affine_act(res, rs, rt, True) + y0
+    gamma, beta = rnd("gamma", (Co,), 0.5, 1.5), rnd("beta", (Co,), -0.3, 0.3)
+    rm0, rv0 = rnd("rm", (Co,), -0.2, 0.2), rnd("rv", (Co,), 0.5, 1.5)
+    # pack mode 2: hi as the forward operand, "lo" buffer = bf16 cross-term operands
+    src = dev32(w.reshape(-1))
+    dst = torch.zeros(2 * w.numel(), device=DEV)
+    table = torch.tensor([[0, 0, w.numel(), Co, Ci, k * k, 2, Co]], dtype=torch.long, device=DEV)
+    call("pack_weights_tc", ptr(src), ptr(dst), ptr(table), 1)
+    hi, x2 = dst[:w.numel()], dst[w.numel():]
+    hi0, _ = _pack_tc(w, 0, Co)
+    assert torch.equal(hi, hi0)
+    dx, db = nhwc(x), dev32(b)
+    dxs, dxt = (dev32(xs), dev32(xt)) if full else (None, None)
+    dres = nhwc(res) if full else None
+    drs, drt = (dev32(rs), dev32(rt)) if full else (None, None)
+    y = nhwc(y0) if full else torch.empty(N, H, W, Co, device=DEV)
+    dg, dbeta, drm, drv = dev32(gamma), dev32(beta), dev32(rm0), dev32(rv0)
+    sc, sh, sm, si = (torch.zeros(Co, device=DEV) for _ in range(4))
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    ssum = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    ssq = torch.zeros(Co, device=DEV, dtype=torch.float64)
+    call("conv_tc_bn_x2_nhwc", ptr(dx), ptr(dxs), ptr(dxt), 1, N, H, W, Ci, ptr(hi), ptr(x2), k, ptr(db), Co,
+         ptr(dres), ptr(drs), ptr(drt), 1, ptr(y), int(full), ptr(ssum), ptr(ssq), ptr(dg), ptr(dbeta), 1e-5, 0.1, ptr(drm),
+         ptr(drv), ptr(sc), ptr(sh), ptr(sm), ptr(si), ptr(ticket))
+    torch.cuda.synchronize()
+    assert int(ticket.item()) == 0
+    err = relerr(from_nhwc(y), ref)
+    print("TF32 + 2xBF16 %s %s: rel-to-max error %.2e" % (shape, variant, err))
+    assert err < 2e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 2e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
+    mean = ref.mean(dim=(0, 2, 3))
+    invstd = 1.0 / torch.sqrt(ref.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    assert relerr(sm.cpu(), mean) < 2e-5 and relerr(si.cpu(), invstd) < 2e-5
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 3), (2, 8, 8, 128, 128, 3), (1, 64, 64, 128, 64, 1)])
 def test_bn_bwd_fused_finalizers(shape):
     """dgrad + BN-backward sums + finaliser in one launch, and bn_bwd_reduce + finaliser in one launch, both against
