@@ -27,29 +27,37 @@ __device__ __forceinline__ void stem_load_patch(float* patch, const float* img, 
     }
 }
 
-// Persistent CTAs (3 per SM) walk over the output tiles; 256 threads: tx = tid&15 -> 4 couts, ty = tid>>4 -> 8 pixels of one
-// tile row.  The [k][co] weight tile is staged ONCE per CTA (a per-tile transposing store with a 64-float stride was a
-// 32-way bank conflict: ~9 400 LSU cycles per tile, 40 % of the kernel), and a thread reads the 21 consecutive patch floats
-// its eight stride-2 windows cover as six LDS.128 per (channel, kh) row instead of one scalar load per tap and pixel
-// (13 shared-memory loads per 224 FFMA; it was 9 per 32, LSU-bound).  Patch rows are padded to 40 floats (alignment).
+// Persistent CTAs (3 per SM) walk over the output tiles; 128 threads: tx = tid&7 -> 8 couts, ty = tid>>3 -> 8 pixels of one tile
+// row (64 accumulators per thread).  The [k][co] weight tile is staged ONCE per CTA (a per-tile transposing store with a
+// 64-float stride was a 32-way bank conflict: ~9 400 LSU cycles per tile, 40 % of the first kernel), and a thread reads the 21
+// consecutive patch floats its eight stride-2 windows cover as six LDS.128 per (channel, kh) row.  An LDS.128 costs four LSU
+// cycles per warp: with 8 x 4 outputs per thread (13 loads = 52 LSU cycles per 224 FFMA = 56 issue cycles) the kernel was
+// LSU- and FFMA-bound at the same time (ncu: FMA pipe 51 %); 8 x 8 needs 80 LSU cycles per 448 FFMA (112 issue cycles).
+// Patch rows are padded to 40 floats (alignment).  (Measured and rejected: rows of 44 floats + couts interleaved as {4 tx ..} and
+// {32 + 4 tx ..}, which removes the two-way bank conflicts ncu reports, made the kernel slower: 240 us against 210.)
 constexpr int ST_PWF = 40;
+constexpr int ST_FWD_THREADS = 128;
 
-__global__ void __launch_bounds__(256, 3) stem_conv7_fwd_kernel(const float* __restrict__ img, int N, int H, int W,
-                                                                const float* __restrict__ w, const float* __restrict__ bias,
-                                                                float* __restrict__ y, double* stat_sum, double* stat_sq,
-                                                                int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(ST_FWD_THREADS, 3) stem_conv7_fwd_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                                           float* __restrict__ y, double* stat_sum, double* stat_sq,
+                                                                           int tiles_x, int tiles_y) {
     __shared__ __align__(16) float Ws[ST_K * ST_CO];          // [k][co]
     __shared__ __align__(16) float patch[3 * ST_PH * ST_PWF];
     const int tid = threadIdx.x;
     const int OH = H / 2, OW = W / 2;
-    for (int i = tid; i < ST_K * ST_CO; i += 256) {           // consecutive threads -> consecutive co: conflict-free stores
+    for (int i = tid; i < ST_K * ST_CO; i += ST_FWD_THREADS) {   // consecutive threads -> consecutive co: conflict-free stores
         const int k = i >> 6, co = i & 63;
         Ws[i] = __ldg(w + co * ST_K + k);
     }
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 7, ty = tid >> 3;
     const int oy = ty >> 1, oxb = (ty & 1) * 8;
-    const float4 bv = bias ? ldg4(bias + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+    float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
+    if (bias) { bv0 = ldg4(bias + tx * 8); bv1 = ldg4(bias + tx * 8 + 4); }
+    const float bvv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+    double d1[8], d2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
     const int total = tiles_x * tiles_y * N;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int n = t / (tiles_x * tiles_y);
@@ -58,7 +66,7 @@ __global__ void __launch_bounds__(256, 3) stem_conv7_fwd_kernel(const float* __r
         const int oy0 = tyi * ST_TH, ox0 = txi * ST_TW;
         const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
         __syncthreads();                                      // previous tile's patch fully consumed (first trip: Ws staged)
-        for (int i = tid; i < 3 * ST_PH * ST_PWF; i += 256) {
+        for (int i = tid; i < 3 * ST_PH * ST_PWF; i += ST_FWD_THREADS) {
             const int cc = i / (ST_PH * ST_PWF);
             const int rr = i - cc * (ST_PH * ST_PWF);
             const int py = rr / ST_PWF, px = rr - py * ST_PWF;
@@ -69,11 +77,11 @@ __global__ void __launch_bounds__(256, 3) stem_conv7_fwd_kernel(const float* __r
             patch[i] = v;
         }
         __syncthreads();
-        float acc[8][4];
+        float acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 1
         for (int ck = 0; ck < 21; ++ck) {                     // (channel, kh) patch rows
             const int c = ck / 7, kh = ck - c * 7;
@@ -86,53 +94,58 @@ __global__ void __launch_bounds__(256, 3) stem_conv7_fwd_kernel(const float* __r
             }
 #pragma unroll
             for (int kw = 0; kw < 7; ++kw) {
-                const float4 b = ld4(Ws + (ck * 7 + kw) * ST_CO + tx * 4);
+                const float4 b0 = ld4(Ws + (ck * 7 + kw) * ST_CO + tx * 8), b1 = ld4(Ws + (ck * 7 + kw) * ST_CO + tx * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float av = pv[i * 2 + kw];
-                    acc[i][0] = fmaf(av, b.x, acc[i][0]);
-                    acc[i][1] = fmaf(av, b.y, acc[i][1]);
-                    acc[i][2] = fmaf(av, b.z, acc[i][2]);
-                    acc[i][3] = fmaf(av, b.w, acc[i][3]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av, bb[j], acc[i][j]);
                 }
             }
         }
-        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
         const int gy = oy0 + oy;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int gx = ox0 + oxb + i;
             if (gy < OH && gx < OW) {
-                const float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
-                st4(y + (((size_t)n * OH + gy) * OW + gx) * ST_CO + tx * 4, v);
-                s1[0] += v.x; s2[0] = fmaf(v.x, v.x, s2[0]);
-                s1[1] += v.y; s2[1] = fmaf(v.y, v.y, s2[1]);
-                s1[2] += v.z; s2[2] = fmaf(v.z, v.z, s2[2]);
-                s1[3] += v.w; s2[3] = fmaf(v.w, v.w, s2[3]);
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[j] = acc[i][j] + bvv[j];
+                    s1[j] += v[j];
+                    s2[j] = fmaf(v[j], v[j], s2[j]);
+                }
+                float* yo = y + (((size_t)n * OH + gy) * OW + gx) * ST_CO + tx * 8;
+                st4(yo, make_float4(v[0], v[1], v[2], v[3]));
+                st4(yo + 4, make_float4(v[4], v[5], v[6], v[7]));
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }   // fp32 over 8 pixels, fp64 from here on
+        for (int j = 0; j < 8; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; }   // fp32 over 8 pixels, fp64 from here on
     }
     if (stat_sum != nullptr) {
         __syncthreads();
-        double* red = reinterpret_cast<double*>(Ws);          // [8 warps][64][2]
+        double* red = reinterpret_cast<double*>(Ws);          // [4 warps][64][2]
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double e1 = d1[j], e2 = d2[j];
-            e1 += __shfl_xor_sync(0xffffffffu, e1, 16);
-            e2 += __shfl_xor_sync(0xffffffffu, e2, 16);
-            if (lane < 16) {
-                red[(warp * 64 + tx * 4 + j) * 2 + 0] = e1;
-                red[(warp * 64 + tx * 4 + j) * 2 + 1] = e2;
+        for (int j = 0; j < 8; ++j) {
+            double e1 = d1[j], e2 = d2[j];                    // lanes = 4 ty x 8 tx: sum over ty
+            e1 += __shfl_xor_sync(0xffffffffu, e1, 8);  e2 += __shfl_xor_sync(0xffffffffu, e2, 8);
+            e1 += __shfl_xor_sync(0xffffffffu, e1, 16); e2 += __shfl_xor_sync(0xffffffffu, e2, 16);
+            if (lane < 8) {
+                red[(warp * 64 + lane * 8 + j) * 2 + 0] = e1;
+                red[(warp * 64 + lane * 8 + j) * 2 + 1] = e2;
             }
         }
         __syncthreads();
         if (tid < 64) {
             double e1 = 0.0, e2 = 0.0;
 #pragma unroll
-            for (int wv = 0; wv < 8; ++wv) {
+            for (int wv = 0; wv < ST_FWD_THREADS / 32; ++wv) {
                 e1 += red[(wv * 64 + tid) * 2 + 0];
                 e2 += red[(wv * 64 + tid) * 2 + 1];
             }
@@ -307,11 +320,13 @@ __global__ void __launch_bounds__(ST_WG2_THREADS, 2) stem_conv7_wgrad2_kernel(co
 //     stand-alone pass over the 100 MB tensor (read g, read z, write dz) and the re-read of dz disappear;
 //   * tiles of 4 x 16 output pixels, double-buffered with cp.async (the next tile's g, z and image patch stream in while
 //     the current one is in the FFMA loop; the old kernel alternated a load phase and a compute phase per CTA).
-// Thread -> 4 couts x the 7 kw taps of one (channel, kh) patch row, as in the second generation.
+// Thread -> EIGHT couts x the 7 kw taps of one (channel, kh) patch row (56 accumulators): an LDS.128 costs four LSU cycles per
+// warp, so the second generation's 4 x 7 tile (four LDS.128 + one LDS.32 = 17 LSU cycles per 56 FFMA = 14 issue cycles) was
+// LSU-bound; 8 x 7 needs 25 LSU cycles per 112 FFMA (28 issue cycles).
 constexpr int ST3_TH = 4, ST3_TW = 16;
 constexpr int ST3_PH = 2 * ST3_TH + 5;                     // 13 input rows
 constexpr int ST3_PX = ST3_TH * ST3_TW;                    // 64 output pixels per tile
-constexpr int ST3_THREADS = 352;                           // 21 x 16 workers + 16 idle lanes
+constexpr int ST3_THREADS = 192;                           // 21 x 8 workers + 24 idle lanes
 constexpr int ST3_BUF_FLOATS = 2 * ST3_PX * ST_CO + 3 * ST3_PH * ST_PWP;       // g | z | patch
 constexpr int ST3_SMEM = 2 * ST3_BUF_FLOATS * 4 + 6 * ST_CO * 4;
 
@@ -335,16 +350,16 @@ __global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const
     float* vecs = st3_smem + 2 * ST3_BUF_FLOATS;           // scale | shift | mean | cA | cB | cC, 64 each
     const int tid = threadIdx.x;
     const int OH = H / 2, OW = W / 2;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 7, ty = tid >> 3;                 // tx: cout octet, ty: (channel, kh) patch row
     const bool worker = ty < 21;
     const int c = worker ? ty / 7 : 0, kh = worker ? ty - (ty / 7) * 7 : 0;
     if (tid < ST_CO) {
         vecs[tid] = __ldg(scale + tid); vecs[64 + tid] = __ldg(shift + tid); vecs[128 + tid] = __ldg(mean + tid);
         vecs[192 + tid] = __ldg(cA + tid); vecs[256 + tid] = __ldg(cB + tid); vecs[320 + tid] = __ldg(cC + tid);
     }
-    float acc[4][7];
+    float acc[8][7];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);          // bias gradient of channel quad (tid & 15), this thread's share
@@ -393,7 +408,7 @@ __global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const
         float* gs = st3_smem + b * ST3_BUF_FLOATS;
         const float* zs = gs + ST3_PX * ST_CO;
         const float* patch = gs + 2 * ST3_PX * ST_CO;
-        {   // BatchNorm-backward apply in place: g -> dz (this thread always meets channel quad tid & 15: 352 % 16 == 0)
+        {   // BatchNorm-backward apply in place: g -> dz (this thread always meets channel quad tid & 15: 192 % 16 == 0)
             const int cv = tid & 15;
             const float4 s4 = ld4(vecs + cv * 4), t4 = ld4(vecs + 64 + cv * 4), mu = ld4(vecs + 128 + cv * 4);
             const float4 a4 = ld4(vecs + 192 + cv * 4), b4 = ld4(vecs + 256 + cv * 4), c4 = ld4(vecs + 320 + cv * 4);
@@ -424,24 +439,23 @@ __global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const
 #pragma unroll 1
             for (int oy = 0; oy < ST3_TH; ++oy) {
                 const float* prow = patch + (c * ST3_PH + 2 * oy + kh) * ST_PWP;
-                const float* arow = gs + (oy * ST3_TW) * ST_CO + tx * 4;
+                const float* arow = gs + (oy * ST3_TW) * ST_CO + tx * 4;           // couts {4 tx ..} and {32 + 4 tx ..}
 #pragma unroll 2
                 for (int p = 0; p < ST3_TW / 2; ++p) {
-                    const float4 a0 = ld4(arow + (2 * p) * ST_CO);
-                    const float4 a1 = ld4(arow + (2 * p + 1) * ST_CO);
+                    const float4 a00 = ld4(arow + (2 * p) * ST_CO), a01 = ld4(arow + (2 * p) * ST_CO + 32);
+                    const float4 a10 = ld4(arow + (2 * p + 1) * ST_CO), a11 = ld4(arow + (2 * p + 1) * ST_CO + 32);
                     const float4 b0 = ld4(prow + 4 * p), b1 = ld4(prow + 4 * p + 4);
                     const float b8 = prow[4 * p + 8];
                     const float bb[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b8};
+                    const float a0[8] = {a00.x, a00.y, a00.z, a00.w, a01.x, a01.y, a01.z, a01.w};
+                    const float a1[8] = {a10.x, a10.y, a10.z, a10.w, a11.x, a11.y, a11.z, a11.w};
 #pragma unroll
                     for (int kw = 0; kw < 7; ++kw) {
-                        acc[0][kw] = fmaf(a0.x, bb[kw], acc[0][kw]);
-                        acc[1][kw] = fmaf(a0.y, bb[kw], acc[1][kw]);
-                        acc[2][kw] = fmaf(a0.z, bb[kw], acc[2][kw]);
-                        acc[3][kw] = fmaf(a0.w, bb[kw], acc[3][kw]);
-                        acc[0][kw] = fmaf(a1.x, bb[kw + 2], acc[0][kw]);
-                        acc[1][kw] = fmaf(a1.y, bb[kw + 2], acc[1][kw]);
-                        acc[2][kw] = fmaf(a1.z, bb[kw + 2], acc[2][kw]);
-                        acc[3][kw] = fmaf(a1.w, bb[kw + 2], acc[3][kw]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            acc[i][kw] = fmaf(a0[i], bb[kw], acc[i][kw]);
+                            acc[i][kw] = fmaf(a1[i], bb[kw + 2], acc[i][kw]);
+                        }
                     }
                 }
             }
@@ -450,10 +464,10 @@ __global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const
     }
     if (worker) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int kw = 0; kw < 7; ++kw)
-                atomicAdd(dw + (size_t)(tx * 4 + i) * ST_K + (c * 7 + kh) * 7 + kw, acc[i][kw]);
+                atomicAdd(dw + (size_t)((i >> 2) * 32 + tx * 4 + (i & 3)) * ST_K + (c * 7 + kh) * 7 + kw, acc[i][kw]);
     }
     if (dbias != nullptr) {
         const int cv = tid & 15;
@@ -477,7 +491,7 @@ extern "C" int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const f
     const long long total = (long long)tiles_x * tiles_y * N;
     HGK_REQUIRE(total < (1LL << 31), "hgk_stem_conv7_fwd: too many tiles");
     const int grid = (int)(total < 3 * kNumSMs ? total : 3 * kNumSMs);
-    stem_conv7_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, H, W, w, bias, y, stat_sum, stat_sq, tiles_x, tiles_y);
+    stem_conv7_fwd_kernel<<<grid, ST_FWD_THREADS, 0, (cudaStream_t)stream>>>(img, N, H, W, w, bias, y, stat_sum, stat_sq, tiles_x, tiles_y);
     HGK_CHECK_LAUNCH("hgk_stem_conv7_fwd");
     return HGK_OK;
 }
