@@ -414,7 +414,7 @@ def dominant_kernel_roofline(tr, pk, torch):
         a = rec[1]
         if rec[2] == "conv_nhwc":
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[9], a[12]
-        elif rec[2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc"):
+        elif rec[2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc", "conv_tc_x2_nhwc"):
             N, H, W, Cin, k, Cout = a[4], a[5], a[6], a[7], a[10], a[12]
         else:
             continue
@@ -444,7 +444,7 @@ def dominant_kernel_roofline(tr, pk, torch):
     ms = e0.elapsed_time(e1) / (reps * len(recs))
     a = recs[0][1]
     N, H, W, Cin, Cout = a[4], a[5], a[6], a[7], a[12]
-    tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc")
+    tc = recs[0][2] in ("conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc", "conv_tc_x2_nhwc")
     x2 = recs[0][2] == "conv_tc_bn_x2_nhwc"
     achieved = top / (ms / 1e3) / 1e12
     tile = tc and H % 16 == 0 and W % 16 == 0

@@ -91,9 +91,15 @@ int hgk_conv_tc_bn_nhwc(const float* x, const float* x_scale, const float* x_shi
 /* hgk_conv_tc_dgrad_bnstats_nhwc + hgk_bn_bwd_finalize of that BatchNorm executed by the last CTA. */
 /* Forward 3x3 convolution with TF32 + 2xBF16 products (fp32-class: x*w ~= xh*wh [tf32] + bf16(xl)*bf16(wh) + bf16(xh)*bf16(wl),
  * ~3 * 2^-20 per product; 4 instead of 6 tensor-core instructions per 16 channels and tap).  Same contract as
- * hgk_conv_tc_bn_nhwc; w_x2 is the "lo" buffer written by hgk_pack_weights_tc in mode 2.  Covered shapes:
- * hgk_conv_tc_x2_supported (3x3, H and W multiples of 16, 64 / 128 output channels, not a split-K layer). */
+ * hgk_conv_tc_bn_nhwc / hgk_conv_tc_nhwc; w_x2 is the "lo" buffer written by hgk_pack_weights_tc in mode 2.  Covered shapes:
+ * hgk_conv_tc_x2_supported (3x3 with H and W multiples of 16 and 64 / 128 output channels on the image-tile kernel; 1x1 with
+ * 128 / 256 output channels on the persistent kernel; never a split-K layer). */
 int hgk_conv_tc_x2_supported(int N, int H, int W, int Cin, int Cout, int ksize);
+int hgk_conv_tc_x2_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                        int N, int H, int W, int Cin,
+                        const float* w_hi, const float* w_x2, int ksize, const float* bias, int Cout,
+                        const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                        float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream);
 int hgk_conv_tc_bn_x2_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
                            int N, int H, int W, int Cin,
                            const float* w_hi, const float* w_x2, int ksize, const float* bias, int Cout,

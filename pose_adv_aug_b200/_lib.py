@@ -20,6 +20,7 @@ SIGNATURES = {
     "hgk_conv_tc_dgrad_bnstats_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P, P],
     "hgk_conv_tc_bn_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P,
                             P, P, F, F, P, P, P, P, P, P, P, P],
+    "hgk_conv_tc_x2_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P, P],
     "hgk_conv_tc_bn_x2_nhwc": [P, P, P, I, I, I, I, I, P, P, I, P, I, P, P, P, I, P, I, P, P,
                                P, P, F, F, P, P, P, P, P, P, P, P],
     "hgk_conv_tc_dgrad_bnfin_nhwc": [P, I, I, I, I, P, P, I, I, P, P, I, P, P, P, I, P, P, P, P,

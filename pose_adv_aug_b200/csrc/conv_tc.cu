@@ -1262,20 +1262,32 @@ extern "C" int hgk_conv_tc_bn_nhwc(const float* x, const float* x_scale, const f
                         stream);
 }
 
-// 1 when a forward convolution of this shape runs on the image-tile kernel with TF32 + 2xBF16 products (3x3, H and W multiples
-// of 16, 64 / 128 output channels, not one of the small split-K layers, 3x3 forward not routed to conv_tc3).  HGK_X2=0 disables it.
+// 1 when a forward convolution of this shape runs with TF32 + 2xBF16 products: 3x3 on the image-tile kernel (H and W multiples of
+// 16, 64 / 128 output channels), 1x1 on the persistent kernel (128 / 256 output channels); never one of the small split-K
+// layers.  HGK_X2=0 disables it.
 extern "C" int hgk_conv_tc_x2_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("HGK_X2");
         on = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    if (!on || ksize != 3 || !hgk_conv_tc_supported(Cin, Cout, ksize) || (Cout != 64 && Cout != 128) || N <= 0 || H <= 0 || W <= 0)
-        return 0;
+    if (!on || !hgk_conv_tc_supported(Cin, Cout, ksize) || N <= 0 || H <= 0 || W <= 0) return 0;
     TcArgs ta{};
     ta.c.N = N; ta.c.H = H; ta.c.W = W; ta.c.Cin = Cin; ta.c.Cout = Cout; ta.c.ksize = ksize;
     ta.c.P = (long long)N * H * W;
     if (splitk_factor(ta.c.P, Cin, Cout, ksize) > 1) return 0;
+    static int mask = -1;   // developer bisection: HGK_X2_MASK bit 0: 3x3, bit 1: 1x1 -> 128, bit 2: 1x1 -> 256, bit 3: 1x1 with Cin == 64
+    if (mask < 0) {
+        const char* e = getenv("HGK_X2_MASK");
+        mask = e != nullptr ? atoi(e) : 15;
+    }
+    if (ksize == 3 && !(mask & 1)) return 0;
+    if (ksize == 1 && Cout == 128 && !(mask & 2)) return 0;
+    if (ksize == 1 && Cout == 256 && !(mask & 4)) return 0;
+    if (ksize == 1 && Cin == 64 && !(mask & 8)) return 0;
+    if (ksize == 1)         // 1x1: the persistent kernel (conv_tc3.cu) when it takes the layer
+        return (use_tc3(1, true) && conv_tc3_eligible(ta)) ? 1 : 0;
+    if (Cout != 64 && Cout != 128) return 0;
     if (use_tc3(ksize, true) && conv_tc3_eligible(ta)) return 0;
     return (use_tile_kernel() && conv_tc2_eligible(ta)) ? 1 : 0;
 }
@@ -1294,6 +1306,17 @@ extern "C" int hgk_conv_tc_bn_x2_nhwc(const float* x, const float* x_scale, cons
     BnFwdFin f{gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, ticket, eps, momentum};
     return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_x2, ksize, bias, Cout, res, res_scale, res_shift,
                         res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &f, nullptr,
+                        stream, nullptr, 1);
+}
+
+extern "C" int hgk_conv_tc_x2_nhwc(const float* x, const float* x_scale, const float* x_shift, int x_relu,
+                                   int N, int H, int W, int Cin,
+                                   const float* w_hi, const float* w_x2, int ksize, const float* bias, int Cout,
+                                   const float* res, const float* res_scale, const float* res_shift, int res_relu,
+                                   float* y, int accumulate, double* stat_sum, double* stat_sq, void* stream) {
+    HGK_REQUIRE(w_x2 != nullptr, "hgk_conv_tc_x2_nhwc: null pointer");
+    return conv_tc_impl(x, x_scale, x_shift, x_relu, N, H, W, Cin, w_hi, w_x2, ksize, bias, Cout, res, res_scale, res_shift,
+                        res_relu, y, accumulate, stat_sum, stat_sq, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
                         stream, nullptr, 1);
 }
 

@@ -131,10 +131,16 @@ struct T3Cfg {
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY>
+// XBF (1x1 forward only): TF32 + 2xBF16 products as in conv_tc2.cu -- the lo plane of an activation chunk holds the bf16 tiles
+// xl | xh in the K-major no-swizzle layout [k/8 (2)][pixel][8 x bf16], the lo half of a weight stage the pack-mode-2 pair
+// [wh_bf16 | wl_bf16]; per 16-channel chunk two kind::f16 MMAs (K = 16) replace four of the six kind::tf32 ones.
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, bool XBF = false>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z) {
     static_assert(!(BNAPPLY && SPLIT), "the fused BatchNorm-backward apply is a data-gradient (plain TF32) mode");
+    static_assert(!XBF || (SPLIT && KS == 1), "bf16 cross terms: 1x1 error-compensated forward only");
+    constexpr uint32_t XPLANE = (uint32_t)T3Cfg<BN, SPLIT, KS, BNAPPLY>::NPIX * 16u;
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     using Cfg = T3Cfg<BN, SPLIT, KS, BNAPPLY>;
     constexpr int NJ = Cfg::NJ, NSA = Cfg::NSA, NSB = Cfg::NSB, NACC = Cfg::NACC, NM = Cfg::NM, NSUBS = Cfg::NSUBS, CPS = Cfg::CPS;
     constexpr int HWD = Cfg::HWD, PAD = Cfg::PAD, TAPS = Cfg::TAPS, SETCOLS = Cfg::SETCOLS, TH = Cfg::TH, TW = Cfg::TW;
@@ -312,9 +318,18 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                             const float4 hi = tf32_rna4(v);
                             if (ALLV || ((smask >> j) & 1u)) {
                                 *reinterpret_cast<float4*>(base + s_off[j]) = hi;
-                                if (SPLIT) {
+                                if (SPLIT && !XBF) {
                                     const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
                                     *reinterpret_cast<float4*>(base2 + s_off[j]) = lo;
+                                }
+                                if (XBF) {      // plane = channel quad / 2, row = pixel (16 B), 8-byte half = quad & 1
+                                    const uint32_t boff = (uint32_t)(quad >> 1) * XPLANE + (uint32_t)((tid + T3_NTT * j) >> 2) * 16u +
+                                                          (uint32_t)(quad & 1) * 8u;
+                                    uint2 xl, xh;
+                                    xl.x = pack_bf16x2(v.x - hi.x, v.y - hi.y); xl.y = pack_bf16x2(v.z - hi.z, v.w - hi.w);
+                                    xh.x = pack_bf16x2(hi.x, hi.y); xh.y = pack_bf16x2(hi.z, hi.w);
+                                    *reinterpret_cast<uint2*>(base2 + boff) = xl;
+                                    *reinterpret_cast<uint2*>(base2 + 2u * XPLANE + boff) = xh;
                                 }
                             }
                         }
@@ -357,6 +372,23 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint32_t x_tap = x_hi0 + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
                             const uint32_t w_hi0 = sbase + B_OFF + sb * B_STAGE;
+                            if (XBF) {
+                                // cross terms of this chunk: wh_bf16 * xl and wl_bf16 * xh_bf16, one K = 16 MMA each
+                                const uint32_t xb = x_hi0 + CPS * A_PLANE;
+#pragma unroll
+                                for (int s = 0; s < NSUBS; ++s) {
+                                    const uint64_t dxl = umma_desc(xb + s * 128 * 16, XPLANE, 128u);
+                                    const uint64_t dxh = umma_desc(xb + 2u * XPLANE + s * 128 * 16, XPLANE, 128u);
+#pragma unroll
+                                    for (int mh = 0; mh < NM; ++mh) {
+                                        const uint64_t dwh = umma_desc(w_hi0 + B_HALF + mh * (128 * 16), LBO_W, SBO_W);
+                                        const uint64_t dwl = umma_desc(w_hi0 + B_HALF + BN * 32 + mh * (128 * 16), LBO_W, SBO_W);
+                                        const uint32_t t_main = t_set + (uint32_t)(((mh * NACC) * NSUBS + s) * 128);
+                                        umma_bf16(t_main, dwh, dxl, IDESC_BF, first ? 0u : 1u);
+                                        umma_bf16(t_main, dwl, dxh, IDESC_BF, 1u);
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
                                 const uint32_t acc_flag = (first && k == 0) ? 0u : 1u;
@@ -368,7 +400,9 @@ conv_tc3_kernel(const TcArgs args, const __grid_constant__ CUtensorMap tm_x, con
                                     for (int mh = 0; mh < NM; ++mh) {
                                         const uint64_t dw = umma_desc(w_hi0 + mh * (128 * 16) + k * 2 * LBO_W, LBO_W, SBO_W);
                                         const uint32_t t_main = t_set + (uint32_t)(((mh * NACC) * NSUBS + s) * 128);
-                                        if (SPLIT) {
+                                        if (XBF) {
+                                            umma_tf32(t_main, dw, dx, IDESC, 1u);      // (the bf16 MMAs above initialised the tile)
+                                        } else if (SPLIT) {
                                             const uint64_t dwl = umma_desc(w_hi0 + B_HALF + mh * (128 * 16) + k * 2 * LBO_W, LBO_W, SBO_W);
                                             const uint32_t t_small = t_set + (uint32_t)(((mh * NACC + (NACC - 1)) * NSUBS + s) * 128);
                                             if (NACC == 1) {
@@ -724,13 +758,13 @@ static int make_map(CUtensorMap* m, const float* base, int N, int H, int W, int 
     return HGK_OK;
 }
 
-template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY>
+template <int BN, bool SPLIT, int KS, bool BWDSTATS, bool BNAPPLY, bool XBF = false>
 static int launch_tc3(TcArgs ta, cudaStream_t st) {
     using Cfg = T3Cfg<BN, SPLIT, KS, BNAPPLY>;
     static bool configured = false;
     constexpr int smem = Cfg::SMEM;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("hgk_conv_tc_nhwc (persistent tile kernel): cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
             return HGK_ECUDA;
@@ -754,7 +788,7 @@ static int launch_tc3(TcArgs ta, cudaStream_t st) {
     const long long tiles = (long long)ta.c.N * ((ta.c.H + Cfg::TH - 1) / Cfg::TH) * (ta.c.W / Cfg::TW);
     const long long rounds = (tiles + kNumSMs - 1) / kNumSMs;
     const unsigned grid = (unsigned)((tiles + rounds - 1) / rounds);
-    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY>, dim3(grid), dim3(T3_THREADS), (size_t)smem, st, ta, mx, mz);
+    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, SPLIT, KS, BWDSTATS, BNAPPLY, XBF>, dim3(grid), dim3(T3_THREADS), (size_t)smem, st, ta, mx, mz);
     if (le != cudaSuccess) {
         set_error("hgk_conv_tc_nhwc (persistent tile kernel): launch: %s", cudaGetErrorString(le));
         return HGK_ECUDA;
@@ -767,7 +801,14 @@ static int launch_tc3_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream
     if (ta.c.ap.z != nullptr)        // data gradient with the BatchNorm-backward apply evaluated on load
         return bwdstats ? launch_tc3<BN, false, KS, true, true>(ta, st) : launch_tc3<BN, false, KS, false, true>(ta, st);
     if (bwdstats) return launch_tc3<BN, false, KS, true, false>(ta, st);
-    if (split) return launch_tc3<BN, true, KS, false, false>(ta, st);
+    if (split) {
+        if (ta.lo_bf16) {       // TF32 + 2xBF16 products (w_lo in pack mode 2): 1x1 forward
+            if (KS == 1) return launch_tc3<BN, true, 1, false, false, KS == 1>(ta, st);
+            set_error("hgk_conv_tc_x2_nhwc: no TF32 + 2xBF16 instantiation of the persistent kernel for k=%d", KS);
+            return HGK_EINVAL;
+        }
+        return launch_tc3<BN, true, KS, false, false>(ta, st);
+    }
     return launch_tc3<BN, false, KS, false, false>(ta, st);
 }
 

@@ -222,6 +222,7 @@ class Plan(object):
         self.bytes_alloc = 0
         self.finished = False
         self.low_recs = set()      # id() of forward launches built inside a low_scope() (off the critical path)
+        self.x2_ok = True          # TF32 + 2xBF16 forward products allowed (the model clears it for deep stacks, see asn_stacked_hg)
         self.pre = []              # launches that run BEFORE the weight repack (derived weights: Plan.head_comb)
         self.aux_grad = {}         # id(derived weight / bias tensor) -> its gradient tensor (not part of any flat store)
         self.aux_zero = []         # ... which are zeroed at the start of every backward pass
@@ -685,7 +686,7 @@ class Plan(object):
 
 # argument positions written by each entry point (everything else is read-only); used by schedule_streams
 _WRITES = {
-    "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20), "conv_tc_dgrad_bnstats_nhwc": (10, 18, 19),
+    "conv_nhwc": (17, 19, 20), "conv_tc_nhwc": (17, 19, 20), "conv_tc_x2_nhwc": (17, 19, 20), "conv_tc_dgrad_bnstats_nhwc": (10, 18, 19),
     "conv_tc_bn_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31), "conv_tc_bn_x2_nhwc": (17, 19, 20, 25, 26, 27, 28, 29, 30, 31),
     "conv_tc_dgrad_bnfin_nhwc": (10, 18, 19, 22, 23, 24, 25, 26, 27),
     "bn_bwd_reduce_fin": (9, 10, 13, 14, 15, 16, 17, 18),
@@ -924,7 +925,7 @@ class _ConvOp(object):
             # tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class accuracy)
             # 3x3 layers on the image-tile kernel: TF32 + 2xBF16 products (4 instead of 6 tensor-core instructions per product
             # group, same fp32-class accuracy class; csrc/conv_tc2.cu)
-            x2 = (stats and p.fuse_bn_fin and not p.precise_grads     # (PRECISE_GRADS: the all-3xTF32 / fp32 mode)
+            x2 = (p.x2_ok and not p.precise_grads                      # (PRECISE_GRADS: the all-3xTF32 / fp32 mode)
                   and p.lib.conv_tc_x2_supported(x.N, x.H, x.W, Cin, Cout, k))
             hi, lo = p.packed_weight_tc(w, 2 if x2 else 0, True)
             base = x.act_args() + [x.N, x.H, x.W, Cin, hi, lo, k, p.param_ptr(conv.bias), Cout] + ra
@@ -935,7 +936,8 @@ class _ConvOp(object):
                                                              _ptr(r.shift), _ptr(r.mean), _ptr(r.invstd), p.ticket_alloc()]))
                 fin_fused = True
             else:
-                p.launch(p.fwd, "conv_tc_nhwc", *(base + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
+                p.launch(p.fwd, "conv_tc_x2_nhwc" if x2 else "conv_tc_nhwc",
+                         *(base + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
         else:
             p.launch(p.fwd, "conv_nhwc", *(x.act_args() + [x.N, x.H, x.W, Cin, _PackRef(p.packed_weight(w, 0)), k, 0,
                                                            p.param_ptr(conv.bias), Cout] + ra +

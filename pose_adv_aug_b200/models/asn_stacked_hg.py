@@ -32,6 +32,11 @@ DEFER_SKIPS = _os.environ.get("HGK_DEFER_SKIPS", "1") == "1"
 # (engine.Plan.head_comb, csrc/heads.cu): the 16->C pass over the activation, its data gradient and its weight gradient
 # become weight-space products.  HGK_FUSE_HEAD=0 restores the three separate convolutions of ref:332-334.
 FUSE_HEAD = _os.environ.get("HGK_FUSE_HEAD", "1") == "1"
+# Forward products: TF32 + 2xBF16 (csrc/conv_tc2.cu, conv_tc3.cu) is ~3 * 2^-20 per product against ~2^-22 for 3xTF32.  A
+# train-mode hourglass amplifies forward rounding by ~2x every 1.5 stacks (measured at 2 images, heat-map error relative to the
+# map maximum vs the fp64 oracle, stacks 1..8: fp32 reference 1e-5 .. 4e-4, 3xTF32 2e-5 .. 5e-4, TF32 + 2xBF16 3e-5 .. 1.2e-3):
+# inside the 1e-3 tolerance with a wide margin up to 4 stacks (2.4e-4), over it at 8.  Deeper nets therefore keep 3xTF32.
+X2_MAX_STACKS = int(_os.environ.get("HGK_X2_MAX_STACKS", "4"))
 
 
 def _reference_init(root):
@@ -127,7 +132,7 @@ def _run(root, extra_roots, key, inputs, build):
     # which inputs want a gradient is baked into the plan (input_nchw(needs_grad=...)): it is part of the key, so a module
     # first called on a constant input and later inside a larger autograd graph gets a plan with the input-gradient path
     in_grad = tuple(bool(x.requires_grad) and need_grad for x in inputs)
-    pkey = (key, shapes, modes, need_grad, in_grad, ids, CONV_PATH, PRECISE_GRADS, FUSE_HEAD)
+    pkey = (key, shapes, modes, need_grad, in_grad, ids, CONV_PATH, PRECISE_GRADS, FUSE_HEAD, X2_MAX_STACKS)
     cache = _state(root).plans
     plan = cache.get(pkey)
     if plan is None:
@@ -365,6 +370,7 @@ class _Hourglass_Wrapper(nn.Module):
 
     def _build(self, plan, img, asn=None, is_half_hg=False, is_dropout=False):
         """ref:282-342.  Returns (list of per-stack heat-map tensors, agent outputs or None)."""
+        plan.x2_ok = self.num_stacks <= X2_MAX_STACKS                   # forward numerics by depth, see X2_MAX_STACKS
         x = plan.stem(img, self.conv1, self.bn1)                        # ref:283-285
         x = self.residual1._build(plan, x)
         x = plan.maxpool(x)

@@ -94,8 +94,8 @@ def test_plan_builds_and_covers_every_parameter():
     names = [r[2] for r in plan.fwd]
     # 101 convolutions in the reference graph; the inter-stack in_conv is folded into forth_conv (Plan.head_comb)
     n_conv = 100 if M.FUSE_HEAD else 101
-    n_x2 = names.count("conv_tc_bn_x2_nhwc")          # 3x3 layers on the image-tile kernel: TF32 + 2xBF16 products
-    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_bn_nhwc") + n_x2 + names.count("conv_nhwc") == n_conv
+    n_x2 = names.count("conv_tc_bn_x2_nhwc")          # large 3x3 / 1x1 layers: TF32 + 2xBF16 products
+    assert (names.count("conv_tc_nhwc") + names.count("conv_tc_x2_nhwc") + names.count("conv_tc_bn_nhwc") + n_x2 + names.count("conv_nhwc") == n_conv
             and names.count("stem_conv7_fwd") == 1)
     assert [r[2] for r in plan.pre] == (["head_combine_fwd"] if M.FUSE_HEAD else [])
     # 96 BatchNorms: 95 finalised by the last CTA of their tensor-core convolution, the stem's by its own launch

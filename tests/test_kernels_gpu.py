@@ -582,10 +582,13 @@ def test_conv_tc_fused_bn_finalize(shape):
 
 
 @pytest.mark.parametrize("shape", [(8, 16, 16, 128, 128, 3), (3, 32, 48, 128, 128, 3), (2, 64, 64, 64, 64, 3),
-                                   (10, 64, 64, 128, 128, 3), (2, 128, 128, 64, 64, 3), (8, 16, 16, 256, 128, 3)])
+                                   (10, 64, 64, 128, 128, 3), (2, 128, 128, 64, 64, 3), (8, 16, 16, 256, 128, 3),
+                                   (5, 64, 64, 128, 256, 1), (10, 64, 64, 256, 128, 1), (2, 32, 48, 256, 256, 1),
+                                   (3, 20, 28, 64, 128, 1)])
 @pytest.mark.parametrize("variant", ["plain", "full"])
 def test_conv_tc_fwd_tf32_plus_2xbf16(shape, variant):
-    """hgk_conv_tc_bn_x2_nhwc: x*w ~= xh*wh (TF32) + bf16(xl)*bf16(wh) + bf16(xh)*bf16(wl) on the image-tile kernel (pack mode 2)
+    """hgk_conv_tc_bn_x2_nhwc: x*w ~= xh*wh (TF32) + bf16(xl)*bf16(wh) + bf16(xh)*bf16(wl) on the image-tile kernel (3x3) and the
+    persistent kernel (1x1, incl. a ragged last tile) with the weights in pack mode 2
     against the fp64 convolution: same tolerance as the 3xTF32 kernel (error ~3 * 2^-20 per product), BN+ReLU on load,
     shortcut, accumulate, fused BatchNorm statistics / finaliser."""
     N, H, W, Ci, Co, k = shape

@@ -163,10 +163,13 @@ def test_whole_net_vs_reference_golden(case):
 
 @pytest.mark.parametrize("precise", [False, True])
 def test_whole_net_vs_oracle_two_stack_c64(precise, monkeypatch):
-    """A shape class the goldens do not hold (C=64, N=4, 128x128), oracle run live in fp64."""
+    """A shape class the goldens do not hold (C=64, N=4, 256x256), oracle run live in fp64.  (256x256 so that the deepest rung is
+    4x4 as in the reference's configurations: at 128x128 it is 2x2 -- BatchNorm statistics over 16 samples -- and the whole-net
+    gradient becomes a lottery of single ReLU flips: mathematically equivalent forward variants, 1e-6 apart, measured anywhere
+    between 2.3e-3 and 4.7e-2.)"""
     M = _mods()
     monkeypatch.setattr(M, "PRECISE_GRADS", precise)
-    S, Mo, K, C, N, R = 2, 1, 16, 64, 4, 128
+    S, Mo, K, C, N, R = 2, 1, 16, 64, 4, 256
     sd64 = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=31, dtype=torch.float64)
     x64 = synth.make_images(N, R, seed=32, dtype=torch.float64)
     t64 = synth.make_heatmaps(N, R, K, seed=33, dtype=torch.float64)
@@ -187,8 +190,9 @@ def test_whole_net_vs_oracle_two_stack_c64(precise, monkeypatch):
     den = sum(float(grads64[k].pow(2).sum()) for k in names)
     num32 = sum(float((grads32[k].double() - grads64[k]).pow(2).sum()) for k in names)
     ours, floor = (num / den) ** 0.5, (num32 / den) ** 0.5
+    print("two-stack C=64 gradient rel-L2 vs fp64: ours %.3e, fp32 oracle %.3e (precise=%s)" % (ours, floor, precise))
     # see the note in test_whole_net_vs_reference_golden; TF32 gradients: absolute bound instead
-    assert ours < (8 * floor + 1e-4 if precise else 1e-2), (ours, floor)
+    assert ours < (8 * floor + 1e-4 if precise else 3 * floor + 1e-3), (ours, floor)
     for k, v in st.updates.items():
         if "num_batches" not in k:
             assert relerr(net.state_dict()[k], v) < 1e-4, k

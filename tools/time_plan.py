@@ -60,7 +60,7 @@ for i, (fn, a, name) in enumerate(recs):
     elif name == "conv_tc_dgrad_bnapply_nhwc":
         key = "%s k%d" % (name, a[15])
         desc = "%dx%d %d->%d%s" % (a[11], a[12], a[13], a[16], " +red" if a[20] else "")
-    elif name in ("conv_nhwc", "conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc"):
+    elif name in ("conv_nhwc", "conv_tc_nhwc", "conv_tc_bn_nhwc", "conv_tc_bn_x2_nhwc", "conv_tc_x2_nhwc"):
         N, H, W, Cin = a[4:8]
         if name != "conv_nhwc":
             k, Cout, split = a[10], a[12], a[9] != 0
