@@ -345,6 +345,7 @@ def run_ours(args):
     roof = dominant_kernel_roofline(tr, pk, torch)
     if rank != 0:
         if world > 1:
+            tr.close()          # the step graph holds captured NCCL kernels: release it before the communicator goes
             dist.destroy_process_group()
         return
     value = world * args.batch * args.steps / (ms / 1e3)
@@ -366,6 +367,12 @@ def run_ours(args):
                            "heatmaps_pinned) -> loss.item() with the copies in front of the step"},
             "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
             "cuda_graph": not args.no_graph, "graph_streams": args.streams, "low_priority_streams": args.low_streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
+    if world > 1:
+        line["allreduce"] = {"in_graph": bool(tr.ar_in_graph), "graph_launches_per_step": 1 if tr.ar_in_graph else 2,
+                             "buckets_mb": [round((hi - lo) * 4e-6, 2) for lo, hi in tr.bucket_ranges()],
+                             "note": "NCCL sum of the flat gradient buffer, bucketed back to front on a communication stream "
+                                     "and captured inside the step graph" if tr.ar_in_graph else
+                                     "one eager NCCL all-reduce between two graphs"}
     if world == 1 and not args.no_cpu_baseline:
         # ---- cpu_baseline leg (the only place this arm executes anything under oracle/): the reference's CPU step on
         #      the host cores, timed on a bounded sample, and -- as the checker -- its heat-maps against ours ----
@@ -381,7 +388,9 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % e}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        tr.close()
         dist.destroy_process_group()
 
 

@@ -226,6 +226,7 @@ class Plan(object):
         self.pre = []              # launches that run BEFORE the weight repack (derived weights: Plan.head_comb)
         self.aux_grad = {}         # id(derived weight / bias tensor) -> its gradient tensor (not part of any flat store)
         self.aux_zero = []         # ... which are zeroed at the start of every backward pass
+        self.rw_override = {}      # id(launch) -> (read pointers, written pointers) for launches that take arena base pointers
         self.after = {}            # id(launch) -> id(earlier launch) it must additionally wait for (scheduling-only edge)
 
     # ---- allocation helpers ----
@@ -556,22 +557,49 @@ class Plan(object):
         return op
 
     # ---- finish / run ----
-    def finish(self):
+    def finish(self, grad_splits=None):
+        """Close the plan: emit the backward list and resolve the scratch / packed-weight references.
+
+        `grad_splits` (sorted element offsets into the flat gradient buffer, at parameter-slot boundaries; or a callable
+        plan -> offsets evaluated once the backward list exists) cuts the 3x3
+        weight-gradient unpack into one launch per gradient bucket, placed right behind the last weight-gradient kernel of
+        that bucket, so that a bucket of the flat buffer is final long before the end of the backward pass (the bucketed
+        all-reduce of HourglassTrainer overlaps the remaining backward)."""
         if self.need_grad:
             for op in reversed(self.tape):
                 op.emit_bwd()
+        if callable(grad_splits):          # chosen from the emitted backward list (trainer.plan_bucket_splits)
+            grad_splits = grad_splits(self)
+        self.grad_splits = grad_splits
         if self.wg_entries:
+            import bisect
             self.wg_buf = torch.zeros(self.wg_used, device=self.device, dtype=torch.float32)
             self.bytes_alloc += self.wg_used * 4
             gbase = min(st.grad.data_ptr() for st in self.stores)
-            rows = []
+            wb = self.wg_buf.data_ptr()
+            groups = {}
             for (w, off) in self.wg_entries:
                 d = self.param_grad_ptr(w) - gbase
                 assert d >= 0 and d % 4 == 0
-                rows.append([off, d // 4, w.shape[0], w.shape[1], w.shape[2] * w.shape[3]])
+                g = bisect.bisect_right(grad_splits, d // 4) if grad_splits else 0
+                groups.setdefault(g, []).append([off, d // 4, w.shape[0], w.shape[1], w.shape[2] * w.shape[3]])
+            order = sorted(groups)
+            rows = [r for g in order for r in groups[g]]
             self.wg_table = torch.tensor(rows, dtype=torch.long, device=self.device)
-            self.launch(self.bwd, "unpack_add_grads", self.wg_buf.data_ptr(), gbase, self.wg_table.data_ptr(), len(rows))
-            wb = self.wg_buf.data_ptr()
+            place, start = [], 0
+            for g in order:
+                offs = set(r[0] for r in groups[g])
+                last = max(i for i, rec in enumerate(self.bwd)
+                           if any(isinstance(a, _WgRef) and a.off in offs for a in rec[1]))
+                rec = [self.lib.unpack_add_grads,
+                       [wb, gbase, self.wg_table.data_ptr() + start * 5 * 8, len(groups[g])], "unpack_add_grads"]
+                if grad_splits:
+                    # precise dependencies instead of "ordered against everything" (schedule_streams)
+                    self.rw_override[id(rec)] = ([wb + 4 * r[0] for r in groups[g]], [gbase + 4 * r[1] for r in groups[g]])
+                place.append((last if grad_splits else len(self.bwd) - 1, rec))
+                start += len(groups[g])
+            for last, rec in sorted(place, key=lambda t: -t[0]):
+                self.bwd.insert(last + 1, rec)
             for rec in self.bwd:
                 rec[1] = [wb + 4 * a.off if isinstance(a, _WgRef) else a for a in rec[1]]
         if self.pack_entries:
@@ -709,13 +737,13 @@ _NO_PACK_DEP = ("stem_conv7_fwd", "nchw_to_nhwc")
 
 
 def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads"),
-                     low_names=(), n_low=0, low_ids=(), after=None):
+                     low_names=(), n_low=0, low_ids=(), after=None, rw_override=None):
     """Assign each launch of a static list to one of `n_streams` streams.
 
     Dependencies are derived from the launch arguments (device pointers; `_WRITES` says which positions
     an entry point writes): read-after-write, write-after-write and write-after-read orderings are kept,
     read-read sharing is free.  Launches named in `barrier_names` take base pointers of whole arenas and are
-    ordered against everything.  Returns (stream index per launch, for each launch the launches on OTHER
+    ordered against everything (unless `rw_override` gives their real read / write pointer sets).  Returns (stream index per launch, for each launch the launches on OTHER
     streams it has to wait for).  The hourglass has coarse branch parallelism (skip residuals vs the down/up
     chain, weight- vs data-gradients): this lets the latency-bound 4x4 / 8x8 / 16x16 layers run under the
     large 64x64 ones inside one CUDA graph.
@@ -736,10 +764,15 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
         index_of[id(launches[i])] = i
         wpos = _WRITES.get(name)
         rd, wr = [], []
-        for j, a in enumerate(args):
-            if isinstance(a, int) and a >= PTR_MIN:
-                (wr if (wpos is None or j in wpos) else rd).append(a)
-        if name in barrier_names:
+        override = rw_override.get(id(launches[i])) if rw_override else None
+        if override is not None:            # a launch over arena base pointers whose real read / write sets are known
+            rd, wr = list(override[0]), list(override[1])
+        else:
+            for j, a in enumerate(args):
+                if isinstance(a, int) and a >= PTR_MIN:
+                    (wr if (wpos is None or j in wpos) else rd).append(a)
+        is_barrier = name in barrier_names and override is None
+        if is_barrier:
             deps = set(t for t in tail if t >= 0)
         else:
             deps = set()
@@ -788,7 +821,7 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
         for p in wr:
             last_write[p] = i
             readers[p] = []
-        if name in barrier_names:
+        if is_barrier:
             barrier = i
     return stream_of, cross
 

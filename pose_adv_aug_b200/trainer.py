@@ -31,9 +31,99 @@ class _HyperGroup(dict):
             self[k] = v
 
 
+def bucket_splits(offsets, numel, nb):
+    """Element offsets cutting a flat gradient buffer into (at most) `nb` buckets of about equal size, each cut on a
+    parameter-slot boundary (so that every kernel's gradient write falls into exactly one bucket)."""
+    target = numel / float(nb)
+    splits = []
+    for o in offsets[1:]:
+        if len(splits) < nb - 1 and o >= target * (len(splits) + 1):
+            splits.append(o)
+    return splits
+
+
+def param_completion(plan, store):
+    """Index in plan.bwd of the last launch that contributes to each parameter's gradient (-1: none), read off the emitted
+    backward list before the weight-gradient scratch references are resolved."""
+    import bisect
+    from .engine import _WRITES, _WgRef
+    g0, g1 = store.grad.data_ptr(), store.grad.data_ptr() + 4 * store.numel
+    offs = store.offsets
+    wg_param = {}
+    for (w, off) in plan.wg_entries:
+        a = plan.param_grad_ptr(w)
+        if g0 <= a < g1:
+            wg_param[off] = bisect.bisect_right(offs, (a - g0) // 4) - 1
+    pos = [-1] * len(offs)
+    for i, rec in enumerate(plan.bwd):
+        wpos = _WRITES.get(rec[2])
+        for j, a in enumerate(rec[1]):
+            if isinstance(a, _WgRef):
+                if a.off in wg_param:
+                    pos[wg_param[a.off]] = i
+            elif isinstance(a, int) and g0 <= a < g1 and (wpos is None or j in wpos):
+                pos[bisect.bisect_right(offs, (a - g0) // 4) - 1] = i
+    return pos
+
+
+def plan_bucket_splits(plan, store, nb):
+    """Cut the flat gradient buffer into `nb` contiguous buckets so that as many bytes as possible are final EARLY in the
+    backward pass: minimise sum over buckets of (bucket elements x position of the bucket's last writer) by dynamic
+    programming over the parameter slots.  Parameters are laid out in registration order and the backward pass finishes
+    them roughly back to front (second hourglass, first hourglass' up path, its skips, its down path, the stem), so the
+    buckets follow those groups and the all-reduce exposed behind the last kernel is the small stem bucket."""
+    pos = param_completion(plan, store)
+    P = len(pos)
+    nb = max(1, min(nb, P))
+    edges = list(store.offsets) + [store.numel]
+    n_bwd = float(max(len(plan.bwd), 1))
+    c = [(p + 1) / n_bwd for p in pos]
+    INF = float("inf")
+    best = [[INF] * (P + 1) for _ in range(nb + 1)]
+    arg = [[0] * (P + 1) for _ in range(nb + 1)]
+    best[0][0] = 0.0
+    for k in range(1, nb + 1):
+        for j in range(1, P + 1):
+            cmax = 0.0
+            for i in range(j - 1, -1, -1):           # bucket = parameters i .. j-1
+                if c[i] > cmax:
+                    cmax = c[i]
+                if best[k - 1][i] < INF:
+                    v = best[k - 1][i] + (edges[j] - edges[i]) * cmax
+                    if v < best[k][j]:
+                        best[k][j], arg[k][j] = v, i
+    k = min(range(1, nb + 1), key=lambda q: best[q][P])
+    cuts, j = [], P
+    while k > 0:
+        i = arg[k][j]
+        if i > 0:
+            cuts.append(edges[i])
+        j, k = i, k - 1
+    return sorted(cuts)
+
+
+def bucket_last_writers(launches, rw_override, grad_ptr, numel, splits):
+    """For each gradient bucket the index of the last launch (list order = a topological order) that writes into it."""
+    import bisect
+    from .engine import _WRITES
+    g0, g1 = grad_ptr, grad_ptr + 4 * numel
+    last = [-1] * (len(splits) + 1)
+    for i, rec in enumerate(launches):
+        ov = rw_override.get(id(rec))
+        if ov is not None:
+            wr = ov[1]
+        else:
+            wpos = _WRITES.get(rec[2])
+            wr = [a for j, a in enumerate(rec[1]) if isinstance(a, int) and (wpos is None or j in wpos)]
+        for a in wr:
+            if g0 <= a < g1:
+                last[bisect.bisect_right(splits, (a - g0) // 4)] = i
+    return last
+
+
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None, n_streams=8, n_low=3):
+                 distributed=None, n_streams=8, n_low=3, ar_buckets=None, fake_collective=None):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)
@@ -61,7 +151,16 @@ class HourglassTrainer(object):
         for o in outs:
             plan.mse_loss(o, tgt, self.loss_acc)
             plan.output_nchw(o, no_grad=True)
-        plan.finish()
+        # gradient buckets of the in-graph all-reduce: contiguous ranges of the flat gradient buffer cut at parameter-slot
+        # boundaries.  Parameters are laid out in registration order and the backward pass completes them back to front, so
+        # the LAST bucket is final first and its all-reduce runs under the rest of the backward.
+        import os
+        nb = int(os.environ.get("HGK_AR_BUCKETS", "5")) if ar_buckets is None else int(ar_buckets)
+        self.ar_in_graph = (self.world > 1 or fake_collective is not None) and use_graph and n_streams > 1 and nb > 0 \
+            and os.environ.get("HGK_AR_INGRAPH", "1") == "1"
+        self.fake_collective = fake_collective
+        plan.finish(grad_splits=(lambda pl: plan_bucket_splits(pl, self.store, nb)) if self.ar_in_graph else None)
+        self.grad_splits = plan.grad_splits
         self.plan = plan
         self.graph = None
         self.graph_update = None
@@ -75,6 +174,22 @@ class HourglassTrainer(object):
     @property
     def launches_per_step(self):
         return len(self.plan.head_launches()) + len(self.plan.fwd) + len(self.plan.bwd) + 2
+
+    def bucket_ranges(self):
+        """[(lo, hi)) element ranges of the gradient buckets (one range when the all-reduce is not bucketed)."""
+        edges = [0] + list(self.grad_splits or []) + [self.store.numel]
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+
+    def _bucket_last_writers(self, launches):
+        return bucket_last_writers(launches, self.plan.rw_override, self.store.grad.data_ptr(), self.store.numel,
+                                   self.grad_splits or [])
+
+    def _allreduce_bucket(self, lo, hi):
+        g = self.store.grad[lo:hi]
+        if self.fake_collective is not None:
+            self.fake_collective(g)
+        else:
+            hdist.allreduce_flat_grads(g)
 
     def _body_grads(self):
         """zero grads/loss -> forward -> fused MSE -> backward (local gradients in the flat buffer)."""
@@ -114,9 +229,15 @@ class HourglassTrainer(object):
             low_on = os.environ.get("HGK_LOW_SKIPS", "0") == "1" or M.DEFER_SKIPS
             low_ids = plan.low_recs if low_on else ()
             self._sched = schedule_streams(launches, n_streams, n_low=n_low, low_ids=low_ids,
-                                           after=plan.after if M.DEFER_SKIPS else None,
+                                           after=plan.after if M.DEFER_SKIPS else None, rw_override=plan.rw_override,
                                            low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad", "stem_conv7_wgrad_bnapply"))
         stream_of, cross = self._sched
+        ar_after = {}
+        if self.ar_in_graph:
+            for b, i_last in enumerate(self._bucket_last_writers(launches)):
+                ar_after.setdefault(max(i_last, 0), []).append(b)
+            ranges = self.bucket_ranges()
+            comm = torch.cuda.Stream(self.device, priority=-1)
         # with a low-priority pool the other side streams are high priority (-1); the capture stream keeps priority 0
         side = [torch.cuda.Stream(self.device, priority=(0 if (n_low and i >= n_streams - 1 - n_low) else (-1 if n_low else 0)))
                 for i in range(n_streams - 1)]
@@ -145,6 +266,20 @@ class HourglassTrainer(object):
                 ev = torch.cuda.Event()
                 ev.record(sk)
                 events[i] = ev
+            for b in ar_after.get(i, ()):
+                # bucket b of the flat gradient buffer is final once everything issued so far has run (list order is a
+                # topological order): the communication stream joins every compute stream here and all-reduces the bucket
+                # while the streams go on with the rest of the backward pass (captured: NCCL kernel nodes in the step graph)
+                for s_ in streams:
+                    ev = torch.cuda.Event()
+                    ev.record(s_)
+                    comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    self._allreduce_bucket(*ranges[b])
+        if self.ar_in_graph:
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            main.wait_event(ev)
         for s_ in side:                      # join
             ev = torch.cuda.Event()
             ev.record(s_)
@@ -177,9 +312,8 @@ class HourglassTrainer(object):
         if self.use_graph:
             if self.graph is None:
                 self._capture()
-            if self.world > 1:
-                # two graphs around the eager NCCL call: NCCL's watchdog thread makes stream-capture of the
-                # collective fragile, and one extra graph launch per step costs a few microseconds
+            if self.world > 1 and not self.ar_in_graph:
+                # HGK_AR_INGRAPH=0: two graphs around ONE eager NCCL call over the whole flat buffer
                 self.graph.replay()
                 hdist.allreduce_flat_grads(self.store.grad)
                 self.graph_update.replay()
@@ -197,6 +331,11 @@ class HourglassTrainer(object):
             saved = (self.store.flat.clone(), self.square_avg.clone(), self.store.fbuf_flat.clone(),
                      self.store.ibuf_flat.clone())
             self._step_body()            # warm-up outside capture (lazy init, NCCL communicator)
+            if self.ar_in_graph and self.world > 1:
+                scratch = torch.zeros_like(self.store.grad)
+                for lo, hi in self.bucket_ranges():      # NCCL picks algorithm / protocol by size: touch every bucket size once
+                    hdist.allreduce_flat_grads(scratch[lo:hi])
+                del scratch
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
@@ -208,7 +347,7 @@ class HourglassTrainer(object):
         gc.collect()
         gc.disable()
         try:
-            if self.world > 1:
+            if self.world > 1 and not self.ar_in_graph:
                 with torch.cuda.graph(self.graph):
                     grads()
                 self.graph_update = torch.cuda.CUDAGraph()
@@ -227,6 +366,17 @@ class HourglassTrainer(object):
         self.store.fbuf_flat.copy_(saved[2])
         self.store.ibuf_flat.copy_(saved[3])
         torch.cuda.synchronize(self.device)
+
+    def close(self):
+        """Drop the captured step graph(s).  With the all-reduce captured inside the graph this MUST happen before
+        torch.distributed.destroy_process_group(): NCCL keeps a reference per captured collective and its communicator
+        teardown waits until those graphs are gone."""
+        if self.graph is not None or self.graph_update is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph = None
+            self.graph_update = None
+            import gc
+            gc.collect()
 
     def step(self, images, heatmaps):
         """Public end-to-end step: images [N,3,R,R], heatmaps [N,K,R/4,R/4] (host pinned or device).

@@ -389,6 +389,39 @@ def test_multistream_graph_equals_single_stream():
         assert abs(la[i] - lb[i]) < (2e-3 if i == 2 else 5e-3) * abs(la[i]), (la, lb)
 
 
+@pytest.mark.gpu
+def test_in_graph_bucketed_collective_sees_final_gradients():
+    """The bucketed all-reduce captured inside the step graph (trainer.py) on ONE GPU: the collective is replaced by
+    `bucket *= 2` on the communication stream.  Every bucket must be doubled exactly once and only after its last writer
+    (weight-gradient atomics, the per-bucket 3x3 unpack, BatchNorm-backward finalisers) has run: the gradient buffer after a
+    replay equals twice the plain trainer's, replay after replay."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer
+    S, Mo, K, C, N, R = 2, 1, 16, 64, 4, 128
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=81)
+    x = synth.make_images(N, R, seed=82).to(DEV)
+    t = synth.make_heatmaps(N, R, K, seed=83).to(DEV)
+    tr_a = HourglassTrainer(_load(M.create_hg(S, Mo, K, C), sd).to(DEV), N, R, use_graph=True)
+    tr_b = HourglassTrainer(_load(M.create_hg(S, Mo, K, C), sd).to(DEV), N, R, use_graph=True, ar_buckets=5,
+                            fake_collective=lambda g: g.mul_(2.0))
+    assert tr_b.ar_in_graph and not tr_a.ar_in_graph
+    rng = tr_b.bucket_ranges()
+    assert len(rng) >= 3 and rng[0][0] == 0 and rng[-1][1] == tr_b.store.numel
+    assert sum(1 for r in tr_b.plan.bwd if r[2] == "unpack_add_grads") >= 1
+    for it in range(3):
+        # same parameters on both sides before every step (the doubled gradient changes RMSprop's eps term only, but the
+        # comparison should not depend on that)
+        tr_b.store.flat.copy_(tr_a.store.flat)
+        tr_b.square_avg.copy_(tr_a.square_avg)
+        tr_b.store.fbuf_flat.copy_(tr_a.store.fbuf_flat)
+        la, lb = float(tr_a.step(x, t)), float(tr_b.step(x, t))
+        assert abs(la - lb) < 1e-6 * abs(la)
+        ga, gb = tr_a.store.grad, tr_b.store.grad
+        for lo, hi in rng:
+            d = float((gb[lo:hi] - 2.0 * ga[lo:hi]).norm() / (2.0 * ga[lo:hi]).norm())
+            assert d < 1e-4, (it, lo, hi, d)
+
+
 def test_cpu_input_fails_loudly():
     M = _mods()
     from pose_adv_aug_b200 import HGKError

@@ -161,3 +161,75 @@ def test_plan_structure_of_agent_and_dropout_modes_on_cpu():
     assert tuple(plan.mask_indexes.shape) == (2, 2)
     with torch.no_grad():
         assert M.create_asn(C, C, 7, 7, is_aug=True)({"x": 0}, is_aug=False, is_dropout=False) is None   # ref:430-439
+
+
+def test_bucketed_gradient_unpack_and_allreduce_points():
+    """In-graph bucketed all-reduce (trainer.py): with `grad_splits` the 3x3 weight-gradient unpack becomes one launch per
+    bucket behind that bucket's last weight-gradient kernel, scheduled by its real read / write sets; every bucket of the
+    flat gradient buffer has a last writer, and the buckets of the later layers are final well before the end of the
+    backward pass (that is what the all-reduce overlaps with)."""
+    from pose_adv_aug_b200.trainer import plan_bucket_splits, bucket_last_writers
+    net = M.create_hg(2, 1, 16, 256)
+    dev = torch.device("cpu")
+    st = ParamStore(net, dev)
+    plan = Plan([st], dev, True, True)
+    img = plan.input_image(2, 256, 256)
+    tgt = plan.target_nchw(2, 16, 64, 64)
+    acc = torch.zeros(1, dtype=torch.float64)
+    outs, _ = net._build(plan, img)
+    for o in outs:
+        plan.mse_loss(o, tgt, acc)
+        plan.output_nchw(o, no_grad=True)
+    plan.finish(grad_splits=lambda pl: plan_bucket_splits(pl, st, 5))
+    splits = plan.grad_splits
+    assert len(splits) == 4 and all(s in st.offsets for s in splits) and splits == sorted(splits)
+    sizes = [b - a for a, b in zip([0] + splits, splits + [st.numel])]
+    keep = (torch.zeros(2, 3, 256, 256), torch.zeros(2, 16, 64, 64))
+    plan.patch("image", keep[0].data_ptr())
+    plan.patch("target", keep[1].data_ptr())
+    L = plan.head_launches() + plan.fwd + plan.bwd
+    unp = [i for i, r in enumerate(L) if r[2] == "unpack_add_grads"]
+    assert len(unp) == 5 and all(id(L[i]) in plan.rw_override for i in unp)
+    # every scratch range an unpack reads was written by earlier launches only, every row appears exactly once
+    n_rows = 0
+    for i in unp:
+        rd, wr = plan.rw_override[id(L[i])]
+        n_rows += len(rd)
+        for p in rd:
+            writers = [j for j, r in enumerate(L) if r[2].startswith("conv_wgrad") and p in r[1]]
+            assert writers and max(writers) < i
+    assert n_rows == len(plan.wg_entries)
+    last = bucket_last_writers(L, plan.rw_override, st.grad.data_ptr(), st.numel, splits)
+    assert all(l >= 0 for l in last)
+    n_head, n_fwd = len(plan.head_launches()), len(plan.fwd)
+    assert all(l >= n_head + n_fwd for l in last)                 # gradients are written by the backward list
+    frac = [(l - n_head - n_fwd) / float(len(plan.bwd)) for l in last]
+    # back-to-front completion: at least half of the bytes are final before 55 % of the backward list has been issued,
+    # and the bucket that is final last (the stem side of the buffer) is a small one
+    early = sum(sz for sz, f in zip(sizes, frac) if f < 0.55)
+    assert early > 0.5 * st.numel, (sizes, frac)
+    assert sizes[frac.index(max(frac))] < 0.15 * st.numel, (sizes, frac)
+    # the scheduler orders each unpack after the weight-gradient launches it reads, without making it a barrier
+    ns = 8
+    so, cross = schedule_streams(L, ns, n_low=3, low_ids=plan.low_recs, after=plan.after, rw_override=plan.rw_override,
+                                 low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad", "stem_conv7_wgrad_bnapply"))
+    vc, tail = [], [-1] * ns
+    for i in range(len(L)):
+        k = so[i]
+        c = list(vc[tail[k]]) if tail[k] >= 0 else [-1] * ns
+        for d in cross[i]:
+            c = [max(x, y) for x, y in zip(c, vc[d])]
+        c[k] = i
+        vc.append(c)
+        tail[k] = i
+    for i in unp:
+        rd, wr = plan.rw_override[id(L[i])]
+        for p in rd:
+            if p < (1 << 32):
+                continue        # schedule_streams tells pointers from sizes by magnitude (device pointers are > 2^32); a CPU
+                                # heap block can lie below that when this test runs late in a long pytest process
+            for j, r in enumerate(L[:i]):
+                if r[2].startswith("conv_wgrad") and p in r[1]:
+                    assert vc[i][so[j]] >= j
+        # not a barrier: some launch issued before it is NOT ordered before it
+        assert any(vc[i][so[j]] < j for j in range(i))

@@ -1,5 +1,6 @@
 """Multi-GPU check (torchrun): after 3 data-parallel steps every rank holds bitwise-identical parameters,
-and the all-reduced flat gradient equals the sum of the per-rank local gradients.
+the all-reduced flat gradient equals the sum of the per-rank local gradients, and the bucketed all-reduce captured INSIDE
+the step graph (default) gives the same gradients / losses as one eager all-reduce between two graphs (ar_buckets=0).
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_dp.py"""
 import os
 import sys
@@ -19,10 +20,21 @@ S, C, N, R = 2, 64, 4, 128
 net = M.create_hg(S, 1, 16, C)
 # different initial weights per rank on purpose: the trainer must broadcast rank 0's
 net.load_state_dict(synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=50 + rank))
-tr = HourglassTrainer(net, N, R, device=dev, use_graph=True)
 x = synth.make_images(N, R, seed=60 + rank).to(dev)
 t = synth.make_heatmaps(N, R, 16, seed=70 + rank).to(dev)
+# reference run: two graphs around ONE eager all-reduce of the whole flat buffer
+net_e = M.create_hg(S, 1, 16, C)
+net_e.load_state_dict(synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=50 + rank))
+tr_e = HourglassTrainer(net_e, N, R, device=dev, use_graph=True, ar_buckets=0)
+assert not tr_e.ar_in_graph
+losses_e = [float(tr_e.step(x, t)) for _ in range(3)]
+g_e = tr_e.store.grad.clone()
+tr = HourglassTrainer(net, N, R, device=dev, use_graph=True)
+assert tr.ar_in_graph and tr.graph_update is None and len(tr.bucket_ranges()) >= 3
 losses = [float(tr.step(x, t)) for _ in range(3)]
+# same gradients up to the order of the float atomics (three steps of RMSprop's sign-like first updates in between)
+d_first = abs(losses[0] - losses_e[0]) / abs(losses_e[0])
+d_grad = float((tr.store.grad - g_e).norm() / g_e.norm())
 flat = tr.store.flat.clone()
 ref = flat.clone()
 dist.broadcast(ref, src=0)
@@ -43,9 +55,12 @@ tr.store.grad.copy_(g_local)
 hdist.allreduce_flat_grads(tr.store.grad)
 ok_grad = bool(torch.equal(tr.store.grad, g_sum))
 if rank == 0:
-    print("world", world, "losses", losses, "params identical across ranks:", bool(flags.item()),
-          "allreduce == sum of local grads:", ok_grad)
+    print("world", world, "losses", losses, "eager-collective losses", losses_e, "params identical across ranks:",
+          bool(flags.item()), "allreduce == sum of local grads:", ok_grad, "in-graph vs eager: loss[0] rel", d_first,
+          "grad rel-L2 after 3 steps", d_grad, "buckets (MB)", [round((hi - lo) * 4e-6, 2) for lo, hi in tr.bucket_ranges()])
     assert flags.item() == 1 and ok_grad and all(l == l for l in losses)
+    assert d_first < 1e-6 and abs(losses[2] - losses_e[2]) < 5e-3 * abs(losses_e[2]) and d_grad < 0.2
     print("DP CHECK OK")
 dist.barrier()
+tr.close(); tr_e.close()          # captured NCCL kernels must be gone before the communicator is destroyed
 dist.destroy_process_group()
