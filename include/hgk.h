@@ -320,6 +320,39 @@ int hgk_mask_mul_fwd(const float* x, const float* x_scale, const float* x_shift,
 int hgk_mask_mul_bwd(const float* g, const float* mask, int N, int H, int W, int C, int MH, int MW, float* gx,
                      int accumulate, void* stream);
 
+/* ---- image crop / rotate / resize augmentation (pylib/HumanAug.py:117-175 `crop`, reached by load_batch_data of
+ * joint-train-pose-s-r-agent.py:425-450 through gen_img_heatmap, data/joint_train_s_r_agent.py:198-204) ----
+ * Byte-exact GPU versions of the pixel operations `crop` performs through scipy.misc / PIL.  Images are H x W x 3
+ * interleaved; uint8 unless said otherwise; the host (pose_adv_aug_b200/pylib/HumanAug.py) computes the crop geometry
+ * exactly as the reference does with numpy and strings these launches together.
+ * hgk_aug_minmax: out2 = {min, max} (doubles) of the region [y0,y1) x [x0,x1) of a float32 (is_u8 = 0) or uint8 image,
+ *   together with 0 when include_zero (the crop window has zero padding): the cmin / cmax of scipy.misc.bytescale.
+ *   scratch3: three device words in the idle state {0xFFFFFFFF, 0, 0}; the launch leaves them idle again (stream-ordered
+ *   re-use).                                                                                                            */
+int hgk_aug_minmax(const void* img, int is_u8, int H, int W, int y0, int y1, int x0, int x1, int include_zero,
+                   unsigned int* scratch3, double* out2, void* stream);
+/* the zero-padded crop window (`new_img`, ref :156-164) byte-scaled as scipy.misc.toimage does for a float64 array:
+ * window (y, x) = src (y + oy, x + ox) inside [ny0,ny1) x [nx0,nx1), 0 elsewhere; out Hn x Wn x 3                        */
+int hgk_aug_window_bytes(const void* src, int is_u8, int SH, int SW, int oy, int ox, int ny0, int ny1, int nx0, int nx1,
+                         const double* minmax, int Hn, int Wn, unsigned char* out, void* stream);
+/* scipy.misc.toimage of a whole float32 image (the pre-shrink of ref :131): bytescale in float32 arithmetic             */
+int hgk_aug_image_bytes_f32(const float* src, int H, int W, const double* minmax, unsigned char* out, void* stream);
+/* PIL Image.resize(BILINEAR) = ImagingResample, 8 bits per channel: tap count per output index (returns it), the
+ * fixed-point tap table (bounds [out_size][2] = first input index, count; kk [out_size][ksize]), and the two passes:
+ * tmp [in_h][out_w][3] from the in_h x in_w sub-image at (y_off, x_off) of src [SH][SW][3]; out [out_h][out_w][3] from tmp */
+int hgk_aug_resample_ksize(int in_size, int out_size);
+int hgk_aug_resample_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk, void* stream);
+int hgk_aug_resize_h(const unsigned char* src, int SH, int SW, int y_off, int x_off, int in_h, int in_w, int out_w,
+                     const int* bounds, const int* kk, int ksize, unsigned char* tmp, void* stream);
+int hgk_aug_resize_v(const unsigned char* tmp, int in_h, int out_w, int out_h, const int* bounds, const int* kk, int ksize,
+                     unsigned char* out, void* stream);
+/* PIL Image.rotate(BILINEAR) = ImagingGenericTransform(affine, bilinear), fill 0; m6 = HOST array of the six affine
+ * coefficients (output pixel centre -> input position), computed by the host as Image.rotate does                       */
+int hgk_aug_rotate(const unsigned char* in, int H, int W, const double* m6, unsigned char* out, void* stream);
+/* utils/imutils.im_to_torch on a batch of crops: [N][res][res][3] uint8 -> [N][3][res][res] float32, / 255 per image only
+ * when its maximum exceeds 1                                                                                            */
+int hgk_aug_to_chw_float(const unsigned char* img, int N, int res, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

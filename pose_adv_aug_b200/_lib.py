@@ -69,6 +69,14 @@ SIGNATURES = {
     "hgk_softmax_sample": [P, I, I, P, P, P, P],
     "hgk_mask_mul_fwd": [P, P, P, I, P, I, I, I, I, I, I, P, P],
     "hgk_mask_mul_bwd": [P, P, I, I, I, I, I, I, P, I, P],
+    "hgk_aug_minmax": [P, I, I, I, I, I, I, I, I, P, P, P],
+    "hgk_aug_window_bytes": [P, I, I, I, I, I, I, I, I, I, P, I, I, P, P],
+    "hgk_aug_image_bytes_f32": [P, I, I, P, P, P],
+    "hgk_aug_resample_coeffs": [I, I, I, P, P, P],
+    "hgk_aug_resize_h": [P, I, I, I, I, I, I, I, P, P, I, P, P],
+    "hgk_aug_resize_v": [P, I, I, I, P, P, I, P, P],
+    "hgk_aug_rotate": [P, I, I, P, P, P],
+    "hgk_aug_to_chw_float": [P, I, I, P, P],
 }
 
 
@@ -99,6 +107,9 @@ class _Lib(object):
         self.cdll.hgk_conv_tc_x2_supported.argtypes = [I, I, I, I, I, I]
         self.cdll.hgk_conv_wgrad_tc_supported.restype = I
         self.cdll.hgk_conv_wgrad_tc_supported.argtypes = [I, I, I]
+        self.cdll.hgk_aug_resample_ksize.restype = I
+        self.cdll.hgk_aug_resample_ksize.argtypes = [I, I]
+        self.aug_resample_ksize = self.cdll.hgk_aug_resample_ksize
         for name, args in SIGNATURES.items():
             fn = getattr(self.cdll, name)      # AttributeError if the symbol is not exported
             fn.argtypes = args

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libhgk.so")
-SOURCES = ["conv_simt.cu", "conv_skinny.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "wgrad_tc2.cu", "stem.cu", "bn.cu", "heads.cu", "pointwise.cu", "loss_optim.cu", "eval.cu"]
+SOURCES = ["conv_simt.cu", "conv_skinny.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "wgrad_tc2.cu", "stem.cu", "bn.cu", "heads.cu", "pointwise.cu", "loss_optim.cu", "eval.cu", "warp.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 

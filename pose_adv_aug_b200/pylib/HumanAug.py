@@ -6,11 +6,24 @@
   flip_merge(output1, output2)                       = (output1 + shuffle(flip(output2))) / 2 in ONE kernel
 
 The reference does the flip with numpy on a host copy of the output; here the W-flip, the six left/right channel
-swaps and the mean are the index arithmetic of a single pass (`hgk_flip_merge_nchw`).  The image crop / warp
-functions of the reference file (disk + PIL/scipy data pipeline) are out of scope.
+swaps and the mean are the index arithmetic of a single pass (`hgk_flip_merge_nchw`).
+
+and its image crop (the warp half of SURVEY 8f row N3): the function `load_batch_data`
+(joint-train-pose-s-r-agent.py:425-450) reaches through a DataLoader for every batch of agent-sampled scales / rotations:
+
+  crop(img, center, scale, rot, res, size)           ref pylib/HumanAug.py:117-175      (one image, uint8 H x W x 3 out)
+  crop_batch(imgs, centers, scales, rots, res, size) = im_to_torch(crop(...)) per sample, stacked [N,3,res,res] float32
+                                                       (ref data/joint_train_s_r_agent.py:198-204, utils/imutils.py:31-36)
+
+Source images stay resident on the GPU as float32 H x W x 3 tensors in [0,1] (what `im_to_numpy(load_image(...))` hands
+the reference); the pixel work -- scipy.misc's byte-scaling, PIL's two-pass bilinear resize and bilinear rotation -- runs as
+byte-exact CUDA kernels (`csrc/warp.cu`), the crop geometry (a handful of scalars per image) on the host exactly as the
+reference computes it with numpy.  No CPU fallback: CPU tensors raise.
 """
 import ctypes
+import math
 
+import numpy as np
 import torch
 
 from .._lib import get_lib, HGKError
@@ -60,3 +73,211 @@ def shuffle_channels_for_horizontal_flipping(maps):
     out = _launch(None, _check(maps, "shuffle_channels_for_horizontal_flipping"), FLIP_PAIRS, False)
     maps.copy_(out)
     return maps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# crop (ref :117-175)
+# ---------------------------------------------------------------------------------------------------------------------
+def _window(ht, wd, center, scale, rot, res, size):
+    """The integer crop window of ref :121-162 for an ht x wd source: (scale_factor, pre-shrunk size or None, window size,
+    pasted range in the window, matching range in the source, rotation padding)."""
+    f32 = np.float32
+    c = np.asarray(center, dtype=np.float32).reshape(2)                   # the dataset hands float32 tensors (.numpy())
+    s = f32(np.asarray(scale, dtype=np.float32).reshape(-1)[0])
+    sf = float(s * f32(size)) / float(res)                                # :121
+    pre = None
+    if sf < 2:
+        sf = 1
+    else:
+        if np.floor(max(ht, wd) / sf) < 2:                                # :126-129
+            return None
+        wh = (np.array([wd, ht]) * (1 / sf)).astype(int)                  # imresize(size=float): PIL size, truncated
+        pre = (int(wh[1]), int(wh[0]))
+        ht, wd = pre
+    c = c / f32(sf)
+    s = s / f32(sf)
+    # GetTransform(center, scale, 0, res, size) (:10-21) has float32 entries; TransformSinglePts inverts it numerically and
+    # truncates the mapped corners (:38-44)
+    h = f32(size) * s
+    t = np.zeros((3, 3))
+    t[0, 0] = t[1, 1] = f32(res) / h
+    t[0, 2] = f32(res) * (f32(-float(c[0])) / h + f32(.5))
+    t[1, 2] = f32(res) * (f32(-float(c[1])) / h + f32(.5))
+    t[2, 2] = 1
+    inv = np.linalg.inv(t)
+    ul = np.dot(inv, np.array([0, 0, 1.]))[:2].astype(int)
+    br = np.dot(inv, np.array([res, res, 1.]))[:2].astype(int)
+    if sf >= 2:
+        br = br - (br - ul - res)                                         # :142-143
+    pad = int(np.ceil(np.linalg.norm(br - ul) / 2 - float(br[1] - ul[1]) / 2))     # :146
+    if not rot == 0:
+        ul = ul - pad
+        br = br + pad
+    ulx, uly, brx, bry = int(ul[0]), int(ul[1]), int(br[0]), int(br[1])
+    new_x = (max(0, -ulx), min(brx, wd) - ulx)
+    new_y = (max(0, -uly), min(bry, ht) - uly)
+    old_x = (max(0, ulx), min(wd, brx))
+    old_y = (max(0, uly), min(ht, bry))
+    return sf, pre, (bry - uly, brx - ulx), (new_y, new_x), (old_y, old_x), pad
+
+
+def _rotate_matrix(angle, w, h):
+    """The affine coefficients PIL's Image.rotate(angle) (expand = 0, centre = image centre) hands to its transform."""
+    a = -math.radians(angle % 360.0)
+    m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+    cx, cy = w / 2.0, h / 2.0
+    m[2] = m[0] * -cx + m[1] * -cy + m[2]
+    m[5] = m[3] * -cx + m[4] * -cy + m[5]
+    m[2] += cx
+    m[5] += cy
+    return m
+
+
+def GetTransform(center, scale, rot, res, size):
+    """ref :10-36 -- image -> crop transform (3 x 3, float64 storage).  center / scale arrive as float32 arrays, so the
+    similarity entries are float32 arithmetic; the rotation about the crop centre is composed in float64."""
+    f32 = np.float32
+    c = np.asarray(center, dtype=np.float32).reshape(2)
+    h = f32(size) * f32(np.asarray(scale, dtype=np.float32).reshape(-1)[0])
+    t = np.zeros((3, 3))
+    t[0, 0] = t[1, 1] = f32(res) / h
+    t[0, 2] = f32(res) * (f32(-float(c[0])) / h + f32(.5))
+    t[1, 2] = f32(res) * (f32(-float(c[1])) / h + f32(.5))
+    t[2, 2] = 1
+    if not rot == 0:
+        a = -rot * np.pi / 180                                # "to match direction of rotation from cropping"
+        sn, cs = np.sin(a), np.cos(a)
+        rot_mat = np.array([[cs, -sn, 0.], [sn, cs, 0.], [0., 0., 1.]])
+        shift = np.eye(3)
+        shift[0, 2] = shift[1, 2] = -res / 2
+        back = shift.copy()
+        back[:2, 2] *= -1
+        t = np.dot(back, np.dot(rot_mat, np.dot(shift, t)))
+    return t
+
+
+def TransformPts(pts, center, scale, rot, res, size, invert=0):
+    """ref :46-55 -- [M,2] points through the crop transform (or its inverse); float result, no truncation."""
+    t = GetTransform(center, scale, rot, res, size)
+    if invert:
+        t = np.linalg.inv(t)
+    p = np.asarray(pts)
+    homog = np.concatenate((p, np.ones((p.shape[0], 1))), axis=1).T
+    return np.dot(t, homog)[0:2, :].T
+
+
+class _Aug(object):
+    """Launch helper bound to one device / stream."""
+
+    _scratch = {}          # per device: the three idle words of hgk_aug_minmax (stream-ordered re-use)
+
+    def __init__(self, device):
+        self.lib = get_lib()
+        self.dev = device
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+        key = (device.type, device.index)
+        if key not in _Aug._scratch:
+            _Aug._scratch[key] = torch.tensor([-1, 0, 0], device=device, dtype=torch.int32)
+        self.scratch = _Aug._scratch[key]
+
+    def u8(self, *shape):
+        return torch.empty(shape, device=self.dev, dtype=torch.uint8)
+
+    def minmax(self, img, is_u8, H, W, ys, xs, include_zero):
+        out = torch.empty(2, device=self.dev, dtype=torch.float64)
+        self.lib.check(self.lib.aug_minmax(img.data_ptr(), int(is_u8), H, W, ys[0], ys[1], xs[0], xs[1], int(include_zero),
+                                           self.scratch.data_ptr(), out.data_ptr(), self.stream), "hgk_aug_minmax")
+        return out
+
+    def resize(self, src, SH, SW, y_off, x_off, in_h, in_w, out_h, out_w):
+        """PIL Image.resize((out_w, out_h), BILINEAR) of the in_h x in_w sub-image of the uint8 image `src`."""
+        lib = self.lib
+        tabs = []
+        for n_in, n_out in ((in_w, out_w), (in_h, out_h)):
+            ks = lib.aug_resample_ksize(n_in, n_out)
+            bounds = torch.empty(n_out * 2, device=self.dev, dtype=torch.int32)
+            kk = torch.empty(n_out * ks, device=self.dev, dtype=torch.int32)
+            lib.check(lib.aug_resample_coeffs(n_in, n_out, ks, bounds.data_ptr(), kk.data_ptr(), self.stream),
+                      "hgk_aug_resample_coeffs")
+            tabs.append((ks, bounds, kk))
+        tmp = self.u8(in_h, out_w, 3)
+        out = self.u8(out_h, out_w, 3)
+        (kh, bh, kkh), (kv, bv, kkv) = tabs
+        lib.check(lib.aug_resize_h(src.data_ptr(), SH, SW, y_off, x_off, in_h, in_w, out_w, bh.data_ptr(), kkh.data_ptr(), kh,
+                                   tmp.data_ptr(), self.stream), "hgk_aug_resize_h")
+        lib.check(lib.aug_resize_v(tmp.data_ptr(), in_h, out_w, out_h, bv.data_ptr(), kkv.data_ptr(), kv, out.data_ptr(),
+                                   self.stream), "hgk_aug_resize_v")
+        return out
+
+
+def crop(img, center, scale, rot, res, size):
+    """ref :117-175.  img: float32 CUDA tensor H x W x 3 in [0,1]; center (x, y), scale, rot (degrees): host numbers.
+    Returns the res x res x 3 uint8 CUDA tensor the reference returns as a numpy array (or `img` itself in the degenerate
+    early return of ref :128-129)."""
+    if not isinstance(img, torch.Tensor) or not img.is_cuda:
+        raise HGKError("HumanAug.crop runs on CUDA tensors only (no CPU fallback)")
+    if img.dim() != 3 or img.shape[2] != 3 or img.dtype != torch.float32:
+        raise ValueError("crop: expected a float32 H x W x 3 image, got %s %s" % (tuple(img.shape), img.dtype))
+    img = img.contiguous()
+    H, W = int(img.shape[0]), int(img.shape[1])
+    if min(H, W) <= 4:
+        raise ValueError("crop: image too small (scipy.misc.toimage would take a 3- or 4-pixel side for the channel axis)")
+    rot = float(np.asarray(rot).reshape(-1)[0])
+    win = _window(H, W, center, scale, rot, res, size)
+    if win is None:
+        return img
+    sf, pre, (Hn, Wn), (new_y, new_x), (old_y, old_x), pad = win
+    if Hn <= 4 or Wn <= 4 or old_y[1] <= old_y[0] or old_x[1] <= old_x[0] or \
+            (new_y[1] - new_y[0], new_x[1] - new_x[0]) != (old_y[1] - old_y[0], old_x[1] - old_x[0]):
+        # numpy would refuse the slice assignment of ref :164 (window entirely off the image)
+        raise ValueError("crop: the crop window does not intersect the image")
+    A = _Aug(img.device)
+    lib, st = A.lib, A.stream
+    src, src_u8, SH, SW = img, 0, H, W
+    if pre is not None:                                                    # :131 imresize(img, 1 / scale_factor)
+        mm = A.minmax(img, 0, H, W, (0, H), (0, W), False)
+        b = A.u8(H, W, 3)
+        lib.check(lib.aug_image_bytes_f32(img.data_ptr(), H, W, mm.data_ptr(), b.data_ptr(), st), "hgk_aug_image_bytes_f32")
+        src = A.resize(b, H, W, 0, 0, H, W, pre[0], pre[1])
+        src_u8, SH, SW = 1, pre[0], pre[1]
+    # new_img = zeros; new_img[new] = img[old] (:156-164), then toimage's byte-scaling of that float64 array
+    has_zero = (new_y[1] - new_y[0]) < Hn or (new_x[1] - new_x[0]) < Wn
+    mm = A.minmax(src, src_u8, SH, SW, old_y, old_x, has_zero)
+    wb = A.u8(Hn, Wn, 3)
+    lib.check(lib.aug_window_bytes(src.data_ptr(), src_u8, SH, SW, old_y[0] - new_y[0], old_x[0] - new_x[0], new_y[0], new_y[1],
+                                   new_x[0], new_x[1], mm.data_ptr(), Hn, Wn, wb.data_ptr(), st), "hgk_aug_window_bytes")
+    off = 0
+    if not rot == 0:                                                       # :166-170 imrotate + padding removed
+        if (rot % 360.0) in (0.0, 90.0, 180.0, 270.0):
+            raise HGKError("crop: rotation by a multiple of 90 degrees takes PIL's transpose path, which is not built")
+        if pad <= 0 or Hn - 2 * pad <= 0 or Wn - 2 * pad <= 0:
+            raise ValueError("crop: empty image after removing the rotation padding")
+        m = (ctypes.c_double * 6)(*_rotate_matrix(rot, Wn, Hn))
+        rb = A.u8(Hn, Wn, 3)
+        lib.check(lib.aug_rotate(wb.data_ptr(), Hn, Wn, ctypes.cast(m, ctypes.c_void_p).value, rb.data_ptr(), st), "hgk_aug_rotate")
+        wb, off = rb, pad
+    return A.resize(wb, Hn, Wn, off, off, Hn - 2 * off, Wn - 2 * off, res, res)     # :175 imresize(new_img, (res, res))
+
+
+def crop_batch(imgs, centers, scales, rots, res=256, size=200):
+    """`inp = im_to_torch(crop(im_to_numpy(img), c, s, r, res, size)).float()` (ref data/joint_train_s_r_agent.py:200-203)
+    for every sample of a batch: imgs = list of float32 CUDA H x W x 3 tensors (any sizes), centers [N,2], scales [N],
+    rots [N] host arrays.  Returns [N,3,res,res] float32 on the GPU -- the `img` batch of load_batch_data."""
+    n = len(imgs)
+    if n == 0:
+        raise ValueError("crop_batch: empty batch")
+    centers = np.asarray(centers, dtype=np.float32).reshape(n, 2)
+    scales = np.asarray(scales, dtype=np.float32).reshape(n)
+    rots = np.asarray(rots, dtype=np.float64).reshape(n)
+    dev = imgs[0].device
+    stack = torch.empty(n, res, res, 3, device=dev, dtype=torch.uint8)
+    for k in range(n):
+        c = crop(imgs[k], centers[k], scales[k], rots[k], res, size)
+        if c.dtype != torch.uint8:
+            raise ValueError("crop_batch: sample %d hit the degenerate early return of crop (image smaller than 2 px after shrinking)" % k)
+        stack[k].copy_(c)
+    out = torch.empty(n, 3, res, res, device=dev, dtype=torch.float32)
+    lib = get_lib()
+    lib.check(lib.aug_to_chw_float(stack.data_ptr(), n, res, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+              "hgk_aug_to_chw_float")
+    return out

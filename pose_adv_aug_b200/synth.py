@@ -94,3 +94,22 @@ def make_tensor(name, shape, seed=0, lo=-1.0, hi=1.0, dtype=torch.float32):
     """Generic named uniform tensor for per-kernel tests."""
     r = _rng(name, seed)
     return torch.from_numpy(r.uniform(lo, hi, size=shape)).to(dtype)
+
+
+def make_photo(h, w, seed=0):
+    """A synthetic 'photograph' for the crop / rotate / resize augmentation: H x W x 3 float32 in [0,1] with smooth
+    large-scale structure (a bilinearly up-sampled random 1/16-resolution field) plus fine noise, numpy only (the same
+    bytes on every machine)."""
+    r = np.random.Generator(np.random.PCG64(zlib.crc32(b"photo") ^ (seed * 7919 + h * 31 + w)))
+    gh, gw = h // 16 + 2, w // 16 + 2
+    g = r.random((gh, gw, 3))
+    ys = np.linspace(0.0, gh - 1.001, h)
+    xs = np.linspace(0.0, gw - 1.001, w)
+    y0 = np.floor(ys).astype(np.int64)
+    x0 = np.floor(xs).astype(np.int64)
+    fy = (ys - y0)[:, None, None]
+    fx = (xs - x0)[None, :, None]
+    rows = g[y0] * (1.0 - fy) + g[y0 + 1] * fy
+    img = rows[:, x0] * (1.0 - fx) + rows[:, x0 + 1] * fx
+    img = img * r.uniform(0.55, 1.0) + r.uniform(0.0, 0.1) + r.normal(0.0, 0.02, size=img.shape)
+    return np.clip(img, 0.0, 1.0).astype(np.float32)
