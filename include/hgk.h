@@ -171,6 +171,13 @@ int hgk_stem_conv7_fwd(const float* img, int N, int H, int W, const float* w, co
                        float* y, double* stat_sum, double* stat_sq, void* stream);
 int hgk_stem_conv7_wgrad(const float* img, int N, int H, int W, const float* dz, int Cout,
                          float* dw, float* dbias, void* stream);
+/* Tensor-core form of the same forward convolution: space-to-depth.  xs [N,H/2,W/2,16] (NHWC) holds
+ * xs[sy][sx][(dy*2+dx)*3 + c] = img[c][2 sy + dy][2 sx + dx] (channels 12..15 zero), ws [Cout,32,4,4] (OIHW; channels 16..31
+ * zero: the weight packer works in blocks of 32) the matching rearrangement of w; the stem is then hgk_conv_tc_bn_nhwc /
+ * hgk_conv_tc_nhwc (or their _x2 forms) over xs with the packed ws and ksize = 4 (4x4 taps at offsets -2 .. +1; Cin = 16,
+ * Cout = 64, H/2 and W/2 multiples of 16). */
+int hgk_stem_s2d_image(const float* img, int N, int H, int W, float* xs, void* stream);
+int hgk_stem_s2d_weight(const float* w, int Cout, float* ws, void* stream);
 /* The same with bn1's BatchNorm-backward apply evaluated on load: g = dL/d relu(bn1(z)), z = the stem's pre-BN output;
  * dz = cA*((g*[z*scale+shift > 0] - cC) - (z - mean)*cB) is formed in shared memory (the expression of hgk_bn_bwd_apply) and
  * never written to global memory. */

@@ -69,6 +69,8 @@ SIGNATURES = {
     "hgk_softmax_sample": [P, I, I, P, P, P, P],
     "hgk_mask_mul_fwd": [P, P, P, I, P, I, I, I, I, I, I, P, P],
     "hgk_mask_mul_bwd": [P, P, I, I, I, I, I, I, P, I, P],
+    "hgk_stem_s2d_image": [P, I, I, I, P, P],
+    "hgk_stem_s2d_weight": [P, I, P, P],
     "hgk_aug_minmax": [P, I, I, I, I, I, I, I, I, P, P, P],
     "hgk_aug_window_bytes": [P, I, I, I, I, I, I, I, I, I, P, I, I, P, P],
     "hgk_aug_image_bytes_f32": [P, I, I, P, P, P],

@@ -1190,8 +1190,17 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
                         const BnApply* ap = nullptr, int lo_bf16 = 0) {
     HGK_REQUIRE(x && w_hi && y, "hgk_conv_tc_nhwc: null pointer");
     HGK_REQUIRE(N > 0 && H > 0 && W > 0, "hgk_conv_tc_nhwc: empty tensor");
-    HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
-                "(need Cin %% 32 == 0, Cout in {64,128,256}, k in {1,3})", Cin, Cout, ksize);
+    // k = 4: the 7x7 stride-2 stem convolution in space-to-depth form (hgk_stem_s2d_image / hgk_stem_s2d_weight, stem.cu):
+    // 4x4 taps at offsets -2 .. +1 over the 16-channel half-resolution image (weights packed as K = 32, upper half zero),
+    // 64 outputs, forward only, image-tile kernel
+    const bool stem4 = ksize == 4;
+    if (stem4)
+        HGK_REQUIRE(Cin == 16 && Cout == 64 && H % 16 == 0 && W % 16 == 0 && w_lo != nullptr && ap == nullptr && bz == nullptr &&
+                    res == nullptr && !accumulate && (long long)N * H * W * 64 < (1LL << 32),
+                    "hgk_conv_tc_nhwc: k = 4 (space-to-depth stem) needs Cin = 16, Cout = 64, H and W multiples of 16, w_lo");
+    else
+        HGK_REQUIRE(hgk_conv_tc_supported(Cin, Cout, ksize), "hgk_conv_tc_nhwc: unsupported shape Cin=%d Cout=%d k=%d "
+                    "(need Cin %% 32 == 0, Cout in {64,128,256}, k in {1,3})", Cin, Cout, ksize);
     HGK_REQUIRE((stat_sum == nullptr) == (stat_sq == nullptr), "hgk_conv_tc_nhwc: stat_sum/stat_sq must both be set");
     HGK_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), "hgk_conv_tc_nhwc: x scale/shift must both be set");
     HGK_REQUIRE((res_scale == nullptr) == (res_shift == nullptr), "hgk_conv_tc_nhwc: res scale/shift must both be set");
@@ -1212,7 +1221,7 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
                     "hgk_conv_tc_dgrad_bnapply_nhwc: shape not covered by the "
                     "image-tile kernel (see hgk_conv_tc_bnapply_supported)");
     ta.w_hi = w_hi; ta.w_lo = w_lo; ta.dbg = g_dbg_buf; ta.lo_bf16 = lo_bf16;
-    if (lo_bf16)
+    if (lo_bf16 && !stem4)
         HGK_REQUIRE(w_lo != nullptr && ap == nullptr && hgk_conv_tc_x2_supported(N, H, W, Cin, Cout, ksize),
                     "hgk_conv_tc_bn_x2_nhwc: shape not covered by the TF32 + 2xBF16 tile kernel (see hgk_conv_tc_x2_supported)");
     HGK_REQUIRE((ta.c.P + TBM - 1) / TBM < 2147483647LL, "hgk_conv_tc_nhwc: too many pixels");
@@ -1222,7 +1231,8 @@ static int conv_tc_impl(const float* x, const float* x_scale, const float* x_shi
     if (bz != nullptr)
         HGK_REQUIRE(!split, "hgk_conv_tc_dgrad_bnstats_nhwc: only plain-TF32 data gradients carry the fused BN reduction");
     const bool small = ap == nullptr && splitk_factor(ta.c.P, Cin, Cout, ksize) > 1;      // cluster split-K (conv_tc_kernel)
-    if (!small && use_tc3(ksize, split) && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
+    if (stem4) rc = conv_tc2_launch(ta, split, false, stream);
+    else if (!small && use_tc3(ksize, split) && conv_tc3_eligible(ta)) rc = conv_tc3_launch(ta, split, bz != nullptr, stream);
     else if (!small && use_tile_kernel() && conv_tc2_eligible(ta)) rc = conv_tc2_launch(ta, split, bz != nullptr, stream);
     else if (bz != nullptr) {
         rc = Cout == 64 ? launch_tc<64, false, true>(ta, st)

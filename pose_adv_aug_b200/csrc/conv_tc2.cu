@@ -52,8 +52,9 @@ constexpr int T2_THREADS = 320;      // 8 producer/epilogue warps + MMA warp + w
 template <int BN, bool SPLIT, int KS, int NSUB = 2>
 struct T2Cfg {
     static constexpr int TH = 16, TW = 8 * NSUB;
-    static constexpr int PAD = KS / 2;
-    static constexpr int HH = TH + 2 * PAD, HWD = TW + 2 * PAD;           // halo tile
+    // KS = 4: the space-to-depth form of the 7x7 stride-2 stem convolution (stem.cu) -- 4x4 taps at offsets -2 .. +1
+    static constexpr int PAD = KS / 2;                                     // halo rows / columns in FRONT of the tile
+    static constexpr int HH = TH + KS - 1, HWD = TW + KS - 1;             // halo tile
     static constexpr int NPIX = HH * HWD;
     static constexpr int TAPS = KS * KS;
     static constexpr int BK = 16, QP = 4;                                  // channels / 16-byte quads per chunk
@@ -67,7 +68,9 @@ struct T2Cfg {
     // accumulators per 128-pixel half, see conv_tc.cu (fp32 accumulator truncation of the tensor core): 3x3 chains
     // (K = 9 Cin) split into hi*hi / cross-term accumulators; a 1x1 chain is at most 3*256/8 = 96 MMAs long -- the
     // same length conv_tc.cu accepts for its single-accumulator BN = 256 case
-    static constexpr int NMAIN = (SPLIT && KS == 3 && BN <= 64) ? 2 : 1;
+    // (the stem, KS = 4, keeps them too: with ONE accumulator for its 96-MMA chain the error was 1.6e-6 of max instead of 4e-7,
+    //  and the launch was no faster: 115 vs 117 us)
+    static constexpr int NMAIN = (SPLIT && KS > 1 && BN <= 64) ? 2 : 1;
     static constexpr int NACC = (!SPLIT || KS == 1 || BN >= 256) ? 1 : NMAIN + 1;
     static constexpr int SUBCOLS = NACC * BN;
     static constexpr int TMEM_COLS = (NSUB * SUBCOLS <= 64) ? 64 : (NSUB * SUBCOLS <= 128) ? 128 : (NSUB * SUBCOLS <= 256) ? 256 : 512;
@@ -81,8 +84,10 @@ struct T2Cfg {
     // switches it off for the BNAPPLY instantiations (measured slower there: 113 -> 119 us on the 64x64 256->128 data
     // gradient; the doubled register sets spill inside the producer loop).
     static constexpr bool PAIR = KS == 1 && NSUB == 1 && !SPLIT;
-    static constexpr int NSA = KS == 3 ? 2 : (PAIR ? 4 : (OCC2 && SPLIT ? 2 : 3));      // activation stages (one per chunk)
-    static constexpr int NSB = KS == 3 ? (OCC2 ? (SPLIT ? 3 : 4) : 8) : NSA;   // weight stages (one per chunk x tap)
+    // KS = 4 (stem): a single 16-channel chunk (12 real channels), so one activation stage; its sixteen 8 KB weight stages
+    // are latency-bound bulk copies -- eight in flight (three left the tile waiting ~0.25 us per tap: 199 us per launch)
+    static constexpr int NSA = KS == 4 ? 1 : KS > 1 ? 2 : (PAIR ? 4 : (OCC2 && SPLIT ? 2 : 3));      // activation stages (one per chunk)
+    static constexpr int NSB = KS == 4 ? 8 : KS > 1 ? (OCC2 ? (SPLIT ? 3 : 4) : 8) : NSA;   // weight stages (one per chunk x tap)
     static constexpr int PIPE = NSA * A_STAGE + NSB * B_STAGE;
     static constexpr int CH = BN > 128 ? 128 : BN;                         // epilogue column chunk
     static constexpr int STG_BYTES = TBM * (CH + 4) * 4 + 16384;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
     const int n_img = blockIdx.x / tiles_hw;
     const int trem = blockIdx.x - n_img * tiles_hw;
     const int th0 = (trem / tiles_w) << 4, tw0 = (trem % tiles_w) * Cfg::TW;
-    const int KC = a.Cin >> 4;
+    const int KC = KS == 4 ? 1 : a.Cin >> 4;     // stem: 16-channel pixels; the weights are packed as K = 32 (upper half zero)
     const uint32_t bar_fa = smem_u32(&bars[0]), bar_ea = smem_u32(&bars[NSA]);
     const uint32_t bar_fb = smem_u32(&bars[2 * NSA]), bar_eb = smem_u32(&bars[2 * NSA + NSB]);
     const uint32_t bar_done = smem_u32(&bars[2 * NSA + 2 * NSB]);
@@ -312,14 +317,14 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
                     if (it == 0) HGK_STAMP(9);
                     if (tap == 0) HGK_TRACE(3, kc);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_tap = a_stage + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 64u : 0u);
+                    const uint32_t a_tap = a_stage + (KS > 1 ? (uint32_t)((tap / KS) * HWD + (tap % KS)) * 64u : 0u);
                     const uint32_t b_hi = sbase + B_OFF + sb * B_STAGE;
 #pragma unroll
                     for (int sub = 0; sub < NSUB; ++sub) {
                         const uint32_t t_sub = tmem + sub * SUBCOLS;
                         if (XBF) {
                             // cross terms, one K = 16 bf16 MMA each: xl * wh_bf16 and xh_bf16 * wl_bf16
-                            const uint32_t x_tap = a_stage + A_HALF + (KS == 3 ? (uint32_t)((tap / 3) * HWD + (tap % 3)) * 16u : 0u) + sub * 128;
+                            const uint32_t x_tap = a_stage + A_HALF + (KS > 1 ? (uint32_t)((tap / KS) * HWD + (tap % KS)) * 16u : 0u) + sub * 128;
                             const uint64_t dxl = umma_desc(x_tap, XPLANE, (uint32_t)HWD * 16u);
                             const uint64_t dxh = umma_desc(x_tap + 2u * XPLANE, XPLANE, (uint32_t)HWD * 16u);
                             const uint64_t dwh = umma_desc(b_hi + B_HALF, LBO_B, SBO_B);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(T2_THREADS, (T2Cfg<BN, SPLIT, KS, NSUB>::OCC2 
         // ===== weight stream: one cp.async.bulk per (chunk, tap) stage; packed blocks are [tap][Cin/32][8 quads][BN][4] =====
         T2_RENDEZVOUS();
         if (lane == 0) {
-            const int KC32 = a.Cin >> 5;
+            const int KC32 = KS == 4 ? 1 : a.Cin >> 5;
             int sb = 0, it = 0;
             unsigned eb_par = 1;
             for (int kc = 0; kc < KC; ++kc) {
@@ -593,6 +598,10 @@ static int launch_tc2_bn(const TcArgs& ta, bool split, bool bwdstats, cudaStream
     if (split) {
         // TF32 + 2xBF16 products (w_lo in pack mode 2): 3x3 forward with 64 / 128 output channels only
         if (ta.lo_bf16) {
+            // 64 output channels (the 128x128 layer): 16x8 tiles -- 192 TMEM columns, so two CTAs share an SM and the
+            // producer chain / epilogue of one runs under the MMAs of the other (283 -> 227 us; the data gradient of the
+            // same layer is faster on 16x16 tiles and keeps them)
+            if (KS == 3 && BN == 64) return launch_tc2_sub<BN, true, KS == 3 ? 3 : 1, false, false, 1, (KS == 3 && BN == 64)>(ta, st);
             if (KS == 3 && BN <= 128) return launch_tc2_cfg<BN, true, KS == 3 ? 3 : 1, false, false, (KS == 3 && BN <= 128)>(ta, st);
             set_error("hgk_conv_tc_bn_x2_nhwc: no TF32 + 2xBF16 instantiation for k=%d Cout=%d", KS, BN);
             return HGK_EINVAL;
@@ -616,6 +625,15 @@ bool conv_tc2_eligible(const TcArgs& ta) {
 int conv_tc2_launch(const TcArgs& ta, bool split, bool bwdstats, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int BN = ta.c.Cout;
+    if (ta.c.ksize == 4) {
+        // the stem in space-to-depth form (32 -> 64 channels, forward only): 16x8 tiles, two CTAs per SM
+        if (BN != 64 || !split || bwdstats || ta.c.ap.z != nullptr) {
+            set_error("hgk_conv_tc_nhwc: k = 4 is the forward stem convolution only (32 -> 64 channels, w_lo given)");
+            return HGK_EINVAL;
+        }
+        return ta.lo_bf16 ? launch_tc2_sub<64, true, 4, false, false, 1, true>(ta, st)
+                          : launch_tc2_sub<64, true, 4, false, false, 1, false>(ta, st);
+    }
     if (ta.c.ksize == 3) {
         if (BN == 64) return launch_tc2_bn<64, 3>(ta, split, bwdstats, st);
         return launch_tc2_bn<128, 3>(ta, split, bwdstats, st);

@@ -476,6 +476,54 @@ __global__ void __launch_bounds__(ST3_THREADS, 2) stem_conv7_wgrad3_kernel(const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core stem (forward): the 7x7 stride-2 convolution in SPACE-TO-DEPTH form.  With x'[sy][sx][(dy*2+dx)*3 + c] =
+// X[c][2 sy + dy][2 sx + dx] (half resolution, 12 real channels padded to 16) the stem is a stride-1 convolution with 4x4
+// taps at offsets -2 .. +1:  out[oy][ox] = sum_{ty,tx,c'} W'[co][c'][ty][tx] x'[oy + ty - 2][ox + tx - 2][c'],
+// W'[co][(dy*2+dx)*3 + c][ty][tx] = W[co][c][2 ty + dy - 1][2 tx + dx - 1] (zero where the 7x7 index falls outside) -- exactly
+// the shape the image-tile tcgen05 kernel runs (conv_tc2.cu, KS = 4): halo tile staged once, sixteen taps as shifted
+// descriptors, TF32 + 2xBF16 (or 3xTF32) products, bias + BatchNorm statistics + finaliser in its epilogue.  The zero padding
+// of 3 pixels becomes the zero rows / columns of x' outside [0, H/2) x [0, W/2).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_s2d_image_kernel(const float* __restrict__ img, int H, int W, unsigned total,
+                                                              float* __restrict__ xs) {
+    const int H2 = H >> 1, W2 = W >> 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned q = i & 3u, pix = i >> 2;                // 16-byte channel quad of one half-resolution pixel
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < 3u) {
+            const unsigned sx = pix % (unsigned)W2, r = pix / (unsigned)W2;
+            const unsigned sy = r % (unsigned)H2, n = r / (unsigned)H2;
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned cp = q * 4u + j;                  // c' = (dy*2 + dx)*3 + c
+                const unsigned c = cp % 3u, d = cp / 3u;
+                e[j] = __ldg(img + (((size_t)n * 3 + c) * H + (2u * sy + (d >> 1))) * W + (2u * sx + (d & 1u)));
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        st4(xs + (size_t)i * 4, v);
+    }
+}
+
+// W [Cout][3][7][7] -> W' [Cout][32][4][4] (OIHW, the layout the weight packer of the tensor-core kernels reads: it packs K in
+// blocks of 32 channels, so the 16 image channels are followed by 16 zero ones that the kernel never streams)
+__global__ void stem_s2d_weight_kernel(const float* __restrict__ w, int Cout, float* __restrict__ ws) {
+    const int total = Cout * 32 * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tx = i & 3, ty = (i >> 2) & 3, cp = (i >> 4) & 31, co = i >> 9;
+        float v = 0.f;
+        if (cp < 12) {
+            const int c = cp % 3, d = cp / 3;
+            const int ky = 2 * ty + (d >> 1) - 1, kx = 2 * tx + (d & 1) - 1;
+            if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = __ldg(w + ((co * 3 + c) * 7 + ky) * 7 + kx);
+        }
+        ws[i] = v;
+    }
+}
+
 }  // namespace hgk
 
 using namespace hgk;
@@ -541,5 +589,25 @@ extern "C" int hgk_stem_conv7_wgrad_bnapply(const float* img, int N, int H, int 
     stem_conv7_wgrad3_kernel<<<grid, ST3_THREADS, ST3_SMEM, (cudaStream_t)stream>>>(img, N, H, W, g, z, scale, shift, relu, mean,
                                                                                   cA, cB, cC, dw, dbias, tiles_x, tiles_y);
     HGK_CHECK_LAUNCH("hgk_stem_conv7_wgrad_bnapply");
+    return HGK_OK;
+}
+
+
+extern "C" int hgk_stem_s2d_image(const float* img, int N, int H, int W, float* xs, void* stream) {
+    HGK_REQUIRE(img && xs, "hgk_stem_s2d_image: null pointer");
+    HGK_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hgk_stem_s2d_image: H and W must be even");
+    const long long total = (long long)N * (H / 2) * (W / 2) * 4;
+    HGK_REQUIRE(total < (1LL << 32), "hgk_stem_s2d_image: too many pixels");
+    long long g = (total + 255) / 256;
+    if (g > (long long)kNumSMs * 16) g = (long long)kNumSMs * 16;
+    stem_s2d_image_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(img, H, W, (unsigned)total, xs);
+    HGK_CHECK_LAUNCH("hgk_stem_s2d_image");
+    return HGK_OK;
+}
+
+extern "C" int hgk_stem_s2d_weight(const float* w, int Cout, float* ws, void* stream) {
+    HGK_REQUIRE(w && ws && Cout > 0, "hgk_stem_s2d_weight: bad arguments");
+    stem_s2d_weight_kernel<<<(Cout * 512 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, ws);
+    HGK_CHECK_LAUNCH("hgk_stem_s2d_weight");
     return HGK_OK;
 }

@@ -226,6 +226,7 @@ class Plan(object):
         self.pre = []              # launches that run BEFORE the weight repack (derived weights: Plan.head_comb)
         self.aux_grad = {}         # id(derived weight / bias tensor) -> its gradient tensor (not part of any flat store)
         self.aux_zero = []         # ... which are zeroed at the start of every backward pass
+        self.no_pack_dep = set()   # id() of launches that read neither packed-weight arena (see _NO_PACK_DEP)
         self.rw_override = {}      # id(launch) -> (read pointers, written pointers) for launches that take arena base pointers
         self.after = {}            # id(launch) -> id(earlier launch) it must additionally wait for (scheduling-only edge)
 
@@ -725,6 +726,7 @@ _WRITES = {
     "maxpool2_fwd": (8,), "maxpool2_bwd": (9,), "add_fwd": (13,), "upsample2_bwd": (5,), "add_into": (1,),
     "maxpool2_bwd_bnred": (9, 13, 14, 17, 18, 19, 20, 21, 22), "upsample2_bwd_bnred": (5, 13, 14, 17, 18, 19, 20, 21, 22),
     "nchw_to_nhwc": (5,), "nhwc_to_nchw": (8,),
+    "stem_s2d_image": (4,), "stem_s2d_weight": (2,),
     "stem_conv7_fwd": (7, 8, 9), "stem_conv7_wgrad": (6, 7), "stem_conv7_wgrad_bnapply": (14, 15),
     "head_combine_fwd": (6, 7), "head_combine_bwd": (4, 5, 6, 7, 8, 9),
     "mse_fwd_bwd": (5, 7), "avgpool_fwd": (9,), "avgpool_bwd": (6,), "linear_fwd": (6,), "linear_bwd": (6, 7, 8),
@@ -733,11 +735,11 @@ _WRITES = {
 
 # entry points that read neither packed-weight arena: they need not wait for the weight repack at the head of the step
 # (the stem convolution reads the raw OIHW weights, the target transpose no weights at all)
-_NO_PACK_DEP = ("stem_conv7_fwd", "nchw_to_nhwc")
+_NO_PACK_DEP = ("stem_conv7_fwd", "stem_s2d_image", "nchw_to_nhwc")
 
 
 def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack_weights_tc", "unpack_add_grads"),
-                     low_names=(), n_low=0, low_ids=(), after=None, rw_override=None):
+                     low_names=(), n_low=0, low_ids=(), after=None, rw_override=None, no_pack_ids=()):
     """Assign each launch of a static list to one of `n_streams` streams.
 
     Dependencies are derived from the launch arguments (device pointers; `_WRITES` says which positions
@@ -783,7 +785,8 @@ def schedule_streams(launches, n_streams=4, barrier_names=("pack_weights", "pack
                 if p in last_write:
                     deps.add(last_write[p])
                 deps.update(readers.get(p, ()))
-            if barrier >= 0 and not (name in _NO_PACK_DEP and launches[barrier][2] in ("pack_weights", "pack_weights_tc")):
+            if barrier >= 0 and not ((name in _NO_PACK_DEP or id(launches[i]) in no_pack_ids)
+                                     and launches[barrier][2] in ("pack_weights", "pack_weights_tc")):
                 deps.add(barrier)
             if after:
                 anchor = index_of.get(after.get(id(launches[i])))
@@ -877,13 +880,52 @@ class _StemOp(object):
             raise ValueError("stem conv must be Conv2d(3,64,7,stride=2,padding=3)")
         z = p.buf(N, H // 2, W // 2, Cout)
         self.bn = r = p.bn_rec(bn)
-        rec = p.launch(p.fwd, "stem_conv7_fwd", 0, N, H, W, p.param_ptr(conv.weight), p.param_ptr(conv.bias), Cout,
-                       _ptr(z), _ptr(r.sum), _ptr(r.sq))
+        H2, W2 = H // 2, W // 2
+        fin_fused = False
+        if (p.use_tc and os.environ.get("HGK_STEM_TC", "0") == "1" and H2 % 16 == 0 and W2 % 16 == 0
+                and N * H2 * W2 * 64 < (1 << 32)):
+            # HGK_STEM_TC=1 (off by default: measured on the config-2 step the launch itself is faster -- 205 us FFMA against
+            # 14.5 + 139 us -- but the step is 0.06 ms SLOWER, 10.15 vs 10.08 ms, profiles/r6_stem_ab.txt).
+            # tensor cores: space-to-depth turns the 7x7 stride-2 convolution into 4x4 taps over the 16-channel half-resolution
+            # image (csrc/stem.cu), which the image-tile tcgen05 kernel runs as ksize = 4 with the usual fp32-class products,
+            # bias, batch statistics and (when fused) the BatchNorm finaliser in its epilogue.  The rearranged weight is a
+            # derived tensor rebuilt in front of the weight repack every step, like the folded head (Plan.head_comb).
+            xs = p.buf(N, H2, W2, 16)
+            self.ws = torch.zeros(Cout, 32, 4, 4, device=p.device, dtype=torch.float32)
+            rec = p.launch(p.fwd, "stem_s2d_image", 0, N, H, W, _ptr(xs))
+            p.launch(p.pre, "stem_s2d_weight", p.param_ptr(conv.weight), Cout, _ptr(self.ws))
+            # its own (one-entry) repack into its own buffer: the stem is the first kernel of the step and must not wait for the
+            # repack of all the other weights (the FFMA stem reads the raw weights and never did)
+            nw = self.ws.numel()
+            self.wpk = torch.zeros(2 * nw, device=p.device, dtype=torch.float32)
+            self.wtab = torch.tensor([[0, 0, nw, Cout, 32, 16, 0, Cout]], dtype=torch.long, device=p.device)
+            rec_pk = p.launch(p.pre, "pack_weights_tc", _ptr(self.ws), _ptr(self.wpk), _ptr(self.wtab), 1)
+            hi, lo = _ptr(self.wpk), _ptr(self.wpk) + 4 * nw
+            p.rw_override[id(rec_pk)] = ([_ptr(self.ws)], [hi, lo])
+            # 3xTF32 products here even where the other layers take TF32 + 2xBF16: an error in the first layer is amplified by
+            # every BatchNorm / ReLU of the network behind it (measured on the headline shape: whole-net gradient 7.8e-3 of
+            # fp64 with bf16 cross terms in the stem, against the 2 x 3.2e-3 + 1e-3 gate), and the stem is not tensor-bound
+            x2 = False
+            stats = r.training
+            base = [_ptr(xs), 0, 0, 0, N, H2, W2, 16, hi, lo, 4, p.param_ptr(conv.bias), Cout, 0, 0, 0, 0]
+            if stats and p.fuse_bn_fin:
+                crec = p.launch(p.fwd, "conv_tc_bn_x2_nhwc" if x2 else "conv_tc_bn_nhwc",
+                                *(base + [_ptr(z), 0, _ptr(r.sum), _ptr(r.sq), _ptr(r.gamma), _ptr(r.beta), BN_EPS, BN_MOMENTUM,
+                                          _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean), _ptr(r.invstd),
+                                          p.ticket_alloc()]))
+                fin_fused = True
+            else:
+                crec = p.launch(p.fwd, "conv_tc_x2_nhwc" if x2 else "conv_tc_nhwc",
+                                *(base + [_ptr(z), 0, _ptr(r.sum) if stats else 0, _ptr(r.sq) if stats else 0]))
+            p.no_pack_dep.add(id(crec))
+        else:
+            rec = p.launch(p.fwd, "stem_conv7_fwd", 0, N, H, W, p.param_ptr(conv.weight), p.param_ptr(conv.bias), Cout,
+                           _ptr(z), _ptr(r.sum), _ptr(r.sq))
         p.dynamic("image", rec, 0)
         self.out = T(z, N, H // 2, W // 2, Cout, r.scale, r.shift, True, needs_grad=p.need_grad, name="stem")
         self.out.producer = self
         self.out.bn = r
-        if r.training:
+        if r.training and not fin_fused:
             p.launch(p.fwd, "bn_finalize", _ptr(r.sum), _ptr(r.sq), self.out.P, _ptr(r.gamma), _ptr(r.beta), BN_EPS,
                      BN_MOMENTUM, _ptr(r.rmean), _ptr(r.rvar), _ptr(r.scale), _ptr(r.shift), _ptr(r.mean),
                      _ptr(r.invstd), Cout)

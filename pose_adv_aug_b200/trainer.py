@@ -230,6 +230,7 @@ class HourglassTrainer(object):
             low_ids = plan.low_recs if low_on else ()
             self._sched = schedule_streams(launches, n_streams, n_low=n_low, low_ids=low_ids,
                                            after=plan.after if M.DEFER_SKIPS else None, rw_override=plan.rw_override,
+                                           no_pack_ids=plan.no_pack_dep,
                                            low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad", "stem_conv7_wgrad_bnapply"))
         stream_of, cross = self._sched
         ar_after = {}

@@ -33,6 +33,32 @@ def test_library_exports_every_declared_symbol():
     assert lib.cdll.hgk_version() >= 100
 
 
+def test_plan_with_tensor_core_stem(monkeypatch):
+    """HGK_STEM_TC=1: the stem is planned as space-to-depth + the image-tile tensor-core kernel with ksize = 4, fed by its own
+    one-entry weight repack in front of the global one (so that it does not wait for it)."""
+    from pose_adv_aug_b200.engine import Plan, ParamStore, schedule_streams
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    monkeypatch.setenv("HGK_STEM_TC", "1")
+    net = M.create_hg(1, 1, 16, 128)
+    dev = torch.device("cpu")
+    st = ParamStore(net, dev)
+    plan = Plan([st], dev, True, True)
+    img = plan.input_image(2, 256, 256)
+    outs, _ = net._build(plan, img)
+    for o in outs:
+        plan.output_nchw(o, no_grad=True)
+    plan.finish()
+    names = [r[2] for r in plan.fwd]
+    stem = [r for r in plan.fwd if r[2] in ("conv_tc_bn_x2_nhwc", "conv_tc_bn_nhwc") and r[1][10] == 4]
+    assert len(stem) == 1 and stem[0][1][7] == 16 and stem[0][1][12] == 64 and names.count("stem_s2d_image") == 1
+    assert names.index("stem_s2d_image") < plan.fwd.index(stem[0]) and names.count("stem_conv7_fwd") == 0
+    assert names.count("bn_finalize") == 0
+    pre = [r[2] for r in plan.pre]
+    assert pre.index("stem_s2d_weight") < pre.index("pack_weights_tc") and id(stem[0]) in plan.no_pack_dep
+    own = [r for r in plan.pre if r[2] == "pack_weights_tc"][0]
+    assert stem[0][1][8] in plan.rw_override[id(own)][1] and stem[0][1][9] in plan.rw_override[id(own)][1]
+
+
 def test_argument_validation_without_gpu():
     from pose_adv_aug_b200._lib import get_lib
     lib = get_lib()

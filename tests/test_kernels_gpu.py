@@ -832,3 +832,70 @@ def test_conv_wgrad_tc(shape):
     call("unpack_add_grads", ptr(src), ptr(dst), ptr(table), 1)
     torch.cuda.synchronize()
     assert relerr(dst.cpu().double() - dst0, w.grad) < 3e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64), (3, 32, 96), (2, 256, 256)])
+@pytest.mark.parametrize("x2", [False, True])
+def test_stem_tensor_core_space_to_depth_fwd(shape, x2):
+    """nn.Conv2d(3,64,7,2,3) (ref models/asn_stacked_hg.py:223) on the tensor cores: hgk_stem_s2d_image + hgk_stem_s2d_weight
+    turn it into a 4x4-tap stride-1 convolution over the 16-channel half-resolution image, run by the image-tile kernel
+    (ksize = 4) with 3xTF32 or TF32 + 2xBF16 products, bias, batch statistics and the fused BatchNorm finaliser."""
+    N, H, W = shape
+    x = rnd("img", (N, 3, H, W), 0.0, 1.0)
+    w = rnd("w", (64, 3, 7, 7), -0.1, 0.1)
+    b = rnd("b", (64,))
+    ref = F.conv2d(x, w, b, stride=2, padding=3)
+    H2, W2 = H // 2, W // 2
+    dimg, dw_, db_ = dev32(x), dev32(w), dev32(b)
+    xs = torch.full((N, H2, W2, 16), float("nan"), device=DEV)
+    ws = torch.full((64, 32, 4, 4), float("nan"), device=DEV)
+    call("stem_s2d_image", ptr(dimg), N, H, W, ptr(xs))
+    call("stem_s2d_weight", ptr(dw_), 64, ptr(ws))
+    torch.cuda.synchronize()
+    # the rearrangements themselves: exact
+    want = torch.zeros(N, H2, W2, 16)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                want[..., (dy * 2 + dx) * 3 + c] = x[:, c, dy::2, dx::2].float()
+    assert torch.equal(xs.cpu(), want)
+    wwant = torch.zeros(64, 32, 4, 4)
+    for ty in range(4):
+        for tx in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    ky, kx = 2 * ty + dy - 1, 2 * tx + dx - 1
+                    if 0 <= ky < 7 and 0 <= kx < 7:
+                        for c in range(3):
+                            wwant[:, (dy * 2 + dx) * 3 + c, ty, tx] = w[:, c, ky, kx].float()
+    assert torch.equal(ws.cpu(), wwant)
+    # the 4x4-tap form equals the 7x7 stride-2 convolution (fp64 identity check of the mapping)
+    ident = F.conv2d(F.pad(want.permute(0, 3, 1, 2).double(), (2, 1, 2, 1)), wwant[:, :16].double(), b)
+    assert relerr(ident, ref) < 1e-6
+    dst = torch.zeros(2 * ws.numel(), device=DEV)
+    table = torch.tensor([[0, 0, ws.numel(), 64, 32, 16, 2 if x2 else 0, 64]], dtype=torch.long, device=DEV)
+    call("pack_weights_tc", ptr(ws), ptr(dst), ptr(table), 1)
+    hi, lo = dst[:ws.numel()], dst[ws.numel():]
+    gamma, beta = rnd("gamma", (64,), 0.5, 1.5), rnd("beta", (64,), -0.3, 0.3)
+    dg, dbeta, drm, drv = dev32(gamma), dev32(beta), torch.zeros(64, device=DEV), torch.ones(64, device=DEV)
+    sc, sh, sm, si = (torch.zeros(64, device=DEV) for _ in range(4))
+    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
+    ssum = torch.zeros(64, device=DEV, dtype=torch.float64)
+    ssq = torch.zeros(64, device=DEV, dtype=torch.float64)
+    y = torch.full((N, H2, W2, 64), float("nan"), device=DEV)
+    call("conv_tc_bn_x2_nhwc" if x2 else "conv_tc_bn_nhwc", ptr(xs), 0, 0, 0, N, H2, W2, 16, ptr(hi), ptr(lo), 4, ptr(db_), 64,
+         0, 0, 0, 0, ptr(y), 0, ptr(ssum), ptr(ssq), ptr(dg), ptr(dbeta), 1e-5, 0.1, ptr(drm), ptr(drv), ptr(sc), ptr(sh),
+         ptr(sm), ptr(si), ptr(ticket))
+    torch.cuda.synchronize()
+    err = relerr(from_nhwc(y), ref)
+    print("tensor-core stem %s x2=%s: rel-to-max error %.2e" % (shape, x2, err))
+    assert err < 2e-5
+    assert relerr(ssum.cpu(), ref.sum(dim=(0, 2, 3))) < 2e-5
+    assert relerr(ssq.cpu(), (ref * ref).sum(dim=(0, 2, 3))) < 2e-5
+    mean = ref.mean(dim=(0, 2, 3))
+    invstd = 1.0 / torch.sqrt(ref.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    assert relerr(sm.cpu(), mean) < 2e-5 and relerr(si.cpu(), invstd) < 2e-5
+    assert int(ticket.item()) == 0
+    # anything else with ksize = 4 is refused
+    rc = lib().conv_tc_nhwc(ptr(xs), 0, 0, 0, N, H2, W2, 16, ptr(hi), 0, 4, ptr(db_), 64, 0, 0, 0, 0, ptr(y), 0, 0, 0, 0)
+    assert rc != 0 and "k = 4" in lib().last_error()

@@ -422,6 +422,31 @@ def test_in_graph_bucketed_collective_sees_final_gradients():
             assert d < 1e-4, (it, lo, hi, d)
 
 
+@pytest.mark.gpu
+def test_tensor_core_stem_equals_ffma_stem_in_a_train_step(monkeypatch):
+    """HGK_STEM_TC=1 (space-to-depth + tcgen05 image-tile kernel with ksize = 4, 3xTF32) against the default FFMA stem:
+    same heat-maps, loss and gradients of one captured train step up to the products' rounding."""
+    M = _mods()
+    from pose_adv_aug_b200 import HourglassTrainer
+    S, Mo, K, C, N, R = 2, 1, 16, 64, 4, 128
+    sd = synth.make_state_dict(O.hg_schema(S, Mo, K, C), seed=91)
+    x = synth.make_images(N, R, seed=92).to(DEV)
+    t = synth.make_heatmaps(N, R, K, seed=93).to(DEV)
+    res = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("HGK_STEM_TC", on)
+        tr = HourglassTrainer(_load(M.create_hg(S, Mo, K, C), sd).to(DEV), N, R, use_graph=True)
+        names = [r[2] for r in tr.plan.fwd]
+        assert ("stem_s2d_image" in names) == (on == "1") and ("stem_conv7_fwd" in names) == (on == "0")
+        loss = float(tr.step(x, t))
+        res.append((loss, [h.clone() for h in tr.heatmaps()], tr.store.grad.clone()))
+    (la, ha, ga), (lb, hb, gb) = res
+    assert abs(la - lb) < 1e-5 * abs(la)
+    for a, b in zip(ha, hb):
+        assert relerr(a, b) < 1e-4
+    assert float((ga - gb).norm() / ga.norm()) < 5e-3
+
+
 def test_cpu_input_fails_loudly():
     M = _mods()
     from pose_adv_aug_b200 import HGKError

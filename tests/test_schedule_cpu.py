@@ -63,7 +63,7 @@ def test_schedule_respects_every_dependency():
                     deps.update(readers.get(p, ()))
                 # (the stem convolution and the target transpose read neither packed-weight arena: they may start
                 #  while the weight repack at the head of the step is still running)
-                if barrier >= 0 and not (name in ("stem_conv7_fwd", "nchw_to_nhwc") and L[barrier][2].startswith("pack_weights")):
+                if barrier >= 0 and not (name in ("stem_conv7_fwd", "stem_s2d_image", "nchw_to_nhwc") and L[barrier][2].startswith("pack_weights")):
                     deps.add(barrier)
             for d in deps:
                 if d == i:
