@@ -616,6 +616,11 @@ class Plan(object):
             self.pack_launch = [self.lib.pack_weights,
                                 [base, self.pack_buf.data_ptr(), self.pack_table.data_ptr(), len(rows)], "pack_weights"]
             pb = self.pack_buf.data_ptr()
+            # real read / write sets of the repack (schedule_streams): it reads the weights (the derived ones are written by
+            # the launches of self.pre) and writes exactly the packed blocks the convolutions point at -- launches that read
+            # no packed weight (the FFMA stem, the target transpose) are then free to run next to it
+            self.rw_override[id(self.pack_launch)] = ([e[0].data_ptr() for e in self.pack_entries],
+                                                      [pb + 4 * e[1] for e in self.pack_entries])
             for lst in (self.fwd, self.bwd):
                 for rec in lst:
                     rec[1] = [pb + 4 * a.off if isinstance(a, _PackRef) else a for a in rec[1]]
@@ -634,6 +639,8 @@ class Plan(object):
             self.tc_launch = [self.lib.pack_weights_tc,
                               [base, self.tc_buf.data_ptr(), self.tc_table.data_ptr(), len(rows)], "pack_weights_tc"]
             tb = self.tc_buf.data_ptr()
+            self.rw_override[id(self.tc_launch)] = ([e[0].data_ptr() for e in self.tc_entries],
+                                                    [tb + 4 * o for e in self.tc_entries for o in (e[3], e[4]) if o >= 0])
             for lst in (self.fwd, self.bwd):
                 for rec in lst:
                     rec[1] = [tb + 4 * a.off if isinstance(a, _TcRef) else a for a in rec[1]]
@@ -645,6 +652,17 @@ class Plan(object):
                 mine = set(id(b) for b in st.ibufs)
                 self.nbt_bufs = [b for b in self.nbt_bufs if id(b) not in mine]
         self.finished = True
+
+    def step_launches(self):
+        """head + forward + backward in ISSUE order for the dependency-scheduled step: the forward launches in front of the
+        first one that reads packed weights (target transpose, FFMA stem) are issued BEFORE the two weight repacks.  The
+        hardware dispatches grids of one priority in launch order, so the persistent stem grid goes first and the repack
+        blocks fill the SMs next to it, instead of the stem waiting ~60 us behind them."""
+        packs = [r for r in (self.pack_launch, self.tc_launch) if r is not None]
+        k = 0
+        while k < len(self.fwd) and (self.fwd[k][2] in _NO_PACK_DEP or id(self.fwd[k]) in self.no_pack_dep):
+            k += 1
+        return list(self.pre) + self.fwd[:k] + packs + self.fwd[k:] + self.bwd
 
     def head_launches(self):
         """The launches in front of the forward list: derived weights, then the two weight repacks."""

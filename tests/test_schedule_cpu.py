@@ -233,3 +233,42 @@ def test_bucketed_gradient_unpack_and_allreduce_points():
                     assert vc[i][so[j]] >= j
         # not a barrier: some launch issued before it is NOT ordered before it
         assert any(vc[i][so[j]] < j for j in range(i))
+
+
+def test_weight_repack_has_real_dependencies_and_the_stem_is_issued_first():
+    """Plan.step_launches(): target transpose and FFMA stem are issued in front of the two weight repacks, which are scheduled
+    by their real read / write sets (derived weights in, packed blocks out) instead of as barriers: every launch that points
+    at a packed block is ordered behind its repack, the stem is not."""
+    plan, keep, _ = _plan()
+    L = plan.step_launches()
+    names = [r[2] for r in L]
+    assert sorted(map(id, L)) == sorted(map(id, plan.head_launches() + plan.fwd + plan.bwd))
+    i_stem, i_pack, i_tc = names.index("stem_conv7_fwd"), names.index("pack_weights"), names.index("pack_weights_tc")
+    assert i_stem < i_pack < i_tc and names.index("head_combine_fwd") < i_pack
+    ns = 8
+    so, cross = schedule_streams(L, ns, n_low=3, low_ids=plan.low_recs, after=plan.after, rw_override=plan.rw_override,
+                                 no_pack_ids=plan.no_pack_dep,
+                                 low_names=("conv_wgrad_tc_nhwc", "conv_wgrad_nhwc", "stem_conv7_wgrad", "stem_conv7_wgrad_bnapply"))
+    vc, tail = [], [-1] * ns
+    for i in range(len(L)):
+        k = so[i]
+        c = list(vc[tail[k]]) if tail[k] >= 0 else [-1] * ns
+        for d in cross[i]:
+            c = [max(x, y) for x, y in zip(c, vc[d])]
+        c[k] = i
+        vc.append(c)
+        tail[k] = i
+    n_checked = 0
+    for i_p in (i_pack, i_tc):
+        rd, wr = plan.rw_override[id(L[i_p])]
+        wr = set(p for p in wr if p >= (1 << 32))          # (pointers below 2^32 are not recognised as such, see above)
+        for i, r in enumerate(L):
+            if i != i_p and any(isinstance(a, int) and a in wr for a in r[1]):
+                assert i > i_p and vc[i][so[i_p]] >= i_p, "launch %d (%s) reads a packed block but is not behind the repack" % (i, r[2])
+                n_checked += 1
+        # the repack itself waits for the derived weights it reads
+        for j in range(i_p):
+            if L[j][2] == "head_combine_fwd" and any(p in L[j][1] for p in rd if p >= (1 << 32)):
+                assert vc[i_p][so[j]] >= j
+    assert n_checked > 150 or not wr
+    assert vc[i_stem][so[i_pack]] < i_pack if so[i_stem] != so[i_pack] else True
