@@ -15,7 +15,7 @@ NB = 4                                              # rotating buffer sets: 4 x 
 def pack(Co, Ci, k, mode):
     w = torch.randn(Co, Ci, k, k, dtype=torch.float64) * 0.05
     src = dev32(w.reshape(-1)); dst = torch.zeros(2 * w.numel(), device=DEV)
-    Nn, K = (Co, Ci) if mode == 0 else (Ci, Co)
+    Nn, K = (Co, Ci) if mode != 1 else (Ci, Co)
     table = torch.tensor([[0, 0, w.numel(), Nn, K, k * k, mode, Nn]], dtype=torch.long, device=DEV)
     call("pack_weights_tc", ptr(src), ptr(dst), ptr(table), 1)
     return dst[:w.numel()], dst[w.numel():]
@@ -34,11 +34,14 @@ def vec(C, lo=0.5, hi=1.5):
 
 
 def fwd(Ci, Co, k, i):
-    hi, lo = pack(Co, Ci, k, 0)
+    # the shipping forward products: TF32 + 2xBF16 (weight pack mode 2, hgk_conv_tc_x2_nhwc); PROF_X2=0: 3xTF32
+    x2 = os.environ.get("PROF_X2", "1") == "1"
+    hi, lo = pack(Co, Ci, k, 2 if x2 else 0)
     x, y = buf(Ci, i), torch.empty(N, H, W, Co, device=DEV)
     sc, sh, b = vec(Ci), vec(Ci, -0.3, 0.3), vec(Co, -0.1, 0.1)
     s1 = torch.zeros(Co, device=DEV, dtype=torch.float64); s2 = torch.zeros_like(s1)
-    call("conv_tc_nhwc", ptr(x), ptr(sc), ptr(sh), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(b), Co, 0, 0, 0, 0, ptr(y), 0, ptr(s1), ptr(s2))
+    call("conv_tc_x2_nhwc" if x2 else "conv_tc_nhwc", ptr(x), ptr(sc), ptr(sh), 1, N, H, W, Ci, ptr(hi), ptr(lo), k, ptr(b), Co, 0, 0, 0, 0,
+         ptr(y), 0, ptr(s1), ptr(s2))
 
 
 def dgrad(Ci, Co, k, i):            # conv Ci -> Co; gradient Co -> Ci with the fused BN reduction
