@@ -337,7 +337,12 @@ def run_ours(args):
     w2 = time.time()
     sampler.stop()
     tms = torch.tensor([ms, e2e_s * 1e3, e2e_serial_s * 1e3], device=dev, dtype=torch.float64)
+    by_rank = None
     if world > 1:
+        mine = torch.tensor([ms / args.steps], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = [round(float(v), 4) for v in allr]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms, e2e_serial_ms = float(tms[0]), float(tms[1]), float(tms[2])
     clocks = sampler.summary(w0, w1)
@@ -368,6 +373,9 @@ def run_ours(args):
             "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
             "cuda_graph": not args.no_graph, "graph_streams": args.streams, "low_priority_streams": args.low_streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
     if world > 1:
+        line["ms_per_step_by_rank"] = by_rank        # device-timed per rank (equal when every step ends in a collective)
+        if os.environ.get("HGK_AR_SKIP", "0") == "1":
+            line["diagnostic"] = "HGK_AR_SKIP=1: NO gradient all-reduce (timing diagnostic: each rank at its own pace; not a valid bench line)"
         line["allreduce"] = {"in_graph": bool(tr.ar_in_graph), "graph_launches_per_step": 1 if tr.ar_in_graph else 2,
                              "buckets_mb": [round((hi - lo) * 4e-6, 2) for lo, hi in tr.bucket_ranges()],
                              "note": "NCCL sum of the flat gradient buffer, bucketed back to front on a communication stream "

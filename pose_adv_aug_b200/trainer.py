@@ -3,6 +3,8 @@ zero_grad / backward / RMSprop.step) as one planned launch sequence, optionally 
 single CUDA graph: weight repack, every conv / BN / pool / up-add kernel, the fused MSE
 forward+backward, the backward pass, the (optional) NCCL all-reduce of the flat gradient buffer
 and the flat RMSprop update."""
+import os
+
 import torch
 
 from ._lib import get_lib, HGKError
@@ -154,7 +156,6 @@ class HourglassTrainer(object):
         # gradient buckets of the in-graph all-reduce: contiguous ranges of the flat gradient buffer cut at parameter-slot
         # boundaries.  Parameters are laid out in registration order and the backward pass completes them back to front, so
         # the LAST bucket is final first and its all-reduce runs under the rest of the backward.
-        import os
         nb = int(os.environ.get("HGK_AR_BUCKETS", "5")) if ar_buckets is None else int(ar_buckets)
         self.ar_in_graph = (self.world > 1 or fake_collective is not None) and use_graph and n_streams > 1 and nb > 0 \
             and os.environ.get("HGK_AR_INGRAPH", "1") == "1"
@@ -186,6 +187,8 @@ class HourglassTrainer(object):
 
     def _allreduce_bucket(self, lo, hi):
         g = self.store.grad[lo:hi]
+        if os.environ.get("HGK_AR_SKIP", "0") == "1":
+            return          # TIMING DIAGNOSTIC ONLY (wrong gradients): no collective, so every rank runs at its own pace
         if self.fake_collective is not None:
             self.fake_collective(g)
         else:
@@ -222,7 +225,6 @@ class HourglassTrainer(object):
                 plan.patch("gout%d" % op.index, op.gsrc.data_ptr())
         for a in plan.aux_zero:
             a.zero_()
-        import os
         early_stem = os.environ.get("HGK_EARLY_STEM", "0") == "1"      # measured neutral (10.10 vs 10.09 ms): the persistent stem grid leaves no room next to it
         launches = plan.step_launches() if early_stem else plan.head_launches() + plan.fwd + plan.bwd
         n_low = min(self.n_low, n_streams - 1)
