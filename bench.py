@@ -499,8 +499,8 @@ def dominant_kernel_roofline(tr, pk, torch):
 def run_config3(args):
     """BASELINE.json configs[2]: one agent-augmented joint-train iteration (joint-train-pose-s-r-agent.py:245-296) at bs 24:
     half-hourglass forward (hg.train(), agent.eval()) -> ASN (scale, rotation) distributions -> on-GPU sampling ->
-    [CPU data pipeline of the reference: out of scope; the targets of the re-augmented batch are rendered on the GPU from
-    joint coordinates] -> full hourglass train step (CUDA graph) -> PCK on the GPU; plus the agent update
+    the batch re-augmented with the sampled scales / rotations ON THE GPU from resident photographs (agent.AgentBatchLoader =
+    the reference's load_batch_data DataLoader round trip) -> full hourglass train step (CUDA graph) -> PCK on the GPU; plus the agent update
     (train_agent_sr, :323-410: hg.eval(), agent.train(), KL loss, ASN backward, flat RMSprop) timed separately."""
     import numpy as np
     import torch
@@ -521,6 +521,18 @@ def run_config3(args):
     tr.t.copy_(synth.make_heatmaps(N, R, 16, seed=200))
     pts = torch.randint(4, 60, (N, 16, 2), device=dev).float()
     np.random.seed(0)
+    # the re-augmentation of the batch with the agent's sampled (scale, rotation) (load_batch_data, joint-train...:425-450):
+    # 24 MPII-sized synthetic photographs resident in HBM, cropped / rotated / resized on the GPU (agent.AgentBatchLoader)
+    rng = np.random.default_rng(5)
+    photos = [torch.from_numpy(np.ascontiguousarray(np.transpose(synth.make_photo(720, 1280, 500 + k), (2, 0, 1)))).to(dev)
+              for k in range(N)]
+    annos = []
+    for k in range(N):
+        j = np.concatenate([rng.uniform(300, 980, (16, 1)), rng.uniform(150, 570, (16, 1)), np.ones((16, 1))], axis=1)
+        annos.append({"joint_self": j.tolist(), "objpos": [float(rng.uniform(400, 880)), float(rng.uniform(250, 470))],
+                      "scale_provided": float(rng.uniform(0.8, 3.0)), "normalizer": float(rng.uniform(40, 120))})
+    loader = agent.AgentBatchLoader(photos, annos)
+    img_index = list(range(N))
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -534,7 +546,7 @@ def run_config3(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    def iteration():
+    def iteration_synthetic():
         net.train(); asn.eval()
         with torch.no_grad():
             ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
@@ -543,6 +555,20 @@ def run_config3(args):
         tr.t.copy_(hm)
         tr.step_resident()
         return Evaluation.accuracy(tr.heatmaps()[-1], tr.t, list(range(16)))
+
+    def iteration():
+        net.train(); asn.eval()
+        with torch.no_grad():
+            ps, pr = net(x, asn, is_half_hg=True, is_aug=True)
+        _, _, si, ri = agent.sample_scale_rotation(ps, pr)
+        img, hm, c, s_, r_, gp, nz = loader.load_batch(si.tolist(), ri.tolist(), img_index)      # 48 indices D2H, as the reference
+        tr.x.copy_(img)
+        tr.t.copy_(hm)
+        tr.step_resident()
+        return Evaluation.accuracy(tr.heatmaps()[-1], tr.t, list(range(16)))
+
+    def load_only():
+        loader.load_batch([3] * N, [2] * N, img_index)
 
     opt = FlatRMSprop(asn, lr=2.5e-4)
     tgt = torch.softmax(torch.randn(N, 7, device=dev), dim=1)
@@ -558,14 +584,21 @@ def run_config3(args):
 
     steps, warmup = args.steps, max(args.warmup, 3)
     ms = timed(iteration, steps, warmup)
+    ms_syn = timed(iteration_synthetic, steps, warmup)
+    ms_load = timed(load_only, steps, warmup)
     ms_up = timed(agent_update, steps, warmup)
     print(json.dumps({
         "metric": "images/sec 2-stack HG + ASN agent joint-train iteration bs24 256x256", "value": N / ms * 1e3,
         "unit": "images/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: half-hg(train BN)+ASN(eval) forward, on-GPU (s, r) sampling, GPU target "
-                               "rendering, full 2-stack train step (CUDA graph), GPU PCK; S=2 C=256 bs=24 256x256",
+        "config": {"workload": "BASELINE configs[2]: half-hg(train BN)+ASN(eval) forward, on-GPU (s, r) sampling, the batch "
+                               "re-augmented on the GPU with the sampled scales / rotations from 24 resident 720x1280 photographs "
+                               "(AgentBatchLoader: flip, colour, crop / rotate / resize, target rendering), full 2-stack train step "
+                               "(CUDA graph), GPU PCK; S=2 C=256 bs=24 256x256",
                    "batch_per_gpu": N, "parallelism": "dp1"},
+        "without_loader": {"ms_per_step": ms_syn, "what": "the same iteration on a fixed pre-cropped batch (targets rendered from "
+                                                         "fixed joint coordinates): the number of the earlier rounds"},
+        "loader": {"ms_per_batch": ms_load, "what": "AgentBatchLoader.load_batch alone (host geometry + ~10 launches per image)"},
         "agent_update": {"ms_per_update": ms_up, "images_per_s": N / ms_up * 1e3,
                          "what": "train_agent_sr: half-hg(eval) + ASN(train) forward + KL + ASN backward + flat RMSprop (module path)"},
         "gpu_launches": None, "launches_per_train_step": tr.launches_per_step}))
