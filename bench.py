@@ -301,6 +301,23 @@ def run_ours(args):
     # DataLoader with pin_memory does for the reference loop's `.cuda(async=True)`): every timed step contains the H2D
     # copy of ITS inputs (issued one step earlier on the copy stream; the first one is issued inside the region) and the
     # D2H read of its loss
+    # ... read back (4 bytes into pinned memory) while the NEXT step already runs: every step's loss reaches the host inside
+    # the timed region, one step late, and the GPU does not idle across the host's read
+    tr.prefetch(xp, tp)
+    for i in range(e2e_steps):
+        tr.step_prefetched(loss_to_host=True)
+        if i + 1 < e2e_steps:
+            tr.prefetch(xp, tp)
+        if i > 0:
+            last = tr.pop_loss()
+    last = tr.pop_loss()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.time() - t0
+    # the same with the loss read right after its own step (loss.item(): the host waits for the step, then launches the next)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
     tr.prefetch(xp, tp)
     for i in range(e2e_steps):
         loss_dev = tr.step_prefetched()
@@ -309,7 +326,7 @@ def run_ours(args):
         last = float(loss_dev.item())
     torch.cuda.synchronize()
     barrier()
-    e2e_s = time.time() - t0
+    e2e_sync_s = time.time() - t0
     if os.environ.get("HGK_BENCH_E2E_REPEAT"):        # developer: repeatability of the two input paths
         for rep in range(3):
             torch.cuda.synchronize(); ta = time.time()
@@ -336,7 +353,7 @@ def run_ours(args):
     e2e_serial_s = time.time() - t0
     w2 = time.time()
     sampler.stop()
-    tms = torch.tensor([ms, e2e_s * 1e3, e2e_serial_s * 1e3], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms, e2e_s * 1e3, e2e_serial_s * 1e3, e2e_sync_s * 1e3], device=dev, dtype=torch.float64)
     by_rank = None
     if world > 1:
         mine = torch.tensor([ms / args.steps], device=dev, dtype=torch.float64)
@@ -344,7 +361,7 @@ def run_ours(args):
         dist.all_gather(allr, mine)
         by_rank = [round(float(v), 4) for v in allr]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_serial_ms = float(tms[0]), float(tms[1]), float(tms[2])
+    ms, e2e_ms, e2e_serial_ms, e2e_sync_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
     clocks = sampler.summary(w0, w1)
     # ---- dominant kernel, timed live with CUDA events on the launching stream ----
     roof = dominant_kernel_roofline(tr, pk, torch)
@@ -367,9 +384,12 @@ def run_ours(args):
             "e2e": {"value": world * args.batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/s",
                     "h2d_bytes_per_step": int(xp.numel() * 4 + tp.numel() * 4), "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "serial_value": world * args.batch * e2e_steps / (e2e_serial_ms / 1e3),
+                    "sync_loss_value": world * args.batch * e2e_steps / (e2e_sync_ms / 1e3),
                     "api": "HourglassTrainer.prefetch(images_pinned, heatmaps_pinned) [next batch, copy stream] + "
-                           "step_prefetched() -> loss.item(); serial_value = HourglassTrainer.step(images_pinned, "
-                           "heatmaps_pinned) -> loss.item() with the copies in front of the step"},
+                           "step_prefetched(loss_to_host=True) + pop_loss() [every step's loss copied to pinned host memory "
+                           "and read one step later, while the next step runs]; sync_loss_value = the same with "
+                           "step_prefetched() -> loss.item() right after each step; serial_value = HourglassTrainer.step("
+                           "images_pinned, heatmaps_pinned) -> loss.item() with the copies in front of the step"},
             "gpu_launches": tr.launches_per_step * args.steps, "launches_per_step": tr.launches_per_step,
             "cuda_graph": not args.no_graph, "graph_streams": args.streams, "low_priority_streams": args.low_streams, "clocks": clocks, "loss": last, "conv_path": M.CONV_PATH}
     if world > 1:

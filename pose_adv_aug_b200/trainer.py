@@ -416,8 +416,11 @@ class HourglassTrainer(object):
             self._staged.record(cs)
         self._has_staged = True
 
-    def step_prefetched(self):
-        """One train step on the batch uploaded by the last `prefetch()`; returns the fp32 device scalar loss."""
+    def step_prefetched(self, loss_to_host=False):
+        """One train step on the batch uploaded by the last `prefetch()`; returns the fp32 device scalar loss.
+        loss_to_host=True additionally queues the 4-byte device-to-host copy of this step's loss into a pinned slot;
+        `pop_loss()` hands the losses out in order.  Reading step i's loss after step i+1 has been launched keeps the GPU
+        busy across the host's read (a `loss.item()` right after the step leaves it idle for a launch latency every step)."""
         if not getattr(self, "_has_staged", False):
             raise HGKError("step_prefetched() without a preceding prefetch()")
         main = torch.cuda.current_stream(self.device)
@@ -426,7 +429,28 @@ class HourglassTrainer(object):
         self.t.copy_(self.ts, non_blocking=True)
         self._staging_free.record(main)
         self._has_staged = False
-        return self.step_resident()
+        out = self.step_resident()
+        if loss_to_host:
+            if getattr(self, "_loss_pin", None) is None:
+                self._loss_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
+                self._loss_ev = [torch.cuda.Event() for _ in range(4)]
+                self._loss_q, self._loss_n = [], 0
+            if len(self._loss_q) >= 4:
+                raise HGKError("four losses are waiting in the read-back queue: call pop_loss()")
+            slot = self._loss_n % 4
+            self._loss_pin[slot:slot + 1].copy_(self.loss, non_blocking=True)
+            self._loss_ev[slot].record(main)
+            self._loss_q.append(slot)
+            self._loss_n += 1
+        return out
+
+    def pop_loss(self):
+        """The oldest loss queued by step_prefetched(loss_to_host=True) as a Python float (waits for that copy only)."""
+        if not getattr(self, "_loss_q", None):
+            raise HGKError("pop_loss(): no loss queued")
+        slot = self._loss_q.pop(0)
+        self._loss_ev[slot].synchronize()
+        return float(self._loss_pin[slot])
 
     # ---- optimizer protocol of the reference loop (stack-hg.py:51-52,106; utils/checkpoint.py) ----
     @property

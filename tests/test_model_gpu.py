@@ -621,6 +621,21 @@ def test_prefetched_step_equals_serial_step():
     for a, b in zip(la, lb):
         assert abs(a - b) < 1e-5 * abs(a), (la, lb)
     assert len(set(round(v, 6) for v in la)) == 4
+    # lagged read-back: every step's loss arrives, in order, through the pinned queue while the next step runs
+    tc = HourglassTrainer(_load(M.create_hg(S, 1, 16, C), sd), N, R, lr=0.0, use_graph=True, n_streams=1)
+    with pytest.raises(HGKError):
+        tc.pop_loss()
+    tc.prefetch(*batches[0])
+    lc = []
+    for i in range(4):
+        tc.step_prefetched(loss_to_host=True)
+        if i + 1 < 4:
+            tc.prefetch(*batches[i + 1])
+        if i > 0:
+            lc.append(tc.pop_loss())
+    lc.append(tc.pop_loss())
+    for a, c in zip(la, lc):
+        assert abs(a - c) < 1e-5 * abs(a), (la, lc)
 
 
 def test_headline_shape_train_step_vs_fp64_oracle():
