@@ -356,6 +356,16 @@ int hgk_aug_resize_v(const unsigned char* tmp, int in_h, int out_w, int out_h, c
 /* PIL Image.rotate(BILINEAR) = ImagingGenericTransform(affine, bilinear), fill 0; m6 = HOST array of the six affine
  * coefficients (output pixel centre -> input position), computed by the host as Image.rotate does                       */
 int hgk_aug_rotate(const unsigned char* in, int H, int W, const double* m6, unsigned char* out, void* stream);
+/* The whole crop pipeline of a BATCH in about a dozen launches (blockIdx.y = image): desc = N rows of hgk_aug_desc_fields()
+ * int64 fields (struct AugDesc, csrc/warp.cu: source pointer and size, pre-shrink size, crop window, rotation flag / padding,
+ * final-resize input, offsets of every intermediate into the two arenas), given both as a HOST copy (grid sizing) and a DEVICE
+ * copy; mats_dev [N][6] rotation coefficients; arena_u8 / arena_i: byte and int scratch arenas the descriptors point into;
+ * minmax [N][4] doubles; scratch [N][2][3] words in the idle state {0xFFFFFFFF, 0, 0}; out_stack [N][res][res][3] uint8.
+ * Same bytes as the per-image entry points above. */
+int hgk_aug_desc_fields(void);
+int hgk_aug_crop_batch(const long long* desc_host, const long long* desc_dev, const double* mats_dev, int N, int res,
+                       unsigned char* arena_u8, int* arena_i, double* minmax, unsigned int* scratch,
+                       unsigned char* out_stack, void* stream);
 /* utils/imutils.im_to_torch on a batch of crops: [N][res][res][3] uint8 -> [N][3][res][res] float32, / 255 per image only
  * when its maximum exceeds 1                                                                                            */
 int hgk_aug_to_chw_float(const unsigned char* img, int N, int res, float* out, void* stream);

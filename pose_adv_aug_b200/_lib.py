@@ -79,6 +79,7 @@ SIGNATURES = {
     "hgk_aug_resize_v": [P, I, I, I, P, P, I, P, P],
     "hgk_aug_rotate": [P, I, I, P, P, P],
     "hgk_aug_to_chw_float": [P, I, I, P, P],
+    "hgk_aug_crop_batch": [P, P, P, I, I, P, P, P, P, P, P],
 }
 
 
@@ -112,6 +113,8 @@ class _Lib(object):
         self.cdll.hgk_aug_resample_ksize.restype = I
         self.cdll.hgk_aug_resample_ksize.argtypes = [I, I]
         self.aug_resample_ksize = self.cdll.hgk_aug_resample_ksize
+        self.cdll.hgk_aug_desc_fields.restype = I
+        self.cdll.hgk_aug_desc_fields.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(self.cdll, name)      # AttributeError if the symbol is not exported
             fn.argtypes = args

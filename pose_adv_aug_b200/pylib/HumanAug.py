@@ -259,10 +259,102 @@ def crop(img, center, scale, rot, res, size):
     return A.resize(wb, Hn, Wn, off, off, Hn - 2 * off, Wn - 2 * off, res, res)     # :175 imresize(new_img, (res, res))
 
 
-def crop_batch(imgs, centers, scales, rots, res=256, size=200):
+_DESC_FIELDS = ("src", "H", "W", "pre_h", "pre_w", "o_bytes", "o_ptmp", "o_pout", "c_pw_b", "c_pw_k", "ks_pw", "c_ph_b", "c_ph_k",
+                "ks_ph", "Hn", "Wn", "ny0", "ny1", "nx0", "nx1", "oy", "ox", "has_zero", "o_win", "rot", "o_rot", "pad", "in_h", "in_w",
+                "o_ftmp", "c_fw_b", "c_fw_k", "ks_fw", "c_fh_b", "c_fh_k", "ks_fh", "out_index")      # struct AugDesc, csrc/warp.cu
+_batch_scratch = {}
+
+
+def _crop_batch_u8(imgs, centers, scales, rots, res, size):
+    """All crops of a batch through hgk_aug_crop_batch: the host lays out one descriptor row per image (geometry as in
+    `crop`, offsets of every intermediate into two scratch arenas), uploads the table once, and a dozen launches with
+    blockIdx.y = image do the pixel work.  Returns the uint8 stack [N,res,res,3]."""
+    lib = get_lib()
+    n = len(imgs)
+    dev = imgs[0].device
+    assert lib.cdll.hgk_aug_desc_fields() == len(_DESC_FIELDS)
+    rows, mats, keep = [], [], []
+    ou8 = oi = 0
+
+    def take_u8(nbytes):
+        nonlocal ou8
+        o = ou8
+        ou8 += (int(nbytes) + 15) // 16 * 16
+        return o
+
+    def take_i(nints):
+        nonlocal oi
+        o = oi
+        oi += int(nints)
+        return o
+
+    for k in range(n):
+        img = imgs[k]
+        if not isinstance(img, torch.Tensor) or not img.is_cuda:
+            raise HGKError("HumanAug.crop_batch runs on CUDA tensors only (no CPU fallback)")
+        if img.dim() != 3 or img.shape[2] != 3 or img.dtype != torch.float32:
+            raise ValueError("crop_batch: expected float32 H x W x 3 images, got %s %s" % (tuple(img.shape), img.dtype))
+        img = img.contiguous()
+        keep.append(img)
+        H, W = int(img.shape[0]), int(img.shape[1])
+        if min(H, W) <= 4:
+            raise ValueError("crop_batch: image too small")
+        rot = float(rots[k])
+        win = _window(H, W, centers[k], scales[k], rot, res, size)
+        if win is None:
+            raise ValueError("crop_batch: sample %d hit the degenerate early return of crop (image smaller than 2 px after shrinking)" % k)
+        sf, pre, (Hn, Wn), (new_y, new_x), (old_y, old_x), pad = win
+        if Hn <= 4 or Wn <= 4 or old_y[1] <= old_y[0] or old_x[1] <= old_x[0] or \
+                (new_y[1] - new_y[0], new_x[1] - new_x[0]) != (old_y[1] - old_y[0], old_x[1] - old_x[0]):
+            raise ValueError("crop_batch: the crop window of sample %d does not intersect the image" % k)
+        d = dict.fromkeys(_DESC_FIELDS, 0)
+        d.update(src=img.data_ptr(), H=H, W=W, Hn=Hn, Wn=Wn, ny0=new_y[0], ny1=new_y[1], nx0=new_x[0], nx1=new_x[1],
+                 oy=old_y[0] - new_y[0], ox=old_x[0] - new_x[0], out_index=k,
+                 has_zero=int((new_y[1] - new_y[0]) < Hn or (new_x[1] - new_x[0]) < Wn))
+        if pre is not None:
+            ks_w, ks_h = lib.aug_resample_ksize(W, pre[1]), lib.aug_resample_ksize(H, pre[0])
+            d.update(pre_h=pre[0], pre_w=pre[1], o_bytes=take_u8(H * W * 3), o_ptmp=take_u8(H * pre[1] * 3),
+                     o_pout=take_u8(pre[0] * pre[1] * 3), ks_pw=ks_w, ks_ph=ks_h,
+                     c_pw_b=take_i(pre[1] * 2), c_pw_k=take_i(pre[1] * ks_w), c_ph_b=take_i(pre[0] * 2), c_ph_k=take_i(pre[0] * ks_h))
+        d["o_win"] = take_u8(Hn * Wn * 3)
+        off = 0
+        m = [0.0] * 6
+        if not rot == 0:
+            if (rot % 360.0) in (0.0, 90.0, 180.0, 270.0):
+                raise HGKError("crop: rotation by a multiple of 90 degrees takes PIL's transpose path, which is not built")
+            if pad <= 0 or Hn - 2 * pad <= 0 or Wn - 2 * pad <= 0:
+                raise ValueError("crop: empty image after removing the rotation padding")
+            d.update(rot=1, o_rot=take_u8(Hn * Wn * 3), pad=pad)
+            m = _rotate_matrix(rot, Wn, Hn)
+            off = pad
+        in_h, in_w = Hn - 2 * off, Wn - 2 * off
+        ks_w, ks_h = lib.aug_resample_ksize(in_w, res), lib.aug_resample_ksize(in_h, res)
+        d.update(in_h=in_h, in_w=in_w, o_ftmp=take_u8(in_h * res * 3), ks_fw=ks_w, ks_fh=ks_h,
+                 c_fw_b=take_i(res * 2), c_fw_k=take_i(res * ks_w), c_fh_b=take_i(res * 2), c_fh_k=take_i(res * ks_h))
+        rows.append([d[f] for f in _DESC_FIELDS])
+        mats.append(m)
+    desc_h = np.ascontiguousarray(np.array(rows, dtype=np.int64))
+    desc_d = torch.from_numpy(desc_h).to(dev)
+    mats_d = torch.from_numpy(np.array(mats, dtype=np.float64)).to(dev)
+    arena = torch.empty(max(ou8, 16), device=dev, dtype=torch.uint8)
+    arena_i = torch.empty(max(oi, 4), device=dev, dtype=torch.int32)
+    minmax = torch.empty(n * 4, device=dev, dtype=torch.float64)
+    key = (dev.type, dev.index)
+    if key not in _batch_scratch or _batch_scratch[key].numel() < n * 6:
+        _batch_scratch[key] = torch.tensor([-1, 0, 0] * (2 * max(n, 64)), device=dev, dtype=torch.int32)   # idle state, re-armed by the kernels
+    stack = torch.empty(n, res, res, 3, device=dev, dtype=torch.uint8)
+    lib.check(lib.aug_crop_batch(desc_h.ctypes.data, desc_d.data_ptr(), mats_d.data_ptr(), n, res, arena.data_ptr(),
+                                 arena_i.data_ptr(), minmax.data_ptr(), _batch_scratch[key].data_ptr(), stack.data_ptr(),
+                                 torch.cuda.current_stream(dev).cuda_stream), "hgk_aug_crop_batch")
+    return stack
+
+
+def crop_batch(imgs, centers, scales, rots, res=256, size=200, batched=True):
     """`inp = im_to_torch(crop(im_to_numpy(img), c, s, r, res, size)).float()` (ref data/joint_train_s_r_agent.py:200-203)
     for every sample of a batch: imgs = list of float32 CUDA H x W x 3 tensors (any sizes), centers [N,2], scales [N],
-    rots [N] host arrays.  Returns [N,3,res,res] float32 on the GPU -- the `img` batch of load_batch_data."""
+    rots [N] host arrays.  Returns [N,3,res,res] float32 on the GPU -- the `img` batch of load_batch_data.
+    batched=True: one descriptor table and a dozen launches for the whole batch (hgk_aug_crop_batch); False: `crop` per image
+    (the same bytes, ~10 launches per image)."""
     n = len(imgs)
     if n == 0:
         raise ValueError("crop_batch: empty batch")
@@ -270,12 +362,15 @@ def crop_batch(imgs, centers, scales, rots, res=256, size=200):
     scales = np.asarray(scales, dtype=np.float32).reshape(n)
     rots = np.asarray(rots, dtype=np.float64).reshape(n)
     dev = imgs[0].device
-    stack = torch.empty(n, res, res, 3, device=dev, dtype=torch.uint8)
-    for k in range(n):
-        c = crop(imgs[k], centers[k], scales[k], rots[k], res, size)
-        if c.dtype != torch.uint8:
-            raise ValueError("crop_batch: sample %d hit the degenerate early return of crop (image smaller than 2 px after shrinking)" % k)
-        stack[k].copy_(c)
+    if batched:
+        stack = _crop_batch_u8(imgs, centers, scales, rots, res, size)
+    else:
+        stack = torch.empty(n, res, res, 3, device=dev, dtype=torch.uint8)
+        for k in range(n):
+            c = crop(imgs[k], centers[k], scales[k], rots[k], res, size)
+            if c.dtype != torch.uint8:
+                raise ValueError("crop_batch: sample %d hit the degenerate early return of crop (image smaller than 2 px after shrinking)" % k)
+            stack[k].copy_(c)
     out = torch.empty(n, 3, res, res, device=dev, dtype=torch.float32)
     lib = get_lib()
     lib.check(lib.aug_to_chw_float(stack.data_ptr(), n, res, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),

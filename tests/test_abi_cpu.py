@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     launching = [n for n in names if n not in ("hgk_last_error", "hgk_version", "hgk_device_ok", "hgk_conv_tc_supported",
                                                "hgk_conv_wgrad_tc_supported", "hgk_debug_set_timeline",
                                                "hgk_conv_tc_bnapply_supported", "hgk_pdl_arm", "hgk_conv_tc_x2_supported",
-                                               "hgk_aug_resample_ksize")]
+                                               "hgk_aug_resample_ksize", "hgk_aug_desc_fields")]
     assert sorted(launching) == sorted(SIGNATURES.keys())
     assert lib.cdll.hgk_version() >= 100
 

@@ -133,9 +133,23 @@ def test_crop_equals_oracle_on_random_cases_and_batch():
     assert ref.max() == 0
     imgs.append(torch.from_numpy(dark).to(DEV)); cs.append([150, 150]); ss.append(1.0); rs.append(0.0)
     want.append(A.im_to_torch_float(ref))
+    # the batched pipeline (one descriptor table, a dozen launches for the whole batch) and the per-image one: same bytes
     batch = H.crop_batch(imgs, np.array(cs), np.array(ss), np.array(rs), 256, 200)
     assert tuple(batch.shape) == (17, 3, 256, 256) and batch.dtype == torch.float32
     assert np.array_equal(batch.cpu().numpy(), np.stack(want))
+    assert torch.equal(batch, H.crop_batch(imgs, np.array(cs), np.array(ss), np.array(rs), 256, 200, batched=False))
+    assert torch.equal(batch, H.crop_batch(imgs, np.array(cs), np.array(ss), np.array(rs), 256, 200))       # scratch re-armed
+    # a batch without any pre-shrink / rotation, and the golden cases as one batch
+    sub = [k for k in range(17) if float(ss[k]) * 200 / 256 < 2 and rs[k] == 0.0]
+    if sub:
+        b2 = H.crop_batch([imgs[k] for k in sub], np.array([cs[k] for k in sub]), np.array([ss[k] for k in sub]),
+                          np.array([rs[k] for k in sub]), 256, 200)
+        assert np.array_equal(b2.cpu().numpy(), np.stack([want[k] for k in sub]))
+    gi = [case_inputs(k) for k in range(len(CASES))]
+    gb = H._crop_batch_u8([torch.from_numpy(g[0]).to(DEV) for g in gi], np.stack([g[1] for g in gi]),
+                          np.array([g[2][0] for g in gi], dtype=np.float32), np.array([g[3] for g in gi], dtype=np.float64), 256, 200)
+    for k in range(len(CASES)):
+        assert hashlib.sha256(gb[k].cpu().numpy().tobytes()).digest() == G["sha%d" % k].tobytes(), "batched, case %d" % k
 
 
 def test_crop_error_behaviour():

@@ -41,8 +41,16 @@ e1.record()
 torch.cuda.synchronize()
 wall = (time.time() - t0) / args.reps
 gpu_ms = e0.elapsed_time(e1) / args.reps
+for _ in range(2):
+    H.crop_batch(imgs, centers, scales, rots, 256, 200, batched=False)
+torch.cuda.synchronize()
+t1 = time.time()
+for _ in range(max(args.reps // 4, 2)):
+    H.crop_batch(imgs, centers, scales, rots, 256, 200, batched=False)
+torch.cuda.synchronize()
+wall_per_image_path = (time.time() - t1) / max(args.reps // 4, 2)
 line = {"what": "HumanAug.crop_batch: %d photographs 720x1280 -> [N,3,256,256] float32, sampled scale / rotation" % args.batch,
-        "gpu_ms_per_batch": gpu_ms, "wall_ms_per_batch": wall * 1e3, "images_per_s": args.batch / wall,
+        "gpu_ms_per_batch": gpu_ms, "per_image_launch_path_ms_per_batch": wall_per_image_path * 1e3, "wall_ms_per_batch": wall * 1e3, "images_per_s": args.batch / wall,
         "n_shrunk_first": int((scales * 200 / 256 >= 2).sum()), "n_rotated": int((rots != 0).sum())}
 if not args.no_cpu:
     from oracle import aug_oracle as A
