@@ -359,7 +359,8 @@ int hgk_aug_rotate(const unsigned char* in, int H, int W, const double* m6, unsi
 /* The whole crop pipeline of a BATCH in about a dozen launches (blockIdx.y = image): desc = N rows of hgk_aug_desc_fields()
  * int64 fields (struct AugDesc, csrc/warp.cu: source pointer and size, pre-shrink size, crop window, rotation flag / padding,
  * final-resize input, offsets of every intermediate into the two arenas), given both as a HOST copy (grid sizing) and a DEVICE
- * copy; mats_dev [N][6] rotation coefficients; arena_u8 / arena_i: byte and int scratch arenas the descriptors point into;
+ * copy; mats_dev [N][9]: six rotation coefficients + three colour gains (a source flagged `chw` is the resident 3 x H x W
+ * image, read W-flipped when `flip`, times its gains, clamped to [0,1]: data/joint_train_s_r_agent.py:160-168); arena_u8 / arena_i: byte and int scratch arenas the descriptors point into;
  * minmax [N][4] doubles; scratch [N][2][3] words in the idle state {0xFFFFFFFF, 0, 0}; out_stack [N][res][res][3] uint8.
  * Same bytes as the per-image entry points above. */
 int hgk_aug_desc_fields(void);

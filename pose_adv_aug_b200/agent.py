@@ -114,20 +114,19 @@ class AgentBatchLoader(object):
         from .pylib import HumanAug, HumanPts
         idx = [int(i) for i in (img_index.tolist() if isinstance(img_index, torch.Tensor) else img_index)]
         n = len(idx)
-        crops, cs, ss, rs, ptss, norms, pts_aug = [], [], [], [], [], [], []
+        crops, cs, ss, rs, ptss, norms, pts_aug, flips, gainss = [], [], [], [], [], [], [], [], []
         for k, i in enumerate(idx):
             img = self.images[i]
             pts, c, s_aug, r_aug, normalizer, flip, gains = self.sample_params(
                 self.annos[i], int(scale_index_list[k]), int(rotation_index_list[k]), int(img.shape[2]), rng)
-            if flip:
-                img = img.flip(2)
-            g = torch.tensor(gains, dtype=torch.float32, device=img.device).view(3, 1, 1)
-            hwc = (img * g).clamp_(0, 1).permute(1, 2, 0).contiguous()         # colour gain + clamp, im_to_numpy layout
-            crops.append(hwc); cs.append(c); ss.append(s_aug); rs.append(r_aug); ptss.append(pts); norms.append(normalizer)
+            # flip, colour gain + clamp and the CHW -> HWC view are evaluated on load by the batched crop kernels
+            crops.append(img); flips.append(flip); gainss.append(gains)
+            cs.append(c); ss.append(s_aug); rs.append(r_aug); ptss.append(pts); norms.append(normalizer)
             pa = HumanAug.TransformPts(pts, c, np.array([s_aug], dtype=np.float32), r_aug, self.out_res, self.std_size)
             pa[(pts[:, 0] <= 0) | (pts[:, 1] <= 0)] = 0                        # ref :207-210
             pts_aug.append(pa)
-        inp = HumanAug.crop_batch(crops, np.stack(cs), np.array(ss, dtype=np.float32), np.array(rs), self.inp_res, self.std_size)
+        inp = HumanAug.crop_batch_resident(crops, flips, gainss, np.stack(cs), np.array(ss, dtype=np.float32), np.array(rs),
+                                           self.inp_res, self.std_size)
         # the renderer takes float32 points while the reference truncates the float64 ones (draw_gaussian: int(pt -+ 3)):
         # hand it, per coordinate, a float32-exact stand-in with the same validity and the same truncations -- the value
         # itself when it is an integer, the middle of its unit interval otherwise

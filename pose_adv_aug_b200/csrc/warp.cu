@@ -285,7 +285,20 @@ struct AugDesc {
     long long in_h, in_w, o_ftmp;                              // input of the final resize (window minus padding), its horizontal pass
     long long c_fw_b, c_fw_k, ks_fw, c_fh_b, c_fh_k, ks_fh;    // tables of the final resize
     long long out_index;                                       // slot in the [N][res][res][3] output
+    long long chw, flip;                                       // source is 3 x H x W (the resident image as load_image returns it),
+                                                               // read W-flipped, times the colour gains of its mats row, clamped to [0,1]
 };
+constexpr int AUG_MATS = 9;                                    // per image: six rotation coefficients + three colour gains
+
+// source pixel (y, x, channel c) of image d: plain H x W x 3, or -- for the agent's loader (data/joint_train_s_r_agent.py:
+// 160-168: fliplr, then img[c].mul_(gain).clamp_(0, 1), then im_to_numpy) -- the flipped, colour-scaled C x H x W image
+__device__ __forceinline__ float aug_src_px(const AugDesc& d, const float* __restrict__ src, const double* __restrict__ m,
+                                            int y, int x, int c) {
+    if (!d.chw) return src[((size_t)y * d.W + x) * 3 + c];
+    const int xs = d.flip ? (int)d.W - 1 - x : x;
+    const float v = __fmul_rn(src[((size_t)c * d.H + y) * d.W + xs], (float)m[6 + c]);
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
 constexpr int AUG_DESC_FIELDS = sizeof(AugDesc) / 8;
 
 __device__ __forceinline__ void minmax_finish(float lo, float hi, int include_zero, unsigned int* scratch, double* out2) {
@@ -321,10 +334,11 @@ __device__ __forceinline__ void minmax_finish(float lo, float hi, int include_ze
 }
 
 // stage 0: min / max of the whole float32 image (pre-shrink images only); stage 1: of the pasted region of the crop window
-__global__ void __launch_bounds__(256) aug_b_minmax_kernel(const AugDesc* __restrict__ desc, int stage,
+__global__ void __launch_bounds__(256) aug_b_minmax_kernel(const AugDesc* __restrict__ desc, int stage, const double* __restrict__ mats,
                                                             const unsigned char* __restrict__ arena, unsigned int* __restrict__ scratch,
                                                             double* __restrict__ minmax) {
     const AugDesc d = desc[blockIdx.y];
+    const double* m = mats + (size_t)blockIdx.y * AUG_MATS;
     if (stage == 0 && d.pre_h == 0) return;
     unsigned int* scr = scratch + ((size_t)blockIdx.y * 2 + stage) * 3;
     double* out2 = minmax + (size_t)blockIdx.y * 4 + stage * 2;
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(256) aug_b_minmax_kernel(const AugDesc* __rest
         const int rw = (int)d.W * 3;
         for (int r = blockIdx.x; r < (int)d.H; r += gridDim.x)
             for (int c = threadIdx.x; c < rw; c += blockDim.x) {
-                const float v = img[(size_t)r * rw + c];
+                const float v = d.chw ? aug_src_px(d, img, m, r, c / 3, c % 3) : img[(size_t)r * rw + c];
                 lo = fminf(lo, v); hi = fmaxf(hi, v);
             }
         minmax_finish(lo, hi, 0, scr, out2);
@@ -352,17 +366,18 @@ __global__ void __launch_bounds__(256) aug_b_minmax_kernel(const AugDesc* __rest
         const float* img = reinterpret_cast<const float*>(d.src);
         for (int r = y0 + blockIdx.x; r < y1; r += gridDim.x)
             for (int c = threadIdx.x; c < rw; c += blockDim.x) {
-                const float v = img[((size_t)r * d.W + x0) * 3 + c];
+                const float v = d.chw ? aug_src_px(d, img, m, r, x0 + c / 3, c % 3) : img[((size_t)r * d.W + x0) * 3 + c];
                 lo = fminf(lo, v); hi = fmaxf(hi, v);
             }
     }
     minmax_finish(lo, hi, (int)d.has_zero, scr, out2);
 }
 
-__global__ void __launch_bounds__(256) aug_b_image_bytes_kernel(const AugDesc* __restrict__ desc, const double* __restrict__ minmax,
-                                                                 unsigned char* __restrict__ arena) {
+__global__ void __launch_bounds__(256) aug_b_image_bytes_kernel(const AugDesc* __restrict__ desc, const double* __restrict__ mats,
+                                                                 const double* __restrict__ minmax, unsigned char* __restrict__ arena) {
     const AugDesc d = desc[blockIdx.y];
     if (d.pre_h == 0) return;
+    const double* m = mats + (size_t)blockIdx.y * AUG_MATS;
     const float* src = reinterpret_cast<const float*>(d.src);
     const double* mm = minmax + (size_t)blockIdx.y * 4;
     const float cmin = (float)mm[0];
@@ -372,7 +387,14 @@ __global__ void __launch_bounds__(256) aug_b_image_bytes_kernel(const AugDesc* _
     unsigned char* out = arena + d.o_bytes;
     const long long total = d.H * d.W * 3;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float b = __fmul_rn(__fsub_rn(__ldg(src + i), cmin), scale);
+        float v;
+        if (d.chw) {
+            const long long p = i / 3;
+            v = aug_src_px(d, src, m, (int)(p / d.W), (int)(p % d.W), (int)(i - p * 3));
+        } else {
+            v = __ldg(src + i);
+        }
+        float b = __fmul_rn(__fsub_rn(v, cmin), scale);
         b = fminf(fmaxf(b, 0.f), 255.f);
         out[i] = (unsigned char)(int)__fadd_rn(b, 0.5f);
     }
@@ -492,9 +514,10 @@ __global__ void __launch_bounds__(256) aug_b_resize_v_kernel(const AugDesc* __re
     }
 }
 
-__global__ void __launch_bounds__(256) aug_b_window_bytes_kernel(const AugDesc* __restrict__ desc, const double* __restrict__ minmax,
-                                                                  unsigned char* __restrict__ arena) {
+__global__ void __launch_bounds__(256) aug_b_window_bytes_kernel(const AugDesc* __restrict__ desc, const double* __restrict__ mats,
+                                                                  const double* __restrict__ minmax, unsigned char* __restrict__ arena) {
     const AugDesc d = desc[blockIdx.y];
+    const double* m = mats + (size_t)blockIdx.y * AUG_MATS;
     const double* mm = minmax + (size_t)blockIdx.y * 4 + 2;
     const double cmin = mm[0];
     double cscale = __dsub_rn(mm[1], cmin);
@@ -514,7 +537,7 @@ __global__ void __launch_bounds__(256) aug_b_window_bytes_kernel(const AugDesc* 
         double v = 0.0;
         if (y >= ny0 && y < ny1 && x >= nx0 && x < nx1) {
             const size_t idx = ((size_t)(y + oy) * SW + (x + ox)) * 3 + c;
-            v = u8 ? (double)s8[idx] : (double)sf[idx];
+            v = u8 ? (double)s8[idx] : (d.chw ? (double)aug_src_px(d, sf, m, y + oy, x + ox, c) : (double)sf[idx]);
         }
         out[i] = bytescale_f64(v, cmin, scale);
     }
@@ -524,7 +547,7 @@ __global__ void __launch_bounds__(256) aug_b_rotate_kernel(const AugDesc* __rest
                                                             unsigned char* __restrict__ arena) {
     const AugDesc d = desc[blockIdx.y];
     if (!d.rot) return;
-    const double* a = mats + (size_t)blockIdx.y * 6;
+    const double* a = mats + (size_t)blockIdx.y * AUG_MATS;
     const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5];
     const int H = (int)d.Hn, W = (int)d.Wn;
     const unsigned char* in = arena + d.o_win;
@@ -707,14 +730,14 @@ extern "C" int hgk_aug_crop_batch(const long long* desc_host, const long long* d
         return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
     };
     if (any_pre) {
-        aug_b_minmax_kernel<<<dim3(rows_grid, N), 256, 0, st>>>(dd, 0, arena_u8, scratch, minmax);
-        aug_b_image_bytes_kernel<<<dim3(gx(max_img), N), 256, 0, st>>>(dd, minmax, arena_u8);
+        aug_b_minmax_kernel<<<dim3(rows_grid, N), 256, 0, st>>>(dd, 0, mats_dev, arena_u8, scratch, minmax);
+        aug_b_image_bytes_kernel<<<dim3(gx(max_img), N), 256, 0, st>>>(dd, mats_dev, minmax, arena_u8);
         aug_b_coeffs_kernel<<<dim3((unsigned)((max_pre_dim + 127) / 128), N, 2), 128, 0, st>>>(dd, 0, res, arena_i);
         aug_b_resize_h_kernel<<<dim3(gx(max_pre_h_out), N), 256, 0, st>>>(dd, 0, res, arena_i, arena_u8);
         aug_b_resize_v_kernel<<<dim3(gx(max_pre_v_out), N), 256, 0, st>>>(dd, 0, res, arena_i, arena_u8, out_stack);
     }
-    aug_b_minmax_kernel<<<dim3(rows_grid, N), 256, 0, st>>>(dd, 1, arena_u8, scratch, minmax);
-    aug_b_window_bytes_kernel<<<dim3(gx(max_win * 3), N), 256, 0, st>>>(dd, minmax, arena_u8);
+    aug_b_minmax_kernel<<<dim3(rows_grid, N), 256, 0, st>>>(dd, 1, mats_dev, arena_u8, scratch, minmax);
+    aug_b_window_bytes_kernel<<<dim3(gx(max_win * 3), N), 256, 0, st>>>(dd, mats_dev, minmax, arena_u8);
     if (any_rot) aug_b_rotate_kernel<<<dim3(gx(max_win), N), 256, 0, st>>>(dd, mats_dev, arena_u8);
     aug_b_coeffs_kernel<<<dim3((unsigned)((res + 127) / 128), N, 2), 128, 0, st>>>(dd, 1, res, arena_i);
     aug_b_resize_h_kernel<<<dim3(gx(max_fh), N), 256, 0, st>>>(dd, 1, res, arena_i, arena_u8);

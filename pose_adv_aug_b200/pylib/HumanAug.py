@@ -261,14 +261,17 @@ def crop(img, center, scale, rot, res, size):
 
 _DESC_FIELDS = ("src", "H", "W", "pre_h", "pre_w", "o_bytes", "o_ptmp", "o_pout", "c_pw_b", "c_pw_k", "ks_pw", "c_ph_b", "c_ph_k",
                 "ks_ph", "Hn", "Wn", "ny0", "ny1", "nx0", "nx1", "oy", "ox", "has_zero", "o_win", "rot", "o_rot", "pad", "in_h", "in_w",
-                "o_ftmp", "c_fw_b", "c_fw_k", "ks_fw", "c_fh_b", "c_fh_k", "ks_fh", "out_index")      # struct AugDesc, csrc/warp.cu
+                "o_ftmp", "c_fw_b", "c_fw_k", "ks_fw", "c_fh_b", "c_fh_k", "ks_fh", "out_index", "chw", "flip")      # struct AugDesc, csrc/warp.cu
 _batch_scratch = {}
 
 
-def _crop_batch_u8(imgs, centers, scales, rots, res, size):
+def _crop_batch_u8(imgs, centers, scales, rots, res, size, flips=None, gains=None):
     """All crops of a batch through hgk_aug_crop_batch: the host lays out one descriptor row per image (geometry as in
     `crop`, offsets of every intermediate into two scratch arenas), uploads the table once, and a dozen launches with
-    blockIdx.y = image do the pixel work.  Returns the uint8 stack [N,res,res,3]."""
+    blockIdx.y = image do the pixel work.  Returns the uint8 stack [N,res,res,3].
+    flips / gains given: the images are the resident 3 x H x W tensors and every source pixel is read W-flipped (flips[k]),
+    times gains[k][channel], clamped to [0, 1] -- the flip / colour augmentation of the agent's loader, never materialised."""
+    chw = gains is not None
     lib = get_lib()
     n = len(imgs)
     dev = imgs[0].device
@@ -292,11 +295,11 @@ def _crop_batch_u8(imgs, centers, scales, rots, res, size):
         img = imgs[k]
         if not isinstance(img, torch.Tensor) or not img.is_cuda:
             raise HGKError("HumanAug.crop_batch runs on CUDA tensors only (no CPU fallback)")
-        if img.dim() != 3 or img.shape[2] != 3 or img.dtype != torch.float32:
-            raise ValueError("crop_batch: expected float32 H x W x 3 images, got %s %s" % (tuple(img.shape), img.dtype))
+        if img.dim() != 3 or img.shape[0 if chw else 2] != 3 or img.dtype != torch.float32:
+            raise ValueError("crop_batch: expected float32 %s images, got %s %s" % ("3 x H x W" if chw else "H x W x 3", tuple(img.shape), img.dtype))
         img = img.contiguous()
         keep.append(img)
-        H, W = int(img.shape[0]), int(img.shape[1])
+        H, W = (int(img.shape[1]), int(img.shape[2])) if chw else (int(img.shape[0]), int(img.shape[1]))
         if min(H, W) <= 4:
             raise ValueError("crop_batch: image too small")
         rot = float(rots[k])
@@ -309,7 +312,7 @@ def _crop_batch_u8(imgs, centers, scales, rots, res, size):
             raise ValueError("crop_batch: the crop window of sample %d does not intersect the image" % k)
         d = dict.fromkeys(_DESC_FIELDS, 0)
         d.update(src=img.data_ptr(), H=H, W=W, Hn=Hn, Wn=Wn, ny0=new_y[0], ny1=new_y[1], nx0=new_x[0], nx1=new_x[1],
-                 oy=old_y[0] - new_y[0], ox=old_x[0] - new_x[0], out_index=k,
+                 oy=old_y[0] - new_y[0], ox=old_x[0] - new_x[0], out_index=k, chw=int(chw), flip=int(bool(flips[k])) if chw else 0,
                  has_zero=int((new_y[1] - new_y[0]) < Hn or (new_x[1] - new_x[0]) < Wn))
         if pre is not None:
             ks_w, ks_h = lib.aug_resample_ksize(W, pre[1]), lib.aug_resample_ksize(H, pre[0])
@@ -332,7 +335,9 @@ def _crop_batch_u8(imgs, centers, scales, rots, res, size):
         d.update(in_h=in_h, in_w=in_w, o_ftmp=take_u8(in_h * res * 3), ks_fw=ks_w, ks_fh=ks_h,
                  c_fw_b=take_i(res * 2), c_fw_k=take_i(res * ks_w), c_fh_b=take_i(res * 2), c_fh_k=take_i(res * ks_h))
         rows.append([d[f] for f in _DESC_FIELDS])
-        mats.append(m)
+        # (the gains travel as doubles and are narrowed to float32 on the device: torch multiplies a float32 tensor by the
+        #  float32-rounded Python scalar)
+        mats.append(list(m) + ([float(v) for v in gains[k]] if chw else [1.0, 1.0, 1.0]))
     desc_h = np.ascontiguousarray(np.array(rows, dtype=np.int64))
     desc_d = torch.from_numpy(desc_h).to(dev)
     mats_d = torch.from_numpy(np.array(mats, dtype=np.float64)).to(dev)
@@ -371,6 +376,26 @@ def crop_batch(imgs, centers, scales, rots, res=256, size=200, batched=True):
             if c.dtype != torch.uint8:
                 raise ValueError("crop_batch: sample %d hit the degenerate early return of crop (image smaller than 2 px after shrinking)" % k)
             stack[k].copy_(c)
+    out = torch.empty(n, 3, res, res, device=dev, dtype=torch.float32)
+    lib = get_lib()
+    lib.check(lib.aug_to_chw_float(stack.data_ptr(), n, res, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+              "hgk_aug_to_chw_float")
+    return out
+
+
+def crop_batch_resident(imgs_chw, flips, gains, centers, scales, rots, res=256, size=200):
+    """crop_batch for the agent's loader: imgs_chw = the resident float32 3 x H x W CUDA images (what load_image returns);
+    flips[k] / gains[k] = the horizontal flip and the three colour gains `AGENT.__getitem__` applies before the crop
+    (ref data/joint_train_s_r_agent.py:160-168), evaluated on load instead of materialising a flipped, scaled, transposed copy
+    of every image.  Returns [N,3,res,res] float32."""
+    n = len(imgs_chw)
+    if n == 0:
+        raise ValueError("crop_batch_resident: empty batch")
+    centers = np.asarray(centers, dtype=np.float32).reshape(n, 2)
+    scales = np.asarray(scales, dtype=np.float32).reshape(n)
+    rots = np.asarray(rots, dtype=np.float64).reshape(n)
+    stack = _crop_batch_u8(imgs_chw, centers, scales, rots, res, size, flips=list(flips), gains=[list(g) for g in gains])
+    dev = imgs_chw[0].device
     out = torch.empty(n, 3, res, res, device=dev, dtype=torch.float32)
     lib = get_lib()
     lib.check(lib.aug_to_chw_float(stack.data_ptr(), n, res, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
