@@ -200,3 +200,58 @@ def test_agent_batch_loader_equals_oracle():
     assert np.array_equal(got[4].numpy().reshape(-1), want[4].astype(np.float32))
     assert np.array_equal(got[5].numpy(), want[5]) and np.array_equal(got[6].numpy(), want[6])
     assert want[1].reshape(len(img_index), 16, -1).max(axis=2).min() == 0 and want[1].max() == 1      # blobs and an absent joint
+
+
+def test_joint_train_iteration_vs_oracle():
+    """One agent-augmented joint-train iteration end to end (ref joint-train-pose-s-r-agent.py:246-299): half-hourglass
+    forward (hg.train(), agent.eval()) -> ASN scale / rotation distributions -> sampling -> the batch re-augmented with the
+    sampled bins from resident photographs (load_batch_data) -> full train step -> PCK -- every stage against the oracle
+    chain hg_oracle / eval_oracle / aug_oracle fed with the same random numbers."""
+    from collections import OrderedDict
+    from oracle import hg_oracle as O, eval_oracle as E
+    from pose_adv_aug_b200 import HourglassTrainer, agent
+    from pose_adv_aug_b200.models import asn_stacked_hg as M
+    from pose_adv_aug_b200.pylib import Evaluation
+    S, C, N, R = 2, 32, 3, 256
+    sd = synth.make_state_dict(O.hg_schema(S, 1, 16, C), seed=301)
+    asd = synth.make_state_dict(O.asn_schema(C, C, 7, 7, is_aug=True), seed=302)
+    net = M.create_hg(S, 1, 16, C)
+    net.load_state_dict(sd)
+    asn = M.create_asn(C, C, 7, 7, is_aug=True)
+    asn.load_state_dict(asd)
+    net.to(DEV), asn.to(DEV)
+    rng = np.random.default_rng(303)
+    sizes = [(int(rng.integers(400, 700)), int(rng.integers(500, 900))) for _ in range(N)]
+    photos = [np.ascontiguousarray(np.transpose(synth.make_photo(h, w, 310 + k), (2, 0, 1))) for k, (h, w) in enumerate(sizes)]
+    annos = _annos(N, rng, sizes)
+    loader = agent.AgentBatchLoader([torch.from_numpy(p).to(DEV) for p in photos], annos)
+    img_index = list(range(N))
+    x0 = synth.make_images(N, R, seed=304)
+    # 1. half-hourglass + ASN forward (:250-251)
+    net.train(); asn.eval()
+    with torch.no_grad():
+        ps, pr = net(x0.to(DEV), asn, is_half_hg=True, is_aug=True)
+    (ps_o, pr_o), _ = O.hg_forward(OrderedDict((k, v.clone()) for k, v in sd.items()), x0, S, training=True, asn_sd=asd, is_half_hg=True)
+    assert float((ps.cpu() - ps_o).abs().max() / ps_o.abs().max()) < 1e-3 and float((pr.cpu() - pr_o).abs().max() / pr_o.abs().max()) < 1e-3
+    # 2. sampling (:252-271): the same uniforms give the same bins
+    u = torch.from_numpy(np.random.RandomState(305).random_sample(2 * N).reshape(N, 2))
+    _, _, si, ri = agent.sample_scale_rotation(ps, pr, uniforms=u)
+    si_o = E.sample_agent(ps_o.detach().numpy(), u[:, 0].numpy())[1]
+    ri_o = E.sample_agent(pr_o.detach().numpy(), u[:, 1].numpy())[1]
+    assert si.cpu().tolist() == si_o.tolist() and ri.cpu().tolist() == ri_o.tolist()
+    # 3. the re-augmented batch (load_batch_data, :425-450): byte-exact images and targets
+    got = loader.load_batch(si.tolist(), ri.tolist(), img_index, rng=np.random.RandomState(306))
+    want = A.agent_batch(photos, annos, si_o.tolist(), ri_o.tolist(), img_index, np.random.RandomState(306))
+    assert np.array_equal(got[0].cpu().numpy(), want[0]) and np.array_equal(got[1].cpu().numpy(), want[1])
+    # 4. the train step on it (:273-289) and 5. PCK of the last stack (:291-296)
+    tr = HourglassTrainer(net, N, R, use_graph=True)
+    loss = float(tr.step(got[0], got[1]))
+    outs_o, loss_o, _, _ = O.train_step(OrderedDict((k, v.clone()) for k, v in sd.items()), torch.from_numpy(want[0]),
+                                        torch.from_numpy(want[1]), S, 1)
+    assert abs(loss - float(loss_o)) < 1e-3 * abs(float(loss_o)), (loss, float(loss_o))
+    for h, o in zip(tr.heatmaps(), outs_o):
+        assert float((h.cpu() - o).abs().max() / o.abs().max()) < 1e-3
+    idx = list(range(16))
+    acc = Evaluation.accuracy(tr.heatmaps()[-1], got[1], idx)
+    acc_o = E.accuracy(outs_o[-1].detach().numpy(), want[1], idx)
+    assert abs(float(acc[0]) - float(acc_o[0])) <= 0.1
