@@ -640,7 +640,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-path", type=int, default=None)
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=10)
     ap.add_argument("--low-streams", type=int, default=3, help="of --streams, low-priority streams reserved for weight gradients")
     args = ap.parse_args()
     if args.config == 5:

@@ -125,7 +125,7 @@ def bucket_last_writers(launches, rw_override, grad_ptr, numel, splits):
 
 class HourglassTrainer(object):
     def __init__(self, net, batch, res, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, use_graph=True,
-                 distributed=None, n_streams=8, n_low=3, ar_buckets=None, fake_collective=None):
+                 distributed=None, n_streams=10, n_low=3, ar_buckets=None, fake_collective=None):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.net, self.N, self.R, self.device = net, batch, res, torch.device(device)

@@ -11,7 +11,7 @@ from pose_adv_aug_b200.models import asn_stacked_hg as M
 from pose_adv_aug_b200 import HourglassTrainer
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--streams", type=int, default=8)
+ap.add_argument("--streams", type=int, default=10)
 ap.add_argument("--low-streams", type=int, default=3)
 ap.add_argument("--out", default="gpurun_out/graph_timeline.json")
 args = ap.parse_args()
