@@ -1,7 +1,8 @@
 """Measurement of the GPU crop / rotate / resize augmentation (pylib/HumanAug.py::crop_batch, csrc/warp.cu) next to the
 reference's CPU path (oracle/aug_oracle.py::crop = the reference's crop over PIL, one process as inside a DataLoader worker):
 a batch of 24 MPII-sized photographs (720 x 1280) with agent-style sampled scales / rotations.
-  python tools/bench_aug.py [--batch 24] [--reps 20]"""
+  python tools/bench_aug.py [--batch 24] [--reps 20] [--cpu-baseline]
+The GPU arm imports nothing from oracle/; the --cpu-baseline leg is the one place this tool executes the checker."""
 import argparse
 import json
 import os
@@ -19,7 +20,8 @@ from pose_adv_aug_b200.pylib import HumanAug as H            # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=24)
 ap.add_argument("--reps", type=int, default=20)
-ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--cpu-baseline", action="store_true",
+                help="also time the reference's CPU path (oracle/aug_oracle.py, the checker) on the same batch and compare the bytes")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
@@ -52,7 +54,7 @@ wall_per_image_path = (time.time() - t1) / max(args.reps // 4, 2)
 line = {"what": "HumanAug.crop_batch: %d photographs 720x1280 -> [N,3,256,256] float32, sampled scale / rotation" % args.batch,
         "gpu_ms_per_batch": gpu_ms, "per_image_launch_path_ms_per_batch": wall_per_image_path * 1e3, "wall_ms_per_batch": wall * 1e3, "images_per_s": args.batch / wall,
         "n_shrunk_first": int((scales * 200 / 256 >= 2).sum()), "n_rotated": int((rots != 0).sum())}
-if not args.no_cpu:
+if args.cpu_baseline:
     from oracle import aug_oracle as A
     t0 = time.time()
     ref = [A.im_to_torch_float(A.crop(p, c, s, r, 256, 200)) for p, c, s, r in zip(photos, centers, scales, rots)]

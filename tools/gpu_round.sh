@@ -15,7 +15,7 @@ timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 tail -c 3500 $OUT/${TAG}_bench.json
 timeout 300 python bench.py --config 5 --no-cpu-baseline > $OUT/${TAG}_bench_config5.json 2>> $OUT/${TAG}_bench.err; cut -c 1-400 $OUT/${TAG}_bench_config5.json
 timeout 300 python bench.py --config 3 > $OUT/${TAG}_bench_config3.json 2>> $OUT/${TAG}_bench.err; cut -c 1-400 $OUT/${TAG}_bench_config3.json
-timeout 300 python tools/bench_aug.py > $OUT/${TAG}_bench_aug.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench_aug.json
+timeout 300 python tools/bench_aug.py --cpu-baseline > $OUT/${TAG}_bench_aug.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench_aug.json
 timeout 300 python tools/time_plan.py --top 30 --filter conv > $OUT/${TAG}_time_plan.txt 2>&1
 head -34 $OUT/${TAG}_time_plan.txt
 timeout 300 python tools/graph_timeline.py --out $OUT/${TAG}_graph_timeline.json > $OUT/${TAG}_graph_timeline.txt 2>&1
