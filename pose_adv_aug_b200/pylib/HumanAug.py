@@ -248,8 +248,8 @@ def crop(img, center, scale, rot, res, size):
                                    new_x[0], new_x[1], mm.data_ptr(), Hn, Wn, wb.data_ptr(), st), "hgk_aug_window_bytes")
     off = 0
     if not rot == 0:                                                       # :166-170 imrotate + padding removed
-        if (rot % 360.0) in (0.0, 90.0, 180.0, 270.0):
-            raise HGKError("crop: rotation by a multiple of 90 degrees takes PIL's transpose path, which is not built")
+        # (multiples of 90 degrees: PIL takes copy / transpose fast paths there; the generic inverse-affine kernel lands on
+        #  exact pixel centres for them -- dx = dy = 0 -- and returns the same bytes, tests/test_aug_gpu.py)
         if pad <= 0 or Hn - 2 * pad <= 0 or Wn - 2 * pad <= 0:
             raise ValueError("crop: empty image after removing the rotation padding")
         m = (ctypes.c_double * 6)(*_rotate_matrix(rot, Wn, Hn))
@@ -323,8 +323,6 @@ def _crop_batch_u8(imgs, centers, scales, rots, res, size, flips=None, gains=Non
         off = 0
         m = [0.0] * 6
         if not rot == 0:
-            if (rot % 360.0) in (0.0, 90.0, 180.0, 270.0):
-                raise HGKError("crop: rotation by a multiple of 90 degrees takes PIL's transpose path, which is not built")
             if pad <= 0 or Hn - 2 * pad <= 0 or Wn - 2 * pad <= 0:
                 raise ValueError("crop: empty image after removing the rotation padding")
             d.update(rot=1, o_rot=take_u8(Hn * Wn * 3), pad=pad)

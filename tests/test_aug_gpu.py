@@ -61,8 +61,10 @@ def test_resize_kernels_equal_pil():
 def test_rotate_kernel_equals_pil():
     H = _aug()
     rng = np.random.default_rng(6)
+    # (the multiples of 90 degrees are PIL's copy / transpose fast paths: the inverse-affine kernel returns the same bytes)
     for (h, w, ang) in [(300, 300, 17.3), (411, 411, -33.0), (200, 260, 5.5), (333, 333, 61.2), (128, 128, -0.7), (90, 64, 200.0),
-                        (725, 725, 44.9)]:
+                        (725, 725, 44.9), (200, 200, 90.0), (200, 260, 90.0), (301, 301, 270.0), (333, 332, 180.0), (200, 260, 360.0),
+                        (120, 120, -90.0), (64, 90, 450.0)]:
         a = (rng.random((h, w, 3)) * 255).astype(np.uint8)
         ref = np.array(Image.fromarray(a).rotate(ang, resample=Image.BILINEAR))
         t = torch.from_numpy(a).to(DEV)
@@ -163,6 +165,10 @@ def test_crop_error_behaviour():
         H.crop(t, [5000, 5000], 1.0, 0, 256, 200)                                  # window off the image (numpy raises too)
     with pytest.raises(ValueError):
         H.crop(t.double(), [200, 150], 1.0, 0, 256, 200)
+    # rotations by multiples of 90 degrees (PIL's fast paths) give the oracle's bytes too
+    for r in (90.0, 180.0, -90.0, 360.0):
+        c, s_ = np.array([200.0, 150.0], dtype=np.float32), np.float32(0.9)
+        assert np.array_equal(H.crop(t, c, s_, r, 256, 200).cpu().numpy(), A.crop(img, c, s_, r, 256, 200)), r
     tiny = torch.from_numpy(synth.make_photo(8, 8, 3)).to(DEV)
     assert H.crop(tiny, [4, 4], 12.0, 0, 256, 200) is tiny                         # degenerate early return (ref :128-129)
 
