@@ -42,6 +42,21 @@ def _worker(rank, world, port, ret):
     local = x[lo:hi].mean().reshape(1)
     dist.all_reduce(local)
     assert abs(float(local) / world - float(x.mean())) < 1e-12
+    # bucketed all-reduce (trainer.py: the flat gradient buffer is reduced bucket by bucket, back to front, as the backward
+    # pass completes the buckets): slices of the flat buffer reduced in any order == one all-reduce of the whole buffer
+    from pose_adv_aug_b200.trainer import bucket_splits
+    offsets = [0, 128, 1024, 1152, 4096, 4224, 9000, 9128, 20000]
+    numel = 24064
+    splits = bucket_splits(offsets, numel, 4)
+    assert splits == sorted(splits) and all(s_ in offsets for s_ in splits) and 1 <= len(splits) <= 3
+    edges = [0] + splits + [numel]
+    gen = torch.Generator().manual_seed(100 + rank)
+    gflat = torch.randn(numel, generator=gen)
+    whole = gflat.clone()
+    hdist.allreduce_flat_grads(whole)
+    for lo, hi in reversed(list(zip(edges[:-1], edges[1:]))):
+        hdist.allreduce_flat_grads(gflat[lo:hi])
+    assert torch.equal(gflat, whole)
     dist.barrier()
     dist.destroy_process_group()
     ret[rank] = 1
