@@ -79,6 +79,17 @@ class AgentBatchLoader(object):
             if not isinstance(im, torch.Tensor) or not im.is_cuda or im.dtype != torch.float32 or im.dim() != 3 or im.shape[0] != 3:
                 raise HGKError("AgentBatchLoader keeps float32 CUDA images [3,H,W] (no CPU fallback)")
         self.images, self.annos = images, annos
+        # per annotation, once: the float32 arrays __getitem__ builds from the json entry on every call (ref :105-124)
+        f32 = np.float32
+        self._prep = []
+        for a in annos:
+            s = f32(a['scale_provided'])
+            c = np.asarray(a['objpos'], dtype=np.float32).copy()
+            c[1] = c[1] + f32(15) * s                                          # ref :122-124 (torch float32 arithmetic)
+            self._prep.append((np.asarray(a['joint_self'], dtype=np.float32)[:, 0:2].copy(), c, s * f32(1.25), a['normalizer'] * 0.6))
+        self._perm = np.arange(16)
+        for i, j in self.MATCHED:
+            self._perm[[i, j]] = self._perm[[j, i]]
         self.inp_res, self.out_res, self.std_size = inp_res, out_res, std_size
         self.scale_means = np.arange(-0.6, 0.61, 0.2)                          # ref :31-35
         self.scale_var = 0.05
@@ -90,20 +101,23 @@ class AgentBatchLoader(object):
         flip, gains)."""
         r = np.random if rng is None else rng
         f32 = np.float32
-        pts = np.asarray(a['joint_self'], dtype=np.float32)[:, 0:2].copy()
-        c = np.asarray(a['objpos'], dtype=np.float32).copy()
-        s = f32(a['scale_provided'])
-        c[1] = c[1] + f32(15) * s                                              # ref :122-124 (torch float32 arithmetic)
-        s = s * f32(1.25)
-        normalizer = a['normalizer'] * 0.6
+        if isinstance(a, (int, np.integer)):                                   # index into the annotations prepared in __init__
+            pts, c, s, normalizer = self._prep[a]
+            pts, c = pts.copy(), c.copy()
+        else:
+            pts = np.asarray(a['joint_self'], dtype=np.float32)[:, 0:2].copy()
+            c = np.asarray(a['objpos'], dtype=np.float32).copy()
+            s = f32(a['scale_provided'])
+            c[1] = c[1] + f32(15) * s                                          # ref :122-124 (torch float32 arithmetic)
+            s = s * f32(1.25)
+            normalizer = a['normalizer'] * 0.6
         scale_factor = sample_from_small_gaussian(self.scale_means[scale_index], self.scale_var, r)       # ref :139-143
         r_aug = sample_from_small_gaussian(self.rotation_means[rotation_index], self.rotation_var, r)
         s_aug = s * f32(2 ** scale_factor)
         flip = bool(r.random() <= 0.5)                                         # ref :160
         if flip:
             pts[:, 0] = f32(width) - pts[:, 0]
-            for i, j in self.MATCHED:
-                pts[[i, j]] = pts[[j, i]]
+            pts = pts[self._perm]                                              # the six left / right swaps of shufflelr
             c[0] = f32(width) - c[0]
         gains = [r.uniform(0.6, 1.4) for _ in range(3)]                        # ref :166-168
         return pts, c, s_aug, r_aug, normalizer, flip, gains
@@ -118,7 +132,7 @@ class AgentBatchLoader(object):
         for k, i in enumerate(idx):
             img = self.images[i]
             pts, c, s_aug, r_aug, normalizer, flip, gains = self.sample_params(
-                self.annos[i], int(scale_index_list[k]), int(rotation_index_list[k]), int(img.shape[2]), rng)
+                i, int(scale_index_list[k]), int(rotation_index_list[k]), int(img.shape[2]), rng)
             # flip, colour gain + clamp and the CHW -> HWC view are evaluated on load by the batched crop kernels
             crops.append(img); flips.append(flip); gainss.append(gains)
             cs.append(c); ss.append(s_aug); rs.append(r_aug); ptss.append(pts); norms.append(normalizer)
