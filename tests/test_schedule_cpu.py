@@ -272,3 +272,45 @@ def test_weight_repack_has_real_dependencies_and_the_stem_is_issued_first():
                 assert vc[i_p][so[j]] >= j
     assert n_checked > 150 or not wr
     assert vc[i_stem][so[i_pack]] < i_pack if so[i_stem] != so[i_pack] else True
+
+
+def test_bucket_split_dynamic_programme_is_optimal_on_small_cases():
+    """plan_bucket_splits minimises sum(bucket elements x completion position of the bucket) over contiguous partitions:
+    compared with brute force over every partition of small random instances."""
+    import itertools
+    import random
+    from pose_adv_aug_b200 import trainer as T
+
+    class _Store(object):
+        pass
+
+    class _Plan(object):
+        pass
+
+    rnd = random.Random(7)
+    for trial in range(30):
+        P = rnd.randint(2, 9)
+        sizes = [rnd.randint(1, 50) * 32 for _ in range(P)]
+        pos = [rnd.randint(-1, 40) for _ in range(P)]
+        nb = rnd.randint(1, 4)
+        st = _Store()
+        st.offsets = [sum(sizes[:i]) for i in range(P)]
+        st.numel = sum(sizes)
+        plan = _Plan()
+        plan.bwd = [None] * 41
+        orig = T.param_completion
+        T.param_completion = lambda pl, s_: pos
+        try:
+            cuts = T.plan_bucket_splits(plan, st, nb)
+        finally:
+            T.param_completion = orig
+        assert cuts == sorted(cuts) and all(c in st.offsets[1:] for c in cuts) and len(cuts) <= nb - 1
+        c = [(p + 1) / 41.0 for p in pos]
+
+        def cost(cut_idx):
+            edges = [0] + list(cut_idx) + [P]
+            return sum(sum(sizes[a:b]) * max(c[a:b]) for a, b in zip(edges[:-1], edges[1:]))
+
+        best = min(cost(ci) for k in range(0, nb) for ci in itertools.combinations(range(1, P), k))
+        got = cost([st.offsets.index(x) for x in cuts])
+        assert abs(got - best) < 1e-9 * max(best, 1.0), (sizes, pos, nb, cuts, got, best)
